@@ -1,0 +1,497 @@
+"""CPU oracle for PINOCCHIO's collapse-time hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a NumPy restatement of the reference algorithm (pigimonaco/Pinocchio V5.1) for
+GenIC -> per-radius Hessian -> ellipsoidal collapse -> Fmax/Rmax -> 2LPT/3LPT displacements.
+It is the checker for the CUDA path: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  Nothing under
+``pinocchio_b200/`` does, and the product path has no CPU fallback.
+
+Parity pin: ``tests/test_oracle_golden.py`` checks this module against the reference's own
+shipped run ``HMF_Validation/`` (sigma(R) per smoothing radius to the 4 printed digits, the
+210-bin FmaxPDF histogram, the collapsed-particle count; fixtures copied to tests/golden/),
+plus the GSL rng known answers (mt19937 seed 4357, ranlxd1 seed 1).
+
+Every function cites the reference file:line it follows (paths relative to the reference root).
+Third-party arithmetic that is not in the reference tree (GSL 2.7.1 rng + cspline, FFTW/PFFT)
+is restated from its published algorithm.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+PI = 3.14159265358979323846      # src/pinocchio.h:56
+SMALL = 1.0e-20                  # src/collapse_times.c:38
+NBINS_PDF = 210                  # NBINS, src/pinocchio.h:65
+
+# slot order of second_derivatives[0][ider-1]: xx,yy,zz,xy,xz,yz (src/fmax.c:235-239)
+HESSIAN_PAIRS = ((1, 1), (2, 2), (3, 3), (1, 2), (1, 3), (2, 3))
+
+
+# ======================================================================================
+# GSL random number generators
+# ======================================================================================
+def mt19937_outputs(seed: int, count: int) -> np.ndarray:
+    """First ``count`` 32-bit outputs of gsl_rng_mt19937 seeded with ``seed``.
+
+    gsl mt19937 == reference MT19937 with init_genrand seeding (seed 0 -> 4357).
+    """
+    if seed == 0:
+        seed = 4357
+    bg = np.random.MT19937()
+    bg._legacy_seeding(int(seed) & 0xFFFFFFFF)
+    return bg.random_raw(count).astype(np.uint32)
+
+
+class RanLxd1:
+    """gsl_rng_ranlxd1 (Luescher RANLUX, double precision, luxury pr = 202), vectorised
+    over independent generators (one per (kx,ky) column).  All generators advance in lock
+    step, so the integer pointers ir/jr/ir_old are scalars.
+
+    Seeding reproduces GSL's signed-int quirk: ``int i = seed & 0xFFFFFFFF`` followed by
+    ``i % 2 ; i /= 2`` yields the binary digits of |(int32)seed|.
+    """
+
+    ONE_BIT = 1.0 / 281474976710656.0   # 2^-48
+    NEXT = tuple((i + 1) % 12 for i in range(12))
+
+    def __init__(self, seeds, pr: int = 202):
+        seeds = np.atleast_1d(np.asarray(seeds, dtype=np.uint32)).astype(np.int64)
+        seeds = np.where(seeds == 0, 1, seeds)
+        i32 = np.where(seeds >= 2 ** 31, seeds - 2 ** 32, seeds)      # signed 32-bit view
+        mag = np.abs(i32)                                              # C: digits of |i|
+        n = seeds.size
+        xbit = np.zeros((31, n), dtype=np.int64)
+        for k in range(31):
+            xbit[k] = mag % 2
+            mag //= 2
+        ibit, jbit = 0, 18
+        self.xdbl = np.zeros((12, n))
+        for k in range(12):
+            x = np.zeros(n)
+            for _ in range(48):
+                y = (xbit[ibit] + 1) % 2
+                x = x + x + y
+                xbit[ibit] = (xbit[ibit] + xbit[jbit]) % 2
+                ibit = (ibit + 1) % 31
+                jbit = (jbit + 1) % 31
+            self.xdbl[k] = self.ONE_BIT * x
+        self.carry = np.zeros(n)
+        self.ir, self.jr, self.ir_old = 11, 7, 0
+        self.pr = pr
+
+    def _step(self):
+        ir, jr = self.ir, self.jr
+        y = self.xdbl[jr] - self.xdbl[ir] - self.carry
+        neg = y < 0
+        self.carry = np.where(neg, self.ONE_BIT, 0.0)
+        self.xdbl[ir] = np.where(neg, y + 1.0, y)
+        self.ir = self.NEXT[ir]
+        self.jr = self.NEXT[jr]
+
+    def _increment_state(self):
+        k = 0
+        while self.ir > 0:
+            self._step()
+            k += 1
+        while k < self.pr:
+            self._step()
+            k += 1
+        self.ir_old = self.ir
+
+    def get_double(self) -> np.ndarray:
+        self.ir = self.NEXT[self.ir]
+        if self.ir == self.ir_old:
+            self._increment_state()
+        return self.xdbl[self.ir].copy()
+
+    def get(self) -> np.ndarray:
+        """gsl_rng_get: (unsigned long)(get_double * 2^32)."""
+        return (self.get_double() * 4294967296.0).astype(np.uint64)
+
+
+# ======================================================================================
+# Seed plane (src/GenIC.c:482-990, App. A.2)
+# ======================================================================================
+def get_map(px, py):
+    """Ordinal of a point along the square spiral, src/GenIC.c:840-855."""
+    px = np.asarray(px, dtype=np.int64)
+    py = np.asarray(py, dtype=np.int64)
+    l = 2 * np.maximum(np.abs(px), np.abs(py))
+    c = (py > px).astype(np.int64) + ((px > 0) & (px == py)).astype(np.int64)
+    d = np.where(c != 0, l * 3 + px + py, l - px - py)
+    return (l - 1) * (l - 1) + d
+
+
+def seed_table(nmesh: int, random_seed: int) -> np.ndarray:
+    """SEEDTABLE[j*Nmesh + i] for the whole plane (src/GenIC.c:629-647,875-990).
+
+    Plane coordinate c maps to spiral coordinate c (c < N/2) or c - N (transpose_subregion,
+    src/GenIC.c:1017-1041); the seed is the get_map()-th output (1-based) of
+    mt19937(RandomSeed).  Returned with shape [j, i] (y slow, x fast) like the reference.
+    """
+    n2 = nmesh // 2
+    c = np.arange(nmesh, dtype=np.int64)
+    s = np.where(c >= n2, c - nmesh, c)
+    sx = s[None, :]          # i (x) fast
+    sy = s[:, None]          # j (y) slow
+    m = get_map(sx, sy)
+    out = mt19937_outputs(random_seed, int(m.max()))
+    return out[m - 1].astype(np.uint32)
+
+
+# ======================================================================================
+# GenIC (src/GenIC.c:73-460)
+# ======================================================================================
+def genic(nmesh: int, box: float, random_seed: int, power_spectrum,
+          fixed_ic: bool = False, paired_ic: bool = False, seeds: np.ndarray | None = None):
+    """kdensity[x][y][kz] (complex128, shape [N,N,N/2+1]) as left by GenIC_large, including
+    the final N^3 normalisation (:430-445).  ``box`` in true Mpc; ``power_spectrum(k)`` is
+    the reference's PowerSpectrum (src/cosmo.c:953-1007).  Even N only."""
+    assert nmesh % 2 == 0
+    N, N2 = nmesh, nmesh // 2
+    if seeds is None:
+        seeds = seed_table(N, random_seed)          # [j, i]
+    fac = (1.0 / box) ** 1.5
+    kd = np.zeros((N, N, N2 + 1), dtype=np.complex128)
+
+    # one generator per (ii, jj) column, flattened as ii*N + jj
+    ii = np.repeat(np.arange(N), N)
+    jj = np.tile(np.arange(N), N)
+    col_seed = seeds[jj, ii]
+    rng = RanLxd1(col_seed)
+
+    def kcomp(idx):
+        return np.where(idx < N2, idx, -(N - idx)) * 2 * PI / box
+
+    kx = kcomp(ii)
+    ky = kcomp(jj)
+    kmag2_ij = kx * kx + ky * ky
+    col_ok = (ii != N2) & (jj != N2)                 # :193, :212
+
+    # mirrored generator for the k=0 plane (:289-368)
+    mirror = (ii > N2) | ((ii == 0) & (jj > N2))
+    jjj = np.where(mirror, (N - jj) % N, jj)
+    iii = np.where(mirror & (ii > N2), N - ii, ii)
+    k0 = RanLxd1(seeds[jjj, iii])
+    ph0 = k0.get_double() * 2 * PI
+    am0 = k0.get_double()
+    if np.any(am0 == 0):
+        raise NotImplementedError("zero amplitude draw (p = 2^-48) not vectorised")
+
+    for kk in range(N2):
+        phase = rng.get_double() * 2 * PI
+        ampl = rng.get_double()
+        if np.any(ampl == 0):
+            raise NotImplementedError("zero amplitude draw (p = 2^-48) not vectorised")
+        kz = kk * 2 * PI / box
+        kmag = np.sqrt(kmag2_ij + kz * kz)
+        ok = col_ok.copy()
+        if kk == 0:
+            ok &= ~((ii == 0) & (jj == 0))
+        ok &= ~(kmag * box / (2 * PI) > 1.0 * N / 2)          # NYQUIST = 1 (:280)
+        sign = np.ones(ii.size)
+        if kk == 0:
+            ok &= ~((ii == 0) & (jj == N2))
+            ok &= ~(ii == N2)
+            phase = np.where(mirror, ph0, phase)
+            ampl = np.where(mirror, am0, ampl)
+            sign = np.where(mirror, -1.0, 1.0)
+        if paired_ic:
+            phase = phase + PI
+        with np.errstate(divide="ignore", invalid="ignore"):
+            p_of_k = power_spectrum(np.where(kmag > 0, kmag, 1.0))
+        if not fixed_ic:
+            p_of_k = p_of_k * (-np.log(ampl))
+        delta = fac * np.sqrt(p_of_k)
+        val = delta * np.cos(phase) + 1j * sign * delta * np.sin(phase)
+        val = np.where(ok, val, 0.0)
+        kd[:, :, kk] = val.reshape(N, N)
+    kd *= float(N) ** 3
+    return kd
+
+
+# ======================================================================================
+# k-space derivative + c2r (src/fmax-pfft.c:255-456, 203-228; App. A.3, A.5)
+# ======================================================================================
+def _kgrid(N):
+    n = np.arange(N)
+    n = np.where(n > N // 2, n - N, n)            # index N/2 stays +N/2 (:312-313)
+    k = 2.0 * PI / N * n
+    kx = k[:, None, None]
+    ky = k[None, :, None]
+    kz = k[None, None, : N // 2 + 1]
+    return kx, ky, kz
+
+
+def derivative_kspace(ck: np.ndarray, d1: int, d2: int, rsmooth: float, growth: float = 1.0):
+    """The k-space multiply of compute_derivative (before the c2r).  ``ck`` is [N,N,N/2+1]
+    complex; returns a new array.  d1,d2 in {-1,0,1,2,3} as in the reference."""
+    N = ck.shape[0]
+    kx, ky, kz = _kgrid(N)
+    k2 = (kx * kx + ky * ky) + kz * kz
+    comp = (np.ones_like(k2), kx + 0 * k2, ky + 0 * k2, kz + 0 * k2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        smoothing = np.exp(-0.5 * k2 * rsmooth * rsmooth)
+        if d1 == -1 and d2 == -1:
+            green = np.ones_like(k2)
+        elif d1 == 0 and d2 == 0:
+            green = -comp[d1] * comp[d2] / k2
+        else:
+            green = comp[d1] * comp[d2] / k2
+        factor = green * smoothing * growth
+    out = np.where(k2 != 0.0, ck * np.where(k2 != 0.0, factor, 1.0), ck)
+    swap = (d1 == 0 and d2 > 0) or (d1 > 0 and d2 == 0)
+    if swap:
+        out = -out.imag + 1j * out.real         # (re,im) -> (-im,re), all modes (:389-394)
+    return out
+
+
+def reverse_transform(ck: np.ndarray) -> np.ndarray:
+    """c2r with the 1/N^3 normalisation (src/fmax-pfft.c:203-228).  numpy.fft.irfftn has
+    FFTW's literal half-complex semantics (App. A.5) and includes 1/N^3."""
+    N = ck.shape[0]
+    return np.fft.irfftn(ck, s=(N, N, N), axes=(0, 1, 2))
+
+
+def forward_transform(r: np.ndarray) -> np.ndarray:
+    """r2c, unnormalised (src/fmax-pfft.c:191-200)."""
+    return np.fft.rfftn(r, axes=(0, 1, 2))
+
+
+def compute_derivative(ck, d1, d2, rsmooth, growth=1.0):
+    return reverse_transform(derivative_kspace(ck, d1, d2, rsmooth, growth))
+
+
+def second_derivatives(kdensity, radius, cell_size):
+    """compute_second_derivatives (src/fmax.c:225-258): six real fields, slot order
+    xx,yy,zz,xy,xz,yz; ScaleDep.order = 0 (growth 1)."""
+    rs = radius / cell_size
+    return [compute_derivative(kdensity, a, b, rs) for (a, b) in HESSIAN_PAIRS]
+
+
+# ======================================================================================
+# Ellipsoidal collapse (src/collapse_times.c:114-221, 404-427, 679-776, 1354-1362)
+# ======================================================================================
+def ell_classic(l1, l2, l3):
+    """Vectorised ell_classic (src/collapse_times.c:114-221).  NaNs propagate as in C."""
+    l1 = np.asarray(l1, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        dele = l1 + l2 + l3
+        det = l1 * l2 * l3
+        den = det / 126.0 + 5.0 * l1 * dele * (dele - l1) / 84.0
+
+        # --- |den| < SMALL branch (:135-155)
+        dis = 7.0 * l1 * (l1 + 6.0 * dele)
+        e2 = (7.0 * l1 - np.sqrt(dis)) / (3.0 * l1 * (l1 - dele))
+        e2 = np.where(e2 < 0.0, -0.1, e2)
+        e2 = np.where(dis < 0.0, -0.1, e2)
+        e1 = np.where(l1 > 0.0, 1.0 / l1, -0.1)
+        ell_small_den = np.where(np.abs(dele - l1) < SMALL, e1, e2)
+
+        # --- 3rd order (:156-212)
+        rden = 1.0 / den
+        a1 = 3.0 * l1 * (dele - l1) / 14.0 * rden
+        a1_2 = a1 * a1
+        a2 = l1 * rden
+        a3 = -1.0 * rden
+        q = (a1_2 - 3.0 * a2) / 9.0
+        r = (2.0 * a1_2 * a1 - 9.0 * a1 * a2 + 27.0 * a3) / 54.0
+        r_2_q_3 = r * r - q * q * q
+
+        fabs_r = np.abs(r)
+        sq = np.power(np.sqrt(r_2_q_3) + fabs_r, 0.333333333333333)
+        ea = -fabs_r / r * (sq + q / sq) - a1 / 3.0
+        ea = np.where(ea < 0.0, -0.1, ea)
+
+        sq2 = 2 * np.sqrt(q)
+        inv_3 = 1.0 / 3
+        t = np.arccos(2 * r / q / sq2)
+        s1 = -sq2 * np.cos(t * inv_3) - a1 * inv_3
+        s2 = -sq2 * np.cos((t + 2.0 * PI) * inv_3) - a1 * inv_3
+        s3 = -sq2 * np.cos((t + 4.0 * PI) * inv_3) - a1 * inv_3
+        s1 = np.where(s1 < 0.0, 1.0e10, s1)
+        s2 = np.where(s2 < 0.0, 1.0e10, s2)
+        s3 = np.where(s3 < 0.0, 1.0e10, s3)
+        eb = np.where(s1 < s2, s1, s2)
+        eb = np.where(s3 < eb, s3, eb)
+        eb = np.where(eb == 1.0e10, -0.1, eb)
+
+        ell3 = np.where(r_2_q_3 > 0, ea, eb)
+        ell = np.where(np.abs(den) < SMALL, ell_small_den, ell3)
+        ell = np.where(np.abs(l1) < SMALL, -0.1, ell)
+
+        # spherical-collapse correction (:215-218)
+        inv_del = 1.0 / dele
+        corr = -0.364 * inv_del * np.exp(-6.5 * (l1 - l2) * inv_del - 2.8 * (l2 - l3) * inv_del)
+        ell = np.where((dele > 0.0) & (ell > 0.0), ell + corr, ell)
+    return ell
+
+
+def eigenvalues(h):
+    """Eigenvalues of the Hessian as in inverse_collapse_time (src/collapse_times.c:679-749).
+    ``h`` = sequence of six arrays (xx,yy,zz,xy,xz,yz).  Returns (x1,x2,x3,bad) with x1>=x2>=x3
+    (``ord``, :1354-1362) and ``bad`` flagging the -10 early return (:734-736)."""
+    d0, d1, d2, d3, d4, d5 = [np.asarray(a, dtype=np.float64) for a in h]
+    with np.errstate(all="ignore"):
+        mu1 = d0 + d1 + d2
+        mu1_2 = mu1 * mu1
+        mu2 = 0.5 * mu1_2
+        mu2 = mu2 - 0.5 * ((d0 * d0 + d1 * d1) + d2 * d2)
+        a0, a1_, a2_ = d3 * d3, d4 * d4, d5 * d5
+        mu2 = mu2 - ((a0 + a1_) + a2_)
+        mu3 = d0 * d1 * d2 + 2.0 * d3 * d4 * d5 - d0 * a2_ - d1 * a1_ - d2 * a0
+        q = (mu1_2 - 3.0 * mu2) / 9.0
+        r = -(2.0 * mu1_2 * mu1 - 9.0 * mu1 * mu2 + 27.0 * mu3) / 54.0
+        bad = (q != 0.0) & ((q * q * q < r * r) | (q < 0.0))
+        sq = 2 * np.sqrt(q)
+        t = np.arccos(2 * r / q / sq)
+        inv_3 = 1.0 / 3.0
+        x1 = -sq * np.cos(t * inv_3) + mu1 * inv_3
+        x2 = -sq * np.cos((t + 2.0 * PI) * inv_3) + mu1 * inv_3
+        x3 = -sq * np.cos((t + 4.0 * PI) * inv_3) + mu1 * inv_3
+        diag = q == 0.0
+        x1 = np.where(diag, d0, x1)
+        x2 = np.where(diag, d1, x2)
+        x3 = np.where(diag, d2, x3)
+        # ord(): C macros max/min (NaN-propagation as `a>b?a:b`)
+        hi = np.where(np.where(x1 > x2, x1, x2) > x3, np.where(x1 > x2, x1, x2), x3)
+        lo = np.where(np.where(x1 < x2, x1, x2) < x3, np.where(x1 < x2, x1, x2), x3)
+        mid = x1 + x2 + x3 - lo - hi
+    return hi, mid, lo, bad
+
+
+def inverse_collapse_time(h, inverse_growing_mode):
+    """F = 1 + z_collapse per cell (src/collapse_times.c:679-776 with ELL_CLASSIC, :404-415).
+    ``inverse_growing_mode(b_c)`` is InverseGrowingMode (src/cosmo.c:1822-1832)."""
+    x1, x2, x3, bad = eigenvalues(h)
+    bc = ell_classic(x1, x2, x3)
+    with np.errstate(all="ignore"):
+        pos = bc > 0.0
+        F = np.where(pos, 1.0 + inverse_growing_mode(np.where(pos, bc, 1.0)), 0.0)
+    F = np.where(bad, -10.0, F)
+    return F
+
+
+def init_products(shape):
+    """ismooth == 0 initialisation (src/collapse_times.c:461-492)."""
+    return np.full(shape, -10.0, dtype=np.float32), np.full(shape, -1, dtype=np.int32)
+
+
+def update_fmax(Fmax, Rmax, Fnew, ismooth):
+    """Running max (src/collapse_times.c:587-590): float Fmax promoted to double for the
+    compare; store (float)Fnew."""
+    upd = Fmax.astype(np.float64) < Fnew
+    Fmax[upd] = Fnew[upd].astype(np.float32)
+    Rmax[upd] = ismooth
+    return upd
+
+
+def true_variance(h):
+    """Sum(delta^2)/N^3 with delta = trace of the Hessian (src/collapse_times.c:554-556,662)."""
+    delta = h[0] + h[1] + h[2]
+    return float(np.sum(delta * delta) / delta.size), float(np.sum(delta) / delta.size)
+
+
+def fmax_pdf(Fmax):
+    """Fmax_PDF histogram (src/fmax.c:509-550)."""
+    xF = (Fmax.astype(np.float64) * 10.0).astype(np.int64)      # (int)(float*10.) truncation
+    xF = np.clip(xF, 0, NBINS_PDF - 1)
+    return np.bincount(xF.ravel(), minlength=NBINS_PDF).astype(np.uint64)
+
+
+# ======================================================================================
+# LPT sources and displacements (src/LPT.c:32-235, src/fmax.c:193-222, 292-367)
+# ======================================================================================
+def lpt_sources(h):
+    """source_2LPT, source_3LPT_1 and the first part of source_3LPT_2 (src/LPT.c:64-93)."""
+    s0, s1, s2, s3, s4, s5 = h
+    src2 = s0 * s1 + s0 * s2 + s1 * s2 - s3 * s3 - s4 * s4 - s5 * s5
+    src31 = 3.0 * (s0 * (s1 * s2 - s5 * s5) - s3 * (s3 * s2 - s4 * s5) + s4 * (s3 * s5 - s4 * s1))
+    src32 = 2.0 * (s0 + s1 + s2) * src2
+    return src2, src31, src32
+
+
+def lpt_kvectors(h):
+    """kvector_2LPT, kvector_3LPT_1, kvector_3LPT_2 (src/LPT.c:98-172).  ``h`` are the six
+    Hessians of the R = 0 radius; Rsmooth = 0, ScaleDep.order = 0 throughout."""
+    src2, src31, src32 = lpt_sources(h)
+    k2 = forward_transform(src2)
+    src32 = src32.copy()
+    for idx, (a, b) in enumerate(HESSIAN_PAIRS):
+        ider = idx + 1
+        rv = compute_derivative(k2, a, b, 0.0)
+        src32 -= 2.0 * (1.0 if ider <= 3 else 2.0) * rv * h[idx]
+    k31 = forward_transform(src31)
+    k32 = forward_transform(src32)
+    return k2, k31, k32
+
+
+def first_derivatives(kvec, growth):
+    """compute_first_derivatives (src/fmax.c:193-222): three real fields, Rsmooth = 0, then
+    cast to PRODFLOAT=float by write_from_rvector_to_products (src/fmax-pfft.c:563-631)."""
+    return [compute_derivative(kvec, ia, 0, 0.0, growth).astype(np.float32) for ia in (1, 2, 3)]
+
+
+# ======================================================================================
+# Driver: compute_fmax + compute_displacements (src/fmax.c:36-190, 292-367)
+# ======================================================================================
+def compute_fmax(kdensity, radii, cell_size, inverse_growing_mode, growth=None,
+                 lpt_order=3, keep=False):
+    """Returns dict with Fmax (f32), Rmax (i32), TrueVariance[], Vel, Vel_2LPT, Vel_3LPT_1,
+    Vel_3LPT_2 (each [3] list of f32 fields).  ``growth`` = (D, D2, D31, D32) at the segment
+    redshift (growth_rate of src/fmax-pfft.c:344-364); default all ones."""
+    N = kdensity.shape[0]
+    if growth is None:
+        growth = (1.0, 1.0, 1.0, 1.0)
+    Fmax, Rmax = init_products((N, N, N))
+    tv = []
+    extra = {}
+    h = None
+    for ismooth, R in enumerate(radii):
+        h = second_derivatives(kdensity, R, cell_size)
+        Fnew = inverse_collapse_time(h, inverse_growing_mode)
+        update_fmax(Fmax, Rmax, Fnew, ismooth)
+        tv.append(true_variance(h)[0])
+        if keep:
+            extra.setdefault("F", []).append(Fnew)
+    out = {"Fmax": Fmax, "Rmax": Rmax, "TrueVariance": np.array(tv)}
+    if lpt_order >= 2:
+        if lpt_order >= 3:
+            k2, k31, k32 = lpt_kvectors(h)
+            out["Vel_3LPT_1"] = first_derivatives(k31, growth[2])
+            out["Vel_3LPT_2"] = first_derivatives(k32, growth[3])
+        else:
+            k2 = forward_transform(lpt_sources(h)[0])
+        out["Vel_2LPT"] = first_derivatives(k2, growth[1])
+        if keep:
+            extra["kvector_2LPT"] = k2
+            if lpt_order >= 3:
+                extra["kvector_3LPT_1"], extra["kvector_3LPT_2"] = k31, k32
+    out["Vel"] = first_derivatives(kdensity, growth[0])
+    if keep:
+        extra["hessian_R0"] = h
+        out.update(extra)
+    return out
+
+
+# product_data layout for TWO_LPT+THREE_LPT, float products, no SNAPSHOT/RECOMPUTE
+# (src/pinocchio.h:233-259): sizeof = 56
+PRODUCT_DTYPE_3LPT = np.dtype([("Rmax", "<i4"), ("Fmax", "<f4"), ("Vel", "<f4", 3),
+                               ("Vel_2LPT", "<f4", 3), ("Vel_3LPT_1", "<f4", 3),
+                               ("Vel_3LPT_2", "<f4", 3)])
+assert PRODUCT_DTYPE_3LPT.itemsize == 56
+
+
+def pack_products(res) -> np.ndarray:
+    """AoS products[] (index = z + N*(y + N*x), src/pinocchio.h:84-85)."""
+    n = res["Fmax"].size
+    p = np.zeros(n, dtype=PRODUCT_DTYPE_3LPT)
+    p["Rmax"] = res["Rmax"].ravel()
+    p["Fmax"] = res["Fmax"].ravel()
+    for name in ("Vel", "Vel_2LPT", "Vel_3LPT_1", "Vel_3LPT_2"):
+        if name in res:
+            for a in range(3):
+                p[name][:, a] = res[name][a].ravel()
+    return p
