@@ -1,0 +1,120 @@
+/* pinb200 -- C ABI of the B200-native collapse-time engine for PINOCCHIO V5.1.
+ *
+ * Drop-in boundary: the reference has no plugin system; the boundary is
+ * the set of C symbols the rest of PINOCCHIO calls on this path.  shim/fmax_b200.c defines
+ * those reference symbols (GenIC_large, compute_fmax, compute_displacements, ...) on top of the
+ * entry points below; INTEGRATION.md shows the binding.  Plain pointers and sizes only, no
+ * CUDA/torch types.  Every function returns 0 on success and non-zero on failure, like the
+ * reference (src/pinocchio.c:229-230,259-263); pinb200_last_error() gives the message.
+ *
+ * There is no CPU fallback: every entry point that computes runs sm_100a kernels and fails
+ * if no CUDA device is usable.
+ */
+#ifndef PINB200_H
+#define PINB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pinb200_ctx pinb200_ctx;
+
+#define PINB200_NBINS 210 /* NBINS, reference src/pinocchio.h:65 */
+
+/* Run descriptor: the reference globals this path reads (SURVEY.md 8b "inputs read from
+ * globals"), passed as runtime values instead of -D switches. */
+typedef struct {
+  int grid_size;      /* params.GridSize[0]; cubic, power of two in [32, 2048]              */
+  double box_size;    /* MyGrids[0].BoxSize = params.BoxSize_htrue, true Mpc                */
+  int random_seed;    /* params.RandomSeed                                                  */
+  int fixed_ic;       /* params.FixedIC                                                     */
+  int paired_ic;      /* params.PairedIC                                                    */
+  int lpt_order;      /* 1: Zel'dovich only, 2: -DTWO_LPT, 3: -DTWO_LPT -DTHREE_LPT          */
+  int rank, nranks;   /* ThisTask, NTasks: slab decomposition along x (src/initialization.c:1317-1325) */
+  int device;         /* CUDA device ordinal for this rank                                  */
+} pinb200_desc;
+
+/* Layout of one product_data record (reference src/pinocchio.h:233-259): byte offsets of the
+ * members inside the record, -1 for members compiled out; prodfloat_bytes = sizeof(PRODFLOAT). */
+typedef struct {
+  size_t stride;      /* sizeof(product_data)                                               */
+  int prodfloat_bytes;/* 4 (default) or 8 (-DDOUBLE_PRECISION_PRODUCTS)                      */
+  int off_Rmax, off_Fmax, off_Vel, off_Vel_2LPT, off_Vel_3LPT_1, off_Vel_3LPT_2;
+} pinb200_product_layout;
+
+/* cputime_data members this path fills (reference src/pinocchio.h:368-378), in seconds of
+ * device time measured with CUDA events. */
+typedef struct {
+  double dens, fmax, deriv, fft, coll, lpt, mem_transf;
+  double per_radius[64];   /* wall of each smoothing radius (src/fmax.c:140-146)             */
+  unsigned long long kernel_launches;  /* kernels launched by this context so far            */
+} pinb200_timers;
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out);
+int pinb200_destroy(pinb200_ctx* ctx);
+const char* pinb200_last_error(const pinb200_ctx* ctx); /* ctx may be NULL: creation errors */
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*). */
+int pinb200_set_stream(pinb200_ctx* ctx, void* cuda_stream);
+int pinb200_synchronize(pinb200_ctx* ctx);
+
+/* ---- tables computed by the unchanged host code ----------------------------------------- */
+/* P(k) on the integer lattice: pk[m] = PowerSpectrum(2*pi*sqrt(m)/box_size), m = 0..(N/2)^2
+ * (replaces the per-mode PowerSpectrum() call of src/GenIC.c:283). */
+int pinb200_set_power_table(pinb200_ctx* ctx, const double* pk, size_t n);
+/* Smoothing ladder: Smoothing.Nsmooth, Smoothing.Radius[] in true Mpc (src/initialization.c:386-435). */
+int pinb200_set_smoothing(pinb200_ctx* ctx, int nsmooth, const double* radius);
+/* Knots of the inverse growing mode spline, x = log10 D, y = log10 a: SPLINE[SP_INVGROW]
+ * (src/cosmo.c:401) when ismooth < 0, else SPLINE_INVGROW[ismooth] (src/initialization.c:1704-1708).
+ * The natural-cubic-spline coefficients are recomputed here as gsl_interp_cspline does. */
+int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const double* x, const double* y, int n);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+/* GenIC_large (src/GenIC.c:73-460): fills kdensity on the device. */
+int pinb200_genic(pinb200_ctx* ctx);
+/* Alternative to genic: supply / fetch kdensity in the reference's host layout
+ * [x_local? no: x (N)][y (N)][N/2+1] complex128 (src/GenIC.c:384), single rank only. */
+int pinb200_upload_kdensity(pinb200_ctx* ctx, const double* kdensity);
+int pinb200_download_kdensity(pinb200_ctx* ctx, double* kdensity);
+/* compute_fmax (src/fmax.c:36-190) without the final displacement call: loop over the
+ * smoothing radii; true_variance[ismooth] = Smoothing.TrueVariance (may be NULL). */
+int pinb200_fmax(pinb200_ctx* ctx, double* true_variance);
+/* compute_displacements(compute_sources, 0, z) (src/fmax.c:292-367): growth[] = growth_rate of
+ * src/fmax-pfft.c:344-364 for ScaleDep.order 1..4 at the segment redshift, i.e.
+ * {GrowingMode, GrowingMode_2LPT, GrowingMode_3LPT_1 (negative), GrowingMode_3LPT_2}. */
+int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, const double growth[4]);
+/* Fmax_PDF (src/fmax.c:509-550): local histogram, counts[PINB200_NBINS]. */
+int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts);
+
+/* ---- results ----------------------------------------------------------------------------- */
+/* Pack cells [cell_begin, cell_begin+ncells) of the local slab (index = z + N*(y + N*x_local),
+ * src/pinocchio.h:84-85) into host AoS records. */
+int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* layout,
+                              size_t cell_begin, size_t ncells);
+/* Structure-of-arrays access for tests: which = 0 Fmax(f32) 1 Rmax(i32) 2..4 Vel 5..7 Vel_2LPT
+ * 8..10 Vel_3LPT_1 11..13 Vel_3LPT_2; dst holds N^3 (local) 4-byte values. */
+int pinb200_download_field(pinb200_ctx* ctx, int which, void* dst);
+int pinb200_get_timers(pinb200_ctx* ctx, pinb200_timers* t);
+
+/* ---- finer-grained entry points (reference function granularity; used by the parity tests) */
+/* forward_transform / reverse_transform (src/fmax-pfft.c:191-228) on host arrays:
+ * real [N][N][N] doubles <-> half-complex [N][N][N/2+1]; reverse includes the 1/N^3. */
+int pinb200_fft_r2c(pinb200_ctx* ctx, const double* real_in, double* cplx_out);
+int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* real_out);
+/* compute_second_derivatives(R) (src/fmax.c:225-258) of the resident kdensity: six real
+ * [N][N][N] double fields in slot order xx,yy,zz,xy,xz,yz written to hessian_out (6*N^3). */
+int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, double* hessian_out);
+/* inverse_collapse_time over ncells Hessians given as six arrays (SoA), ismooth selects the
+ * spline; F_out[ncells] doubles (src/collapse_times.c:679-776). */
+int pinb200_collapse_cells(pinb200_ctx* ctx, int ismooth, const double* hessian6, size_t ncells, double* F_out);
+/* kvector_2LPT / kvector_3LPT_1 / kvector_3LPT_2 (src/LPT.c:98-172) in the host layout of
+ * kdensity; which = 0,1,2.  Valid after pinb200_displacements(compute_sources=1). */
+int pinb200_download_kvector(pinb200_ctx* ctx, int which, double* kvec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINB200_H */

@@ -1,0 +1,854 @@
+// pinb200 engine: C ABI (include/pinb200.h) + host orchestration of the sm_100a kernels.
+//
+// Schedules (reference counterparts in brackets):
+//   pinb200_fmax            [compute_fmax radii loop, src/fmax.c:66-150]
+//       per radius: x pass (K2 fused, 3 outputs) -> y pass (6 outputs) -> z pass + collapse
+//   pinb200_displacements   [compute_displacements, src/fmax.c:292-367; compute_LPT_displacements,
+//                            src/LPT.c:32-235]
+//       sources -> r2c -> 3 groups of {x,y,z-contraction} -> 2 r2c -> 4 x {x,y,z-float}
+// All device memory is owned here (stream-ordered allocations from the default pool); nothing
+// points into the caller's arena (SURVEY.md 8b "ownership").
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pinb200.h"
+#include "launch.h"
+
+using namespace pinb;
+
+static thread_local std::string g_create_error;
+
+struct pinb200_ctx {
+  pinb200_desc d{};
+  Geom g{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  size_t field_elems = 0;  // double2 elements of one field (lx*N*P)
+  size_t ncells = 0;       // lx*N*N
+
+  // tables
+  double2* tw = nullptr;
+  double* gauss = nullptr;
+  double* dc = nullptr;
+  double* sums = nullptr;          // [2*64]
+  unsigned int* seeds = nullptr;
+  double* pk = nullptr;
+  size_t pk_n = 0;
+  std::vector<double> radius;
+  std::vector<std::vector<double>> spl_host;  // index 0: global spline, 1+i: per radius
+  double* spl_dev = nullptr;                  // [(1+nsmooth)][5][nspl]
+  int nspl = 0;
+  bool spl_dirty = true;
+
+  // fields
+  double2* kdens = nullptr;
+  double2* A[3] = {nullptr, nullptr, nullptr};   // x-pass outputs; later sources / k-vectors
+  double2* B[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // y-pass outputs; Hessian of the last radius
+  double2* W[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};           // displacement-stage work
+  bool hessian_valid = false, kvec_valid = false;
+  float* fmax = nullptr;
+  int* rmax = nullptr;
+  float* vel[12] = {nullptr};
+
+  pinb200_timers tm{};
+  unsigned long long launches = 0;
+  cudaEvent_t ev[2 * 64 + 8] = {nullptr};
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      char buf__[512];                                                                        \
+      snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      ctx->err = buf__;                                                                       \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+#define LAUNCH(call) do { CK(call); ctx->launches++; } while (0)
+#define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
+
+template <class T> static int dev_alloc(pinb200_ctx* ctx, T** p, size_t n) {
+  if (*p) return 0;
+  CK(cudaMallocAsync((void**)p, n * sizeof(T), ctx->stream));
+  return 0;
+}
+template <class T> static int dev_free(pinb200_ctx* ctx, T** p) {
+  if (!*p) return 0;
+  CK(cudaFreeAsync(*p, ctx->stream));
+  *p = nullptr;
+  return 0;
+}
+#define TRY(x) do { if (x) return 1; } while (0)
+
+// ---- gsl_interp_cspline coefficients (natural spline) -------------------
+static void cspline_table(const double* x, const double* y, int n, std::vector<double>& t) {
+  t.assign((size_t)5 * n, 0.0);
+  std::vector<double> c(n, 0.0);
+  const int m = n - 2;
+  if (m > 0) {
+    std::vector<double> diag(m), off(m), rhs(m), cp(m, 0.0), dp(m, 0.0);
+    for (int i = 0; i < m; i++) {
+      const double h_i = x[i + 1] - x[i], h_ip1 = x[i + 2] - x[i + 1];
+      const double ydiff_i = y[i + 1] - y[i], ydiff_ip1 = y[i + 2] - y[i + 1];
+      off[i] = h_ip1;
+      diag[i] = 2.0 * (h_ip1 + h_i);
+      rhs[i] = 3.0 * (ydiff_ip1 / h_ip1 - ydiff_i / h_i);
+    }
+    cp[0] = m > 1 ? off[0] / diag[0] : 0.0;
+    dp[0] = rhs[0] / diag[0];
+    for (int i = 1; i < m; i++) {
+      const double den = diag[i] - off[i - 1] * cp[i - 1];
+      if (i < m - 1) cp[i] = off[i] / den;
+      dp[i] = (rhs[i] - off[i - 1] * dp[i - 1]) / den;
+    }
+    c[m] = dp[m - 1];
+    for (int i = m - 2; i >= 0; i--) c[i + 1] = dp[i] - cp[i] * c[i + 2];
+  }
+  for (int i = 0; i < n; i++) {
+    t[i] = x[i];
+    t[n + i] = y[i];
+    t[3 * n + i] = c[i];
+  }
+  for (int i = 0; i < n - 1; i++) {
+    const double dx = x[i + 1] - x[i], dy = y[i + 1] - y[i];
+    t[2 * n + i] = dy / dx - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
+    t[4 * n + i] = (c[i + 1] - c[i]) / (3.0 * dx);
+  }
+}
+
+// ---- seed plane (src/GenIC.c:482-990): MT19937 along the square spiral ---
+namespace {
+struct MT19937 {
+  uint32_t mt[624];
+  int idx;
+  explicit MT19937(uint32_t s) {
+    if (s == 0) s = 4357;  // gsl default seed
+    mt[0] = s;
+    for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    idx = 624;
+  }
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int k = 0; k < 624; k++) {
+        const uint32_t yv = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        mt[k] = mt[(k + 397) % 624] ^ (yv >> 1) ^ ((yv & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t yv = mt[idx++];
+    yv ^= (yv >> 11);
+    yv ^= (yv << 7) & 0x9d2c5680u;
+    yv ^= (yv << 15) & 0xefc60000u;
+    yv ^= (yv >> 18);
+    return yv;
+  }
+};
+}  // namespace
+
+static long long spiral_ordinal(long long px, long long py) {  // get_map, src/GenIC.c:840-855
+  const long long mx = px < 0 ? -px : px, my = py < 0 ? -py : py;
+  const long long l = 2 * (mx > my ? mx : my);
+  const long long c = (py > px) + (px > 0) * (px == py);
+  const long long dd = c ? l * 3 + px + py : l - px - py;
+  return (l - 1) * (l - 1) + dd;
+}
+
+static void build_seed_plane(int N, int random_seed, std::vector<unsigned int>& seeds) {
+  const int N2 = N / 2;
+  long long mmax = 0;
+  std::vector<long long> ord((size_t)N * N);
+  for (int j = 0; j < N; j++)
+    for (int i = 0; i < N; i++) {
+      const long long sx = i >= N2 ? i - N : i, sy = j >= N2 ? j - N : j;
+      const long long m = spiral_ordinal(sx, sy);
+      ord[(size_t)j * N + i] = m;
+      if (m > mmax) mmax = m;
+    }
+  std::vector<unsigned int> out((size_t)mmax);
+  MT19937 rng((uint32_t)random_seed);
+  for (long long k = 0; k < mmax; k++) out[(size_t)k] = rng.next();
+  seeds.resize((size_t)N * N);
+  for (size_t k = 0; k < seeds.size(); k++) seeds[k] = out[(size_t)(ord[k] - 1)];
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" const char* pinb200_last_error(const pinb200_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
+  if (!desc || !out) { g_create_error = "null argument"; return 1; }
+  *out = nullptr;
+  if (!grid_supported(desc->grid_size)) { g_create_error = "grid_size must be a power of two in [32, 2048]"; return 1; }
+  if (desc->nranks != 1 || desc->rank != 0) { g_create_error = "multi-rank slabs are not wired in this build (nranks must be 1)"; return 1; }
+  if (desc->lpt_order < 1 || desc->lpt_order > 3) { g_create_error = "lpt_order must be 1, 2 or 3"; return 1; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
+    return 1;
+  }
+  if ((e = cudaSetDevice(desc->device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return 1; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, desc->device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return 1; }
+  if (prop.major != 10) {
+    g_create_error = "device is not sm_100 (this library ships sm_100a code only)";
+    return 1;
+  }
+  pinb200_ctx* ctx = new pinb200_ctx;
+  ctx->d = *desc;
+  Geom& g = ctx->g;
+  g.N = desc->grid_size;
+  g.M = g.N / 2;
+  g.P = g.M + 8;
+  g.lx = g.N / desc->nranks;
+  g.ly = g.N / desc->nranks;
+  g.x0 = desc->rank * g.lx;
+  g.y0 = desc->rank * g.ly;
+  g.knorm = 2. * PINB_PI / (double)g.N;
+  ctx->field_elems = (size_t)g.lx * g.N * g.P;
+  ctx->ncells = (size_t)g.lx * g.N * g.N;
+  auto fail = [&](cudaError_t err) {
+    g_create_error = cudaGetErrorString(err);
+    delete ctx;
+    return 1;
+  };
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+  ctx->own_stream = true;
+  cudaMemPool_t pool;
+  if ((e = cudaDeviceGetDefaultMemPool(&pool, desc->device)) != cudaSuccess) return fail(e);
+  unsigned long long thr = ~0ull;
+  cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  // twiddles: N-th roots of unity, computed in long double
+  std::vector<double2> tw(g.N);
+  for (int k = 0; k < g.N; k++) {
+    const long double a = 2.0L * 3.141592653589793238462643383279502884L * (long double)k / (long double)g.N;
+    tw[k] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+  if ((e = cudaMalloc(&ctx->tw, sizeof(double2) * g.N)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpy(ctx->tw, tw.data(), sizeof(double2) * g.N, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&ctx->gauss, sizeof(double) * (g.M + 1))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&ctx->dc, sizeof(double))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&ctx->sums, sizeof(double) * 2 * 64)) != cudaSuccess) return fail(e);
+  for (auto& ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->d.device);
+  cudaStreamSynchronize(ctx->stream);
+  auto fr = [&](void* p) { if (p) cudaFree(p); };
+  fr(ctx->tw); fr(ctx->gauss); fr(ctx->dc); fr(ctx->sums); fr(ctx->seeds); fr(ctx->pk); fr(ctx->spl_dev);
+  fr(ctx->kdens);
+  for (auto p : ctx->A) fr(p);
+  for (auto p : ctx->B) fr(p);
+  for (auto p : ctx->W) fr(p);
+  fr(ctx->fmax); fr(ctx->rmax);
+  for (auto p : ctx->vel) fr(p);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+extern "C" int pinb200_set_stream(pinb200_ctx* ctx, void* s) {
+  if (!ctx) return 1;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) CK(cudaStreamDestroy(ctx->stream));
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return 0;
+}
+
+extern "C" int pinb200_synchronize(pinb200_ctx* ctx) {
+  if (!ctx) return 1;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int pinb200_set_power_table(pinb200_ctx* ctx, const double* pk, size_t n) {
+  if (!ctx || !pk) return 1;
+  const size_t need = (size_t)ctx->g.M * ctx->g.M + 1;
+  if (n < need) FAIL("power table too short: need (N/2)^2 + 1 entries");
+  if (ctx->pk) { CK(cudaFree(ctx->pk)); ctx->pk = nullptr; }
+  CK(cudaMalloc(&ctx->pk, need * sizeof(double)));
+  CK(cudaMemcpy(ctx->pk, pk, need * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->pk_n = need;
+  return 0;
+}
+
+extern "C" int pinb200_set_smoothing(pinb200_ctx* ctx, int nsmooth, const double* radius) {
+  if (!ctx || !radius) return 1;
+  if (nsmooth < 1 || nsmooth > 63) FAIL("nsmooth out of range [1, 63]");
+  ctx->radius.assign(radius, radius + nsmooth);
+  ctx->spl_host.resize(1 + (size_t)nsmooth);
+  ctx->spl_dirty = true;
+  return 0;
+}
+
+extern "C" int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const double* x, const double* y, int n) {
+  if (!ctx || !x || !y) return 1;
+  if (n < 3 || n > 1024) FAIL("spline size out of range [3, 1024]");
+  for (int i = 1; i < n; i++)
+    if (!(x[i] > x[i - 1])) FAIL("spline abscissae must be strictly increasing");
+  if (ctx->nspl && ctx->nspl != n) FAIL("all inverse-growth splines must have the same number of knots");
+  const size_t slot = ismooth < 0 ? 0 : (size_t)ismooth + 1;
+  if (ctx->spl_host.size() <= slot) ctx->spl_host.resize(slot + 1);
+  cspline_table(x, y, n, ctx->spl_host[slot]);
+  ctx->nspl = n;
+  ctx->spl_dirty = true;
+  return 0;
+}
+
+static int upload_splines(pinb200_ctx* ctx) {
+  if (!ctx->spl_dirty) return 0;
+  if (ctx->spl_host.empty() || ctx->nspl == 0) FAIL("inverse-growth spline not set (pinb200_set_invgrow_spline)");
+  const size_t per = (size_t)5 * ctx->nspl, ns = ctx->spl_host.size();
+  std::vector<double> all(per * ns, 0.0);
+  for (size_t s = 0; s < ns; s++) {
+    const std::vector<double>& src = ctx->spl_host[s].empty() ? ctx->spl_host[0] : ctx->spl_host[s];
+    if (src.empty()) FAIL("global inverse-growth spline (ismooth < 0) missing");
+    memcpy(all.data() + s * per, src.data(), per * sizeof(double));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->spl_dev) { CK(cudaFree(ctx->spl_dev)); ctx->spl_dev = nullptr; }
+  CK(cudaMalloc(&ctx->spl_dev, all.size() * sizeof(double)));
+  CK(cudaMemcpy(ctx->spl_dev, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->spl_dirty = false;
+  return 0;
+}
+
+static const double* spline_for(pinb200_ctx* ctx, int ismooth) {
+  size_t slot = (size_t)ismooth + 1;
+  if (slot >= ctx->spl_host.size() || ctx->spl_host[slot].empty()) slot = 0;
+  return ctx->spl_dev + slot * (size_t)5 * ctx->nspl;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int pinb200_genic(pinb200_ctx* ctx) {
+  if (!ctx) return 1;
+  if (!ctx->pk) FAIL("power table not set (pinb200_set_power_table)");
+  const Geom& g = ctx->g;
+  CK(cudaSetDevice(ctx->d.device));
+  if (!ctx->seeds) {
+    std::vector<unsigned int> seeds;
+    build_seed_plane(g.N, ctx->d.random_seed, seeds);
+    CK(cudaMalloc(&ctx->seeds, seeds.size() * sizeof(unsigned int)));
+    CK(cudaMemcpy(ctx->seeds, seeds.data(), seeds.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+  }
+  TRY(dev_alloc(ctx, &ctx->kdens, ctx->field_elems));
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CK(cudaMemsetAsync(ctx->kdens, 0, ctx->field_elems * sizeof(double2), ctx->stream));
+  GenicParams p{};
+  p.seeds = ctx->seeds;
+  p.pk = ctx->pk;
+  p.kd = ctx->kdens;
+  p.box = ctx->d.box_size;
+  p.fixed_ic = ctx->d.fixed_ic;
+  p.paired_ic = ctx->d.paired_ic;
+  p.g = g;
+  LAUNCH(launch_genic(p, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  ctx->tm.dens += ms * 1e-3;
+  return 0;
+}
+
+// host half-complex [rows][M+1] <-> device [rows][P]
+static int upload_cplx(pinb200_ctx* ctx, const double* host, double2* dev) {
+  const Geom& g = ctx->g;
+  const size_t rows = (size_t)g.lx * g.N;
+  double2* tmp = nullptr;
+  TRY(dev_alloc(ctx, &tmp, rows * (g.M + 1)));
+  CK(cudaMemcpyAsync(tmp, host, rows * (g.M + 1) * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(dev, 0, ctx->field_elems * sizeof(double2), ctx->stream));
+  LAUNCH(launch_repitch_c(tmp, dev, rows, g.M + 1, g.M + 1, g.P, ctx->stream));
+  TRY(dev_free(ctx, &tmp));
+  return 0;
+}
+static int download_cplx(pinb200_ctx* ctx, const double2* dev, double* host) {
+  const Geom& g = ctx->g;
+  const size_t rows = (size_t)g.lx * g.N;
+  double2* tmp = nullptr;
+  TRY(dev_alloc(ctx, &tmp, rows * (g.M + 1)));
+  LAUNCH(launch_repitch_c(dev, tmp, rows, g.M + 1, g.P, g.M + 1, ctx->stream));
+  CK(cudaMemcpyAsync(host, tmp, rows * (g.M + 1) * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  TRY(dev_free(ctx, &tmp));
+  return 0;
+}
+static int download_real(pinb200_ctx* ctx, const double2* dev, double* host) {
+  const Geom& g = ctx->g;
+  const size_t rows = (size_t)g.lx * g.N;
+  double* tmp = nullptr;
+  TRY(dev_alloc(ctx, &tmp, rows * g.N));
+  LAUNCH(launch_repitch_r(reinterpret_cast<const double*>(dev), tmp, rows, g.N, 2 * g.P, g.N, ctx->stream));
+  CK(cudaMemcpyAsync(host, tmp, rows * g.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  TRY(dev_free(ctx, &tmp));
+  return 0;
+}
+
+extern "C" int pinb200_upload_kdensity(pinb200_ctx* ctx, const double* kd) {
+  if (!ctx || !kd) return 1;
+  CK(cudaSetDevice(ctx->d.device));
+  TRY(dev_alloc(ctx, &ctx->kdens, ctx->field_elems));
+  TRY(upload_cplx(ctx, kd, ctx->kdens));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int pinb200_download_kdensity(pinb200_ctx* ctx, double* kd) {
+  if (!ctx || !kd) return 1;
+  if (!ctx->kdens) FAIL("kdensity not resident (call pinb200_genic or pinb200_upload_kdensity)");
+  CK(cudaSetDevice(ctx->d.device));
+  return download_cplx(ctx, ctx->kdens, kd);
+}
+
+// ---- pass helpers --------------------------------------------------------------------------
+static int ntiles(const pinb200_ctx* ctx, bool with_nyq) {
+  const int tk = xpass_tk(ctx->g.N);
+  return ctx->g.M / tk + (with_nyq ? 1 : 0);
+}
+
+// x pass (inverse) of `src` with the Green/window factor; outputs for the powers in pmask
+static int run_xpass_inv(pinb200_ctx* ctx, const double2* src, double2* const dst[3], int pmask, bool gauss, int green,
+                         int times_i, double scalar, bool with_nyq) {
+  XPassParams p{};
+  p.src = src;
+  for (int i = 0; i < 3; i++) p.dst[i] = dst[i];
+  p.pmask = pmask;
+  p.ntiles_z = ntiles(ctx, with_nyq);
+  p.kf.gauss = gauss ? ctx->gauss : nullptr;
+  p.kf.scalar = scalar;
+  p.kf.green = green;
+  p.kf.times_i = times_i;
+  p.g = ctx->g;
+  p.tw = ctx->tw;
+  LAUNCH(launch_xpass(ctx->g.N, +1, p, ctx->g.ly, ctx->stream));
+  return 0;
+}
+
+static int run_ypass(pinb200_ctx* ctx, int dir, const double2* const src[3], double2* const dst[6], const YJob* jobs,
+                     int njobs, bool with_nyq) {
+  YPassParams p{};
+  for (int i = 0; i < 3; i++) p.src[i] = src[i];
+  for (int i = 0; i < 6; i++) p.dst[i] = dst[i];
+  for (int i = 0; i < njobs; i++) p.job[i] = jobs[i];
+  p.njobs = njobs;
+  p.ntiles_z = ntiles(ctx, with_nyq);
+  p.g = ctx->g;
+  p.tw = ctx->tw;
+  LAUNCH(launch_ypass(ctx->g.N, dir, p, ctx->g.lx, ctx->stream));
+  return 0;
+}
+
+// forward r2c of a real field held in `f` (in place): z r2c, y forward, x forward
+static int run_r2c_inplace(pinb200_ctx* ctx, double2* f) {
+  const Geom& g = ctx->g;
+  ZR2CParams z{};
+  z.src = f;
+  z.dst = f;
+  z.g = g;
+  z.tw = ctx->tw;
+  LAUNCH(launch_zpass_r2c(g.N, z, (size_t)g.lx * g.N, ctx->stream));
+  const double2* ysrc[3] = {f, nullptr, nullptr};
+  double2* ydst[6] = {f, nullptr, nullptr, nullptr, nullptr, nullptr};
+  YJob job{0, 0, 0};
+  TRY(run_ypass(ctx, -1, ysrc, ydst, &job, 1, true));
+  XPassParams p{};
+  p.src = f;
+  p.dst[0] = f;
+  p.pmask = 1;
+  p.ntiles_z = ntiles(ctx, true);
+  p.kf.gauss = nullptr;
+  p.kf.scalar = 1.0;
+  p.kf.green = 0;
+  p.kf.times_i = 0;
+  p.g = g;
+  p.tw = ctx->tw;
+  LAUNCH(launch_xpass(g.N, -1, p, g.ly, ctx->stream));
+  return 0;
+}
+
+static int ensure_products(pinb200_ctx* ctx) {
+  TRY(dev_alloc(ctx, &ctx->fmax, ctx->ncells));
+  TRY(dev_alloc(ctx, &ctx->rmax, ctx->ncells));
+  return 0;
+}
+
+// Hessian passes for one radius: fills B[0..5] (half-complex, after x and y passes).
+// slot order xx,yy,zz,xy,xz,yz (src/fmax.c:239)
+static int hessian_xy(pinb200_ctx* ctx, const double2* src, double rsmooth, bool with_nyq) {
+  const Geom& g = ctx->g;
+  const double norm = 1.0 / ((double)g.N * g.N * g.N);
+  LAUNCH(launch_gauss_table(ctx->gauss, g.M, g.knorm, rsmooth, ctx->stream));
+  LAUNCH(launch_dc_scalar(src, ctx->dc, norm, 0, ctx->stream));
+  TRY(run_xpass_inv(ctx, src, ctx->A, 0x7, true, 1, 0, norm, with_nyq));
+  static const YJob jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
+  TRY(run_ypass(ctx, +1, ctx->A, ctx->B, jobs, 6, with_nyq));
+  return 0;
+}
+static const int kHessKzPow[6] = {0, 0, 2, 0, 1, 1};
+
+extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
+  if (!ctx) return 1;
+  if (!ctx->kdens) FAIL("kdensity not resident (call pinb200_genic or pinb200_upload_kdensity)");
+  if (ctx->radius.empty()) FAIL("smoothing ladder not set (pinb200_set_smoothing)");
+  CK(cudaSetDevice(ctx->d.device));
+  TRY(upload_splines(ctx));
+  const Geom& g = ctx->g;
+  const int ns = (int)ctx->radius.size();
+  const double cell = ctx->d.box_size / g.N;  // GRID.CellSize, src/fmax-pfft.c:88
+  // the k-vectors of a previous displacement call alias A: they die here
+  ctx->kvec_valid = false;
+  for (auto& w : ctx->W) TRY(dev_free(ctx, &w));
+  TRY(ensure_products(ctx));
+  for (int i = 0; i < 3; i++) TRY(dev_alloc(ctx, &ctx->A[i], ctx->field_elems));
+  for (int i = 0; i < 6; i++) TRY(dev_alloc(ctx, &ctx->B[i], ctx->field_elems));
+  CK(cudaMemsetAsync(ctx->sums, 0, sizeof(double) * 2 * 64, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  for (int is = 0; is < ns; is++) {
+    const double rs = ctx->radius[is] / cell;  // Rsmooth in grid units, src/fmax.c:233
+    TRY(hessian_xy(ctx, ctx->kdens, rs, false));
+    CK(cudaEventRecord(ctx->ev[8 + 2 * is], ctx->stream));
+    CollapseParams c{};
+    for (int k = 0; k < 6; k++) {
+      c.zs.src[k] = ctx->B[k];
+      c.zs.kzpow[k] = kHessKzPow[k];
+      c.hdst[k] = (is == ns - 1) ? ctx->B[k] : nullptr;  // keep the R=0 Hessian for the LPT sources
+    }
+    c.zs.ncomp = 6;
+    c.zs.has_nyq = 0;
+    c.zs.dc_add = ctx->dc;
+    c.g = g;
+    c.tw = ctx->tw;
+    c.spline = spline_for(ctx, is);
+    c.nspl = ctx->nspl;
+    c.ismooth = is;
+    c.Fmax = ctx->fmax;
+    c.Rmax = ctx->rmax;
+    c.sums = ctx->sums + 2 * is;
+    LAUNCH(launch_zpass_collapse(g.N, c, (size_t)g.lx * g.N, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[8 + 2 * is + 1], ctx->stream));
+  }
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->hessian_valid = true;
+  std::vector<double> sums(2 * 64);
+  CK(cudaMemcpyAsync(sums.data(), ctx->sums, sizeof(double) * 2 * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const double ntot = (double)g.N * g.N * g.N;
+  if (true_variance)
+    for (int is = 0; is < ns; is++) true_variance[is] = sums[2 * is + 1] / ntot;  // src/collapse_times.c:662
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  ctx->tm.fmax += ms * 1e-3;
+  for (int is = 0; is < ns; is++) {
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, is == 0 ? ctx->ev[0] : ctx->ev[8 + 2 * is - 1], ctx->ev[8 + 2 * is]));
+    CK(cudaEventElapsedTime(&b, ctx->ev[8 + 2 * is], ctx->ev[8 + 2 * is + 1]));
+    ctx->tm.deriv += a * 1e-3;
+    ctx->tm.coll += b * 1e-3;
+    ctx->tm.per_radius[is] = (a + b) * 1e-3;
+  }
+  return 0;
+}
+
+// first derivatives of a k-vector -> three float fields (compute_first_derivatives, src/fmax.c:193-222)
+static int first_derivs_to_vel(pinb200_ctx* ctx, const double2* kvec, double growth, float* const out[3], bool with_nyq) {
+  const Geom& g = ctx->g;
+  const double norm = 1.0 / ((double)g.N * g.N * g.N);
+  LAUNCH(launch_dc_scalar(kvec, ctx->dc, norm, 1, ctx->stream));
+  double2* xdst[3] = {ctx->W[1], ctx->W[0], nullptr};  // p=0 -> W1, p=1 -> W0
+  // Rsmooth = 0 (src/fmax.c:200 with R = 0): window = 1
+  TRY(run_xpass_inv(ctx, kvec, xdst, 0x3, false, 1, 1, norm * growth, with_nyq));
+  const double2* ysrc[3] = {ctx->W[0], ctx->W[1], nullptr};
+  double2* ydst[6] = {ctx->W[2], ctx->W[3], ctx->W[4], nullptr, nullptr, nullptr};
+  static const YJob jobs[3] = {{0, 0, 0}, {1, 1, 1}, {1, 0, 2}};
+  TRY(run_ypass(ctx, +1, ysrc, ydst, jobs, 3, with_nyq));
+  ZOutParams z{};
+  for (int k = 0; k < 3; k++) {
+    z.zs.src[k] = ydst[k];
+    z.fdst[k] = out[k];
+  }
+  z.zs.kzpow[0] = 0; z.zs.kzpow[1] = 0; z.zs.kzpow[2] = 1;
+  z.zs.ncomp = 3;
+  z.zs.has_nyq = with_nyq ? 1 : 0;
+  z.zs.dc_add = ctx->dc;
+  z.g = g;
+  z.tw = ctx->tw;
+  z.mode = 1;
+  LAUNCH(launch_zpass_out(g.N, z, (size_t)g.lx * g.N, ctx->stream));
+  return 0;
+}
+
+extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, const double growth[4]) {
+  if (!ctx || !growth) return 1;
+  if (!ctx->kdens) FAIL("kdensity not resident");
+  CK(cudaSetDevice(ctx->d.device));
+  const Geom& g = ctx->g;
+  const int order = ctx->d.lpt_order;
+  const size_t nrows = (size_t)g.lx * g.N;
+  const double norm = 1.0 / ((double)g.N * g.N * g.N);
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (order >= 2 && compute_sources) {
+    if (!ctx->hessian_valid) FAIL("second derivatives of the R=0 radius are not in place (call pinb200_fmax first)");
+    // ---- sources (src/LPT.c:64-93): A0 = S2, A1 = S31, A2 = S32 (real layout)
+    SourcesParams sp{};
+    for (int k = 0; k < 6; k++) sp.h[k] = reinterpret_cast<const double*>(ctx->B[k]);
+    sp.s2 = reinterpret_cast<double*>(ctx->A[0]);
+    sp.s31 = reinterpret_cast<double*>(ctx->A[1]);
+    sp.s32 = reinterpret_cast<double*>(ctx->A[2]);
+    sp.nrows = nrows;
+    sp.N = g.N;
+    sp.pitch = 2 * g.P;
+    sp.lpt_order = order;
+    LAUNCH(launch_sources(sp, ctx->stream));
+    TRY(run_r2c_inplace(ctx, ctx->A[0]));  // kvector_2LPT
+    if (order >= 3) {
+      // ---- second derivatives of phi_2 contracted with the Hessian (src/LPT.c:116-141),
+      //      in three groups (by power of kx) to bound the workspace to 4 fields
+      for (int i = 0; i < 4; i++) TRY(dev_alloc(ctx, &ctx->W[i], ctx->field_elems));
+      LAUNCH(launch_dc_scalar(ctx->A[0], ctx->dc, norm, 0, ctx->stream));
+      struct Grp { int pw; int n; YJob jobs[3]; int kz[3]; int slot[3]; };
+      // slots: 0 xx,1 yy,2 zz,3 xy,4 xz,5 yz ; weight 2 (diagonal) or 4 (off-diagonal)
+      const Grp grp[3] = {{2, 1, {{0, 0, 0}}, {0, 0, 0}, {0, 0, 0}},
+                          {1, 2, {{0, 1, 0}, {0, 0, 1}}, {0, 1, 0}, {3, 4, 0}},
+                          {0, 3, {{0, 2, 0}, {0, 1, 1}, {0, 0, 2}}, {0, 1, 2}, {1, 5, 2}}};
+      for (const Grp& gr : grp) {
+        double2* xdst[3] = {nullptr, nullptr, nullptr};
+        xdst[gr.pw] = ctx->W[0];
+        TRY(run_xpass_inv(ctx, ctx->A[0], xdst, 1 << gr.pw, false, 1, 0, norm, true));
+        const double2* ysrc[3] = {ctx->W[0], nullptr, nullptr};
+        double2* ydst[6] = {ctx->W[1], ctx->W[2], ctx->W[3], nullptr, nullptr, nullptr};
+        TRY(run_ypass(ctx, +1, ysrc, ydst, gr.jobs, gr.n, true));
+        ZOutParams z{};
+        for (int k = 0; k < gr.n; k++) {
+          z.zs.src[k] = ydst[k];
+          z.zs.kzpow[k] = gr.kz[k];
+          z.hsrc[k] = reinterpret_cast<const double*>(ctx->B[gr.slot[k]]);
+          z.weight[k] = 2.0 * (gr.slot[k] <= 2 ? 1.0 : 2.0);
+        }
+        z.zs.ncomp = gr.n;
+        z.zs.has_nyq = 1;
+        z.zs.dc_add = ctx->dc;
+        z.g = g;
+        z.tw = ctx->tw;
+        z.mode = 2;
+        z.acc = reinterpret_cast<double*>(ctx->A[2]);
+        LAUNCH(launch_zpass_out(g.N, z, nrows, ctx->stream));
+      }
+      TRY(run_r2c_inplace(ctx, ctx->A[1]));  // kvector_3LPT_1
+      TRY(run_r2c_inplace(ctx, ctx->A[2]));  // kvector_3LPT_2
+    }
+    // the Hessian fields are dead now
+    for (auto& b : ctx->B) TRY(dev_free(ctx, &b));
+    ctx->hessian_valid = false;
+    ctx->kvec_valid = true;
+  }
+  if (order >= 2 && !ctx->kvec_valid) FAIL("LPT k-vectors are not resident (compute_sources = 0 needs an earlier call with compute_sources = 1)");
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  for (int i = 0; i < 5; i++) TRY(dev_alloc(ctx, &ctx->W[i], ctx->field_elems));
+  const int nvel = order == 1 ? 3 : (order == 2 ? 6 : 12);
+  for (int i = 0; i < nvel; i++) TRY(dev_alloc(ctx, &ctx->vel[i], ctx->ncells));
+  if (order >= 2) TRY(first_derivs_to_vel(ctx, ctx->A[0], growth[1], ctx->vel + 3, true));   // ScaleDep.order = 2
+  if (order >= 3) {
+    TRY(first_derivs_to_vel(ctx, ctx->A[1], growth[2], ctx->vel + 6, true));                 // order 3
+    TRY(first_derivs_to_vel(ctx, ctx->A[2], growth[3], ctx->vel + 9, true));                 // order 4
+  }
+  TRY(first_derivs_to_vel(ctx, ctx->kdens, growth[0], ctx->vel + 0, false));                 // order 1, src/fmax.c:342-346
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float a = 0, b = 0;
+  CK(cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]));
+  CK(cudaEventElapsedTime(&b, ctx->ev[3], ctx->ev[4]));
+  ctx->tm.lpt += (a + b) * 1e-3;
+  return 0;
+}
+
+extern "C" int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts) {
+  if (!ctx || !counts) return 1;
+  if (!ctx->fmax) FAIL("Fmax not computed");
+  CK(cudaSetDevice(ctx->d.device));
+  unsigned long long* d = nullptr;
+  TRY(dev_alloc(ctx, &d, (size_t)PINB200_NBINS));
+  CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * PINB200_NBINS, ctx->stream));
+  LAUNCH(launch_fmax_pdf(ctx->fmax, ctx->ncells, d, ctx->stream));
+  CK(cudaMemcpyAsync(counts, d, sizeof(unsigned long long) * PINB200_NBINS, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  TRY(dev_free(ctx, &d));
+  return 0;
+}
+
+extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t cell_begin,
+                                         size_t ncells) {
+  if (!ctx || !products || !L) return 1;
+  if (!ctx->fmax) FAIL("products not computed");
+  if (cell_begin + ncells > ctx->ncells) FAIL("cell range outside the local slab");
+  if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
+  CK(cudaSetDevice(ctx->d.device));
+  if (ncells == 0) return 0;
+  unsigned char* d = nullptr;
+  TRY(dev_alloc(ctx, &d, ncells * L->stride));
+  CK(cudaMemsetAsync(d, 0, ncells * L->stride, ctx->stream));
+  PackParams p{};
+  p.fmax = ctx->fmax;
+  p.rmax = ctx->rmax;
+  for (int i = 0; i < 12; i++) p.vel[i] = ctx->vel[i];
+  p.out = d;
+  p.stride = L->stride;
+  p.prodfloat_bytes = L->prodfloat_bytes;
+  p.off_rmax = L->off_Rmax;
+  p.off_fmax = L->off_Fmax;
+  p.off_vel[0] = L->off_Vel;
+  p.off_vel[1] = L->off_Vel_2LPT;
+  p.off_vel[2] = L->off_Vel_3LPT_1;
+  p.off_vel[3] = L->off_Vel_3LPT_2;
+  p.cell_begin = cell_begin;
+  p.ncells = ncells;
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  LAUNCH(launch_pack_products(p, ctx->stream));
+  CK(cudaMemcpyAsync(products, d, ncells * L->stride, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+  ctx->tm.mem_transf += ms * 1e-3;
+  TRY(dev_free(ctx, &d));
+  return 0;
+}
+
+extern "C" int pinb200_download_field(pinb200_ctx* ctx, int which, void* dst) {
+  if (!ctx || !dst) return 1;
+  const void* src = nullptr;
+  if (which == 0) src = ctx->fmax;
+  else if (which == 1) src = ctx->rmax;
+  else if (which >= 2 && which < 14) src = ctx->vel[which - 2];
+  if (!src) FAIL("requested field is not resident");
+  CK(cudaSetDevice(ctx->d.device));
+  CK(cudaMemcpyAsync(dst, src, ctx->ncells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int pinb200_get_timers(pinb200_ctx* ctx, pinb200_timers* t) {
+  if (!ctx || !t) return 1;
+  ctx->tm.kernel_launches = ctx->launches;
+  *t = ctx->tm;
+  return 0;
+}
+
+// ---- finer-grained entry points -------------------------------------------------------------
+extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* real_out) {
+  if (!ctx || !cplx_in || !real_out) return 1;
+  CK(cudaSetDevice(ctx->d.device));
+  const Geom& g = ctx->g;
+  const double norm = 1.0 / ((double)g.N * g.N * g.N);
+  double2* f = nullptr;
+  TRY(dev_alloc(ctx, &f, ctx->field_elems));
+  TRY(upload_cplx(ctx, cplx_in, f));
+  double2* xdst[3] = {f, nullptr, nullptr};
+  TRY(run_xpass_inv(ctx, f, xdst, 1, false, 0, 0, norm, true));
+  const double2* ysrc[3] = {f, nullptr, nullptr};
+  double2* ydst[6] = {f, nullptr, nullptr, nullptr, nullptr, nullptr};
+  YJob job{0, 0, 0};
+  TRY(run_ypass(ctx, +1, ysrc, ydst, &job, 1, true));
+  ZOutParams z{};
+  z.zs.src[0] = f;
+  z.zs.kzpow[0] = 0;
+  z.zs.ncomp = 1;
+  z.zs.has_nyq = 1;
+  z.zs.dc_add = nullptr;
+  z.g = g;
+  z.tw = ctx->tw;
+  z.mode = 0;
+  z.rdst[0] = f;
+  LAUNCH(launch_zpass_out(g.N, z, (size_t)g.lx * g.N, ctx->stream));
+  TRY(download_real(ctx, f, real_out));
+  TRY(dev_free(ctx, &f));
+  return 0;
+}
+
+extern "C" int pinb200_fft_r2c(pinb200_ctx* ctx, const double* real_in, double* cplx_out) {
+  if (!ctx || !real_in || !cplx_out) return 1;
+  CK(cudaSetDevice(ctx->d.device));
+  const Geom& g = ctx->g;
+  const size_t rows = (size_t)g.lx * g.N;
+  double2* f = nullptr;
+  double* tmp = nullptr;
+  TRY(dev_alloc(ctx, &f, ctx->field_elems));
+  TRY(dev_alloc(ctx, &tmp, rows * g.N));
+  CK(cudaMemcpyAsync(tmp, real_in, rows * g.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(f, 0, ctx->field_elems * sizeof(double2), ctx->stream));
+  LAUNCH(launch_repitch_r(tmp, reinterpret_cast<double*>(f), rows, g.N, g.N, 2 * g.P, ctx->stream));
+  TRY(run_r2c_inplace(ctx, f));
+  TRY(download_cplx(ctx, f, cplx_out));
+  TRY(dev_free(ctx, &tmp));
+  TRY(dev_free(ctx, &f));
+  return 0;
+}
+
+extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, double* hessian_out) {
+  if (!ctx || !hessian_out) return 1;
+  if (!ctx->kdens) FAIL("kdensity not resident");
+  CK(cudaSetDevice(ctx->d.device));
+  const Geom& g = ctx->g;
+  ctx->kvec_valid = false;
+  for (int i = 0; i < 3; i++) TRY(dev_alloc(ctx, &ctx->A[i], ctx->field_elems));
+  for (int i = 0; i < 6; i++) TRY(dev_alloc(ctx, &ctx->B[i], ctx->field_elems));
+  const double cell = ctx->d.box_size / g.N;
+  TRY(hessian_xy(ctx, ctx->kdens, radius / cell, false));
+  ZOutParams z{};
+  for (int k = 0; k < 6; k++) {
+    z.zs.src[k] = ctx->B[k];
+    z.zs.kzpow[k] = kHessKzPow[k];
+    z.rdst[k] = ctx->B[k];
+  }
+  z.zs.ncomp = 6;
+  z.zs.has_nyq = 0;
+  z.zs.dc_add = ctx->dc;
+  z.g = g;
+  z.tw = ctx->tw;
+  z.mode = 0;
+  LAUNCH(launch_zpass_out(g.N, z, (size_t)g.lx * g.N, ctx->stream));
+  for (int k = 0; k < 6; k++) TRY(download_real(ctx, ctx->B[k], hessian_out + (size_t)k * ctx->ncells));
+  ctx->hessian_valid = false;
+  return 0;
+}
+
+extern "C" int pinb200_collapse_cells(pinb200_ctx* ctx, int ismooth, const double* hessian6, size_t ncells, double* F_out) {
+  if (!ctx || !hessian6 || !F_out) return 1;
+  CK(cudaSetDevice(ctx->d.device));
+  TRY(upload_splines(ctx));
+  if (ncells == 0) return 0;
+  double *dh = nullptr, *dF = nullptr;
+  TRY(dev_alloc(ctx, &dh, 6 * ncells));
+  TRY(dev_alloc(ctx, &dF, ncells));
+  CK(cudaMemcpyAsync(dh, hessian6, 6 * ncells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(launch_collapse_cells(dh, ncells, spline_for(ctx, ismooth), ctx->nspl, dF, ctx->stream));
+  CK(cudaMemcpyAsync(F_out, dF, ncells * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  TRY(dev_free(ctx, &dh));
+  TRY(dev_free(ctx, &dF));
+  return 0;
+}
+
+extern "C" int pinb200_download_kvector(pinb200_ctx* ctx, int which, double* kvec) {
+  if (!ctx || !kvec) return 1;
+  if (which < 0 || which > 2) FAIL("which must be 0, 1 or 2");
+  if (!ctx->kvec_valid) FAIL("LPT k-vectors are not resident");
+  CK(cudaSetDevice(ctx->d.device));
+  return download_cplx(ctx, ctx->A[which], kvec);
+}

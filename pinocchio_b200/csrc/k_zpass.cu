@@ -1,0 +1,88 @@
+// sm_100a instantiations of the contiguous (z) passes: c2r + collapse, c2r + epilogues, r2c.
+#include "devctx.cuh"
+#include "launch.h"
+
+namespace pinb {
+
+template <int M, int TL, int CG>
+__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT) zpass_collapse_kernel(const __grid_constant__ CollapseParams p) {
+  extern __shared__ double2 smem[];
+  using ZS = ZShape<M, TL, CG>;
+  double* spl = reinterpret_cast<double*>(smem + ZS::fft_elems(6));
+  double* scratch = spl + 5 * p.nspl;
+  DevCtx ctx;
+  zpass_collapse_body<M, TL, CG>(ctx, smem, spl, scratch, p);
+}
+
+template <int M, int TL>
+__global__ void __launch_bounds__(ZShape<M, TL, 1>::NT) zpass_out_kernel(const __grid_constant__ ZOutParams p) {
+  extern __shared__ double2 smem[];
+  DevCtx ctx;
+  zpass_out_body<M, TL, 1>(ctx, smem, p);
+}
+
+template <int M, int TL>
+__global__ void __launch_bounds__(ZShape<M, TL, 1>::NT) zpass_r2c_kernel(const __grid_constant__ ZR2CParams p) {
+  extern __shared__ double2 smem[];
+  DevCtx ctx;
+  zpass_r2c_body<M, TL>(ctx, smem, p);
+}
+
+template <int N> static cudaError_t collapse_launch(const CollapseParams& p, size_t nrows, cudaStream_t s) {
+  constexpr int M = N / 2, TL = ZCfg<M>::TL, CG = 6;
+  using ZS = ZShape<M, TL, CG>;
+  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (size_t)5 * p.nspl * sizeof(double) + 2 * ZS::NT * sizeof(double);
+  cudaError_t e = allow_smem(zpass_collapse_kernel<M, TL, CG>, smem);
+  if (e != cudaSuccess) return e;
+  zpass_collapse_kernel<M, TL, CG><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+template <int N> static cudaError_t out_launch(const ZOutParams& p, size_t nrows, cudaStream_t s) {
+  constexpr int M = N / 2, TL = ZCfg<M>::TL;
+  using ZS = ZShape<M, TL, 1>;
+  const size_t smem = ZS::fft_elems(p.zs.ncomp) * sizeof(double2);
+  cudaError_t e = allow_smem(zpass_out_kernel<M, TL>, ZS::fft_elems(6) * sizeof(double2));
+  if (e != cudaSuccess) return e;
+  zpass_out_kernel<M, TL><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+template <int N> static cudaError_t r2c_launch(const ZR2CParams& p, size_t nrows, cudaStream_t s) {
+  constexpr int M = N / 2, TL = ZCfg<M>::TL;
+  using ZS = ZShape<M, TL, 1>;
+  const size_t smem = ZS::fft_elems(1) * sizeof(double2);
+  cudaError_t e = allow_smem(zpass_r2c_kernel<M, TL>, smem);
+  if (e != cudaSuccess) return e;
+  zpass_r2c_kernel<M, TL><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zpass_collapse(int N, const CollapseParams& p, size_t nrows, cudaStream_t s) {
+  switch (N) {
+#define X(L) case L: return collapse_launch<L>(p, nrows, s);
+    PINB_FOR_EACH_GRID(X)
+#undef X
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_zpass_out(int N, const ZOutParams& p, size_t nrows, cudaStream_t s) {
+  switch (N) {
+#define X(L) case L: return out_launch<L>(p, nrows, s);
+    PINB_FOR_EACH_GRID(X)
+#undef X
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_zpass_r2c(int N, const ZR2CParams& p, size_t nrows, cudaStream_t s) {
+  switch (N) {
+#define X(L) case L: return r2c_launch<L>(p, nrows, s);
+    PINB_FOR_EACH_GRID(X)
+#undef X
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace pinb

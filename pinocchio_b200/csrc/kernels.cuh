@@ -1,0 +1,585 @@
+// Kernel bodies of the collapse-time hot path, written against an execution-context
+// template parameter `Ctx` (tid / bid / sync / atomic_add) so that the identical source runs
+// as sm_100a kernels (kernels.cu, DevCtx) and under the pthread block emulator used by the
+// CPU-only unit tests (tests/host/emu.cpp, HostCtx).  No kernel here is a CPU fallback of the
+// product: the shared library exports only the CUDA instantiations.
+//
+// Data layout (device, per rank):
+//   half-complex field  : double2 [x][y][P]   P = N/2 + 8 (row pitch; kz = 0..N/2 valid)
+//   real field          : double  [x][y][2P]  (z = 0..N-1 valid) -- same bytes, so the z pass
+//                         is in place
+//   K layout = k-space slab split along y : [x (N)][yl (ly)][P]      (x pass domain)
+//   R layout = real-space slab split along x: [xl (lx)][y (N)][P]    (y and z pass domain)
+// Reference counterparts: compute_derivative k loop (src/fmax-pfft.c:306-397), pfft_execute
+// (src/fmax-pfft.c:191-228), compute_collapse_times cell loop (src/collapse_times.c:545-591),
+// LPT sources/contraction (src/LPT.c:64-141), GenIC column loop (src/GenIC.c:188-411).
+#pragma once
+#include "collapse.cuh"
+#include "fft_core.cuh"
+
+#define PINB_NBINS_PDF 210 /* NBINS, src/pinocchio.h:65 */
+
+namespace pinb {
+
+struct Geom {
+  int N, M, P;     // grid side, N/2, complex row pitch
+  int lx, ly;      // local extents: x in R layout, y in K layout
+  int x0, y0;      // global offsets of the local slabs
+  double knorm;    // 2*pi/N  (k in grid units, src/fmax-pfft.c:290)
+};
+
+// Mode factor applied when the x pass loads delta_k (fused K2).
+struct KFactor {
+  const double* gauss;  // gauss[n] = exp(-0.5*(knorm*n)^2*Rs^2), n = 0..M; nullptr -> 1
+  double scalar;        // 1/N^3 normalisation (src/fmax-pfft.c:224-225) times growth_rate
+  int green;            // 1: divide by k^2, k=0 mode dropped here and re-added as a constant
+  int times_i;          // 1: (re,im) -> (-im,re)  (first derivatives, src/fmax-pfft.c:389-394)
+};
+
+// Launch shapes shared by the CUDA instantiations and the host emulator.
+// kz-tile width of the strided passes: 8 complex (128 B contiguous per line element) while the
+// tile fits 128 KB of shared memory.
+template <int L> struct StridedCfg { static constexpr int TK = (L <= 1024) ? 8 : 4; };
+// rows per block of the z passes: >= 16 threads per component group on the tiny test grids,
+// one row per block (three resident blocks per SM at N = 1024) for the production sizes.
+template <int M> struct ZCfg { static constexpr int TL = M <= 32 ? 4 : (M <= 128 ? 2 : 1); };
+
+PINB_HD int fold(int e, int N, int M) { return e > M ? e - N : e; }  // index N/2 stays +N/2
+PINB_HD double ipow(double k, int p) { return p == 0 ? 1.0 : (p == 1 ? k : k * k); }
+
+template <class T> PINB_HD T ld_ro(const T* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------
+// Strided tile FFT: TK adjacent lines (adjacent kz), line elements `stride` apart.
+// Block = Plan::TPL * TK threads; shared memory = L*TK double2.
+// ---------------------------------------------------------------------------------------
+template <int L, int TK, int DIR, class Ctx, class LoadF, class StoreF>
+PINB_HD void strided_tile_fft(Ctx& ctx, double2* s, const double2* __restrict__ tw, int twscale, LoadF load,
+                              StoreF store) {
+  using PL = Plan<L, false>;
+  constexpr int TPL = PL::TPL, RMAX = PL::RMAX;
+  const int tk = ctx.tid() % TK, jl = ctx.tid() / TK;
+  double2 v[RMAX];
+  auto s_in = [&](int e) { return s[e * TK + tk]; };
+  auto s_out = [&](int e, double2 val) { s[e * TK + tk] = val; };
+  auto g_in = [&](int e) { return load(e, tk); };
+  auto g_out = [&](int e, double2 val) { store(e, tk, val); };
+  stage_load<L, PL::R0, TPL, RMAX>(jl, v, g_in);
+  stage_store<L, PL::R0, 1, DIR, TPL, RMAX>(jl, v, s_out, tw, twscale);
+  ctx.sync();
+  if constexpr (PL::NST == 2) {
+    stage_load<L, PL::R1, TPL, RMAX>(jl, v, s_in);
+    stage_store<L, PL::R1, PL::R0, DIR, TPL, RMAX>(jl, v, g_out, tw, twscale);
+  } else {
+    stage_load<L, PL::R1, TPL, RMAX>(jl, v, s_in);
+    ctx.sync();
+    stage_store<L, PL::R1, PL::R0, DIR, TPL, RMAX>(jl, v, s_out, tw, twscale);
+    ctx.sync();
+    stage_load<L, PL::R2, TPL, RMAX>(jl, v, s_in);
+    stage_store<L, PL::R2, PL::R0 * PL::R1, DIR, TPL, RMAX>(jl, v, g_out, tw, twscale);
+  }
+  ctx.sync();  // shared memory free for the next job
+}
+
+// ---------------------------------------------------------------------------------------
+// X pass.  One block = (yl, kz tile).  Up to three jobs: dst[p] = FFT_x[ kx^p * fac * src ].
+// ---------------------------------------------------------------------------------------
+struct XPassParams {
+  const double2* src;   // K layout
+  double2* dst[3];      // R layout (single rank) -- indexed by power p of kx
+  int pmask;            // bit p set -> compute job p
+  int ntiles_z;         // kz tiles per row that are processed (M/TK, +1 with the Nyquist tile)
+  KFactor kf;
+  Geom g;
+  const double2* tw;    // N-th roots of unity
+};
+
+template <int L, int TK, int DIR, class Ctx>
+PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
+  const Geom& g = p.g;
+  const int yl = ctx.bid() / p.ntiles_z;
+  const int kz0 = (ctx.bid() % p.ntiles_z) * TK;
+  const int ny = fold(g.y0 + yl, g.N, g.M);
+  const double ky = g.knorm * ny;
+  const size_t xstride = (size_t)g.ly * g.P;
+  const double2* src = p.src + (size_t)yl * g.P + kz0;
+  for (int pw = 0; pw < 3; pw++) {
+    if (!((p.pmask >> pw) & 1)) continue;
+    double2* dst = p.dst[pw] + (size_t)(g.y0 + yl) * g.P + kz0;  // R layout, lx == N on one rank
+    auto load = [&](int e, int tk) {
+      double2 c = ld_ro(src + (size_t)e * xstride + tk);
+      const int nx = fold(e, g.N, g.M);
+      const int nz = kz0 + tk;  // <= M, never folded
+      const double kx = g.knorm * nx;
+      const double kz = g.knorm * nz;
+      double f = p.kf.scalar;
+      if (p.kf.green) {
+        const double k2 = (kx * kx + ky * ky) + kz * kz;
+        f = (k2 != 0.0) ? f / k2 : 0.0;
+      }
+      if (p.kf.gauss) {
+        const int ax = nx < 0 ? -nx : nx, ay = ny < 0 ? -ny : ny;
+        f *= ld_ro(p.kf.gauss + ax) * ld_ro(p.kf.gauss + ay) * ld_ro(p.kf.gauss + nz);
+      }
+      f *= ipow(kx, pw);
+      c = cscale(c, f);
+      if (p.kf.times_i) c = make_double2(-c.y, c.x);
+      return c;
+    };
+    auto store = [&](int e, int tk, double2 val) { dst[(size_t)e * ((size_t)g.N * g.P) + tk] = val; };
+    strided_tile_fft<L, TK, DIR>(ctx, smem, p.tw, 1, load, store);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Y pass.  One block = (xl, kz tile).  Jobs: dst[j.dst] = FFT_y[ ky^q * src[j.src] ].
+// ---------------------------------------------------------------------------------------
+struct YJob { int src, q, dst; };
+struct YPassParams {
+  const double2* src[3];
+  double2* dst[6];
+  YJob job[6];
+  int njobs;
+  int ntiles_z;
+  Geom g;
+  const double2* tw;
+};
+
+template <int L, int TK, int DIR, class Ctx>
+PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
+  const Geom& g = p.g;
+  const int xl = ctx.bid() / p.ntiles_z;
+  const int kz0 = (ctx.bid() % p.ntiles_z) * TK;
+  const size_t base = (size_t)xl * g.N * g.P + kz0;
+  for (int j = 0; j < p.njobs; j++) {
+    const double2* src = p.src[p.job[j].src] + base;
+    double2* dst = p.dst[p.job[j].dst] + base;
+    const int q = p.job[j].q;
+    auto load = [&](int e, int tk) {
+      double2 c = ld_ro(src + (size_t)e * g.P + tk);
+      if (q) c = cscale(c, ipow(g.knorm * fold(e, g.N, g.M), q));
+      return c;
+    };
+    auto store = [&](int e, int tk, double2 val) { dst[(size_t)e * g.P + tk] = val; };
+    strided_tile_fft<L, TK, DIR>(ctx, smem, p.tw, 1, load, store);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Contiguous (z) lines in shared memory.
+// ---------------------------------------------------------------------------------------
+template <int M, int DIR, class Ctx>
+PINB_HD void zline_fft_smem(Ctx& ctx, double2* ln, int jl, const double2* __restrict__ tw) {
+  using PL = Plan<M, true>;
+  constexpr int TPL = PL::TPL, RMAX = PL::RMAX;
+  double2 v[RMAX];
+  auto s_in = [&](int e) { return ln[zpad(e)]; };
+  auto s_out = [&](int e, double2 val) { ln[zpad(e)] = val; };
+  stage_load<M, PL::R0, TPL, RMAX>(jl, v, s_in);
+  ctx.sync();
+  stage_store<M, PL::R0, 1, DIR, TPL, RMAX>(jl, v, s_out, tw, 2);
+  ctx.sync();
+  stage_load<M, PL::R1, TPL, RMAX>(jl, v, s_in);
+  ctx.sync();
+  stage_store<M, PL::R1, PL::R0, DIR, TPL, RMAX>(jl, v, s_out, tw, 2);
+  ctx.sync();
+  if constexpr (PL::NST == 3) {
+    stage_load<M, PL::R2, TPL, RMAX>(jl, v, s_in);
+    ctx.sync();
+    stage_store<M, PL::R2, PL::R0 * PL::R1, DIR, TPL, RMAX>(jl, v, s_out, tw, 2);
+    ctx.sync();
+  }
+}
+
+struct ZSrc {
+  const double2* src[6];  // R layout half-complex fields
+  int kzpow[6];           // power of kz applied on load
+  int ncomp;
+  int has_nyq;            // 0: the kz = N/2 plane is known to be zero (delta_k-derived fields)
+  const double* dc_add;   // device scalar added to every component in real space (or nullptr)
+};
+
+// c2r of a tile of TL rows x ncomp components into shared memory: on return
+// smem[(c*TL + line)*PITCH + zpad(m)] = (x[2m], x[2m+1]).  Block = TPL*TL*CG threads.
+template <int M, int TL, int CG, class Ctx>
+PINB_HD void zpass_c2r_tile(Ctx& ctx, double2* smem, const ZSrc& zs, const Geom& g, size_t row0,
+                            const double2* __restrict__ tw) {
+  using PL = Plan<M, true>;
+  constexpr int TPL = PL::TPL;
+  constexpr int PITCH = ZLine<M>::PITCH;
+  const int tid = ctx.tid();
+  const int jl = tid % TPL, line = (tid / TPL) % TL, cg = tid / (TPL * TL);
+  for (int c0 = 0; c0 < zs.ncomp; c0 += CG) {
+    const int c = c0 + cg;
+    double2* ln = smem + ((size_t)c * TL + line) * PITCH;
+    const double2* src = zs.src[c] + (row0 + line) * g.P;
+    const int pw = zs.kzpow[c];
+    for (int e = jl; e < M; e += TPL) {
+      double2 x = ld_ro(src + e);
+      if (pw) x = cscale(x, ipow(g.knorm * e, pw));
+      ln[zpad(e)] = x;
+    }
+    if (jl == 0) {
+      double2 x = make_double2(0.0, 0.0);
+      if (zs.has_nyq) x = cscale(ld_ro(src + M), ipow(g.knorm * M, pw));
+      ln[zpad(M)] = x;
+    }
+    ctx.sync();
+    for (int k = jl; k <= M / 2; k += TPL) {
+      if (k == 0) {
+        const double a = ln[zpad(0)].x, b = ln[zpad(M)].x;
+        ln[zpad(0)] = make_double2(a + b, a - b);
+      } else {
+        const double2 xk = ln[zpad(k)], xmk = ln[zpad(M - k)];
+        double2 zk, zmk;
+        c2r_pre_pair(xk, xmk, ld_ro(tw + k), zk, zmk);
+        ln[zpad(k)] = zk;
+        if (k != M / 2) ln[zpad(M - k)] = zmk;
+      }
+    }
+    ctx.sync();
+    zline_fft_smem<M, +1>(ctx, ln, jl, tw);
+  }
+}
+
+template <int M, int TL, int CG> struct ZShape {
+  static constexpr int TPL = Plan<M, true>::TPL;
+  static constexpr int NT = TPL * TL * CG;
+  static constexpr int PITCH = ZLine<M>::PITCH;
+  static constexpr size_t fft_elems(int ncomp) { return (size_t)ncomp * TL * PITCH; }
+};
+
+// block-wide sum of two doubles through shared scratch (2*NT doubles)
+template <int NT, class Ctx> PINB_HD void block_sum2(Ctx& ctx, double* scratch, double& a, double& b) {
+  const int tid = ctx.tid();
+  scratch[tid] = a;
+  scratch[NT + tid] = b;
+  ctx.sync();
+  int n = NT;
+  while (n > 1) {
+    const int half = (n + 1) >> 1;
+    if (tid < n - half) {
+      scratch[tid] += scratch[tid + half];
+      scratch[NT + tid] += scratch[NT + tid + half];
+    }
+    ctx.sync();
+    n = half;
+  }
+  a = scratch[0];
+  b = scratch[NT];
+}
+
+// ---------------------------------------------------------------------------------------
+// Z pass + collapse (fused K4 last pass + K5 + K10).  Six components.
+// ---------------------------------------------------------------------------------------
+struct CollapseParams {
+  ZSrc zs;
+  Geom g;
+  const double2* tw;
+  const double* spline;  // [5][nspl]: x,y,b,c,d (global); staged to shared memory
+  int nspl;
+  int ismooth;
+  float* Fmax;           // [lx][N][N]
+  int* Rmax;
+  double* sums;          // [2]: sum(delta), sum(delta^2)   (atomicAdd)
+  double2* hdst[6];      // if hdst[0] != nullptr: store the six real fields (in place allowed)
+};
+
+template <int M, int TL, int CG, class Ctx>
+PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double* scratch, const CollapseParams& p) {
+  using ZS = ZShape<M, TL, CG>;
+  constexpr int N = 2 * M, NT = ZS::NT, PITCH = ZS::PITCH;
+  const int tid = ctx.tid();
+  const size_t row0 = (size_t)ctx.bid() * TL;
+  for (int i = tid; i < 5 * p.nspl; i += NT) spl_s[i] = ld_ro(p.spline + i);
+  zpass_c2r_tile<M, TL, CG>(ctx, smem, p.zs, p.g, row0, p.tw);  // ends with a barrier
+  SplineView sp{spl_s, spl_s + p.nspl, spl_s + 2 * p.nspl, spl_s + 3 * p.nspl, spl_s + 4 * p.nspl, p.nspl};
+  const double dc = p.zs.dc_add ? ld_ro(p.zs.dc_add) : 0.0;
+  double sd = 0.0, sd2 = 0.0;
+  for (int idx = tid; idx < TL * N; idx += NT) {
+    const int line = idx / N, z = idx % N, m = z >> 1;
+    double h[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      const double2 v = smem[((size_t)c * TL + line) * PITCH + zpad(m)];
+      h[c] = ((z & 1) ? v.y : v.x) + dc;
+    }
+    const double delta = h[0] + h[1] + h[2];
+    sd += delta;
+    sd2 += delta * delta;
+    const double F = inverse_collapse_time(h, sp);
+    const size_t cell = (row0 + line) * N + z;
+    // running max, src/collapse_times.c:587-590 (float Fmax promoted to double for the test);
+    // ismooth == 0 also performs the -10 / -1 initialisation of :468-469
+    float fm = -10.0f;
+    int rm = -1;
+    if (p.ismooth > 0) fm = p.Fmax[cell];
+    if ((double)fm < F) {
+      p.Fmax[cell] = (float)F;
+      p.Rmax[cell] = p.ismooth;
+    } else if (p.ismooth == 0) {
+      p.Fmax[cell] = fm;
+      p.Rmax[cell] = rm;
+    }
+  }
+  block_sum2<NT>(ctx, scratch, sd, sd2);
+  if (tid == 0) {
+    ctx.atomic_add(p.sums + 0, sd);
+    ctx.atomic_add(p.sums + 1, sd2);
+  }
+  if (p.hdst[0]) {
+    constexpr int TPLG = NT / TL;  // threads cooperating on one row in the copy-out
+    const int line = tid / TPLG, jl = tid % TPLG;
+    for (int c = 0; c < 6; c++) {
+      double2* dst = p.hdst[c] + (row0 + line) * p.g.P;
+      const double2* ln = smem + ((size_t)c * TL + line) * PITCH;
+      for (int e = jl; e < M; e += TPLG) {
+        double2 v = ln[zpad(e)];
+        dst[e] = make_double2(v.x + dc, v.y + dc);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Z pass with generic epilogues.
+// ---------------------------------------------------------------------------------------
+struct ZOutParams {
+  ZSrc zs;
+  Geom g;
+  const double2* tw;
+  int mode;              // 0: store real fields (rdst)   1: float displacement (fdst)
+                         // 2: contraction  acc -= sum_c w[c] * val_c * H_c   (src/LPT.c:134-137)
+  double2* rdst[6];      // mode 0: real fields, R layout (row pitch P double2)
+  float* fdst[6];        // mode 1: float fields [lx][N][N]
+  const double* hsrc[6]; // mode 2: Hessian real fields (row pitch 2P doubles)
+  double weight[6];      // mode 2
+  double* acc;           // mode 2: real field (row pitch 2P doubles)
+};
+
+template <int M, int TL, int CG, class Ctx>
+PINB_HD void zpass_out_body(Ctx& ctx, double2* smem, const ZOutParams& p) {
+  using ZS = ZShape<M, TL, CG>;
+  constexpr int N = 2 * M, NT = ZS::NT, PITCH = ZS::PITCH;
+  const int tid = ctx.tid();
+  const size_t row0 = (size_t)ctx.bid() * TL;
+  zpass_c2r_tile<M, TL, CG>(ctx, smem, p.zs, p.g, row0, p.tw);
+  const double dc = p.zs.dc_add ? ld_ro(p.zs.dc_add) : 0.0;
+  const int nc = p.zs.ncomp;
+  if (p.mode == 0) {
+    constexpr int TPLG = NT / TL;
+    const int line = tid / TPLG, jl = tid % TPLG;
+    for (int c = 0; c < nc; c++) {
+      double2* dst = p.rdst[c] + (row0 + line) * p.g.P;
+      const double2* ln = smem + ((size_t)c * TL + line) * PITCH;
+      for (int e = jl; e < M; e += TPLG) {
+        double2 v = ln[zpad(e)];
+        dst[e] = make_double2(v.x + dc, v.y + dc);
+      }
+    }
+    return;
+  }
+  for (int idx = tid; idx < TL * N; idx += NT) {
+    const int line = idx / N, z = idx % N, m = z >> 1;
+    const size_t row = row0 + line;
+    if (p.mode == 1) {
+      for (int c = 0; c < nc; c++) {
+        const double2 v = smem[((size_t)c * TL + line) * PITCH + zpad(m)];
+        p.fdst[c][row * N + z] = (float)(((z & 1) ? v.y : v.x) + dc);
+      }
+    } else {
+      const size_t rcell = row * (2 * (size_t)p.g.P) + z;
+      double a = p.acc[rcell];
+      for (int c = 0; c < nc; c++) {
+        const double2 v = smem[((size_t)c * TL + line) * PITCH + zpad(m)];
+        a -= p.weight[c] * (((z & 1) ? v.y : v.x) + dc) * ld_ro(p.hsrc[c] + rcell);
+      }
+      p.acc[rcell] = a;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Z pass forward (r2c), one component, in place allowed.
+// ---------------------------------------------------------------------------------------
+struct ZR2CParams {
+  const double2* src;  // real field viewed as double2 (row pitch P)
+  double2* dst;        // half-complex field
+  Geom g;
+  const double2* tw;
+};
+
+template <int M, int TL, class Ctx>
+PINB_HD void zpass_r2c_body(Ctx& ctx, double2* smem, const ZR2CParams& p) {
+  using PL = Plan<M, true>;
+  constexpr int TPL = PL::TPL, PITCH = ZLine<M>::PITCH;
+  const int tid = ctx.tid();
+  const int jl = tid % TPL, line = tid / TPL;
+  const size_t row = (size_t)ctx.bid() * TL + line;
+  double2* ln = smem + (size_t)line * PITCH;
+  const double2* src = p.src + row * p.g.P;
+  for (int e = jl; e < M; e += TPL) ln[zpad(e)] = ld_ro(src + e);
+  ctx.sync();
+  zline_fft_smem<M, -1>(ctx, ln, jl, p.tw);
+  double2* dst = p.dst + row * p.g.P;
+  for (int k = jl; k <= M / 2; k += TPL) {
+    if (k == 0) {
+      const double2 z0 = ln[zpad(0)];
+      dst[0] = make_double2(z0.x + z0.y, 0.0);
+      dst[M] = make_double2(z0.x - z0.y, 0.0);
+    } else {
+      const double2 zk = ln[zpad(k)], zmk = ln[zpad(M - k)];
+      double2 xk, xmk;
+      r2c_post_pair(zk, zmk, ld_ro(p.tw + k), xk, xmk);
+      dst[k] = xk;
+      if (k != M / 2) dst[M - k] = xmk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// LPT sources (K6, src/LPT.c:64-93): element-wise over real fields with row pitch 2P.
+// ---------------------------------------------------------------------------------------
+struct SourcesParams {
+  const double* h[6];
+  double *s2, *s31, *s32;
+  size_t nrows;  // lx*N
+  int N, pitch;  // pitch = 2P doubles
+  int lpt_order;
+};
+
+template <class Ctx> PINB_HD void lpt_sources_body(Ctx& ctx, int nthreads_total, const SourcesParams& p) {
+  const size_t total = p.nrows * (size_t)p.N;
+  for (size_t i = (size_t)ctx.bid() * ctx.nthreads() + ctx.tid(); i < total; i += (size_t)nthreads_total) {
+    const size_t row = i / p.N;
+    const int z = (int)(i % p.N);
+    const size_t a = row * p.pitch + z;
+    const double s0 = p.h[0][a], s1 = p.h[1][a], s2 = p.h[2][a], s3 = p.h[3][a], s4 = p.h[4][a], s5 = p.h[5][a];
+    const double src2 = s0 * s1 + s0 * s2 + s1 * s2 - s3 * s3 - s4 * s4 - s5 * s5;
+    p.s2[a] = src2;
+    if (p.lpt_order >= 3) {
+      p.s31[a] = 3.0 * (s0 * (s1 * s2 - s5 * s5) - s3 * (s3 * s2 - s4 * s5) + s4 * (s3 * s5 - s4 * s1));
+      p.s32[a] = 2.0 * (s0 + s1 + s2) * src2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// GenIC (K1, src/GenIC.c:188-411 + gsl ranlxd1).
+// One thread per (kx, ky) column; RANLUX state lives in shared memory, [12][NT] doubles per
+// generator, two generators (column + k=0-plane mirror).
+// ---------------------------------------------------------------------------------------
+struct Ranlxd1 {
+  double* x;   // x[k*stride]
+  int stride;
+  double carry;
+  int ir, jr, ir_old;
+
+  PINB_HD void set(unsigned int seed) {
+    const double one_bit = 1.0 / 281474976710656.0;
+    if (seed == 0) seed = 1;
+    // GSL reads the seed into a signed int; i%2, i/=2 then give the digits of |i|
+    const long long si = (long long)(int)seed;
+    unsigned long long mag = (unsigned long long)(si < 0 ? -si : si);
+    unsigned int bits = (unsigned int)(mag & 0x7FFFFFFFull);  // 31 digits
+    int ibit = 0, jbit = 18;
+    for (int k = 0; k < 12; k++) {
+      double v = 0.0;
+      for (int m = 1; m <= 48; m++) {
+        const unsigned int bi = (bits >> ibit) & 1u, bj = (bits >> jbit) & 1u;
+        const double y = (double)((bi + 1u) & 1u);
+        v += v + y;
+        bits = (bits & ~(1u << ibit)) | ((bi ^ bj) << ibit);
+        ibit = (ibit + 1) % 31;
+        jbit = (jbit + 1) % 31;
+      }
+      x[k * stride] = one_bit * v;
+    }
+    carry = 0.0;
+    ir = 11;
+    jr = 7;
+    ir_old = 0;
+  }
+  PINB_HD void step() {
+    const double one_bit = 1.0 / 281474976710656.0;
+    double y = x[jr * stride] - x[ir * stride] - carry;
+    if (y < 0) { carry = one_bit; y += 1.0; } else carry = 0.0;
+    x[ir * stride] = y;
+    ir = (ir == 11) ? 0 : ir + 1;
+    jr = (jr == 11) ? 0 : jr + 1;
+  }
+  PINB_HD double get_double() {
+    ir = (ir == 11) ? 0 : ir + 1;
+    if (ir == ir_old) {
+      int k = 0;
+      while (ir > 0) { step(); k++; }
+      while (k < 202) { step(); k++; }  // ranlxd1 luxury level pr = 202
+      ir_old = ir;
+    }
+    return x[ir * stride];
+  }
+};
+
+struct GenicParams {
+  const unsigned int* seeds;  // SEEDTABLE[jj*N + ii], whole plane (src/GenIC.c:234-235)
+  const double* pk;           // P(k) at k = 2*pi*sqrt(m)/Box, m = |n|^2 <= (N/2)^2
+  double2* kd;                // K layout, zero-initialised
+  double box;                 // true Mpc (src/GenIC.c:82)
+  int fixed_ic, paired_ic;
+  Geom g;
+};
+
+template <int NT, class Ctx> PINB_HD void genic_body(Ctx& ctx, double* smem, const GenicParams& p) {
+  const Geom& g = p.g;
+  const int N = g.N, N2 = g.M;
+  const long long col = (long long)ctx.bid() * NT + ctx.tid();
+  if (col >= (long long)N * g.ly) return;
+  const int ii = (int)(col / g.ly);
+  const int jl = (int)(col % g.ly);
+  const int jj = g.y0 + jl;
+  if (ii == N2 || jj == N2) return;
+  Ranlxd1 rng, k0;
+  rng.x = smem + ctx.tid();
+  rng.stride = NT;
+  k0.x = smem + 12 * NT + ctx.tid();
+  k0.stride = NT;
+  rng.set(p.seeds[(size_t)jj * N + ii]);
+  const double fac = pow(1. / p.box, 1.5);
+  const double fac2 = pow((double)N, 3.0);
+  const int nx = ii < N2 ? ii : ii - N, ny = jj < N2 ? jj : jj - N;
+  double2* out = p.kd + ((size_t)ii * g.ly + jl) * g.P;
+  for (int kk = 0; kk < N2; kk++) {
+    double phase = rng.get_double() * 2 * PINB_PI;
+    double ampl;
+    do ampl = rng.get_double(); while (ampl == 0);
+    if (ii == 0 && jj == 0 && kk == 0) continue;
+    const long long m = (long long)nx * nx + (long long)ny * ny + (long long)kk * kk;
+    if (m > (long long)N2 * N2) continue;  // |n| > N/2, src/GenIC.c:280
+    double p_of_k = ld_ro(p.pk + m);
+    double sign = 1.0;
+    if (kk == 0) {
+      if (ii == 0 && jj == N2) continue;
+      if (ii > N2 || (ii == 0 && jj > N2)) {
+        int jjj = N - jj;
+        if (jjj == N) jjj = 0;
+        const int iii = ii > N2 ? N - ii : ii;
+        sign = -1.0;
+        k0.set(p.seeds[(size_t)jjj * N + iii]);
+        phase = k0.get_double() * 2 * PINB_PI;
+        do ampl = k0.get_double(); while (ampl == 0);
+      }
+    }
+    if (p.paired_ic) phase += PINB_PI;
+    if (!p.fixed_ic) p_of_k *= -log(ampl);
+    const double delta = fac * sqrt(p_of_k);
+    out[kk] = make_double2(delta * cos(phase) * fac2, sign * delta * sin(phase) * fac2);
+  }
+}
+
+}  // namespace pinb

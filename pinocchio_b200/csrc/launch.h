@@ -1,0 +1,38 @@
+// Host-side launch interface between engine.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+
+namespace pinb {
+
+bool grid_supported(int N);
+
+cudaError_t launch_xpass(int N, int dir, const XPassParams& p, int nblocks_y, cudaStream_t s);
+cudaError_t launch_ypass(int N, int dir, const YPassParams& p, int nblocks_x, cudaStream_t s);
+cudaError_t launch_zpass_collapse(int N, const CollapseParams& p, size_t nrows, cudaStream_t s);
+cudaError_t launch_zpass_out(int N, const ZOutParams& p, size_t nrows, cudaStream_t s);
+cudaError_t launch_zpass_r2c(int N, const ZR2CParams& p, size_t nrows, cudaStream_t s);
+int xpass_tk(int N);  // kz-tile width used by the strided passes for this grid
+
+cudaError_t launch_sources(const SourcesParams& p, cudaStream_t s);
+cudaError_t launch_genic(const GenicParams& p, cudaStream_t s);
+
+// small helpers
+cudaError_t launch_gauss_table(double* gauss, int M, double knorm, double rsmooth, cudaStream_t s);
+cudaError_t launch_dc_scalar(const double2* src, double* out, double scale, int times_i, cudaStream_t s);
+cudaError_t launch_fmax_pdf(const float* fmax, size_t n, unsigned long long* counts, cudaStream_t s);
+cudaError_t launch_collapse_cells(const double* h6, size_t n, const double* spline, int nspl, double* F, cudaStream_t s);
+
+struct PackParams {
+  const float* fmax; const int* rmax; const float* vel[12];
+  unsigned char* out; size_t stride; int prodfloat_bytes;
+  int off_rmax, off_fmax, off_vel[4];
+  size_t cell_begin, ncells;
+};
+cudaError_t launch_pack_products(const PackParams& p, cudaStream_t s);
+
+// host <-> device layout converters (pitch P on the device, N/2+1 or N on the host)
+cudaError_t launch_repitch_c(const double2* src, double2* dst, size_t nrows, int ncols, int spitch, int dpitch, cudaStream_t s);
+cudaError_t launch_repitch_r(const double* src, double* dst, size_t nrows, int ncols, int spitch, int dpitch, cudaStream_t s);
+
+}  // namespace pinb

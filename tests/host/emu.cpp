@@ -1,0 +1,321 @@
+// CPU block emulator for the kernel bodies of pinocchio_b200/csrc/kernels.cuh.  TEST ONLY.
+//
+// Each "block" is executed by NT host threads that share a heap buffer as shared memory and a
+// pthread barrier as __syncthreads(); blocks run one after another.  The bodies are the very
+// same templates that k_*.cu instantiate for sm_100a, so index math, plans, twiddles and the
+// collapse arithmetic are checked on a CPU-only box against the oracle (tests/test_emulator.py).
+// This library is never loaded by the product (pinocchio_b200/), which has no CPU path.
+#include <pthread.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../pinocchio_b200/csrc/kernels.cuh"
+
+using namespace pinb;
+
+namespace {
+std::mutex g_atomic_mutex;
+
+struct HostCtx {
+  int tid_, bid_, nt_;
+  pthread_barrier_t* bar;
+  int tid() const { return tid_; }
+  int bid() const { return bid_; }
+  int nthreads() const { return nt_; }
+  void sync() const { pthread_barrier_wait(bar); }
+  void atomic_add(double* p, double v) const {
+    std::lock_guard<std::mutex> lk(g_atomic_mutex);
+    *p += v;
+  }
+};
+
+template <class F> void run_blocks(long long nblocks, int nt, F body) {
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, nt);
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([&, t]() {
+      HostCtx ctx{t, 0, nt, &bar};
+      for (long long b = 0; b < nblocks; b++) {
+        ctx.bid_ = (int)b;
+        body(ctx);
+        pthread_barrier_wait(&bar);  // block boundary: shared memory is reused
+      }
+    });
+  for (auto& x : th) x.join();
+  pthread_barrier_destroy(&bar);
+}
+
+Geom make_geom(int N) {
+  Geom g;
+  g.N = N;
+  g.M = N / 2;
+  g.P = g.M + 8;
+  g.lx = N;
+  g.ly = N;
+  g.x0 = 0;
+  g.y0 = 0;
+  g.knorm = 2. * PINB_PI / (double)N;
+  return g;
+}
+}  // namespace
+
+#define EMU_GRIDS(X) X(32) X(64)
+#define EMU_LINES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
+// ---- single-tile line FFTs for every supported length ---------------------------------------
+// in/out: [L][TK] complex (tile of TK lines, element-major), tw: NROOT=L roots
+template <int L, int DIR> static void strided_tile(const double2* in, double2* out, const double2* tw) {
+  constexpr int TK = StridedCfg<L>::TK;
+  constexpr int NT = Plan<L, false>::TPL * TK;
+  std::vector<double2> smem((size_t)L * TK);
+  run_blocks(1, NT, [&](HostCtx& ctx) {
+    auto load = [&](int e, int tk) { return in[e * TK + tk]; };
+    auto store = [&](int e, int tk, double2 v) { out[e * TK + tk] = v; };
+    strided_tile_fft<L, TK, DIR>(ctx, smem.data(), tw, 1, load, store);
+  });
+}
+
+extern "C" int emu_strided_tk(int L) {
+  switch (L) {
+#define X(LL) case LL: return StridedCfg<LL>::TK;
+    EMU_LINES(X)
+#undef X
+  }
+  return 0;
+}
+
+extern "C" int emu_strided_tile_fft(int L, int dir, const double* in, double* out, const double* tw) {
+  switch (L) {
+#define X(LL)                                                                                       \
+  case LL:                                                                                          \
+    if (dir > 0) strided_tile<LL, +1>((const double2*)in, (double2*)out, (const double2*)tw);        \
+    else strided_tile<LL, -1>((const double2*)in, (double2*)out, (const double2*)tw);                \
+    return 0;
+    EMU_LINES(X)
+#undef X
+  }
+  return 1;
+}
+
+// contiguous line of M complex in padded smem; tw has 2M roots
+template <int M, int DIR> static void zline(const double2* in, double2* out, const double2* tw) {
+  constexpr int NT = Plan<M, true>::TPL;
+  std::vector<double2> smem(ZLine<M>::PITCH);
+  for (int e = 0; e < M; e++) smem[zpad(e)] = in[e];
+  run_blocks(1, NT, [&](HostCtx& ctx) { zline_fft_smem<M, DIR>(ctx, smem.data(), ctx.tid(), tw); });
+  for (int e = 0; e < M; e++) out[e] = smem[zpad(e)];
+}
+
+extern "C" int emu_zline_fft(int M, int dir, const double* in, double* out, const double* tw) {
+  switch (M) {
+#define X(LL)                                                                                 \
+  case LL:                                                                                    \
+    if (dir > 0) zline<LL, +1>((const double2*)in, (double2*)out, (const double2*)tw);         \
+    else zline<LL, -1>((const double2*)in, (double2*)out, (const double2*)tw);                 \
+    return 0;
+    EMU_LINES(X)
+#undef X
+  }
+  return 1;
+}
+
+// ---- whole kernels on pitched [N][N][P] arrays ------------------------------------------------
+template <int N, int DIR> static void xpass_run(const XPassParams& p) {
+  constexpr int TK = StridedCfg<N>::TK;
+  constexpr int NT = Plan<N, false>::TPL * TK;
+  std::vector<double2> smem((size_t)N * TK);
+  run_blocks((long long)p.g.ly * p.ntiles_z, NT, [&](HostCtx& ctx) { xpass_body<N, TK, DIR>(ctx, smem.data(), p); });
+}
+
+extern "C" int emu_xpass(int N, int dir, const double* src, double* d0, double* d1, double* d2, int pmask, int with_nyq,
+              const double* gauss, double scalar, int green, int times_i, const double* tw) {
+  XPassParams p{};
+  p.src = (const double2*)src;
+  p.dst[0] = (double2*)d0;
+  p.dst[1] = (double2*)d1;
+  p.dst[2] = (double2*)d2;
+  p.pmask = pmask;
+  p.kf.gauss = gauss;
+  p.kf.scalar = scalar;
+  p.kf.green = green;
+  p.kf.times_i = times_i;
+  p.g = make_geom(N);
+  p.tw = (const double2*)tw;
+  switch (N) {
+#define X(LL)                                                         \
+  case LL:                                                            \
+    p.ntiles_z = (LL / 2) / StridedCfg<LL>::TK + (with_nyq ? 1 : 0);  \
+    if (dir > 0) xpass_run<LL, +1>(p); else xpass_run<LL, -1>(p);     \
+    return 0;
+    EMU_GRIDS(X)
+#undef X
+  }
+  return 1;
+}
+
+template <int N, int DIR> static void ypass_run(const YPassParams& p) {
+  constexpr int TK = StridedCfg<N>::TK;
+  constexpr int NT = Plan<N, false>::TPL * TK;
+  std::vector<double2> smem((size_t)N * TK);
+  run_blocks((long long)p.g.lx * p.ntiles_z, NT, [&](HostCtx& ctx) { ypass_body<N, TK, DIR>(ctx, smem.data(), p); });
+}
+
+// srcs[3], dsts[6]: pointers (may be null); jobs: njobs x (src, q, dst)
+extern "C" int emu_ypass(int N, int dir, double** srcs, double** dsts, const int* jobs, int njobs, int with_nyq, const double* tw) {
+  YPassParams p{};
+  for (int i = 0; i < 3; i++) p.src[i] = (const double2*)srcs[i];
+  for (int i = 0; i < 6; i++) p.dst[i] = (double2*)dsts[i];
+  for (int j = 0; j < njobs; j++) p.job[j] = YJob{jobs[3 * j], jobs[3 * j + 1], jobs[3 * j + 2]};
+  p.njobs = njobs;
+  p.g = make_geom(N);
+  p.tw = (const double2*)tw;
+  switch (N) {
+#define X(LL)                                                         \
+  case LL:                                                            \
+    p.ntiles_z = (LL / 2) / StridedCfg<LL>::TK + (with_nyq ? 1 : 0);  \
+    if (dir > 0) ypass_run<LL, +1>(p); else ypass_run<LL, -1>(p);     \
+    return 0;
+    EMU_GRIDS(X)
+#undef X
+  }
+  return 1;
+}
+
+template <int N> static void collapse_run(const CollapseParams& p) {
+  constexpr int M = N / 2, TL = ZCfg<M>::TL, CG = 6;
+  using ZS = ZShape<M, TL, CG>;
+  std::vector<double2> smem(ZS::fft_elems(6));
+  std::vector<double> spl((size_t)5 * p.nspl), scratch(2 * ZS::NT);
+  run_blocks((long long)p.g.lx * N / TL, ZS::NT,
+             [&](HostCtx& ctx) { zpass_collapse_body<M, TL, CG>(ctx, smem.data(), spl.data(), scratch.data(), p); });
+}
+
+extern "C" int emu_zpass_collapse(int N, double** srcs, const int* kzpow, int has_nyq, const double* dc, const double* spline, int nspl,
+                       int ismooth, float* fmax, int* rmax, double* sums, double** hdst, const double* tw) {
+  CollapseParams p{};
+  for (int k = 0; k < 6; k++) {
+    p.zs.src[k] = (const double2*)srcs[k];
+    p.zs.kzpow[k] = kzpow[k];
+    p.hdst[k] = hdst ? (double2*)hdst[k] : nullptr;
+  }
+  p.zs.ncomp = 6;
+  p.zs.has_nyq = has_nyq;
+  p.zs.dc_add = dc;
+  p.g = make_geom(N);
+  p.tw = (const double2*)tw;
+  p.spline = spline;
+  p.nspl = nspl;
+  p.ismooth = ismooth;
+  p.Fmax = fmax;
+  p.Rmax = rmax;
+  p.sums = sums;
+  switch (N) {
+#define X(LL) case LL: collapse_run<LL>(p); return 0;
+    EMU_GRIDS(X)
+#undef X
+  }
+  return 1;
+}
+
+template <int N> static void zout_run(const ZOutParams& p) {
+  constexpr int M = N / 2, TL = ZCfg<M>::TL;
+  using ZS = ZShape<M, TL, 1>;
+  std::vector<double2> smem(ZS::fft_elems(6));
+  run_blocks((long long)p.g.lx * N / TL, ZS::NT, [&](HostCtx& ctx) { zpass_out_body<M, TL, 1>(ctx, smem.data(), p); });
+}
+
+extern "C" int emu_zpass_out(int N, int ncomp, double** srcs, const int* kzpow, int has_nyq, const double* dc, int mode, double** rdst,
+                  float** fdst, double** hsrc, const double* weight, double* acc, const double* tw) {
+  ZOutParams p{};
+  for (int k = 0; k < ncomp; k++) {
+    p.zs.src[k] = (const double2*)srcs[k];
+    p.zs.kzpow[k] = kzpow[k];
+    if (rdst) p.rdst[k] = (double2*)rdst[k];
+    if (fdst) p.fdst[k] = fdst[k];
+    if (hsrc) p.hsrc[k] = hsrc[k];
+    if (weight) p.weight[k] = weight[k];
+  }
+  p.zs.ncomp = ncomp;
+  p.zs.has_nyq = has_nyq;
+  p.zs.dc_add = dc;
+  p.g = make_geom(N);
+  p.tw = (const double2*)tw;
+  p.mode = mode;
+  p.acc = acc;
+  switch (N) {
+#define X(LL) case LL: zout_run<LL>(p); return 0;
+    EMU_GRIDS(X)
+#undef X
+  }
+  return 1;
+}
+
+template <int N> static void r2c_run(const ZR2CParams& p) {
+  constexpr int M = N / 2, TL = ZCfg<M>::TL;
+  using ZS = ZShape<M, TL, 1>;
+  std::vector<double2> smem(ZS::fft_elems(1));
+  run_blocks((long long)p.g.lx * N / TL, ZS::NT, [&](HostCtx& ctx) { zpass_r2c_body<M, TL>(ctx, smem.data(), p); });
+}
+
+extern "C" int emu_zpass_r2c(int N, const double* src, double* dst, const double* tw) {
+  ZR2CParams p{};
+  p.src = (const double2*)src;
+  p.dst = (double2*)dst;
+  p.g = make_geom(N);
+  p.tw = (const double2*)tw;
+  switch (N) {
+#define X(LL) case LL: r2c_run<LL>(p); return 0;
+    EMU_GRIDS(X)
+#undef X
+  }
+  return 1;
+}
+
+extern "C" int emu_sources(int N, double** h, double* s2, double* s31, double* s32, int lpt_order) {
+  SourcesParams p{};
+  Geom g = make_geom(N);
+  for (int k = 0; k < 6; k++) p.h[k] = h[k];
+  p.s2 = s2;
+  p.s31 = s31;
+  p.s32 = s32;
+  p.nrows = (size_t)N * N;
+  p.N = N;
+  p.pitch = 2 * g.P;
+  p.lpt_order = lpt_order;
+  const int nt = 8, nb = 4;
+  run_blocks(nb, nt, [&](HostCtx& ctx) { lpt_sources_body(ctx, nt * nb, p); });
+  return 0;
+}
+
+extern "C" int emu_genic(int N, const unsigned int* seeds, const double* pk, double box, int fixed_ic, int paired_ic, double* kd) {
+  GenicParams p{};
+  p.seeds = seeds;
+  p.pk = pk;
+  p.kd = (double2*)kd;
+  p.box = box;
+  p.fixed_ic = fixed_ic;
+  p.paired_ic = paired_ic;
+  p.g = make_geom(N);
+  constexpr int NT = 8;
+  std::vector<double> smem(2 * 12 * NT);
+  run_blocks(((long long)N * N + NT - 1) / NT, NT, [&](HostCtx& ctx) { genic_body<NT>(ctx, smem.data(), p); });
+  return 0;
+}
+
+extern "C" int emu_collapse_cells(const double* h6, long long n, const double* spline, int nspl, double* F) {
+  SplineView sp{spline, spline + nspl, spline + 2 * nspl, spline + 3 * nspl, spline + 4 * nspl, nspl};
+  for (long long i = 0; i < n; i++) {
+    double h[6];
+    for (int c = 0; c < 6; c++) h[c] = h6[c * n + i];
+    F[i] = inverse_collapse_time(h, sp);
+  }
+  return 0;
+}
+
