@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: Fmax+LPT Mcells/s of the collapse-time hot path (BASELINE.json).
+
+One step = one pass of the hot path over one synthetic box: the S smoothing radii of
+compute_fmax (fused k-space kernel -> 3-D FFT -> collapse -> running max) followed by the
+3LPT displacement stage, on the delta_k that GenIC left resident in HBM (GenIC is excluded
+from the metric, SURVEY.md 8d, and reported separately).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference ...                   # CPU arm: the oracle port on host cores
+
+Prints ONE JSON line (see the task contract): value = device-timed throughput with inputs
+resident; e2e = the same metric through the reference-facing call with host buffers (H2D of
+kdensity from pinned memory + compute + D2H of the AoS products[]).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+HMF_RADII = [20.635922, 13.996056, 9.026099, 5.465945, 3.058354, 1.548258, 0.689079, 0.258729, 0.0]
+METRIC = "Fmax+LPT Mcells/s"
+
+
+def measured_peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def default_grid(ngpus: int) -> int:
+    return 1024
+
+
+def algorithmic_bytes(N: int, S: int):
+    """Per-kernel algorithmic HBM bytes of the radius loop and SURVEY 8d totals."""
+    Nr = float(N) ** 3
+    Nc = float(N) * N * (N // 2)          # half-complex elements the Hessian passes touch (kz < N/2)
+    Ncs = float(N) * N * (N // 2 + 1)     # SURVEY.md 8(d) definition
+    per = {
+        "xpass_kernel": 16 * Nc + 3 * 16 * Nc,           # read delta_k once, write 3 x-transformed fields
+        "ypass_kernel": 3 * 16 * Nc + 6 * 16 * Nc,       # read 3, write 6
+        "zpass_collapse_kernel": 6 * 16 * Nc + 12 * Nr,  # read 6, Fmax r/w (8 B) + Rmax w (4 B)
+    }
+    survey_rad = 400 * Ncs + 12 * Nr
+    survey_lpt = 1680 * Ncs + 288 * Nr
+    return per, survey_rad, survey_lpt, S * survey_rad + survey_lpt
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from pinocchio_b200.build import build
+    build()
+    from pinocchio_b200.cosmology import Cosmology, SmoothingLadder
+    from pinocchio_b200.engine import PRODUCT_DTYPE_3LPT, Pinocchio, RunConfig
+
+    N = args.grid or default_grid(world)
+    cosmo = Cosmology(pk_norm_override=2.03146e7)
+    cfg = RunConfig(GridSize=N, BoxSize_htrue=N / 0.7, lpt_order=3)
+    lad = SmoothingLadder(np.array(HMF_RADII), np.zeros(len(HMF_RADII)))
+    pin = Pinocchio(cfg, cosmo, device=local, smoothing=lad)
+    stream = torch.cuda.current_stream()
+    pin.set_stream(stream.cuda_stream)
+    S = lad.Nsmooth
+
+    t0 = time.time()
+    pin.GenIC_large()
+    genic_s = pin.timers().dens
+
+    def step():
+        pin.compute_fmax(displacements=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    tm0 = pin.timers()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    tm1 = pin.timers()
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    cells = float(N) ** 3 * world      # every rank processes its own box (independent realisations)
+    value = cells / (ms_per_step * 1e-3) / 1e6
+
+    # ---- per-kernel device times measured live (CUDA events inside the engine, same stream)
+    K = args.steps
+    per_launch_ms = {"xpass_kernel": (tm1.hess_x - tm0.hess_x) / (K * S) * 1e3,
+                     "ypass_kernel": (tm1.hess_y - tm0.hess_y) / (K * S) * 1e3,
+                     "zpass_collapse_kernel": (tm1.hess_z - tm0.hess_z) / (K * S) * 1e3}
+    abytes, survey_rad, survey_lpt, survey_total = algorithmic_bytes(N, S)
+    peak, peak_src = measured_peaks()
+    dom = max(per_launch_ms, key=per_launch_ms.get)
+    achieved = abytes[dom] / (per_launch_ms[dom] * 1e-3) / 1e9
+    rad_ms = sum(per_launch_ms.values())
+    lpt_ms = (tm1.lpt - tm0.lpt) / K * 1e3
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": {k: round(v, 3) for k, v in per_launch_ms.items()},
+                "gbs_per_kernel": {k: round(abytes[k] / (v * 1e-3) / 1e9, 1) for k, v in per_launch_ms.items()},
+                "per_radius_ms": round(rad_ms, 3),
+                "per_radius_frac_of_survey_roofline": round(survey_rad / (rad_ms * 1e-3) / 1e9 / peak, 4),
+                "lpt_stage_ms": round(lpt_ms, 3),
+                "lpt_frac_of_survey_roofline": round(survey_lpt / (lpt_ms * 1e-3) / 1e9 / peak, 4),
+                "whole_step_frac_of_survey_roofline": round(survey_total / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
+    launches = int(tm1.kernel_launches - tm0.kernel_launches)
+
+    # ---- e2e: host buffers through the reference-facing calls (H2D kdensity, D2H products[])
+    e2e = None
+    if not args.no_e2e:
+        kd_host = torch.empty((N, N, N // 2 + 1, 2), dtype=torch.float64, pin_memory=True)
+        import ctypes
+        from pinocchio_b200.engine import _PD
+        pin._ck(pin.lib.pinb200_download_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
+        chunk = min(N ** 3, 1 << 26)
+        stage = torch.empty((chunk * PRODUCT_DTYPE_3LPT.itemsize,), dtype=torch.uint8, pin_memory=True)
+        stage_np = stage.numpy().view(PRODUCT_DTYPE_3LPT)
+        from pinocchio_b200.engine import ProductLayout
+        f = PRODUCT_DTYPE_3LPT.fields
+        lay = ProductLayout(56, 4, f["Rmax"][1], f["Fmax"][1], f["Vel"][1], f["Vel_2LPT"][1], f["Vel_3LPT_1"][1],
+                            f["Vel_3LPT_2"][1])
+
+        def e2e_step():
+            pin._ck(pin.lib.pinb200_upload_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
+            pin.compute_fmax(displacements=True)
+            chk = 0.0
+            for b in range(0, N ** 3, chunk):
+                n = min(chunk, N ** 3 - b)
+                pin._ck(pin.lib.pinb200_download_products(pin.h, ctypes.c_void_p(stage.data_ptr()), ctypes.byref(lay), b, n))
+                chk += float(stage_np["Fmax"][0])
+            return chk
+
+        e2e_step()
+        barrier()
+        w0 = time.perf_counter()
+        ne = max(1, min(args.steps, 3))
+        for _ in range(ne):
+            e2e_step()
+        barrier()
+        w = (time.perf_counter() - w0) / ne
+        tw = torch.tensor([w], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(cells / float(tw.item()) / 1e6, 2), "unit": "Mcells/s",
+               "h2d_bytes_per_step": int(N * N * (N // 2 + 1) * 16), "d2h_bytes_per_step": int(N ** 3 * 56),
+               "steps": ne, "ms_per_step": round(float(tw.item()) * 1e3, 2)}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_reference_sample(args.cpu_grid, 1)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": round(value, 2), "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"synthetic {N}^3 grid, full smoothing-radius sweep (S={S}) + 3LPT on 1 B200"
+                          + (f" x {world} independent boxes (one per GPU)" if world > 1 else ""),
+                          "grid": N, "nsmooth": S, "lpt_order": 3, "cosmology": "HMF_Validation (EH, Omega0=.25, h=.7, sigma8=.8)",
+                          "seed": 486604, "parallelism": "1 box per GPU" if world > 1 else "single GPU",
+                          "l2_policy": "inputs larger than L2 (each field 8.7 GB at 1024^3)"},
+               "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+               "cpu_baseline": cpu_baseline, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
+        print(json.dumps(out))
+    pin.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_sample(grid: int, steps: int):
+    """The oracle port (NumPy, one host thread for the collapse math, pocketfft FFTs) timed on a
+    bounded sample of the same workload: the full S-radius sweep + 3LPT on a `grid`^3 box."""
+    from oracle import pinocchio_oracle as po
+    from pinocchio_b200.cosmology import Cosmology
+    cosmo = Cosmology(pk_norm_override=2.03146e7)
+    N = grid
+    kd = po.genic(N, N / 0.7, 486604, cosmo.PowerSpectrum)
+    g = (cosmo.GrowingMode(0.0), cosmo.GrowingMode_2LPT(0.0), cosmo.GrowingMode_3LPT_1(0.0), cosmo.GrowingMode_3LPT_2(0.0))
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        po.compute_fmax(kd, HMF_RADII, 1.0 / 0.7, cosmo.InverseGrowingMode, growth=g, lpt_order=3)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts))
+    return {"value": round(N ** 3 / t / 1e6, 4), "unit": "Mcells/s", "cores": 1, "kind": "port",
+            "sample": f"{N}^3 box, same 9-radius sweep + 3LPT, NumPy oracle (oracle/pinocchio_oracle.py), "
+                      f"{steps} step(s), {t:.1f} s/step", "ms_per_step": round(t * 1e3, 1),
+            "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    N = args.cpu_grid
+    # warmup
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(min(N, 64), 1)
+    cb = cpu_reference_sample(N, max(1, min(args.steps, 3)))
+    S = len(HMF_RADII)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Mcells/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"synthetic {args.grid or default_grid(world)}^3 grid, full smoothing-radius sweep (S={S}) + 3LPT"
+                      f" -- CPU arm timed on a bounded {N}^3 sample of it",
+                      "grid": N, "nsmooth": S, "lpt_order": 3},
+           "cpu_baseline": cb, "gpu_launches": 0,
+           "e2e": {"value": cb["value"], "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=0, help="override the grid side (default 1024)")
+    ap.add_argument("--cpu-grid", type=int, default=128, help="grid of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,9 @@ typedef struct {
 typedef struct {
   double dens, fmax, deriv, fft, coll, lpt, mem_transf;
   double per_radius[64];   /* wall of each smoothing radius (src/fmax.c:140-146)             */
+  double hess_x, hess_y, hess_z; /* device seconds summed over radii: x pass (fused k-space kernel),
+                                    y pass, z pass + collapse                                  */
+  double disp_sources, disp_vel; /* displacement stage: sources + k-vectors; 4 x first derivatives */
   unsigned long long kernel_launches;  /* kernels launched by this context so far            */
 } pinb200_timers;
 

@@ -58,7 +58,7 @@ struct pinb200_ctx {
 
   pinb200_timers tm{};
   unsigned long long launches = 0;
-  cudaEvent_t ev[2 * 64 + 8] = {nullptr};
+  cudaEvent_t ev[3 * 64 + 8] = {nullptr};
 };
 
 #define CK(call)                                                                              \
@@ -491,12 +491,13 @@ static int ensure_products(pinb200_ctx* ctx) {
 
 // Hessian passes for one radius: fills B[0..5] (half-complex, after x and y passes).
 // slot order xx,yy,zz,xy,xz,yz (src/fmax.c:239)
-static int hessian_xy(pinb200_ctx* ctx, const double2* src, double rsmooth, bool with_nyq) {
+static int hessian_xy(pinb200_ctx* ctx, const double2* src, double rsmooth, bool with_nyq, cudaEvent_t mid_event = nullptr) {
   const Geom& g = ctx->g;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
   LAUNCH(launch_gauss_table(ctx->gauss, g.M, g.knorm, rsmooth, ctx->stream));
   LAUNCH(launch_dc_scalar(src, ctx->dc, norm, 0, ctx->stream));
   TRY(run_xpass_inv(ctx, src, ctx->A, 0x7, true, 1, 0, norm, with_nyq));
+  if (mid_event) CK(cudaEventRecord(mid_event, ctx->stream));
   static const YJob jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
   TRY(run_ypass(ctx, +1, ctx->A, ctx->B, jobs, 6, with_nyq));
   return 0;
@@ -522,8 +523,8 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   for (int is = 0; is < ns; is++) {
     const double rs = ctx->radius[is] / cell;  // Rsmooth in grid units, src/fmax.c:233
-    TRY(hessian_xy(ctx, ctx->kdens, rs, false));
-    CK(cudaEventRecord(ctx->ev[8 + 2 * is], ctx->stream));
+    TRY(hessian_xy(ctx, ctx->kdens, rs, false, ctx->ev[8 + 3 * is]));
+    CK(cudaEventRecord(ctx->ev[8 + 3 * is + 1], ctx->stream));
     CollapseParams c{};
     for (int k = 0; k < 6; k++) {
       c.zs.src[k] = ctx->B[k];
@@ -542,7 +543,7 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     c.Rmax = ctx->rmax;
     c.sums = ctx->sums + 2 * is;
     LAUNCH(launch_zpass_collapse(g.N, c, (size_t)g.lx * g.N, ctx->stream));
-    CK(cudaEventRecord(ctx->ev[8 + 2 * is + 1], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[8 + 3 * is + 2], ctx->stream));
   }
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   ctx->hessian_valid = true;
@@ -556,12 +557,16 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   ctx->tm.fmax += ms * 1e-3;
   for (int is = 0; is < ns; is++) {
-    float a = 0, b = 0;
-    CK(cudaEventElapsedTime(&a, is == 0 ? ctx->ev[0] : ctx->ev[8 + 2 * is - 1], ctx->ev[8 + 2 * is]));
-    CK(cudaEventElapsedTime(&b, ctx->ev[8 + 2 * is], ctx->ev[8 + 2 * is + 1]));
-    ctx->tm.deriv += a * 1e-3;
-    ctx->tm.coll += b * 1e-3;
-    ctx->tm.per_radius[is] = (a + b) * 1e-3;
+    float x = 0, y = 0, z = 0;
+    CK(cudaEventElapsedTime(&x, is == 0 ? ctx->ev[0] : ctx->ev[8 + 3 * is - 1], ctx->ev[8 + 3 * is]));
+    CK(cudaEventElapsedTime(&y, ctx->ev[8 + 3 * is], ctx->ev[8 + 3 * is + 1]));
+    CK(cudaEventElapsedTime(&z, ctx->ev[8 + 3 * is + 1], ctx->ev[8 + 3 * is + 2]));
+    ctx->tm.hess_x += x * 1e-3;
+    ctx->tm.hess_y += y * 1e-3;
+    ctx->tm.hess_z += z * 1e-3;
+    ctx->tm.deriv += (x + y) * 1e-3;
+    ctx->tm.coll += z * 1e-3;
+    ctx->tm.per_radius[is] = (x + y + z) * 1e-3;
   }
   return 0;
 }
@@ -675,6 +680,8 @@ extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, cons
   CK(cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]));
   CK(cudaEventElapsedTime(&b, ctx->ev[3], ctx->ev[4]));
   ctx->tm.lpt += (a + b) * 1e-3;
+  ctx->tm.disp_sources += a * 1e-3;
+  ctx->tm.disp_vel += b * 1e-3;
   return 0;
 }
 

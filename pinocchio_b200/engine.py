@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference interface for the collapse-time path, over the C ABI.
+
+``Pinocchio`` keeps the reference's function names and argument meaning for this path
+(``GenIC_large``, ``compute_fmax``, ``compute_displacements``, ``Fmax_PDF``, ... --
+src/pinocchio.h:544-566,575-577,637-648) and its error convention (0 = OK, non-zero = failure,
+message available).  All compute happens in libpinb200.so (sm_100a kernels); this module only
+marshals tables and buffers through ``ctypes``.  There is no CPU fallback: loading fails loudly
+if the library is missing, and every call fails if no B200 is visible.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+from .cosmology import Cosmology, SmoothingLadder, pk_lattice_table, set_smoothing
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libpinb200.so"
+NBINS = 210
+
+_PD = ctypes.POINTER(ctypes.c_double)
+
+
+class Desc(ctypes.Structure):
+    _fields_ = [("grid_size", ctypes.c_int), ("box_size", ctypes.c_double), ("random_seed", ctypes.c_int),
+                ("fixed_ic", ctypes.c_int), ("paired_ic", ctypes.c_int), ("lpt_order", ctypes.c_int),
+                ("rank", ctypes.c_int), ("nranks", ctypes.c_int), ("device", ctypes.c_int)]
+
+
+class ProductLayout(ctypes.Structure):
+    _fields_ = [("stride", ctypes.c_size_t), ("prodfloat_bytes", ctypes.c_int), ("off_Rmax", ctypes.c_int),
+                ("off_Fmax", ctypes.c_int), ("off_Vel", ctypes.c_int), ("off_Vel_2LPT", ctypes.c_int),
+                ("off_Vel_3LPT_1", ctypes.c_int), ("off_Vel_3LPT_2", ctypes.c_int)]
+
+
+class Timers(ctypes.Structure):
+    _fields_ = [("dens", ctypes.c_double), ("fmax", ctypes.c_double), ("deriv", ctypes.c_double),
+                ("fft", ctypes.c_double), ("coll", ctypes.c_double), ("lpt", ctypes.c_double),
+                ("mem_transf", ctypes.c_double), ("per_radius", ctypes.c_double * 64),
+                ("hess_x", ctypes.c_double), ("hess_y", ctypes.c_double), ("hess_z", ctypes.c_double),
+                ("disp_sources", ctypes.c_double), ("disp_vel", ctypes.c_double),
+                ("kernel_launches", ctypes.c_ulonglong)]
+
+
+# every symbol include/pinb200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "pinb200_create", "pinb200_destroy", "pinb200_last_error", "pinb200_set_stream", "pinb200_synchronize",
+    "pinb200_set_power_table", "pinb200_set_smoothing", "pinb200_set_invgrow_spline", "pinb200_genic",
+    "pinb200_upload_kdensity", "pinb200_download_kdensity", "pinb200_fmax", "pinb200_displacements",
+    "pinb200_fmax_pdf", "pinb200_download_products", "pinb200_download_field", "pinb200_get_timers",
+    "pinb200_fft_r2c", "pinb200_fft_c2r", "pinb200_second_derivatives", "pinb200_collapse_cells",
+    "pinb200_download_kvector",
+]
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libpinb200.so (built in-tree by ``pinocchio_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m pinocchio_b200.build` "
+                           "(there is no CPU fallback for the collapse-time path)")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    lib.pinb200_last_error.restype = ctypes.c_char_p
+    lib.pinb200_last_error.argtypes = [ctypes.c_void_p]
+    lib.pinb200_create.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(ctypes.c_void_p)]
+    lib.pinb200_destroy.argtypes = [ctypes.c_void_p]
+    lib.pinb200_set_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.pinb200_synchronize.argtypes = [ctypes.c_void_p]
+    lib.pinb200_set_power_table.argtypes = [ctypes.c_void_p, _PD, ctypes.c_size_t]
+    lib.pinb200_set_smoothing.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
+    lib.pinb200_set_invgrow_spline.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD, _PD, ctypes.c_int]
+    lib.pinb200_genic.argtypes = [ctypes.c_void_p]
+    lib.pinb200_upload_kdensity.argtypes = [ctypes.c_void_p, _PD]
+    lib.pinb200_download_kdensity.argtypes = [ctypes.c_void_p, _PD]
+    lib.pinb200_fmax.argtypes = [ctypes.c_void_p, _PD]
+    lib.pinb200_displacements.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
+    lib.pinb200_fmax_pdf.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]
+    lib.pinb200_download_products.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ProductLayout),
+                                              ctypes.c_size_t, ctypes.c_size_t]
+    lib.pinb200_download_field.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    lib.pinb200_get_timers.argtypes = [ctypes.c_void_p, ctypes.POINTER(Timers)]
+    lib.pinb200_fft_r2c.argtypes = [ctypes.c_void_p, _PD, _PD]
+    lib.pinb200_fft_c2r.argtypes = [ctypes.c_void_p, _PD, _PD]
+    lib.pinb200_second_derivatives.argtypes = [ctypes.c_void_p, ctypes.c_double, _PD]
+    lib.pinb200_collapse_cells.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD, ctypes.c_size_t, _PD]
+    lib.pinb200_download_kvector.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
+    _lib = lib
+    return lib
+
+
+def _dp(a: np.ndarray):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_PD)
+
+
+# product_data for -DTWO_LPT -DTHREE_LPT, float products (src/pinocchio.h:233-259): 56 bytes
+PRODUCT_DTYPE_3LPT = np.dtype([("Rmax", "<i4"), ("Fmax", "<f4"), ("Vel", "<f4", 3), ("Vel_2LPT", "<f4", 3),
+                               ("Vel_3LPT_1", "<f4", 3), ("Vel_3LPT_2", "<f4", 3)])
+FIELD_INDEX = {"Fmax": 0, "Rmax": 1, "Vel": 2, "Vel_2LPT": 5, "Vel_3LPT_1": 8, "Vel_3LPT_2": 11}
+
+
+class PinocchioError(RuntimeError):
+    pass
+
+
+@dataclass
+class RunConfig:
+    """The reference globals this path reads (params, MyGrids[0], Smoothing, outputs)."""
+    GridSize: int = 128
+    BoxSize_htrue: float = 128.0 / 0.7      # true Mpc (params.BoxSize_htrue, src/initialization.c:235-245)
+    RandomSeed: int = 486604
+    FixedIC: int = 0
+    PairedIC: int = 0
+    lpt_order: int = 3                      # TWO_LPT + THREE_LPT
+    zlast: float = 0.0                      # outputs.zlast
+    segment_redshift: float = 0.0           # ScaleDep.z[0]
+
+
+class Pinocchio:
+    """One rank of the collapse-time path.  Method names follow the reference."""
+
+    def __init__(self, cfg: RunConfig, cosmo: Cosmology | None = None, device: int = 0,
+                 smoothing: SmoothingLadder | None = None, rank: int = 0, nranks: int = 1):
+        self.lib = load_library()
+        self.cfg = cfg
+        self.cosmo = cosmo if cosmo is not None else Cosmology()
+        self.N = int(cfg.GridSize)
+        d = Desc(self.N, float(cfg.BoxSize_htrue), int(cfg.RandomSeed), int(cfg.FixedIC), int(cfg.PairedIC),
+                 int(cfg.lpt_order), rank, nranks, device)
+        h = ctypes.c_void_p()
+        if self.lib.pinb200_create(ctypes.byref(d), ctypes.byref(h)):
+            raise PinocchioError(self.lib.pinb200_last_error(None).decode())
+        self.h = h
+        self.CellSize = cfg.BoxSize_htrue / self.N
+        self.Smoothing = smoothing if smoothing is not None else set_smoothing(self.cosmo, self.CellSize, cfg.zlast)
+        self.TrueVariance = np.zeros(self.Smoothing.Nsmooth)
+        self._set_tables()
+
+    # -- plumbing -----------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise PinocchioError(self.lib.pinb200_last_error(self.h).decode())
+
+    def _set_tables(self):
+        pk = np.ascontiguousarray(pk_lattice_table(self.cosmo, self.N, self.cfg.BoxSize_htrue))
+        self._ck(self.lib.pinb200_set_power_table(self.h, _dp(pk), pk.size))
+        r = np.ascontiguousarray(self.Smoothing.Radius, dtype=np.float64)
+        self._ck(self.lib.pinb200_set_smoothing(self.h, r.size, _dp(r)))
+        sp = self.cosmo.sp_invgrow
+        x, y = np.ascontiguousarray(sp.x), np.ascontiguousarray(sp.y)
+        self._ck(self.lib.pinb200_set_invgrow_spline(self.h, -1, _dp(x), _dp(y), x.size))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pinb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.lib.pinb200_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self.lib.pinb200_synchronize(self.h))
+
+    # -- reference entry points ---------------------------------------------------------------
+    def GenIC_large(self, ThisGrid: int = 0) -> int:
+        """src/GenIC.c:73-460."""
+        self._ck(self.lib.pinb200_genic(self.h))
+        return 0
+
+    def compute_fmax(self, displacements: bool = True) -> int:
+        """src/fmax.c:36-190: radii loop, then compute_displacements(1, 0, ScaleDep.z[0])."""
+        tv = np.zeros(self.Smoothing.Nsmooth)
+        self._ck(self.lib.pinb200_fmax(self.h, _dp(tv)))
+        self.TrueVariance = tv
+        if displacements:
+            self.compute_displacements(1, 0, self.cfg.segment_redshift)
+        return 0
+
+    def growth_rates(self, redshift: float) -> np.ndarray:
+        c = self.cosmo
+        return np.array([c.GrowingMode(redshift), c.GrowingMode_2LPT(redshift), c.GrowingMode_3LPT_1(redshift),
+                         c.GrowingMode_3LPT_2(redshift)])
+
+    def compute_displacements(self, compute_sources: int, recompute_sd: int, redshift: float) -> int:
+        """src/fmax.c:292-367 (recompute_sd is the special-mode-3 path and is not supported)."""
+        if recompute_sd:
+            raise PinocchioError("recompute_sd=1 (special mode 3, src/pinocchio.c:186) is not supported")
+        g = self.growth_rates(redshift)
+        self._ck(self.lib.pinb200_displacements(self.h, int(compute_sources), _dp(g)))
+        return 0
+
+    def Fmax_PDF(self) -> np.ndarray:
+        """src/fmax.c:509-550; returns the 210 counts."""
+        c = (ctypes.c_ulonglong * NBINS)()
+        self._ck(self.lib.pinb200_fmax_pdf(self.h, c))
+        return np.array(list(c), dtype=np.uint64)
+
+    # -- data movement ----------------------------------------------------------------------
+    def write_kdensity(self, kdensity: np.ndarray):
+        """Upload kdensity[0] in the reference layout [x][y][N/2+1] complex128."""
+        a = np.ascontiguousarray(kdensity, dtype=np.complex128)
+        assert a.shape == (self.N, self.N, self.N // 2 + 1)
+        self._ck(self.lib.pinb200_upload_kdensity(self.h, a.view(np.float64).ctypes.data_as(_PD)))
+
+    def read_kdensity(self) -> np.ndarray:
+        a = np.zeros((self.N, self.N, self.N // 2 + 1), dtype=np.complex128)
+        self._ck(self.lib.pinb200_download_kdensity(self.h, a.view(np.float64).ctypes.data_as(_PD)))
+        return a
+
+    def read_kvector(self, which: int) -> np.ndarray:
+        a = np.zeros((self.N, self.N, self.N // 2 + 1), dtype=np.complex128)
+        self._ck(self.lib.pinb200_download_kvector(self.h, which, a.view(np.float64).ctypes.data_as(_PD)))
+        return a
+
+    def field(self, name: str, comp: int = 0) -> np.ndarray:
+        idx = FIELD_INDEX[name] + (comp if name.startswith("Vel") else 0)
+        dt = np.int32 if name == "Rmax" else np.float32
+        a = np.zeros((self.N, self.N, self.N), dtype=dt)
+        self._ck(self.lib.pinb200_download_field(self.h, idx, a.ctypes.data_as(ctypes.c_void_p)))
+        return a
+
+    def products(self, cell_begin: int = 0, ncells: int | None = None, dtype=PRODUCT_DTYPE_3LPT) -> np.ndarray:
+        """products[] records in the reference AoS layout (src/pinocchio.h:233-263)."""
+        if ncells is None:
+            ncells = self.N ** 3 - cell_begin
+        out = np.zeros(ncells, dtype=dtype)
+        f = dtype.fields
+        off = lambda n: f[n][1] if n in f else -1
+        lay = ProductLayout(dtype.itemsize, 4, off("Rmax"), off("Fmax"), off("Vel"), off("Vel_2LPT"),
+                            off("Vel_3LPT_1"), off("Vel_3LPT_2"))
+        self._ck(self.lib.pinb200_download_products(self.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(lay),
+                                                    cell_begin, ncells))
+        return out
+
+    def timers(self) -> Timers:
+        t = Timers()
+        self._ck(self.lib.pinb200_get_timers(self.h, ctypes.byref(t)))
+        return t
+
+    # -- finer-grained reference functions (parity tests) ----------------------------------
+    def forward_transform(self, r: np.ndarray) -> np.ndarray:
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = np.zeros((self.N, self.N, self.N // 2 + 1), dtype=np.complex128)
+        self._ck(self.lib.pinb200_fft_r2c(self.h, _dp(r), out.view(np.float64).ctypes.data_as(_PD)))
+        return out
+
+    def reverse_transform(self, c: np.ndarray) -> np.ndarray:
+        c = np.ascontiguousarray(c, dtype=np.complex128)
+        out = np.zeros((self.N, self.N, self.N), dtype=np.float64)
+        self._ck(self.lib.pinb200_fft_c2r(self.h, c.view(np.float64).ctypes.data_as(_PD), _dp(out)))
+        return out
+
+    def compute_second_derivatives(self, R: float) -> np.ndarray:
+        out = np.zeros((6, self.N, self.N, self.N), dtype=np.float64)
+        self._ck(self.lib.pinb200_second_derivatives(self.h, float(R), _dp(out)))
+        return out
+
+    def inverse_collapse_time(self, hessian6: np.ndarray, ismooth: int = 0) -> np.ndarray:
+        h = np.ascontiguousarray(hessian6, dtype=np.float64)
+        assert h.shape[0] == 6
+        n = h[0].size
+        F = np.zeros(n)
+        self._ck(self.lib.pinb200_collapse_cells(self.h, ismooth, _dp(h), n, _dp(F)))
+        return F.reshape(h.shape[1:])

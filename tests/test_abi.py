@@ -1,0 +1,48 @@
+"""The C-ABI library builds for sm_100a, loads on a CPU-only box and exports every symbol that
+include/pinb200.h declares; without a GPU it fails loudly instead of falling back."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pinocchio_b200.build import build
+    build()
+    from pinocchio_b200.engine import load_library
+    return load_library()
+
+
+def test_header_symbols_exported(lib):
+    from pinocchio_b200.engine import ABI_SYMBOLS
+    header = (ROOT / "include" / "pinb200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(pinb200_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_sizes_match_header():
+    from pinocchio_b200.engine import Desc, ProductLayout, Timers
+    assert ctypes.sizeof(Desc) == 48
+    assert ctypes.sizeof(ProductLayout) == 40
+    assert ctypes.sizeof(Timers) == 8 * 7 + 8 * 64 + 8 * 5 + 8
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pinocchio_b200.engine import Pinocchio, PinocchioError, RunConfig
+    with pytest.raises(PinocchioError, match="no usable CUDA device|no CPU fallback"):
+        Pinocchio(RunConfig(GridSize=32))
+
+
+def test_product_does_not_import_oracle():
+    for f in (ROOT / "pinocchio_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h"):
+            assert "oracle" not in f.read_text().replace("the oracle", "").replace("an oracle", ""), f

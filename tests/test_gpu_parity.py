@@ -1,0 +1,240 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Needs a B200: -m gpu.
+
+Tolerances (BASELINE.json north_star): Fmax and displacements within 1e-6 relative in double
+(they are stored as float, so one float ulp ~ 6e-8 is the floor); Rmax bit-exact except cells
+flagged as near-ties in F; integer histograms compared count by count.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import pinocchio_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).resolve().parent / "golden" / "hmf_validation"
+HMF_RADII = [20.635922, 13.996056, 9.026099, 5.465945, 3.058354, 1.548258, 0.689079, 0.258729, 0.0]
+
+
+@pytest.fixture(scope="module")
+def cosmo():
+    from pinocchio_b200.cosmology import Cosmology
+    return Cosmology(pk_norm_override=2.03146e7)      # HMF_Validation/log_RUN.txt:57
+
+
+def make(N, cosmo, radii=None, box=None, lpt_order=3):
+    from pinocchio_b200.cosmology import SmoothingLadder
+    from pinocchio_b200.engine import Pinocchio, RunConfig
+    box = box if box is not None else N / 0.7
+    cfg = RunConfig(GridSize=N, BoxSize_htrue=box, lpt_order=lpt_order)
+    lad = None
+    if radii is not None:
+        lad = SmoothingLadder(np.array(radii, dtype=np.float64), np.zeros(len(radii)))
+    return Pinocchio(cfg, cosmo, smoothing=lad)
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("N", [32, 64, 128, 256])
+def test_fft_forward_reverse(N, cosmo):
+    """forward_transform / reverse_transform (src/fmax-pfft.c:191-228) incl. the literal
+    half-complex c2r semantics on non-Hermitian input."""
+    p = make(N, cosmo, radii=[0.0])
+    rng = np.random.default_rng(N)
+    r = rng.standard_normal((N, N, N))
+    ck = p.forward_transform(r)
+    assert rel(ck, po.forward_transform(r)) < 1e-14
+    c = rng.standard_normal((N, N, N // 2 + 1)) + 1j * rng.standard_normal((N, N, N // 2 + 1))
+    assert rel(p.reverse_transform(c), po.reverse_transform(c)) < 1e-14
+    # round trip
+    assert rel(p.reverse_transform(ck), r) < 1e-13
+    p.close()
+
+
+@pytest.mark.parametrize("N", [32, 64, 128])
+def test_genic(N, cosmo):
+    """GenIC_large mode by mode (src/GenIC.c:188-411): same non-zero pattern, values to libm ulps."""
+    p = make(N, cosmo, radii=[0.0])
+    p.GenIC_large()
+    kd = p.read_kdensity()
+    ref = po.genic(N, N / 0.7, 486604, cosmo.PowerSpectrum)
+    assert np.array_equal(kd != 0, ref != 0)
+    assert rel(kd, ref) < 1e-13
+    # planes that must stay empty: kx = N/2, ky = N/2, kz = N/2, and the (0,0,0) mode
+    assert not kd[N // 2].any() and not kd[:, N // 2].any() and not kd[:, :, N // 2].any()
+    assert kd[0, 0, 0] == 0
+    p.close()
+
+
+def test_genic_fixed_paired(cosmo):
+    from pinocchio_b200.engine import Pinocchio, RunConfig
+    from pinocchio_b200.cosmology import SmoothingLadder
+    N = 32
+    cfg = RunConfig(GridSize=N, BoxSize_htrue=N / 0.7, FixedIC=1, PairedIC=1)
+    p = Pinocchio(cfg, cosmo, smoothing=SmoothingLadder(np.array([0.0]), np.zeros(1)))
+    p.GenIC_large()
+    ref = po.genic(N, N / 0.7, 486604, cosmo.PowerSpectrum, fixed_ic=True, paired_ic=True)
+    assert rel(p.read_kdensity(), ref) < 1e-13
+    p.close()
+
+
+def test_second_derivatives(cosmo):
+    """compute_second_derivatives (src/fmax.c:225-258) for a smoothed and the R=0 radius."""
+    N = 64
+    p = make(N, cosmo, radii=[0.0])
+    kd = po.genic(N, N / 0.7, 486604, cosmo.PowerSpectrum)
+    p.write_kdensity(kd)
+    for R in (3.0, 0.0):
+        h = p.compute_second_derivatives(R)
+        ref = po.second_derivatives(kd, R, 1.0 / 0.7)
+        for k in range(6):
+            assert rel(h[k], ref[k]) < 1e-13
+    p.close()
+
+
+def test_collapse_cells(cosmo):
+    """inverse_collapse_time (src/collapse_times.c:679-776) incl. the degenerate branches."""
+    p = make(32, cosmo, radii=[0.0])
+    rng = np.random.default_rng(3)
+    n = 200000
+    h = rng.standard_normal((6, n)) * np.array([1.5, 1.5, 1.5, 0.7, 0.7, 0.7])[:, None]
+    h[:, 0] = 0.0
+    h[:, 1] = [1.0, 1.0, 1.0, 0, 0, 0]
+    h[:, 2] = [2.0, 0.5, -0.3, 0, 0, 0]
+    h[:, 3] = [-1.0, -2.0, -3.0, 0, 0, 0]
+    h[:, 4] = [1e-25, 0, 0, 0, 0, 0]
+    h[:, 5] = [3.0, 0.0, 0.0, 0, 0, 0]
+    F = p.inverse_collapse_time(h)
+    ref = po.inverse_collapse_time([h[i] for i in range(6)], cosmo.InverseGrowingMode)
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(F), ok)
+    # 1e-6 relative is the contract; libm differences give ~1e-13
+    assert np.abs(F[ok] - ref[ok]).max() < 1e-10 * max(1.0, np.abs(ref[ok]).max())
+    p.close()
+
+
+def _near_tie_mask(Fs, tol=1e-6):
+    """cells whose two largest F over the radii differ by less than tol (relative)."""
+    top2 = np.sort(np.stack(Fs), axis=0)[-2:]
+    return np.abs(top2[1] - top2[0]) <= tol * np.maximum(1.0, np.abs(top2[1]))
+
+
+@pytest.mark.parametrize("N", [64, 128])
+def test_fmax_and_displacements(N, cosmo):
+    """compute_fmax end to end (src/fmax.c:36-190): Fmax, Rmax, TrueVariance, FmaxPDF, the four
+    displacement fields, the LPT k-vectors and the AoS products against the oracle."""
+    p = make(N, cosmo, radii=HMF_RADII)
+    p.GenIC_large()
+    kd = p.read_kdensity()
+    p.compute_fmax()
+    growth = p.growth_rates(0.0)
+    ref = po.compute_fmax(kd, HMF_RADII, 1.0 / 0.7, cosmo.InverseGrowingMode, growth=tuple(growth), keep=True)
+
+    assert np.abs(p.TrueVariance / ref["TrueVariance"] - 1).max() < 1e-12
+    Fmax, Rmax = p.field("Fmax"), p.field("Rmax")
+    dF = np.abs(Fmax.astype(np.float64) - ref["Fmax"].astype(np.float64))
+    assert (dF <= 1e-6 * np.maximum(1.0, np.abs(ref["Fmax"]))).all()
+    ties = _near_tie_mask(ref["F"])
+    bad = (Rmax != ref["Rmax"]) & ~ties
+    assert not bad.any(), f"{bad.sum()} Rmax mismatches outside near-ties"
+    assert (Fmax != ref["Fmax"]).mean() < 1e-3          # last-float-bit flips only
+
+    pdf = p.Fmax_PDF()
+    pdf_ref = po.fmax_pdf(ref["Fmax"])
+    assert pdf.sum() == N ** 3
+    assert np.abs(pdf.astype(np.int64) - pdf_ref.astype(np.int64)).max() <= 2
+
+    for which, name in enumerate(("kvector_2LPT", "kvector_3LPT_1", "kvector_3LPT_2")):
+        assert rel(p.read_kvector(which), ref[name]) < 1e-11, name
+    for name in ("Vel", "Vel_2LPT", "Vel_3LPT_1", "Vel_3LPT_2"):
+        for a in range(3):
+            v = p.field(name, a)
+            scale = np.abs(ref[name][a]).max()
+            assert np.abs(v.astype(np.float64) - ref[name][a]).max() <= 1e-6 * scale, (name, a)
+
+    prod = p.products()
+    assert prod.dtype.itemsize == 56
+    assert np.array_equal(prod["Rmax"].reshape(N, N, N), Rmax)
+    assert np.array_equal(prod["Fmax"].reshape(N, N, N), Fmax)
+    assert np.array_equal(prod["Vel_3LPT_2"][:, 1].reshape(N, N, N), p.field("Vel_3LPT_2", 1))
+    # a window of cells
+    part = p.products(cell_begin=12345, ncells=1000)
+    assert np.array_equal(part, prod[12345:13345])
+    t = p.timers()
+    assert t.kernel_launches > 0 and t.fmax > 0
+    p.close()
+
+
+def test_hmf_validation_golden(cosmo):
+    """The reference's own shipped run (HMF_Validation/, 128^3, seed 486604): sigma per radius
+    to the 4 printed digits, the FmaxPDF histogram and the collapsed count."""
+    N = 128
+    p = make(N, cosmo, radii=HMF_RADII)
+    p.GenIC_large()
+    p.compute_fmax(displacements=False)
+    sigma = np.sqrt(p.TrueVariance)
+    logged = [0.2032, 0.3258, 0.5051, 0.7505, 1.0850, 1.5527, 2.1897, 2.6563, 2.7733]   # log_RUN.txt:135-335
+    assert np.abs(sigma - logged).max() < 6e-5
+    pdf = p.Fmax_PDF().astype(np.int64)
+    gold = np.loadtxt(GOLDEN / "pinocchio.test.FmaxPDF.out")[:, 2].astype(np.int64)
+    d = np.abs(pdf - gold)
+    # residual explained by the 6-digit radii / PkNorm of the log (max 4, sum 68)
+    assert d.max() <= 8 and d.sum() <= 140
+    assert abs(int(pdf[10:].sum()) - 1230386) <= 5                                       # log_RUN.txt:407
+    p.close()
+
+
+def test_recompute_displacements_reentry(cosmo):
+    """RECOMPUTE_DISPLACEMENTS re-entry: compute_displacements(0, 0, z) (src/fragment.c:409)
+    rescales by the growth at the new redshift without recomputing the sources."""
+    N = 64
+    p = make(N, cosmo, radii=[2.0, 0.0])
+    p.GenIC_large()
+    p.compute_fmax()
+    v0 = [p.field("Vel_2LPT", a).astype(np.float64) for a in range(3)]
+    z = 1.0
+    p.compute_displacements(0, 0, z)
+    ratio = cosmo.GrowingMode_2LPT(z) / cosmo.GrowingMode_2LPT(0.0)
+    for a in range(3):
+        v1 = p.field("Vel_2LPT", a).astype(np.float64)
+        assert np.abs(v1 - ratio * v0[a]).max() <= 2e-7 * np.abs(v0[a]).max()
+    p.close()
+
+
+def test_error_paths(cosmo):
+    from pinocchio_b200.engine import Pinocchio, PinocchioError, RunConfig
+    with pytest.raises(PinocchioError):
+        Pinocchio(RunConfig(GridSize=100), cosmo)          # not a power of two
+    p = make(32, cosmo, radii=[0.0])
+    with pytest.raises(PinocchioError):
+        p.compute_fmax()                                    # kdensity not resident
+    with pytest.raises(PinocchioError):
+        p.compute_displacements(1, 1, 0.0)
+    p.close()
+
+
+@pytest.mark.parametrize("N", [512])
+def test_large_grid_properties(N, cosmo):
+    """Size-independent properties at a grid the oracle cannot afford: histogram total,
+    monotone variance ladder, zero-mean displacements, Parseval for the R=0 variance."""
+    p = make(N, cosmo, radii=HMF_RADII)
+    p.GenIC_large()
+    p.compute_fmax()
+    tv = p.TrueVariance
+    assert (np.diff(tv) > 0).all()
+    assert p.Fmax_PDF().sum() == N ** 3
+    kd = p.read_kdensity()
+    w = np.full(kd.shape[2], 2.0)
+    w[0] = 1.0
+    w[-1] = 1.0
+    parseval = (np.abs(kd) ** 2 * w).sum() / float(N) ** 6
+    assert abs(parseval / tv[-1] - 1) < 1e-10
+    Rmax = p.field("Rmax")
+    assert Rmax.min() >= 0 and Rmax.max() <= len(HMF_RADII) - 1
+    for name in ("Vel", "Vel_2LPT"):
+        v = p.field(name, 2).astype(np.float64)
+        assert abs(v.mean()) < 1e-6 * v.std()
+    p.close()
