@@ -374,6 +374,26 @@ def inverse_collapse_time(h, inverse_growing_mode):
     return F
 
 
+def ill_conditioned_mask(h, inverse_growing_mode, eps=1e-13, ntrial=2, tol=1e-7, seed=0):
+    """Cells whose F is numerically ill-conditioned in the REFERENCE algorithm itself.
+
+    ell_classic normalises the cubic by its leading coefficient `den` (src/collapse_times.c:133,
+    160-169); when den is close to zero the coefficients reach 1e9..1e26 and r*r - q*q*q cancels
+    catastrophically, so F jumps by O(1) under 1e-15 relative changes of the Hessian (i.e. under
+    a different compiler, FMA contraction or libm).  For such cells "the reference's value" is
+    not defined to 1e-6; parity tests flag them (F changes by more than `tol` under `eps`
+    relative perturbations) and count them instead of comparing them."""
+    rng = np.random.default_rng(seed)
+    F0 = inverse_collapse_time(h, inverse_growing_mode)
+    mask = np.zeros(F0.shape, dtype=bool)
+    for _ in range(ntrial):
+        hp = [a * (1.0 + eps * rng.standard_normal(a.shape)) for a in h]
+        Fp = inverse_collapse_time(hp, inverse_growing_mode)
+        with np.errstate(invalid="ignore"):
+            mask |= ~(np.abs(Fp - F0) <= tol * np.maximum(1.0, np.abs(F0)))
+    return mask
+
+
 def init_products(shape):
     """ismooth == 0 initialisation (src/collapse_times.c:461-492)."""
     return np.full(shape, -10.0, dtype=np.float32), np.full(shape, -1, dtype=np.int32)
@@ -456,6 +476,7 @@ def compute_fmax(kdensity, radii, cell_size, inverse_growing_mode, growth=None,
         tv.append(true_variance(h)[0])
         if keep:
             extra.setdefault("F", []).append(Fnew)
+            extra["unstable"] = extra.get("unstable", False) | ill_conditioned_mask(h, inverse_growing_mode)
     out = {"Fmax": Fmax, "Rmax": Rmax, "TrueVariance": np.array(tv)}
     if lpt_order >= 2:
         if lpt_order >= 3:
