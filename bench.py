@@ -90,7 +90,9 @@ class ClockSampler:
 
 
 def default_grid(ngpus: int) -> int:
-    return 1024
+    """1024^3 fits one B200 (17 fields of 8.7 GB at peak); 2048^3 needs the 8 GPUs of the box
+    (one FP64 field = 68.7 GB).  2 and 4 GPUs run the 1024^3 box slab-decomposed (strong scaling)."""
+    return 2048 if ngpus >= 8 else 1024
 
 
 def algorithmic_bytes(N: int, S: int):
@@ -128,7 +130,8 @@ def run_b200(args):
     cosmo = Cosmology(pk_norm_override=2.03146e7)
     cfg = RunConfig(GridSize=N, BoxSize_htrue=N / 0.7, lpt_order=3)
     lad = SmoothingLadder(np.array(HMF_RADII), np.zeros(len(HMF_RADII)))
-    pin = Pinocchio(cfg, cosmo, device=local, smoothing=lad)
+    pin = Pinocchio(cfg, cosmo, device=local, smoothing=lad, rank=rank, nranks=world)
+    lx = N // world
     stream = torch.cuda.current_stream()
     pin.set_stream(stream.cuda_stream)
     S = lad.Nsmooth
@@ -165,7 +168,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    cells = float(N) ** 3 * world      # every rank processes its own box (independent realisations)
+    cells = float(N) ** 3              # one box, slab-decomposed over the ranks
     value = cells / (ms_per_step * 1e-3) / 1e6
 
     # ---- per-kernel device times measured live (CUDA events inside the engine, same stream)
@@ -174,6 +177,8 @@ def run_b200(args):
                      "ypass_kernel": (tm1.hess_y - tm0.hess_y) / (K * S) * 1e3,
                      "zpass_collapse_kernel": (tm1.hess_z - tm0.hess_z) / (K * S) * 1e3}
     abytes, survey_rad, survey_lpt, survey_total = algorithmic_bytes(N, S)
+    abytes = {k: v / world for k, v in abytes.items()}            # per rank
+    survey_rad, survey_lpt, survey_total = survey_rad / world, survey_lpt / world, survey_total / world
     peak, peak_src = measured_peaks()
     dom = max(per_launch_ms, key=per_launch_ms.get)
     achieved = abytes[dom] / (per_launch_ms[dom] * 1e-3) / 1e9
@@ -193,11 +198,12 @@ def run_b200(args):
     # ---- e2e: host buffers through the reference-facing calls (H2D kdensity, D2H products[])
     e2e = None
     if not args.no_e2e:
-        kd_host = torch.empty((N, N, N // 2 + 1, 2), dtype=torch.float64, pin_memory=True)
+        kd_host = torch.empty((N, lx, N // 2 + 1, 2), dtype=torch.float64, pin_memory=True)
         import ctypes
         from pinocchio_b200.engine import _PD
         pin._ck(pin.lib.pinb200_download_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
-        chunk = min(N ** 3, 1 << 26)
+        ncell_local = lx * N * N
+        chunk = min(ncell_local, 1 << 26)
         stage = torch.empty((chunk * PRODUCT_DTYPE_3LPT.itemsize,), dtype=torch.uint8, pin_memory=True)
         stage_np = stage.numpy().view(PRODUCT_DTYPE_3LPT)
         from pinocchio_b200.engine import ProductLayout
@@ -209,8 +215,8 @@ def run_b200(args):
             pin._ck(pin.lib.pinb200_upload_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
             pin.compute_fmax(displacements=True)
             chk = 0.0
-            for b in range(0, N ** 3, chunk):
-                n = min(chunk, N ** 3 - b)
+            for b in range(0, ncell_local, chunk):
+                n = min(chunk, ncell_local - b)
                 pin._ck(pin.lib.pinb200_download_products(pin.h, ctypes.c_void_p(stage.data_ptr()), ctypes.byref(lay), b, n))
                 chk += float(stage_np["Fmax"][0])
             return chk
@@ -237,11 +243,11 @@ def run_b200(args):
     if rank == 0:
         out = {"metric": METRIC, "value": round(value, 2), "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": f"synthetic {N}^3 grid, full smoothing-radius sweep (S={S}) + 3LPT on 1 B200"
-                          + (f" x {world} independent boxes (one per GPU)" if world > 1 else ""),
+               "scaling": "weak" if world in (1, 8) else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"synthetic {N}^3 grid, full smoothing-radius sweep (S={S}) + 3LPT on {world} B200"
+                          + (f", x-slabs of {lx} planes, FFT transposes as peer stores over NVLink" if world > 1 else ""),
                           "grid": N, "nsmooth": S, "lpt_order": 3, "cosmology": "HMF_Validation (EH, Omega0=.25, h=.7, sigma8=.8)",
-                          "seed": 486604, "parallelism": "1 box per GPU" if world > 1 else "single GPU",
+                          "seed": 486604, "parallelism": f"slab{world}" if world > 1 else "single GPU",
                           "l2_policy": "inputs larger than L2 (each field 8.7 GB at 1024^3)"},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                "cpu_baseline": cpu_baseline, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}

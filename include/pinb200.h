@@ -60,6 +60,15 @@ typedef struct {
 int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out);
 int pinb200_destroy(pinb200_ctx* ctx);
 const char* pinb200_last_error(const pinb200_ctx* ctx); /* ctx may be NULL: creation errors */
+/* Multi-GPU (nranks > 1): one process per GPU of one box.  The distributed-FFT transposes that
+ * PFFT does with MPI all-to-alls (src/fmax-pfft.c:197,211) are stores into the peers' memory
+ * over NVLink; each rank exports one cudaIpc handle and maps its peers' handles.  The caller
+ * moves the 64-byte handles between processes (MPI_Allgather in the reference's world,
+ * torch.distributed.all_gather in bench.py): all_handles = nranks * 64 bytes, ordered by rank.
+ * Every rank must then make the same sequence of compute calls (they contain barriers). */
+#define PINB200_IPC_HANDLE_BYTES 64
+int pinb200_ipc_handle(pinb200_ctx* ctx, void* handle64);
+int pinb200_connect(pinb200_ctx* ctx, const void* all_handles);
 /* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*). */
 int pinb200_set_stream(pinb200_ctx* ctx, void* cuda_stream);
 int pinb200_synchronize(pinb200_ctx* ctx);
@@ -78,8 +87,9 @@ int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const double* x, c
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* GenIC_large (src/GenIC.c:73-460): fills kdensity on the device. */
 int pinb200_genic(pinb200_ctx* ctx);
-/* Alternative to genic: supply / fetch kdensity in the reference's host layout
- * [x_local? no: x (N)][y (N)][N/2+1] complex128 (src/GenIC.c:384), single rank only. */
+/* Alternative to genic: supply / fetch kdensity as [x (N)][y_local (N/nranks)][N/2+1] complex128.
+ * On one rank this is the reference's host layout (src/GenIC.c:384); on several ranks k-space is
+ * split along y (PFFT's transposed layout, src/fmax-pfft.c:265-281). */
 int pinb200_upload_kdensity(pinb200_ctx* ctx, const double* kdensity);
 int pinb200_download_kdensity(pinb200_ctx* ctx, double* kdensity);
 /* compute_fmax (src/fmax.c:36-190) without the final displacement call: loop over the

@@ -2,11 +2,16 @@
 //
 // Schedules (reference counterparts in brackets):
 //   pinb200_fmax            [compute_fmax radii loop, src/fmax.c:66-150]
-//       per radius: x pass (K2 fused, 3 outputs) -> y pass (6 outputs) -> z pass + collapse
+//       per radius: x pass (K2 fused, 3 outputs, scattered to the owner ranks) -> barrier ->
+//                   y pass (6 outputs) -> z pass + collapse
 //   pinb200_displacements   [compute_displacements, src/fmax.c:292-367; compute_LPT_displacements,
 //                            src/LPT.c:32-235]
 //       sources -> r2c -> 3 groups of {x,y,z-contraction} -> 2 r2c -> 4 x {x,y,z-float}
-// All device memory is owned here (stream-ordered allocations from the default pool); nothing
+//
+// Memory.  One cudaMalloc'ed, cudaIpc-exported *exchange arena* per rank holds every buffer that
+// a peer writes into or reads from: the barrier flags, kdensity (K layout), the three x-pass
+// destinations A[0..2] (R layout) and the three LPT k-vectors KV[0..2] (K layout).  Everything
+// else (y-pass outputs, products, work fields) comes from the stream-ordered pool.  Nothing
 // points into the caller's arena (SURVEY.md 8b "ownership").
 #include <cuda_runtime.h>
 
@@ -26,20 +31,30 @@ static thread_local std::string g_create_error;
 struct pinb200_ctx {
   pinb200_desc d{};
   Geom g{};
+  int P = 1;               // ranks
+  int lx_shift = 0, ly_shift = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
-  size_t field_elems = 0;  // double2 elements of one field (lx*N*P)
+  size_t field_elems = 0;  // double2 elements of one field (lx*N*P == N*ly*P)
   size_t ncells = 0;       // lx*N*N
+
+  // exchange arena
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  unsigned char* peer_arena[PINB_MAXR] = {nullptr};
+  bool connected = false;
+  size_t off_flags = 0, off_kdens = 0, off_A[3] = {0, 0, 0}, off_KV[3] = {0, 0, 0};
+  unsigned long long epoch = 0;
+  int* d_error = nullptr;
 
   // tables
   double2* tw = nullptr;
   double* gauss = nullptr;
   double* dc = nullptr;
-  double* sums = nullptr;          // [2*64]
+  double* sums = nullptr;  // [2*64]
   unsigned int* seeds = nullptr;
   double* pk = nullptr;
-  size_t pk_n = 0;
   std::vector<double> radius;
   std::vector<std::vector<double>> spl_host;  // index 0: global spline, 1+i: per radius
   double* spl_dev = nullptr;                  // [(1+nsmooth)][5][nspl]
@@ -47,11 +62,12 @@ struct pinb200_ctx {
   bool spl_dirty = true;
 
   // fields
-  double2* kdens = nullptr;
-  double2* A[3] = {nullptr, nullptr, nullptr};   // x-pass outputs; later sources / k-vectors
+  double2* kdens = nullptr;                       // arena
+  double2* A[3] = {nullptr, nullptr, nullptr};    // arena: x-pass destinations; LPT sources
+  double2* KV[3] = {nullptr, nullptr, nullptr};   // arena: kvector_2LPT, kvector_3LPT_1, kvector_3LPT_2
   double2* B[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // y-pass outputs; Hessian of the last radius
-  double2* W[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};           // displacement-stage work
-  bool hessian_valid = false, kvec_valid = false;
+  double2* D[3] = {nullptr, nullptr, nullptr};    // y-pass outputs of the displacement stage
+  bool kdens_valid = false, hessian_valid = false, kvec_valid = false;
   float* fmax = nullptr;
   int* rmax = nullptr;
   float* vel[12] = {nullptr};
@@ -73,6 +89,7 @@ struct pinb200_ctx {
   } while (0)
 #define LAUNCH(call) do { CK(call); ctx->launches++; } while (0)
 #define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
+#define TRY(x) do { if (x) return 1; } while (0)
 
 template <class T> static int dev_alloc(pinb200_ctx* ctx, T** p, size_t n) {
   if (*p) return 0;
@@ -85,7 +102,6 @@ template <class T> static int dev_free(pinb200_ctx* ctx, T** p) {
   *p = nullptr;
   return 0;
 }
-#define TRY(x) do { if (x) return 1; } while (0)
 
 // ---- gsl_interp_cspline coefficients (natural spline) -------------------
 static void cspline_table(const double* x, const double* y, int n, std::vector<double>& t) {
@@ -178,6 +194,8 @@ static void build_seed_plane(int N, int random_seed, std::vector<unsigned int>& 
   for (size_t k = 0; k < seeds.size(); k++) seeds[k] = out[(size_t)(ord[k] - 1)];
 }
 
+static int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
+
 // ------------------------------------------------------------------------------------------
 extern "C" const char* pinb200_last_error(const pinb200_ctx* ctx) {
   return ctx ? ctx->err.c_str() : g_create_error.c_str();
@@ -187,7 +205,12 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
   if (!desc || !out) { g_create_error = "null argument"; return 1; }
   *out = nullptr;
   if (!grid_supported(desc->grid_size)) { g_create_error = "grid_size must be a power of two in [32, 2048]"; return 1; }
-  if (desc->nranks != 1 || desc->rank != 0) { g_create_error = "multi-rank slabs are not wired in this build (nranks must be 1)"; return 1; }
+  const int P = desc->nranks;
+  if (P < 1 || P > PINB_MAXR || (P & (P - 1)) || desc->rank < 0 || desc->rank >= P) {
+    g_create_error = "nranks must be 1, 2, 4 or 8 and 0 <= rank < nranks";
+    return 1;
+  }
+  if (desc->grid_size / P < 8) { g_create_error = "slab thinner than 8 planes"; return 1; }
   if (desc->lpt_order < 1 || desc->lpt_order > 3) { g_create_error = "lpt_order must be 1, 2 or 3"; return 1; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -204,15 +227,18 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
   }
   pinb200_ctx* ctx = new pinb200_ctx;
   ctx->d = *desc;
+  ctx->P = P;
   Geom& g = ctx->g;
   g.N = desc->grid_size;
   g.M = g.N / 2;
   g.P = g.M + 8;
-  g.lx = g.N / desc->nranks;
-  g.ly = g.N / desc->nranks;
+  g.lx = g.N / P;
+  g.ly = g.N / P;
   g.x0 = desc->rank * g.lx;
   g.y0 = desc->rank * g.ly;
   g.knorm = 2. * PINB_PI / (double)g.N;
+  ctx->lx_shift = ilog2(g.lx);
+  ctx->ly_shift = ilog2(g.ly);
   ctx->field_elems = (size_t)g.lx * g.N * g.P;
   ctx->ncells = (size_t)g.lx * g.N * g.N;
   auto fail = [&](cudaError_t err) {
@@ -237,9 +263,57 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
   if ((e = cudaMalloc(&ctx->gauss, sizeof(double) * (g.M + 1))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&ctx->dc, sizeof(double))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&ctx->sums, sizeof(double) * 2 * 64)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&ctx->d_error, sizeof(int))) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(ctx->d_error, 0, sizeof(int))) != cudaSuccess) return fail(e);
+  // exchange arena: [flags | kdens | A0 A1 A2 | KV0 KV1 KV2]
+  const size_t fb = ctx->field_elems * sizeof(double2);
+  size_t off = 4096;
+  ctx->off_flags = 0;
+  ctx->off_kdens = off; off += fb;
+  for (int i = 0; i < 3; i++) { ctx->off_A[i] = off; off += fb; }
+  const int nkv = desc->lpt_order >= 3 ? 3 : (desc->lpt_order == 2 ? 1 : 0);
+  for (int i = 0; i < nkv; i++) { ctx->off_KV[i] = off; off += fb; }
+  ctx->arena_bytes = off;
+  if ((e = cudaMalloc(&ctx->arena, ctx->arena_bytes)) != cudaSuccess) {
+    g_create_error = std::string("exchange arena allocation failed: ") + cudaGetErrorString(e);
+    delete ctx;
+    return 1;
+  }
+  if ((e = cudaMemset(ctx->arena, 0, 4096)) != cudaSuccess) return fail(e);
+  ctx->kdens = reinterpret_cast<double2*>(ctx->arena + ctx->off_kdens);
+  for (int i = 0; i < 3; i++) ctx->A[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_A[i]);
+  for (int i = 0; i < nkv; i++) ctx->KV[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_KV[i]);
+  ctx->peer_arena[desc->rank] = ctx->arena;
+  ctx->connected = (P == 1);
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
   *out = ctx;
+  return 0;
+}
+
+extern "C" int pinb200_ipc_handle(pinb200_ctx* ctx, void* handle64) {
+  if (!ctx || !handle64) return 1;
+  static_assert(sizeof(cudaIpcMemHandle_t) == PINB200_IPC_HANDLE_BYTES, "ipc handle size");
+  CK(cudaSetDevice(ctx->d.device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->arena));
+  memcpy(handle64, &h, sizeof h);
+  return 0;
+}
+
+extern "C" int pinb200_connect(pinb200_ctx* ctx, const void* all_handles) {
+  if (!ctx || !all_handles) return 1;
+  CK(cudaSetDevice(ctx->d.device));
+  const unsigned char* hb = static_cast<const unsigned char*>(all_handles);
+  for (int r = 0; r < ctx->P; r++) {
+    if (r == ctx->d.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hb + (size_t)r * sizeof h, sizeof h);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_arena[r] = static_cast<unsigned char*>(p);
+  }
+  ctx->connected = true;
   return 0;
 }
 
@@ -247,14 +321,16 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->d.device);
   cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < ctx->P; r++)
+    if (r != ctx->d.rank && ctx->peer_arena[r]) cudaIpcCloseMemHandle(ctx->peer_arena[r]);
   auto fr = [&](void* p) { if (p) cudaFree(p); };
   fr(ctx->tw); fr(ctx->gauss); fr(ctx->dc); fr(ctx->sums); fr(ctx->seeds); fr(ctx->pk); fr(ctx->spl_dev);
-  fr(ctx->kdens);
-  for (auto p : ctx->A) fr(p);
+  fr(ctx->d_error);
   for (auto p : ctx->B) fr(p);
-  for (auto p : ctx->W) fr(p);
+  for (auto p : ctx->D) fr(p);
   fr(ctx->fmax); fr(ctx->rmax);
   for (auto p : ctx->vel) fr(p);
+  fr(ctx->arena);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -270,10 +346,17 @@ extern "C" int pinb200_set_stream(pinb200_ctx* ctx, void* s) {
   return 0;
 }
 
+static int check_peer_error(pinb200_ctx* ctx) {
+  int err = 0;
+  CK(cudaMemcpy(&err, ctx->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) FAIL("cross-GPU barrier timed out: a peer rank did not arrive (all ranks must make the same calls)");
+  return 0;
+}
+
 extern "C" int pinb200_synchronize(pinb200_ctx* ctx) {
   if (!ctx) return 1;
   CK(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return check_peer_error(ctx);
 }
 
 extern "C" int pinb200_set_power_table(pinb200_ctx* ctx, const double* pk, size_t n) {
@@ -283,7 +366,6 @@ extern "C" int pinb200_set_power_table(pinb200_ctx* ctx, const double* pk, size_
   if (ctx->pk) { CK(cudaFree(ctx->pk)); ctx->pk = nullptr; }
   CK(cudaMalloc(&ctx->pk, need * sizeof(double)));
   CK(cudaMemcpy(ctx->pk, pk, need * sizeof(double), cudaMemcpyHostToDevice));
-  ctx->pk_n = need;
   return 0;
 }
 
@@ -334,6 +416,28 @@ static const double* spline_for(pinb200_ctx* ctx, int ismooth) {
   return ctx->spl_dev + slot * (size_t)5 * ctx->nspl;
 }
 
+#define NEED_PEERS() do { if (!ctx->connected) FAIL("peer arenas not connected: exchange pinb200_ipc_handle() and call pinb200_connect()"); } while (0)
+
+// cross-GPU barrier on the stream (no-op on one rank)
+static int peer_barrier(pinb200_ctx* ctx) {
+  if (ctx->P == 1) return 0;
+  BarrierParams b{};
+  for (int r = 0; r < ctx->P; r++) b.flags[r] = reinterpret_cast<unsigned long long*>(ctx->peer_arena[r] + ctx->off_flags);
+  b.rank = ctx->d.rank;
+  b.nranks = ctx->P;
+  b.epoch = ++ctx->epoch;
+  b.error = ctx->d_error;
+  LAUNCH(launch_barrier(b, ctx->stream));
+  return 0;
+}
+
+static PeerPtrs peers_of(pinb200_ctx* ctx, size_t arena_off) {
+  PeerPtrs p{};
+  for (int r = 0; r < ctx->P; r++) p.r[r] = reinterpret_cast<double2*>(ctx->peer_arena[r] + arena_off);
+  return p;
+}
+static size_t arena_off_of(pinb200_ctx* ctx, const void* p) { return (size_t)((const unsigned char*)p - ctx->arena); }
+
 // ------------------------------------------------------------------------------------------
 extern "C" int pinb200_genic(pinb200_ctx* ctx) {
   if (!ctx) return 1;
@@ -346,7 +450,6 @@ extern "C" int pinb200_genic(pinb200_ctx* ctx) {
     CK(cudaMalloc(&ctx->seeds, seeds.size() * sizeof(unsigned int)));
     CK(cudaMemcpy(ctx->seeds, seeds.data(), seeds.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
   }
-  TRY(dev_alloc(ctx, &ctx->kdens, ctx->field_elems));
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   CK(cudaMemsetAsync(ctx->kdens, 0, ctx->field_elems * sizeof(double2), ctx->stream));
   GenicParams p{};
@@ -363,13 +466,14 @@ extern "C" int pinb200_genic(pinb200_ctx* ctx) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   ctx->tm.dens += ms * 1e-3;
+  ctx->kdens_valid = true;
   return 0;
 }
 
-// host half-complex [rows][M+1] <-> device [rows][P]
+// host half-complex K-layout slab [N][ly][M+1] <-> device [N][ly][P]
 static int upload_cplx(pinb200_ctx* ctx, const double* host, double2* dev) {
   const Geom& g = ctx->g;
-  const size_t rows = (size_t)g.lx * g.N;
+  const size_t rows = (size_t)g.N * g.ly;
   double2* tmp = nullptr;
   TRY(dev_alloc(ctx, &tmp, rows * (g.M + 1)));
   CK(cudaMemcpyAsync(tmp, host, rows * (g.M + 1) * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
@@ -380,7 +484,7 @@ static int upload_cplx(pinb200_ctx* ctx, const double* host, double2* dev) {
 }
 static int download_cplx(pinb200_ctx* ctx, const double2* dev, double* host) {
   const Geom& g = ctx->g;
-  const size_t rows = (size_t)g.lx * g.N;
+  const size_t rows = (size_t)g.N * g.ly;
   double2* tmp = nullptr;
   TRY(dev_alloc(ctx, &tmp, rows * (g.M + 1)));
   LAUNCH(launch_repitch_c(dev, tmp, rows, g.M + 1, g.P, g.M + 1, ctx->stream));
@@ -404,15 +508,15 @@ static int download_real(pinb200_ctx* ctx, const double2* dev, double* host) {
 extern "C" int pinb200_upload_kdensity(pinb200_ctx* ctx, const double* kd) {
   if (!ctx || !kd) return 1;
   CK(cudaSetDevice(ctx->d.device));
-  TRY(dev_alloc(ctx, &ctx->kdens, ctx->field_elems));
   TRY(upload_cplx(ctx, kd, ctx->kdens));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->kdens_valid = true;
   return 0;
 }
 
 extern "C" int pinb200_download_kdensity(pinb200_ctx* ctx, double* kd) {
   if (!ctx || !kd) return 1;
-  if (!ctx->kdens) FAIL("kdensity not resident (call pinb200_genic or pinb200_upload_kdensity)");
+  if (!ctx->kdens_valid) FAIL("kdensity not resident (call pinb200_genic or pinb200_upload_kdensity)");
   CK(cudaSetDevice(ctx->d.device));
   return download_cplx(ctx, ctx->kdens, kd);
 }
@@ -423,12 +527,17 @@ static int ntiles(const pinb200_ctx* ctx, bool with_nyq) {
   return ctx->g.M / tk + (with_nyq ? 1 : 0);
 }
 
-// x pass (inverse) of `src` with the Green/window factor; outputs for the powers in pmask
+// inverse x pass of the local K-layout field `src`; the output for power p of kx is scattered
+// into the arena buffer dst[p] (R layout) of the rank owning each x.  Barriers on both sides:
+// before, so that no peer still reads the destinations; after, so that readers see all stores.
 static int run_xpass_inv(pinb200_ctx* ctx, const double2* src, double2* const dst[3], int pmask, bool gauss, int green,
                          int times_i, double scalar, bool with_nyq) {
   XPassParams p{};
   p.src = src;
-  for (int i = 0; i < 3; i++) p.dst[i] = dst[i];
+  for (int i = 0; i < 3; i++)
+    if (dst[i]) p.dst[i] = peers_of(ctx, arena_off_of(ctx, dst[i]));
+  p.dst_klayout = 0;
+  p.lx_shift = ctx->lx_shift;
   p.pmask = pmask;
   p.ntiles_z = ntiles(ctx, with_nyq);
   p.kf.gauss = gauss ? ctx->gauss : nullptr;
@@ -437,40 +546,57 @@ static int run_xpass_inv(pinb200_ctx* ctx, const double2* src, double2* const ds
   p.kf.times_i = times_i;
   p.g = ctx->g;
   p.tw = ctx->tw;
+  TRY(peer_barrier(ctx));
   LAUNCH(launch_xpass(ctx->g.N, +1, p, ctx->g.ly, ctx->stream));
+  TRY(peer_barrier(ctx));
   return 0;
 }
 
-static int run_ypass(pinb200_ctx* ctx, int dir, const double2* const src[3], double2* const dst[6], const YJob* jobs,
-                     int njobs, bool with_nyq) {
+static int run_ypass_inv(pinb200_ctx* ctx, const double2* const src[3], double2* const dst[6], const YJob* jobs, int njobs,
+                         bool with_nyq) {
   YPassParams p{};
   for (int i = 0; i < 3; i++) p.src[i] = src[i];
   for (int i = 0; i < 6; i++) p.dst[i] = dst[i];
   for (int i = 0; i < njobs; i++) p.job[i] = jobs[i];
   p.njobs = njobs;
+  p.dst_klayout = 0;
+  p.ly_shift = ctx->ly_shift;
   p.ntiles_z = ntiles(ctx, with_nyq);
   p.g = ctx->g;
   p.tw = ctx->tw;
-  LAUNCH(launch_ypass(ctx->g.N, dir, p, ctx->g.lx, ctx->stream));
+  LAUNCH(launch_ypass(ctx->g.N, +1, p, ctx->g.lx, ctx->stream));
   return 0;
 }
 
-// forward r2c of a real field held in `f` (in place): z r2c, y forward, x forward
-static int run_r2c_inplace(pinb200_ctx* ctx, double2* f) {
+// forward r2c: real field in `src` (R layout, arena or pool; destroyed) -> half-complex K-layout
+// field `kdst` (arena buffer).  z r2c in place, y forward scattered to the owner of each y,
+// x forward in place on the K layout.
+static int run_r2c(pinb200_ctx* ctx, double2* src, double2* kdst) {
   const Geom& g = ctx->g;
   ZR2CParams z{};
-  z.src = f;
-  z.dst = f;
+  z.src = src;
+  z.dst = src;
   z.g = g;
   z.tw = ctx->tw;
   LAUNCH(launch_zpass_r2c(g.N, z, (size_t)g.lx * g.N, ctx->stream));
-  const double2* ysrc[3] = {f, nullptr, nullptr};
-  double2* ydst[6] = {f, nullptr, nullptr, nullptr, nullptr, nullptr};
-  YJob job{0, 0, 0};
-  TRY(run_ypass(ctx, -1, ysrc, ydst, &job, 1, true));
+  YPassParams y{};
+  y.src[0] = src;
+  y.kdst = peers_of(ctx, arena_off_of(ctx, kdst));
+  y.dst_klayout = 1;
+  y.ly_shift = ctx->ly_shift;
+  y.job[0] = YJob{0, 0, 0};
+  y.njobs = 1;
+  y.ntiles_z = ntiles(ctx, true);
+  y.g = g;
+  y.tw = ctx->tw;
+  TRY(peer_barrier(ctx));
+  LAUNCH(launch_ypass(g.N, -1, y, g.lx, ctx->stream));
+  TRY(peer_barrier(ctx));
   XPassParams p{};
-  p.src = f;
-  p.dst[0] = f;
+  p.src = kdst;
+  p.dst[0].r[0] = kdst;
+  p.dst_klayout = 1;
+  p.lx_shift = ctx->lx_shift;
   p.pmask = 1;
   p.ntiles_z = ntiles(ctx, true);
   p.kf.gauss = nullptr;
@@ -483,6 +609,13 @@ static int run_r2c_inplace(pinb200_ctx* ctx, double2* f) {
   return 0;
 }
 
+// the k = 0 mode lives on rank 0 (x = 0, yl = 0): read it through the peer mapping
+static int run_dc(pinb200_ctx* ctx, const double2* arena_field, double scale, int times_i) {
+  const double2* on_rank0 = reinterpret_cast<const double2*>(ctx->peer_arena[0] + arena_off_of(ctx, arena_field));
+  LAUNCH(launch_dc_scalar(on_rank0, ctx->dc, scale, times_i, ctx->stream));
+  return 0;
+}
+
 static int ensure_products(pinb200_ctx* ctx) {
   TRY(dev_alloc(ctx, &ctx->fmax, ctx->ncells));
   TRY(dev_alloc(ctx, &ctx->rmax, ctx->ncells));
@@ -491,39 +624,41 @@ static int ensure_products(pinb200_ctx* ctx) {
 
 // Hessian passes for one radius: fills B[0..5] (half-complex, after x and y passes).
 // slot order xx,yy,zz,xy,xz,yz (src/fmax.c:239)
-static int hessian_xy(pinb200_ctx* ctx, const double2* src, double rsmooth, bool with_nyq, cudaEvent_t mid_event = nullptr) {
+static int hessian_xy(pinb200_ctx* ctx, double rsmooth, cudaEvent_t mid_event = nullptr) {
   const Geom& g = ctx->g;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
   LAUNCH(launch_gauss_table(ctx->gauss, g.M, g.knorm, rsmooth, ctx->stream));
-  LAUNCH(launch_dc_scalar(src, ctx->dc, norm, 0, ctx->stream));
-  TRY(run_xpass_inv(ctx, src, ctx->A, 0x7, true, 1, 0, norm, with_nyq));
+  TRY(run_dc(ctx, ctx->kdens, norm, 0));
+  TRY(run_xpass_inv(ctx, ctx->kdens, ctx->A, 0x7, true, 1, 0, norm, false));
   if (mid_event) CK(cudaEventRecord(mid_event, ctx->stream));
   static const YJob jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
-  TRY(run_ypass(ctx, +1, ctx->A, ctx->B, jobs, 6, with_nyq));
+  TRY(run_ypass_inv(ctx, ctx->A, ctx->B, jobs, 6, false));
   return 0;
 }
 static const int kHessKzPow[6] = {0, 0, 2, 0, 1, 1};
 
 extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   if (!ctx) return 1;
-  if (!ctx->kdens) FAIL("kdensity not resident (call pinb200_genic or pinb200_upload_kdensity)");
+  if (!ctx->kdens_valid) FAIL("kdensity not resident (call pinb200_genic or pinb200_upload_kdensity)");
   if (ctx->radius.empty()) FAIL("smoothing ladder not set (pinb200_set_smoothing)");
+  NEED_PEERS();
   CK(cudaSetDevice(ctx->d.device));
   TRY(upload_splines(ctx));
   const Geom& g = ctx->g;
   const int ns = (int)ctx->radius.size();
   const double cell = ctx->d.box_size / g.N;  // GRID.CellSize, src/fmax-pfft.c:88
-  // the k-vectors of a previous displacement call alias A: they die here
+  for (auto& w : ctx->D) TRY(dev_free(ctx, &w));
+  // a new Fmax sweep re-initialises the products (src/collapse_times.c:461-492 zeroes Vel*):
+  // displacement fields of an earlier call are released here and read back as zeros
+  for (auto& v : ctx->vel) TRY(dev_free(ctx, &v));
   ctx->kvec_valid = false;
-  for (auto& w : ctx->W) TRY(dev_free(ctx, &w));
   TRY(ensure_products(ctx));
-  for (int i = 0; i < 3; i++) TRY(dev_alloc(ctx, &ctx->A[i], ctx->field_elems));
   for (int i = 0; i < 6; i++) TRY(dev_alloc(ctx, &ctx->B[i], ctx->field_elems));
   CK(cudaMemsetAsync(ctx->sums, 0, sizeof(double) * 2 * 64, ctx->stream));
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   for (int is = 0; is < ns; is++) {
     const double rs = ctx->radius[is] / cell;  // Rsmooth in grid units, src/fmax.c:233
-    TRY(hessian_xy(ctx, ctx->kdens, rs, false, ctx->ev[8 + 3 * is]));
+    TRY(hessian_xy(ctx, rs, ctx->ev[8 + 3 * is]));
     CK(cudaEventRecord(ctx->ev[8 + 3 * is + 1], ctx->stream));
     CollapseParams c{};
     for (int k = 0; k < 6; k++) {
@@ -550,9 +685,11 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   std::vector<double> sums(2 * 64);
   CK(cudaMemcpyAsync(sums.data(), ctx->sums, sizeof(double) * 2 * 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  TRY(check_peer_error(ctx));
   const double ntot = (double)g.N * g.N * g.N;
+  // local share of Sum(delta^2)/Ntotal: the caller adds the ranks up (MPI_Reduce, src/collapse_times.c:656-662)
   if (true_variance)
-    for (int is = 0; is < ns; is++) true_variance[is] = sums[2 * is + 1] / ntot;  // src/collapse_times.c:662
+    for (int is = 0; is < ns; is++) true_variance[is] = sums[2 * is + 1] / ntot;
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   ctx->tm.fmax += ms * 1e-3;
@@ -571,18 +708,19 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   return 0;
 }
 
-// first derivatives of a k-vector -> three float fields (compute_first_derivatives, src/fmax.c:193-222)
+// first derivatives of a K-layout k-vector -> three float fields (compute_first_derivatives,
+// src/fmax.c:193-222).  Uses A[0], A[1] as x-pass destinations and D[0..2] as y-pass outputs.
 static int first_derivs_to_vel(pinb200_ctx* ctx, const double2* kvec, double growth, float* const out[3], bool with_nyq) {
   const Geom& g = ctx->g;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
-  LAUNCH(launch_dc_scalar(kvec, ctx->dc, norm, 1, ctx->stream));
-  double2* xdst[3] = {ctx->W[1], ctx->W[0], nullptr};  // p=0 -> W1, p=1 -> W0
+  TRY(run_dc(ctx, kvec, norm, 1));
+  double2* xdst[3] = {ctx->A[1], ctx->A[0], nullptr};  // p=0 -> A1, p=1 -> A0
   // Rsmooth = 0 (src/fmax.c:200 with R = 0): window = 1
   TRY(run_xpass_inv(ctx, kvec, xdst, 0x3, false, 1, 1, norm * growth, with_nyq));
-  const double2* ysrc[3] = {ctx->W[0], ctx->W[1], nullptr};
-  double2* ydst[6] = {ctx->W[2], ctx->W[3], ctx->W[4], nullptr, nullptr, nullptr};
+  const double2* ysrc[3] = {ctx->A[0], ctx->A[1], nullptr};
+  double2* ydst[6] = {ctx->D[0], ctx->D[1], ctx->D[2], nullptr, nullptr, nullptr};
   static const YJob jobs[3] = {{0, 0, 0}, {1, 1, 1}, {1, 0, 2}};
-  TRY(run_ypass(ctx, +1, ysrc, ydst, jobs, 3, with_nyq));
+  TRY(run_ypass_inv(ctx, ysrc, ydst, jobs, 3, with_nyq));
   ZOutParams z{};
   for (int k = 0; k < 3; k++) {
     z.zs.src[k] = ydst[k];
@@ -601,16 +739,18 @@ static int first_derivs_to_vel(pinb200_ctx* ctx, const double2* kvec, double gro
 
 extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, const double growth[4]) {
   if (!ctx || !growth) return 1;
-  if (!ctx->kdens) FAIL("kdensity not resident");
+  if (!ctx->kdens_valid) FAIL("kdensity not resident");
+  NEED_PEERS();
   CK(cudaSetDevice(ctx->d.device));
   const Geom& g = ctx->g;
   const int order = ctx->d.lpt_order;
   const size_t nrows = (size_t)g.lx * g.N;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  for (int i = 0; i < 3; i++) TRY(dev_alloc(ctx, &ctx->D[i], ctx->field_elems));
   if (order >= 2 && compute_sources) {
     if (!ctx->hessian_valid) FAIL("second derivatives of the R=0 radius are not in place (call pinb200_fmax first)");
-    // ---- sources (src/LPT.c:64-93): A0 = S2, A1 = S31, A2 = S32 (real layout)
+    // ---- sources (src/LPT.c:64-93): A0 = S2, A1 = S31, A2 = S32 (real, R layout)
     SourcesParams sp{};
     for (int k = 0; k < 6; k++) sp.h[k] = reinterpret_cast<const double*>(ctx->B[k]);
     sp.s2 = reinterpret_cast<double*>(ctx->A[0]);
@@ -621,12 +761,12 @@ extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, cons
     sp.pitch = 2 * g.P;
     sp.lpt_order = order;
     LAUNCH(launch_sources(sp, ctx->stream));
-    TRY(run_r2c_inplace(ctx, ctx->A[0]));  // kvector_2LPT
+    TRY(run_r2c(ctx, ctx->A[0], ctx->KV[0]));  // kvector_2LPT; A0 is free afterwards
     if (order >= 3) {
-      // ---- second derivatives of phi_2 contracted with the Hessian (src/LPT.c:116-141),
-      //      in three groups (by power of kx) to bound the workspace to 4 fields
-      for (int i = 0; i < 4; i++) TRY(dev_alloc(ctx, &ctx->W[i], ctx->field_elems));
-      LAUNCH(launch_dc_scalar(ctx->A[0], ctx->dc, norm, 0, ctx->stream));
+      // ---- second derivatives of phi_2 contracted with the Hessian (src/LPT.c:116-141), in
+      //      three groups (by power of kx); x-pass destination A0, y-pass outputs D0..D2
+      TRY(peer_barrier(ctx));  // kvector_2LPT complete on rank 0 before its k = 0 mode is read
+      TRY(run_dc(ctx, ctx->KV[0], norm, 0));
       struct Grp { int pw; int n; YJob jobs[3]; int kz[3]; int slot[3]; };
       // slots: 0 xx,1 yy,2 zz,3 xy,4 xz,5 yz ; weight 2 (diagonal) or 4 (off-diagonal)
       const Grp grp[3] = {{2, 1, {{0, 0, 0}}, {0, 0, 0}, {0, 0, 0}},
@@ -634,11 +774,11 @@ extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, cons
                           {0, 3, {{0, 2, 0}, {0, 1, 1}, {0, 0, 2}}, {0, 1, 2}, {1, 5, 2}}};
       for (const Grp& gr : grp) {
         double2* xdst[3] = {nullptr, nullptr, nullptr};
-        xdst[gr.pw] = ctx->W[0];
-        TRY(run_xpass_inv(ctx, ctx->A[0], xdst, 1 << gr.pw, false, 1, 0, norm, true));
-        const double2* ysrc[3] = {ctx->W[0], nullptr, nullptr};
-        double2* ydst[6] = {ctx->W[1], ctx->W[2], ctx->W[3], nullptr, nullptr, nullptr};
-        TRY(run_ypass(ctx, +1, ysrc, ydst, gr.jobs, gr.n, true));
+        xdst[gr.pw] = ctx->A[0];
+        TRY(run_xpass_inv(ctx, ctx->KV[0], xdst, 1 << gr.pw, false, 1, 0, norm, true));
+        const double2* ysrc[3] = {ctx->A[0], nullptr, nullptr};
+        double2* ydst[6] = {ctx->D[0], ctx->D[1], ctx->D[2], nullptr, nullptr, nullptr};
+        TRY(run_ypass_inv(ctx, ysrc, ydst, gr.jobs, gr.n, true));
         ZOutParams z{};
         for (int k = 0; k < gr.n; k++) {
           z.zs.src[k] = ydst[k];
@@ -655,8 +795,8 @@ extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, cons
         z.acc = reinterpret_cast<double*>(ctx->A[2]);
         LAUNCH(launch_zpass_out(g.N, z, nrows, ctx->stream));
       }
-      TRY(run_r2c_inplace(ctx, ctx->A[1]));  // kvector_3LPT_1
-      TRY(run_r2c_inplace(ctx, ctx->A[2]));  // kvector_3LPT_2
+      TRY(run_r2c(ctx, ctx->A[1], ctx->KV[1]));  // kvector_3LPT_1
+      TRY(run_r2c(ctx, ctx->A[2], ctx->KV[2]));  // kvector_3LPT_2
     }
     // the Hessian fields are dead now
     for (auto& b : ctx->B) TRY(dev_free(ctx, &b));
@@ -665,17 +805,18 @@ extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, cons
   }
   if (order >= 2 && !ctx->kvec_valid) FAIL("LPT k-vectors are not resident (compute_sources = 0 needs an earlier call with compute_sources = 1)");
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  for (int i = 0; i < 5; i++) TRY(dev_alloc(ctx, &ctx->W[i], ctx->field_elems));
   const int nvel = order == 1 ? 3 : (order == 2 ? 6 : 12);
   for (int i = 0; i < nvel; i++) TRY(dev_alloc(ctx, &ctx->vel[i], ctx->ncells));
-  if (order >= 2) TRY(first_derivs_to_vel(ctx, ctx->A[0], growth[1], ctx->vel + 3, true));   // ScaleDep.order = 2
+  TRY(peer_barrier(ctx));  // all k-vectors complete everywhere before rank 0's k = 0 modes are read
+  if (order >= 2) TRY(first_derivs_to_vel(ctx, ctx->KV[0], growth[1], ctx->vel + 3, true));   // ScaleDep.order = 2
   if (order >= 3) {
-    TRY(first_derivs_to_vel(ctx, ctx->A[1], growth[2], ctx->vel + 6, true));                 // order 3
-    TRY(first_derivs_to_vel(ctx, ctx->A[2], growth[3], ctx->vel + 9, true));                 // order 4
+    TRY(first_derivs_to_vel(ctx, ctx->KV[1], growth[2], ctx->vel + 6, true));                 // order 3
+    TRY(first_derivs_to_vel(ctx, ctx->KV[2], growth[3], ctx->vel + 9, true));                 // order 4
   }
-  TRY(first_derivs_to_vel(ctx, ctx->kdens, growth[0], ctx->vel + 0, false));                 // order 1, src/fmax.c:342-346
+  TRY(first_derivs_to_vel(ctx, ctx->kdens, growth[0], ctx->vel + 0, false));                  // order 1, src/fmax.c:342-346
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  TRY(check_peer_error(ctx));
   float a = 0, b = 0;
   CK(cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]));
   CK(cudaEventElapsedTime(&b, ctx->ev[3], ctx->ev[4]));
@@ -760,20 +901,21 @@ extern "C" int pinb200_get_timers(pinb200_ctx* ctx, pinb200_timers* t) {
 // ---- finer-grained entry points -------------------------------------------------------------
 extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* real_out) {
   if (!ctx || !cplx_in || !real_out) return 1;
+  if (ctx->P != 1) FAIL("pinb200_fft_c2r on host arrays is a single-rank entry point");
   CK(cudaSetDevice(ctx->d.device));
   const Geom& g = ctx->g;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
-  double2* f = nullptr;
-  TRY(dev_alloc(ctx, &f, ctx->field_elems));
-  TRY(upload_cplx(ctx, cplx_in, f));
-  double2* xdst[3] = {f, nullptr, nullptr};
-  TRY(run_xpass_inv(ctx, f, xdst, 1, false, 0, 0, norm, true));
-  const double2* ysrc[3] = {f, nullptr, nullptr};
-  double2* ydst[6] = {f, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // K-layout input in A0, x pass into A1 (R layout), y and z passes in place
+  ctx->hessian_valid = false;
+  TRY(upload_cplx(ctx, cplx_in, ctx->A[0]));
+  double2* xdst[3] = {ctx->A[1], nullptr, nullptr};
+  TRY(run_xpass_inv(ctx, ctx->A[0], xdst, 1, false, 0, 0, norm, true));
+  const double2* ysrc[3] = {ctx->A[1], nullptr, nullptr};
+  double2* ydst[6] = {ctx->A[1], nullptr, nullptr, nullptr, nullptr, nullptr};
   YJob job{0, 0, 0};
-  TRY(run_ypass(ctx, +1, ysrc, ydst, &job, 1, true));
+  TRY(run_ypass_inv(ctx, ysrc, ydst, &job, 1, true));
   ZOutParams z{};
-  z.zs.src[0] = f;
+  z.zs.src[0] = ctx->A[1];
   z.zs.kzpow[0] = 0;
   z.zs.ncomp = 1;
   z.zs.has_nyq = 1;
@@ -781,42 +923,38 @@ extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* 
   z.g = g;
   z.tw = ctx->tw;
   z.mode = 0;
-  z.rdst[0] = f;
+  z.rdst[0] = ctx->A[1];
   LAUNCH(launch_zpass_out(g.N, z, (size_t)g.lx * g.N, ctx->stream));
-  TRY(download_real(ctx, f, real_out));
-  TRY(dev_free(ctx, &f));
+  TRY(download_real(ctx, ctx->A[1], real_out));
   return 0;
 }
 
 extern "C" int pinb200_fft_r2c(pinb200_ctx* ctx, const double* real_in, double* cplx_out) {
   if (!ctx || !real_in || !cplx_out) return 1;
+  if (ctx->P != 1) FAIL("pinb200_fft_r2c on host arrays is a single-rank entry point");
   CK(cudaSetDevice(ctx->d.device));
   const Geom& g = ctx->g;
   const size_t rows = (size_t)g.lx * g.N;
-  double2* f = nullptr;
   double* tmp = nullptr;
-  TRY(dev_alloc(ctx, &f, ctx->field_elems));
   TRY(dev_alloc(ctx, &tmp, rows * g.N));
   CK(cudaMemcpyAsync(tmp, real_in, rows * g.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemsetAsync(f, 0, ctx->field_elems * sizeof(double2), ctx->stream));
-  LAUNCH(launch_repitch_r(tmp, reinterpret_cast<double*>(f), rows, g.N, g.N, 2 * g.P, ctx->stream));
-  TRY(run_r2c_inplace(ctx, f));
-  TRY(download_cplx(ctx, f, cplx_out));
+  CK(cudaMemsetAsync(ctx->A[0], 0, ctx->field_elems * sizeof(double2), ctx->stream));
+  LAUNCH(launch_repitch_r(tmp, reinterpret_cast<double*>(ctx->A[0]), rows, g.N, g.N, 2 * g.P, ctx->stream));
+  TRY(run_r2c(ctx, ctx->A[0], ctx->A[1]));
+  TRY(download_cplx(ctx, ctx->A[1], cplx_out));
   TRY(dev_free(ctx, &tmp));
-  TRY(dev_free(ctx, &f));
   return 0;
 }
 
 extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, double* hessian_out) {
   if (!ctx || !hessian_out) return 1;
-  if (!ctx->kdens) FAIL("kdensity not resident");
+  if (!ctx->kdens_valid) FAIL("kdensity not resident");
+  NEED_PEERS();
   CK(cudaSetDevice(ctx->d.device));
   const Geom& g = ctx->g;
-  ctx->kvec_valid = false;
-  for (int i = 0; i < 3; i++) TRY(dev_alloc(ctx, &ctx->A[i], ctx->field_elems));
   for (int i = 0; i < 6; i++) TRY(dev_alloc(ctx, &ctx->B[i], ctx->field_elems));
   const double cell = ctx->d.box_size / g.N;
-  TRY(hessian_xy(ctx, ctx->kdens, radius / cell, false));
+  TRY(hessian_xy(ctx, radius / cell));
   ZOutParams z{};
   for (int k = 0; k < 6; k++) {
     z.zs.src[k] = ctx->B[k];
@@ -832,7 +970,7 @@ extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, doubl
   LAUNCH(launch_zpass_out(g.N, z, (size_t)g.lx * g.N, ctx->stream));
   for (int k = 0; k < 6; k++) TRY(download_real(ctx, ctx->B[k], hessian_out + (size_t)k * ctx->ncells));
   ctx->hessian_valid = false;
-  return 0;
+  return check_peer_error(ctx);
 }
 
 extern "C" int pinb200_collapse_cells(pinb200_ctx* ctx, int ismooth, const double* hessian6, size_t ncells, double* F_out) {
@@ -854,8 +992,8 @@ extern "C" int pinb200_collapse_cells(pinb200_ctx* ctx, int ismooth, const doubl
 
 extern "C" int pinb200_download_kvector(pinb200_ctx* ctx, int which, double* kvec) {
   if (!ctx || !kvec) return 1;
-  if (which < 0 || which > 2) FAIL("which must be 0, 1 or 2");
+  if (which < 0 || which > 2 || !ctx->KV[which]) FAIL("which must name a k-vector of the configured LPT order");
   if (!ctx->kvec_valid) FAIL("LPT k-vectors are not resident");
   CK(cudaSetDevice(ctx->d.device));
-  return download_cplx(ctx, ctx->A[which], kvec);
+  return download_cplx(ctx, ctx->KV[which], kvec);
 }

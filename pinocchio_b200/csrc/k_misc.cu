@@ -157,3 +157,12 @@ cudaError_t launch_repitch_r(const double* src, double* dst, size_t nrows, int n
 }
 
 }  // namespace pinb
+
+namespace pinb {
+__global__ void __launch_bounds__(PINB_MAXR) barrier_kernel(const __grid_constant__ BarrierParams p) { barrier_body(p); }
+
+cudaError_t launch_barrier(const BarrierParams& p, cudaStream_t s) {
+  barrier_kernel<<<1, PINB_MAXR, 0, s>>>(p);
+  return cudaGetLastError();
+}
+}  // namespace pinb

@@ -4,8 +4,11 @@
 
 namespace pinb {
 
+// The collapse epilogue is a long serial FP64 dependency chain per cell: the kernel is latency
+// bound and gains from occupancy (passbench: 1 block/SM 108 ms, 2 blocks 72 ms, 3 blocks 57 ms at
+// 1024^3), so the register budget is capped to fit three 384-thread blocks per SM.
 template <int M, int TL, int CG>
-__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT) zpass_collapse_kernel(const __grid_constant__ CollapseParams p) {
+__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, (M >= 256 ? 3 : 1)) zpass_collapse_kernel(const __grid_constant__ CollapseParams p) {
   extern __shared__ double2 smem[];
   using ZS = ZShape<M, TL, CG>;
   double* spl = reinterpret_cast<double*>(smem + ZS::fft_elems(6));

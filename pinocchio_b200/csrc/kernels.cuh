@@ -90,9 +90,20 @@ PINB_HD void strided_tile_fft(Ctx& ctx, double2* s, const double2* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // X pass.  One block = (yl, kz tile).  Up to three jobs: dst[p] = FFT_x[ kx^p * fac * src ].
 // ---------------------------------------------------------------------------------------
+// Slab decomposition over the GPUs of one box (reference: 1-D slabs, src/initialization.c:1317-1325).
+// The all-to-all transpose that PFFT performs with MPI inside every 3-D transform is fused into
+// the pass that precedes it: the inverse x pass stores each output element straight into the
+// R-layout buffer of the rank that owns that x (peer memory over NVLink, cudaIpc-mapped), and
+// the forward y pass stores into the K-layout buffer of the rank that owns that y.
+#define PINB_MAXR 8
+struct PeerPtrs { double2* r[PINB_MAXR]; };
+
 struct XPassParams {
-  const double2* src;   // K layout
-  double2* dst[3];      // R layout (single rank) -- indexed by power p of kx
+  const double2* src;   // K layout (local)
+  PeerPtrs dst[3];      // per power p of kx: base pointer of the destination field on every rank
+  int dst_klayout;      // 0: scatter to the R layout of the owner rank (inverse transforms)
+                        // 1: local K layout, dst[p].r[0] (forward transforms, in place allowed)
+  int lx_shift;         // log2(lx)
   int pmask;            // bit p set -> compute job p
   int ntiles_z;         // kz tiles per row that are processed (M/TK, +1 with the Nyquist tile)
   KFactor kf;
@@ -111,7 +122,8 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   const double2* src = p.src + (size_t)yl * g.P + kz0;
   for (int pw = 0; pw < 3; pw++) {
     if (!((p.pmask >> pw) & 1)) continue;
-    double2* dst = p.dst[pw] + (size_t)(g.y0 + yl) * g.P + kz0;  // R layout, lx == N on one rank
+    const PeerPtrs& dp = p.dst[pw];
+    const size_t roff = (size_t)(g.y0 + yl) * g.P + kz0;  // offset of (y, kz0) inside an R-layout x plane
     auto load = [&](int e, int tk) {
       double2 c = ld_ro(src + (size_t)e * xstride + tk);
       const int nx = fold(e, g.N, g.M);
@@ -132,7 +144,14 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
       if (p.kf.times_i) c = make_double2(-c.y, c.x);
       return c;
     };
-    auto store = [&](int e, int tk, double2 val) { dst[(size_t)e * ((size_t)g.N * g.P) + tk] = val; };
+    auto store = [&](int e, int tk, double2 val) {
+      if (p.dst_klayout) {
+        dp.r[0][(size_t)e * xstride + (size_t)yl * g.P + kz0 + tk] = val;
+      } else {
+        const int owner = e >> p.lx_shift, xl = e & (g.lx - 1);
+        dp.r[owner][(size_t)xl * ((size_t)g.N * g.P) + roff + tk] = val;
+      }
+    };
     strided_tile_fft<L, TK, DIR>(ctx, smem, p.tw, 1, load, store);
   }
 }
@@ -142,8 +161,11 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
 // ---------------------------------------------------------------------------------------
 struct YJob { int src, q, dst; };
 struct YPassParams {
-  const double2* src[3];
-  double2* dst[6];
+  const double2* src[3];  // R layout (local)
+  double2* dst[6];        // R layout (local) -- inverse transforms
+  PeerPtrs kdst;          // forward transforms: K-layout destination field on every rank (job 0 only)
+  int dst_klayout;        // 1: scatter job 0 to the K layout of the rank that owns each y
+  int ly_shift;           // log2(ly)
   YJob job[6];
   int njobs;
   int ntiles_z;
@@ -159,17 +181,59 @@ PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
   const size_t base = (size_t)xl * g.N * g.P + kz0;
   for (int j = 0; j < p.njobs; j++) {
     const double2* src = p.src[p.job[j].src] + base;
-    double2* dst = p.dst[p.job[j].dst] + base;
+    double2* dst = p.dst_klayout ? nullptr : p.dst[p.job[j].dst] + base;
     const int q = p.job[j].q;
     auto load = [&](int e, int tk) {
       double2 c = ld_ro(src + (size_t)e * g.P + tk);
       if (q) c = cscale(c, ipow(g.knorm * fold(e, g.N, g.M), q));
       return c;
     };
-    auto store = [&](int e, int tk, double2 val) { dst[(size_t)e * g.P + tk] = val; };
+    auto store = [&](int e, int tk, double2 val) {
+      if (p.dst_klayout) {
+        const int owner = e >> p.ly_shift, yl = e & (g.ly - 1);
+        p.kdst.r[owner][((size_t)(g.x0 + xl) * g.ly + yl) * g.P + kz0 + tk] = val;
+      } else {
+        dst[(size_t)e * g.P + tk] = val;
+      }
+    };
     strided_tile_fft<L, TK, DIR>(ctx, smem, p.tw, 1, load, store);
   }
 }
+
+// ---------------------------------------------------------------------------------------
+// Cross-GPU stream barrier: every rank publishes `epoch` into its slot of every peer's flag
+// array (peer memory), then waits until all slots of its own array have reached `epoch`.
+// One block, PINB_MAXR threads.  Kernels on a stream run in order, so this orders the
+// remote stores of the pass before it against the readers after it.
+// ---------------------------------------------------------------------------------------
+struct BarrierParams {
+  unsigned long long* flags[PINB_MAXR];  // flags[r] = flag array (PINB_MAXR slots) living on rank r
+  int rank, nranks;
+  unsigned long long epoch;
+  int* error;  // set to 1 on timeout
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void barrier_body(const BarrierParams& p) {
+  const int t = threadIdx.x;
+  __threadfence_system();
+  if (t < p.nranks) {
+    volatile unsigned long long* remote = p.flags[t] + p.rank;
+    *remote = p.epoch;
+    __threadfence_system();
+    volatile unsigned long long* mine = p.flags[p.rank] + t;
+    long long spins = 0;
+    while (*mine < p.epoch) {
+      __nanosleep(200);
+      if (++spins > 20000000LL) {  // ~4+ s: a peer died; fail loudly instead of hanging the GPU
+        *p.error = 1;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+}
+#endif
 
 // ---------------------------------------------------------------------------------------
 // Contiguous (z) lines in shared memory.

@@ -17,6 +17,9 @@ int xpass_tk(int N);  // kz-tile width used by the strided passes for this grid
 cudaError_t launch_sources(const SourcesParams& p, cudaStream_t s);
 cudaError_t launch_genic(const GenicParams& p, cudaStream_t s);
 
+// cross-GPU stream barrier over peer-mapped flags
+cudaError_t launch_barrier(const BarrierParams& p, cudaStream_t s);
+
 // small helpers
 cudaError_t launch_gauss_table(double* gauss, int M, double knorm, double rsmooth, cudaStream_t s);
 cudaError_t launch_dc_scalar(const double2* src, double* out, double scale, int times_i, cudaStream_t s);

@@ -48,6 +48,7 @@ class Timers(ctypes.Structure):
 # every symbol include/pinb200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "pinb200_create", "pinb200_destroy", "pinb200_last_error", "pinb200_set_stream", "pinb200_synchronize",
+    "pinb200_ipc_handle", "pinb200_connect",
     "pinb200_set_power_table", "pinb200_set_smoothing", "pinb200_set_invgrow_spline", "pinb200_genic",
     "pinb200_upload_kdensity", "pinb200_download_kdensity", "pinb200_fmax", "pinb200_displacements",
     "pinb200_fmax_pdf", "pinb200_download_products", "pinb200_download_field", "pinb200_get_timers",
@@ -73,6 +74,8 @@ def load_library() -> ctypes.CDLL:
     lib.pinb200_destroy.argtypes = [ctypes.c_void_p]
     lib.pinb200_set_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     lib.pinb200_synchronize.argtypes = [ctypes.c_void_p]
+    lib.pinb200_ipc_handle.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.pinb200_connect.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     lib.pinb200_set_power_table.argtypes = [ctypes.c_void_p, _PD, ctypes.c_size_t]
     lib.pinb200_set_smoothing.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
     lib.pinb200_set_invgrow_spline.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD, _PD, ctypes.c_int]
@@ -127,8 +130,12 @@ class Pinocchio:
     """One rank of the collapse-time path.  Method names follow the reference."""
 
     def __init__(self, cfg: RunConfig, cosmo: Cosmology | None = None, device: int = 0,
-                 smoothing: SmoothingLadder | None = None, rank: int = 0, nranks: int = 1):
+                 smoothing: SmoothingLadder | None = None, rank: int = 0, nranks: int = 1, group=None):
+        """``group``: a torch.distributed process group (or None for the default) used to move the
+        cudaIpc handles and to sum the per-rank reductions when nranks > 1 -- the role MPI plays in
+        the reference (MPI_Reduce / MPI_Bcast, src/collapse_times.c:656-667, src/fmax.c:527)."""
         self.lib = load_library()
+        self.rank, self.nranks, self.group = rank, nranks, group
         self.cfg = cfg
         self.cosmo = cosmo if cosmo is not None else Cosmology()
         self.N = int(cfg.GridSize)
@@ -138,6 +145,10 @@ class Pinocchio:
         if self.lib.pinb200_create(ctypes.byref(d), ctypes.byref(h)):
             raise PinocchioError(self.lib.pinb200_last_error(None).decode())
         self.h = h
+        self.lx = self.N // nranks          # local x extent (real space) == local y extent (k space)
+        if nranks > 1:
+            from .distributed import connect_peers
+            connect_peers(self)
         self.CellSize = cfg.BoxSize_htrue / self.N
         self.Smoothing = smoothing if smoothing is not None else set_smoothing(self.cosmo, self.CellSize, cfg.zlast)
         self.TrueVariance = np.zeros(self.Smoothing.Nsmooth)
@@ -184,6 +195,9 @@ class Pinocchio:
         """src/fmax.c:36-190: radii loop, then compute_displacements(1, 0, ScaleDep.z[0])."""
         tv = np.zeros(self.Smoothing.Nsmooth)
         self._ck(self.lib.pinb200_fmax(self.h, _dp(tv)))
+        if self.nranks > 1:
+            from .distributed import allreduce_sum
+            tv = allreduce_sum(tv, self.group)
         self.TrueVariance = tv
         if displacements:
             self.compute_displacements(1, 0, self.cfg.segment_redshift)
@@ -206,36 +220,40 @@ class Pinocchio:
         """src/fmax.c:509-550; returns the 210 counts."""
         c = (ctypes.c_ulonglong * NBINS)()
         self._ck(self.lib.pinb200_fmax_pdf(self.h, c))
-        return np.array(list(c), dtype=np.uint64)
+        pdf = np.array(list(c), dtype=np.int64)
+        if self.nranks > 1:
+            from .distributed import allreduce_sum
+            pdf = allreduce_sum(pdf, self.group)
+        return pdf.astype(np.uint64)
 
     # -- data movement ----------------------------------------------------------------------
     def write_kdensity(self, kdensity: np.ndarray):
-        """Upload kdensity[0] in the reference layout [x][y][N/2+1] complex128."""
+        """Upload kdensity[0]: [x][y_local][N/2+1] complex128 (the reference layout on one rank)."""
         a = np.ascontiguousarray(kdensity, dtype=np.complex128)
-        assert a.shape == (self.N, self.N, self.N // 2 + 1)
+        assert a.shape == (self.N, self.lx, self.N // 2 + 1)
         self._ck(self.lib.pinb200_upload_kdensity(self.h, a.view(np.float64).ctypes.data_as(_PD)))
 
     def read_kdensity(self) -> np.ndarray:
-        a = np.zeros((self.N, self.N, self.N // 2 + 1), dtype=np.complex128)
+        a = np.zeros((self.N, self.lx, self.N // 2 + 1), dtype=np.complex128)
         self._ck(self.lib.pinb200_download_kdensity(self.h, a.view(np.float64).ctypes.data_as(_PD)))
         return a
 
     def read_kvector(self, which: int) -> np.ndarray:
-        a = np.zeros((self.N, self.N, self.N // 2 + 1), dtype=np.complex128)
+        a = np.zeros((self.N, self.lx, self.N // 2 + 1), dtype=np.complex128)
         self._ck(self.lib.pinb200_download_kvector(self.h, which, a.view(np.float64).ctypes.data_as(_PD)))
         return a
 
     def field(self, name: str, comp: int = 0) -> np.ndarray:
         idx = FIELD_INDEX[name] + (comp if name.startswith("Vel") else 0)
         dt = np.int32 if name == "Rmax" else np.float32
-        a = np.zeros((self.N, self.N, self.N), dtype=dt)
+        a = np.zeros((self.lx, self.N, self.N), dtype=dt)       # local slab: x in [rank*lx, (rank+1)*lx)
         self._ck(self.lib.pinb200_download_field(self.h, idx, a.ctypes.data_as(ctypes.c_void_p)))
         return a
 
     def products(self, cell_begin: int = 0, ncells: int | None = None, dtype=PRODUCT_DTYPE_3LPT) -> np.ndarray:
         """products[] records in the reference AoS layout (src/pinocchio.h:233-263)."""
         if ncells is None:
-            ncells = self.N ** 3 - cell_begin
+            ncells = self.lx * self.N ** 2 - cell_begin
         out = np.zeros(ncells, dtype=dtype)
         f = dtype.fields
         off = lambda n: f[n][1] if n in f else -1
@@ -264,7 +282,7 @@ class Pinocchio:
         return out
 
     def compute_second_derivatives(self, R: float) -> np.ndarray:
-        out = np.zeros((6, self.N, self.N, self.N), dtype=np.float64)
+        out = np.zeros((6, self.lx, self.N, self.N), dtype=np.float64)
         self._ck(self.lib.pinb200_second_derivatives(self.h, float(R), _dp(out)))
         return out
 

@@ -2,8 +2,10 @@
 //
 // Each "block" is executed by NT host threads that share a heap buffer as shared memory and a
 // pthread barrier as __syncthreads(); blocks run one after another.  The bodies are the very
-// same templates that k_*.cu instantiate for sm_100a, so index math, plans, twiddles and the
-// collapse arithmetic are checked on a CPU-only box against the oracle (tests/test_emulator.py).
+// same templates that k_*.cu instantiate for sm_100a, so index math, plans, twiddles, the
+// multi-rank scatter addressing and the collapse arithmetic are checked on a CPU-only box
+// against the oracle (tests/test_emulator.py).  Several ranks are emulated one after the other
+// in one process: "peer memory" is simply another host array.
 // This library is never loaded by the product (pinocchio_b200/), which has no CPU path.
 #include <pthread.h>
 
@@ -52,18 +54,19 @@ template <class F> void run_blocks(long long nblocks, int nt, F body) {
   pthread_barrier_destroy(&bar);
 }
 
-Geom make_geom(int N) {
+Geom make_geom(int N, int rank, int nranks) {
   Geom g;
   g.N = N;
   g.M = N / 2;
   g.P = g.M + 8;
-  g.lx = N;
-  g.ly = N;
-  g.x0 = 0;
-  g.y0 = 0;
+  g.lx = N / nranks;
+  g.ly = N / nranks;
+  g.x0 = rank * g.lx;
+  g.y0 = rank * g.ly;
   g.knorm = 2. * PINB_PI / (double)N;
   return g;
 }
+int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 }  // namespace
 
 #define EMU_GRIDS(X) X(32) X(64)
@@ -126,7 +129,7 @@ extern "C" int emu_zline_fft(int M, int dir, const double* in, double* out, cons
   return 1;
 }
 
-// ---- whole kernels on pitched [N][N][P] arrays ------------------------------------------------
+// ---- whole kernels on pitched arrays (K layout [N][ly][P], R layout [lx][N][P]) ---------------
 template <int N, int DIR> static void xpass_run(const XPassParams& p) {
   constexpr int TK = StridedCfg<N>::TK;
   constexpr int NT = Plan<N, false>::TPL * TK;
@@ -134,19 +137,22 @@ template <int N, int DIR> static void xpass_run(const XPassParams& p) {
   run_blocks((long long)p.g.ly * p.ntiles_z, NT, [&](HostCtx& ctx) { xpass_body<N, TK, DIR>(ctx, smem.data(), p); });
 }
 
-extern "C" int emu_xpass(int N, int dir, const double* src, double* d0, double* d1, double* d2, int pmask, int with_nyq,
-              const double* gauss, double scalar, int green, int times_i, const double* tw) {
+// dsts: 3*nranks pointers, dsts[p*nranks + r] = destination field for power p on rank r
+extern "C" int emu_xpass(int N, int dir, int rank, int nranks, const double* src, double** dsts, int dst_klayout,
+                         int pmask, int with_nyq, const double* gauss, double scalar, int green, int times_i,
+                         const double* tw) {
   XPassParams p{};
   p.src = (const double2*)src;
-  p.dst[0] = (double2*)d0;
-  p.dst[1] = (double2*)d1;
-  p.dst[2] = (double2*)d2;
+  for (int pw = 0; pw < 3; pw++)
+    for (int r = 0; r < nranks; r++) p.dst[pw].r[r] = (double2*)dsts[pw * nranks + r];
+  p.dst_klayout = dst_klayout;
   p.pmask = pmask;
   p.kf.gauss = gauss;
   p.kf.scalar = scalar;
   p.kf.green = green;
   p.kf.times_i = times_i;
-  p.g = make_geom(N);
+  p.g = make_geom(N, rank, nranks);
+  p.lx_shift = ilog2(p.g.lx);
   p.tw = (const double2*)tw;
   switch (N) {
 #define X(LL)                                                         \
@@ -167,14 +173,19 @@ template <int N, int DIR> static void ypass_run(const YPassParams& p) {
   run_blocks((long long)p.g.lx * p.ntiles_z, NT, [&](HostCtx& ctx) { ypass_body<N, TK, DIR>(ctx, smem.data(), p); });
 }
 
-// srcs[3], dsts[6]: pointers (may be null); jobs: njobs x (src, q, dst)
-extern "C" int emu_ypass(int N, int dir, double** srcs, double** dsts, const int* jobs, int njobs, int with_nyq, const double* tw) {
+// srcs[3], dsts[6]: pointers (may be null); kdsts[nranks] (forward scatter); jobs: njobs x (src, q, dst)
+extern "C" int emu_ypass(int N, int dir, int rank, int nranks, double** srcs, double** dsts, double** kdsts,
+                         int dst_klayout, const int* jobs, int njobs, int with_nyq, const double* tw) {
   YPassParams p{};
   for (int i = 0; i < 3; i++) p.src[i] = (const double2*)srcs[i];
-  for (int i = 0; i < 6; i++) p.dst[i] = (double2*)dsts[i];
+  for (int i = 0; i < 6; i++) p.dst[i] = dsts ? (double2*)dsts[i] : nullptr;
+  if (kdsts)
+    for (int r = 0; r < nranks; r++) p.kdst.r[r] = (double2*)kdsts[r];
+  p.dst_klayout = dst_klayout;
   for (int j = 0; j < njobs; j++) p.job[j] = YJob{jobs[3 * j], jobs[3 * j + 1], jobs[3 * j + 2]};
   p.njobs = njobs;
-  p.g = make_geom(N);
+  p.g = make_geom(N, rank, nranks);
+  p.ly_shift = ilog2(p.g.ly);
   p.tw = (const double2*)tw;
   switch (N) {
 #define X(LL)                                                         \
@@ -197,8 +208,9 @@ template <int N> static void collapse_run(const CollapseParams& p) {
              [&](HostCtx& ctx) { zpass_collapse_body<M, TL, CG>(ctx, smem.data(), spl.data(), scratch.data(), p); });
 }
 
-extern "C" int emu_zpass_collapse(int N, double** srcs, const int* kzpow, int has_nyq, const double* dc, const double* spline, int nspl,
-                       int ismooth, float* fmax, int* rmax, double* sums, double** hdst, const double* tw) {
+extern "C" int emu_zpass_collapse(int N, int nranks, double** srcs, const int* kzpow, int has_nyq, const double* dc,
+                                  const double* spline, int nspl, int ismooth, float* fmax, int* rmax, double* sums,
+                                  double** hdst, const double* tw) {
   CollapseParams p{};
   for (int k = 0; k < 6; k++) {
     p.zs.src[k] = (const double2*)srcs[k];
@@ -208,7 +220,7 @@ extern "C" int emu_zpass_collapse(int N, double** srcs, const int* kzpow, int ha
   p.zs.ncomp = 6;
   p.zs.has_nyq = has_nyq;
   p.zs.dc_add = dc;
-  p.g = make_geom(N);
+  p.g = make_geom(N, 0, nranks);
   p.tw = (const double2*)tw;
   p.spline = spline;
   p.nspl = nspl;
@@ -231,8 +243,9 @@ template <int N> static void zout_run(const ZOutParams& p) {
   run_blocks((long long)p.g.lx * N / TL, ZS::NT, [&](HostCtx& ctx) { zpass_out_body<M, TL, 1>(ctx, smem.data(), p); });
 }
 
-extern "C" int emu_zpass_out(int N, int ncomp, double** srcs, const int* kzpow, int has_nyq, const double* dc, int mode, double** rdst,
-                  float** fdst, double** hsrc, const double* weight, double* acc, const double* tw) {
+extern "C" int emu_zpass_out(int N, int nranks, int ncomp, double** srcs, const int* kzpow, int has_nyq, const double* dc,
+                             int mode, double** rdst, float** fdst, double** hsrc, const double* weight, double* acc,
+                             const double* tw) {
   ZOutParams p{};
   for (int k = 0; k < ncomp; k++) {
     p.zs.src[k] = (const double2*)srcs[k];
@@ -245,7 +258,7 @@ extern "C" int emu_zpass_out(int N, int ncomp, double** srcs, const int* kzpow, 
   p.zs.ncomp = ncomp;
   p.zs.has_nyq = has_nyq;
   p.zs.dc_add = dc;
-  p.g = make_geom(N);
+  p.g = make_geom(N, 0, nranks);
   p.tw = (const double2*)tw;
   p.mode = mode;
   p.acc = acc;
@@ -264,11 +277,11 @@ template <int N> static void r2c_run(const ZR2CParams& p) {
   run_blocks((long long)p.g.lx * N / TL, ZS::NT, [&](HostCtx& ctx) { zpass_r2c_body<M, TL>(ctx, smem.data(), p); });
 }
 
-extern "C" int emu_zpass_r2c(int N, const double* src, double* dst, const double* tw) {
+extern "C" int emu_zpass_r2c(int N, int nranks, const double* src, double* dst, const double* tw) {
   ZR2CParams p{};
   p.src = (const double2*)src;
   p.dst = (double2*)dst;
-  p.g = make_geom(N);
+  p.g = make_geom(N, 0, nranks);
   p.tw = (const double2*)tw;
   switch (N) {
 #define X(LL) case LL: r2c_run<LL>(p); return 0;
@@ -278,14 +291,14 @@ extern "C" int emu_zpass_r2c(int N, const double* src, double* dst, const double
   return 1;
 }
 
-extern "C" int emu_sources(int N, double** h, double* s2, double* s31, double* s32, int lpt_order) {
+extern "C" int emu_sources(int N, int nranks, double** h, double* s2, double* s31, double* s32, int lpt_order) {
   SourcesParams p{};
-  Geom g = make_geom(N);
+  Geom g = make_geom(N, 0, nranks);
   for (int k = 0; k < 6; k++) p.h[k] = h[k];
   p.s2 = s2;
   p.s31 = s31;
   p.s32 = s32;
-  p.nrows = (size_t)N * N;
+  p.nrows = (size_t)g.lx * N;
   p.N = N;
   p.pitch = 2 * g.P;
   p.lpt_order = lpt_order;
@@ -294,7 +307,8 @@ extern "C" int emu_sources(int N, double** h, double* s2, double* s31, double* s
   return 0;
 }
 
-extern "C" int emu_genic(int N, const unsigned int* seeds, const double* pk, double box, int fixed_ic, int paired_ic, double* kd) {
+extern "C" int emu_genic(int N, int rank, int nranks, const unsigned int* seeds, const double* pk, double box,
+                         int fixed_ic, int paired_ic, double* kd) {
   GenicParams p{};
   p.seeds = seeds;
   p.pk = pk;
@@ -302,10 +316,10 @@ extern "C" int emu_genic(int N, const unsigned int* seeds, const double* pk, dou
   p.box = box;
   p.fixed_ic = fixed_ic;
   p.paired_ic = paired_ic;
-  p.g = make_geom(N);
+  p.g = make_geom(N, rank, nranks);
   constexpr int NT = 8;
   std::vector<double> smem(2 * 12 * NT);
-  run_blocks(((long long)N * N + NT - 1) / NT, NT, [&](HostCtx& ctx) { genic_body<NT>(ctx, smem.data(), p); });
+  run_blocks(((long long)N * p.g.ly + NT - 1) / NT, NT, [&](HostCtx& ctx) { genic_body<NT>(ctx, smem.data(), p); });
   return 0;
 }
 
@@ -318,4 +332,3 @@ extern "C" int emu_collapse_cells(const double* h6, long long n, const double* s
   }
   return 0;
 }
-

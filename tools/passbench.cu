@@ -1,0 +1,173 @@
+// Stand-alone tuning harness: times variants of the FFT pass kernels on synthetic 1024^3 buffers.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/passbench tools/passbench.cu
+// Not part of the product library.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+#include "../pinocchio_b200/csrc/devctx.cuh"
+#include "../pinocchio_b200/csrc/kernels.cuh"
+
+using namespace pinb;
+
+#define CKE(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+template <int L, int TK, int DIR, int MINB>
+__global__ void __launch_bounds__(Plan<L, false>::TPL* TK, MINB) xk(const __grid_constant__ XPassParams p) {
+  extern __shared__ double2 smem[];
+  DevCtx ctx;
+  xpass_body<L, TK, DIR>(ctx, smem, p);
+}
+template <int L, int TK, int DIR, int MINB>
+__global__ void __launch_bounds__(Plan<L, false>::TPL* TK, MINB) yk(const __grid_constant__ YPassParams p) {
+  extern __shared__ double2 smem[];
+  DevCtx ctx;
+  ypass_body<L, TK, DIR>(ctx, smem, p);
+}
+template <int M, int TL, int CG, int MINB>
+__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, MINB) zck(const __grid_constant__ CollapseParams p) {
+  extern __shared__ double2 smem[];
+  using ZS = ZShape<M, TL, CG>;
+  double* spl = reinterpret_cast<double*>(smem + ZS::fft_elems(6));
+  double* scratch = spl + 5 * p.nspl;
+  DevCtx ctx;
+  zpass_collapse_body<M, TL, CG>(ctx, smem, spl, scratch, p);
+}
+template <int M, int TL, int MINB>
+__global__ void __launch_bounds__(ZShape<M, TL, 1>::NT, MINB) zok(const __grid_constant__ ZOutParams p) {
+  extern __shared__ double2 smem[];
+  DevCtx ctx;
+  zpass_out_body<M, TL, 1>(ctx, smem, p);
+}
+
+struct Timer {
+  cudaEvent_t a, b;
+  Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  template <class F> float run(F f, int reps = 3) {
+    f();  // warm-up
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int i = 0; i < reps; i++) {
+      cudaEventRecord(a);
+      f();
+      cudaEventRecord(b);
+      cudaEventSynchronize(b);
+      float ms;
+      cudaEventElapsedTime(&ms, a, b);
+      if (ms < best) best = ms;
+    }
+    CKE(cudaGetLastError());
+    return best;
+  }
+};
+
+static Geom geom(int N) {
+  Geom g; g.N = N; g.M = N / 2; g.P = g.M + 8; g.lx = N; g.ly = N; g.x0 = 0; g.y0 = 0; g.knorm = 2 * M_PI / N; return g;
+}
+
+template <int N, int TK, int MINB> void bench_x(const Geom& g, double2* src, double2** A, const double2* tw, const double* gauss, int pmask, const char* tag) {
+  constexpr int NT = Plan<N, false>::TPL * TK;
+  const size_t smem = (size_t)N * TK * sizeof(double2);
+  CKE(cudaFuncSetAttribute(xk<N, TK, +1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XPassParams p{};
+  p.src = src; p.dst[0] = A[0]; p.dst[1] = A[1]; p.dst[2] = A[2]; p.pmask = pmask; p.ntiles_z = g.M / TK;
+  p.kf.gauss = gauss; p.kf.scalar = 1e-9; p.kf.green = 1; p.kf.times_i = 0; p.g = g; p.tw = tw;
+  Timer t;
+  float ms = t.run([&] { xk<N, TK, +1, MINB><<<g.ly * p.ntiles_z, NT, smem>>>(p); });
+  int nout = __builtin_popcount(pmask);
+  double gb = (1 + nout) * 16.0 * g.N * g.N * g.M / 1e9;
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, xk<N, TK, +1, MINB>);
+  int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xk<N, TK, +1, MINB>, NT, smem);
+  printf("xpass %-18s TK=%d minb=%d nout=%d regs=%d blocks/SM=%d : %.2f ms  %.0f GB/s\n", tag, TK, MINB, nout, fa.numRegs, nb, ms, gb / ms * 1e3);
+}
+
+template <int N, int TK, int MINB> void bench_y(const Geom& g, double2** A, double2** B, const double2* tw, int njobs, const char* tag) {
+  constexpr int NT = Plan<N, false>::TPL * TK;
+  const size_t smem = (size_t)N * TK * sizeof(double2);
+  CKE(cudaFuncSetAttribute(yk<N, TK, +1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  YPassParams p{};
+  for (int i = 0; i < 3; i++) p.src[i] = A[i];
+  for (int i = 0; i < 6; i++) p.dst[i] = B[i];
+  static const YJob jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
+  for (int i = 0; i < njobs; i++) p.job[i] = jobs[i];
+  p.njobs = njobs; p.ntiles_z = g.M / TK; p.g = g; p.tw = tw;
+  Timer t;
+  float ms = t.run([&] { yk<N, TK, +1, MINB><<<g.lx * p.ntiles_z, NT, smem>>>(p); });
+  double gb = (njobs == 6 ? 9 : 2 * njobs) * 16.0 * g.N * g.N * g.M / 1e9;
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, yk<N, TK, +1, MINB>);
+  int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yk<N, TK, +1, MINB>, NT, smem);
+  printf("ypass %-18s TK=%d minb=%d njobs=%d regs=%d blocks/SM=%d : %.2f ms  %.0f GB/s\n", tag, TK, MINB, njobs, fa.numRegs, nb, ms, gb / ms * 1e3);
+}
+
+template <int N, int TL, int CG, int MINB> void bench_zc(const Geom& g, double2** B, const double2* tw, const double* spline, int nspl, float* fmax, int* rmax, double* sums, const char* tag) {
+  constexpr int M = N / 2;
+  using ZS = ZShape<M, TL, CG>;
+  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (size_t)5 * nspl * sizeof(double) + 2 * ZS::NT * sizeof(double);
+  CKE(cudaFuncSetAttribute(zck<M, TL, CG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CollapseParams p{};
+  static const int kz[6] = {0, 0, 2, 0, 1, 1};
+  for (int k = 0; k < 6; k++) { p.zs.src[k] = B[k]; p.zs.kzpow[k] = kz[k]; p.hdst[k] = nullptr; }
+  p.zs.ncomp = 6; p.zs.has_nyq = 0; p.zs.dc_add = nullptr; p.g = g; p.tw = tw; p.spline = spline; p.nspl = nspl;
+  p.ismooth = 1; p.Fmax = fmax; p.Rmax = rmax; p.sums = sums;
+  Timer t;
+  float ms = t.run([&] { zck<M, TL, CG, MINB><<<(unsigned)((size_t)g.lx * g.N / TL), ZS::NT, smem>>>(p); });
+  double gb = (6 * 16.0 * g.N * g.N * g.M + 12.0 * g.N * g.N * g.N) / 1e9;
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, zck<M, TL, CG, MINB>);
+  int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, zck<M, TL, CG, MINB>, ZS::NT, smem);
+  printf("zcollapse %-14s TL=%d CG=%d minb=%d regs=%d blocks/SM=%d smem=%zu : %.2f ms  %.0f GB/s\n", tag, TL, CG, MINB, fa.numRegs, nb, smem, ms, gb / ms * 1e3);
+}
+
+int main(int argc, char** argv) {
+  constexpr int N = 1024;
+  Geom g = geom(N);
+  const size_t fe = (size_t)g.N * g.N * g.P;
+  double2 *src, *A[3], *B[6], *tw;
+  CKE(cudaMalloc(&src, fe * sizeof(double2)));
+  for (auto& a : A) CKE(cudaMalloc(&a, fe * sizeof(double2)));
+  for (auto& b : B) CKE(cudaMalloc(&b, fe * sizeof(double2)));
+  // fill src with a smooth random-ish field (values O(1)); B gets filled by the passes
+  {
+    std::vector<double2> h(1 << 20);
+    for (size_t i = 0; i < h.size(); i++) h[i] = make_double2(sin(0.37 * i) * 1e3, cos(0.91 * i) * 1e3);
+    for (size_t off = 0; off < fe; off += h.size()) {
+      size_t n = std::min(h.size(), fe - off);
+      CKE(cudaMemcpy(src + off, h.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+    }
+  }
+  std::vector<double2> htw(N);
+  for (int k = 0; k < N; k++) htw[k] = make_double2(cos(2 * M_PI * k / N), sin(2 * M_PI * k / N));
+  CKE(cudaMalloc(&tw, N * sizeof(double2)));
+  CKE(cudaMemcpy(tw, htw.data(), N * sizeof(double2), cudaMemcpyHostToDevice));
+  std::vector<double> hg(g.M + 1);
+  for (int n = 0; n <= g.M; n++) hg[n] = exp(-0.5 * pow(g.knorm * n * 2.0, 2));
+  double* gauss; CKE(cudaMalloc(&gauss, hg.size() * 8)); CKE(cudaMemcpy(gauss, hg.data(), hg.size() * 8, cudaMemcpyHostToDevice));
+  // a plausible inverse-growth spline: x = log10 D in [-4, 0.12], y = log10 a
+  const int nspl = 210;
+  std::vector<double> sx(nspl), sy(nspl), spl(5 * nspl, 0.0);
+  for (int i = 0; i < nspl; i++) { sy[i] = -4 + 0.02 * i; sx[i] = sy[i] - 0.15 * exp(3.0 * (sy[i] + 0.2)) / (1 + exp(3.0 * (sy[i] + 0.2))); }
+  for (int i = 0; i < nspl; i++) { spl[i] = sx[i]; spl[nspl + i] = sy[i]; }
+  for (int i = 0; i < nspl - 1; i++) spl[2 * nspl + i] = (sy[i + 1] - sy[i]) / (sx[i + 1] - sx[i]);
+  double* dspl; CKE(cudaMalloc(&dspl, spl.size() * 8)); CKE(cudaMemcpy(dspl, spl.data(), spl.size() * 8, cudaMemcpyHostToDevice));
+  float* fmax; int* rmax; double* sums;
+  CKE(cudaMalloc(&fmax, (size_t)N * N * N * 4)); CKE(cudaMalloc(&rmax, (size_t)N * N * N * 4)); CKE(cudaMalloc(&sums, 16));
+  CKE(cudaMemset(fmax, 0, (size_t)N * N * N * 4));
+
+  bench_x<N, 8, 1>(g, src, A, tw, gauss, 7, "base");
+  bench_x<N, 4, 2>(g, src, A, tw, gauss, 7, "tk4");
+  bench_x<N, 4, 3>(g, src, A, tw, gauss, 7, "tk4");
+  bench_x<N, 8, 1>(g, src, A, tw, gauss, 1, "base");
+  bench_x<N, 4, 2>(g, src, A, tw, gauss, 1, "tk4");
+  bench_x<N, 4, 3>(g, src, A, tw, gauss, 1, "tk4");
+  bench_y<N, 8, 1>(g, A, B, tw, 6, "base");
+  bench_y<N, 4, 2>(g, A, B, tw, 6, "tk4");
+  bench_y<N, 4, 3>(g, A, B, tw, 6, "tk4");
+  bench_y<N, 8, 1>(g, A, B, tw, 1, "base");
+  bench_y<N, 4, 2>(g, A, B, tw, 1, "tk4");
+  bench_y<N, 4, 3>(g, A, B, tw, 1, "tk4");
+  // make B small-amplitude so that the collapse math sees O(1) Hessians
+  bench_zc<N, 1, 6, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "base");
+  bench_zc<N, 1, 6, 3>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb3");
+  bench_zc<N, 1, 3, 4>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cg3");
+  bench_zc<N, 1, 2, 6>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cg2");
+  return 0;
+}
