@@ -1,0 +1,265 @@
+/* fmax_b200.c -- drop-in replacement of PINOCCHIO's collapse-time path on top of libpinb200.
+ *
+ * Build PINOCCHIO V5.1 with this file INSTEAD OF src/fmax.c, src/fmax-pfft.c, src/collapse_times.c,
+ * src/LPT.c and src/GenIC.c (see INTEGRATION.md for the Makefile lines) and link -lpinb200.
+ * It defines the reference's own external symbols for this path (src/pinocchio.h:544-566,
+ * 575-577, 637-648) by marshalling the reference globals into the C ABI of include/pinb200.h.
+ * Everything else -- parameter file, cosmology tables, memory arena, products[] layout,
+ * fragmentation, output -- is the unchanged reference code.
+ *
+ * This file is host glue in the reference's own language (C); it contains no numerics.
+ */
+#include "pinocchio.h"
+#include "def_splines.h"
+#include "pinb200.h"
+
+#include <stddef.h>
+
+static pinb200_ctx *pinb = NULL;
+
+static int pinb_fail(const char *where)
+{
+  printf("ERROR on task %d: %s: %s\n", ThisTask, where, pinb200_last_error(pinb));
+  fflush(stdout);
+  return 1;
+}
+
+/* product_data as compiled (whatever -D switches are on): offsets taken from the real struct */
+static pinb200_product_layout product_layout(void)
+{
+  pinb200_product_layout L;
+  L.stride = sizeof(product_data);
+  L.prodfloat_bytes = (int)sizeof(PRODFLOAT);
+  L.off_Rmax = (int)offsetof(product_data, Rmax);
+  L.off_Fmax = (int)offsetof(product_data, Fmax);
+  L.off_Vel = (int)offsetof(product_data, Vel);
+  L.off_Vel_2LPT = L.off_Vel_3LPT_1 = L.off_Vel_3LPT_2 = -1;
+#ifdef TWO_LPT
+  L.off_Vel_2LPT = (int)offsetof(product_data, Vel_2LPT);
+#ifdef THREE_LPT
+  L.off_Vel_3LPT_1 = (int)offsetof(product_data, Vel_3LPT_1);
+  L.off_Vel_3LPT_2 = (int)offsetof(product_data, Vel_3LPT_2);
+#endif
+#endif
+  return L;
+}
+
+/* ---- replaces src/fmax-pfft.c:80-134 ---------------------------------------------------- */
+int set_one_grid(int ThisGrid)
+{
+  /* same slab geometry PFFT returns for NTasks <= GridSize (src/initialization.c:1317-1325) */
+  grid_data *G = &MyGrids[ThisGrid];
+  ptrdiff_t N = G->GSglobal[_x_];
+  if (N % NTasks)
+  {
+    if (!ThisTask)
+      printf("ERROR: GridSize must be divisible by the number of tasks for the GPU path\n");
+    return 1;
+  }
+  G->norm = 1.0 / (double)G->Ntotal;
+  G->CellSize = G->BoxSize / N;
+  G->GSlocal[_x_] = N / NTasks; G->GSlocal[_y_] = N; G->GSlocal[_z_] = N;
+  G->GSstart[_x_] = ThisTask * (N / NTasks); G->GSstart[_y_] = 0; G->GSstart[_z_] = 0;
+  G->GSlocal_k[_x_] = N; G->GSlocal_k[_y_] = N / NTasks; G->GSlocal_k[_z_] = N / 2 + 1;   /* y slabs in k space */
+  G->GSstart_k[_x_] = 0; G->GSstart_k[_y_] = ThisTask * (N / NTasks); G->GSstart_k[_z_] = 0;
+  G->total_local_size = (unsigned int)(G->GSlocal[_x_] * N * N);
+  G->total_local_size_fft = (unsigned int)(2 * G->GSlocal[_x_] * N * (N / 2 + 1));
+  G->off = 0;
+  return 0;
+}
+
+/* ---- replaces src/fmax-pfft.c:139-188: creates the device context and uploads the tables -- */
+int compute_fft_plans(void)
+{
+  pinb200_desc d;
+  int N = params.GridSize[0], i, ngpu = 8;
+  char *env = getenv("PINB200_GPUS_PER_NODE");
+  if (env) ngpu = atoi(env);
+
+  d.grid_size = N;
+  d.box_size = MyGrids[0].BoxSize;            /* params.BoxSize_htrue, src/initialization.c:490 */
+  d.random_seed = params.RandomSeed;
+  d.fixed_ic = params.FixedIC;
+  d.paired_ic = params.PairedIC;
+  d.lpt_order = 1;
+#ifdef TWO_LPT
+  d.lpt_order = 2;
+#ifdef THREE_LPT
+  d.lpt_order = 3;
+#endif
+#endif
+  d.rank = ThisTask;
+  d.nranks = NTasks;
+  d.device = ThisTask % ngpu;
+  if (pinb200_create(&d, &pinb))
+    return pinb_fail("pinb200_create");
+
+  if (NTasks > 1)
+  {
+    /* the only inter-process traffic of the GPU path on the host: one 64-byte handle per rank */
+    unsigned char mine[PINB200_IPC_HANDLE_BYTES];
+    unsigned char *all = (unsigned char *)malloc((size_t)NTasks * PINB200_IPC_HANDLE_BYTES);
+    if (pinb200_ipc_handle(pinb, mine))
+      return pinb_fail("pinb200_ipc_handle");
+    MPI_Allgather(mine, PINB200_IPC_HANDLE_BYTES, MPI_BYTE, all, PINB200_IPC_HANDLE_BYTES, MPI_BYTE, MPI_COMM_WORLD);
+    if (pinb200_connect(pinb, all))
+      return pinb_fail("pinb200_connect");
+    free(all);
+    MPI_Barrier(MPI_COMM_WORLD);
+  }
+
+  /* P(k) on the integer lattice |n|^2 (replaces the per-mode call of src/GenIC.c:283) */
+  {
+    size_t m, n = (size_t)(N / 2) * (N / 2) + 1;
+    double *pk = (double *)malloc(n * sizeof(double));
+    pk[0] = 0.0;
+    for (m = 1; m < n; m++)
+      pk[m] = PowerSpectrum(2. * PI * sqrt((double)m) / MyGrids[0].BoxSize);
+    if (pinb200_set_power_table(pinb, pk, n))
+      return pinb_fail("pinb200_set_power_table");
+    free(pk);
+  }
+
+  if (pinb200_set_smoothing(pinb, Smoothing.Nsmooth, Smoothing.Radius))
+    return pinb_fail("pinb200_set_smoothing");
+
+  /* inverse growing mode: knots only, the cspline coefficients are recomputed by the library */
+  if (pinb200_set_invgrow_spline(pinb, -1, SPLINE[SP_INVGROW]->x, SPLINE[SP_INVGROW]->y, (int)SPLINE[SP_INVGROW]->size))
+    return pinb_fail("pinb200_set_invgrow_spline");
+#if defined(SCALE_DEPENDENT) && defined(ELL_CLASSIC)
+  for (i = 0; i < Smoothing.Nsmooth; i++)
+    if (pinb200_set_invgrow_spline(pinb, i, SPLINE_INVGROW[i]->x, SPLINE_INVGROW[i]->y, (int)SPLINE_INVGROW[i]->size))
+      return pinb_fail("pinb200_set_invgrow_spline");
+#else
+  (void)i;
+#endif
+  return 0;
+}
+
+int finalize_fft(void)
+{
+#ifndef RECOMPUTE_DISPLACEMENTS
+  /* with RECOMPUTE_DISPLACEMENTS the k-vectors must survive until the last segment
+     (src/allocations.c:578-600): the context is then released at exit */
+  pinb200_destroy(pinb);
+  pinb = NULL;
+#endif
+  return 0;
+}
+
+/* ---- replaces src/GenIC.c:73-460 ------------------------------------------------------------ */
+int GenIC_large(int ThisGrid)
+{
+  (void)ThisGrid;
+  if (pinb200_genic(pinb))
+    return pinb_fail("GenIC_large");
+  return 0;
+}
+
+/* ---- replaces src/fmax.c:292-367 ------------------------------------------------------------- */
+int compute_displacements(int compute_sources, int recompute_sd, double redshift)
+{
+  double growth[4], t0 = MPI_Wtime();
+  pinb200_product_layout L = product_layout();
+
+  if (recompute_sd)
+  {
+    printf("ERROR on task %d: recompute_sd (special mode 3) is not supported by the GPU path\n", ThisTask);
+    return 1;
+  }
+  /* growth_rate of src/fmax-pfft.c:344-364 for ScaleDep.order = 1..4 */
+  growth[0] = GrowingMode(redshift, params.k_for_GM);
+  growth[1] = GrowingMode_2LPT(redshift, params.k_for_GM);
+  growth[2] = GrowingMode_3LPT_1(redshift, params.k_for_GM);
+  growth[3] = GrowingMode_3LPT_2(redshift, params.k_for_GM);
+  if (pinb200_displacements(pinb, compute_sources, growth))
+    return pinb_fail("compute_displacements");
+  cputime.lpt += MPI_Wtime() - t0;
+
+  /* products[] is carved from the reference's arena; it is only filled here, never retained */
+  t0 = MPI_Wtime();
+  if (pinb200_download_products(pinb, products, &L, 0, MyGrids[0].total_local_size))
+    return pinb_fail("download products");
+  cputime.mem_transf += MPI_Wtime() - t0;
+  return 0;
+}
+
+/* ---- replaces src/fmax.c:509-550 -------------------------------------------------------------- */
+int Fmax_PDF(void)
+{
+  unsigned long long my_counter[NBINS], counter[NBINS], coll = 0;
+  int i;
+  if (pinb200_fmax_pdf(pinb, my_counter))
+    return pinb_fail("Fmax_PDF");
+  MPI_Reduce(my_counter, counter, NBINS, MPI_UNSIGNED_LONG_LONG, MPI_SUM, 0, MPI_COMM_WORLD);
+  if (!ThisTask)
+  {
+    char filename[LBLENGTH];
+    FILE *file;
+    for (i = 10; i < NBINS; i++)
+      coll += counter[i];
+    printf("[%s] Number of collapsed particles to z=0: %Lu\n", fdate(), coll);
+    sprintf(filename, "pinocchio.%s.FmaxPDF.out", params.RunFlag);
+    file = fopen(filename, "w");
+    fprintf(file, "# Fmax PDF over %Lu particles\n", MyGrids[0].Ntotal);
+    fprintf(file, "# 1-2: F interval\n# 3: number of particles in that interval\n#\n");
+    for (i = 0; i < NBINS; i++)
+      fprintf(file, " %6.1f   %6.1f  %Lu\n", (double)i / 10., (i == NBINS - 1 ? 999.0 : (double)(i + 1) / 10.), counter[i]);
+    fclose(file);
+  }
+  return 0;
+}
+
+/* ---- replaces src/fmax.c:36-190 ----------------------------------------------------------------- */
+int compute_fmax(void)
+{
+  int ismooth;
+  double *tv = (double *)malloc(Smoothing.Nsmooth * sizeof(double));
+  pinb200_timers tm;
+
+  cputime.fmax = MPI_Wtime();
+  if (!ThisTask)
+    printf("[%s] First part: computation of collapse times (B200 path)\n", fdate());
+
+  ScaleDep.order = 0;
+  ScaleDep.redshift = 0.0;
+  if (pinb200_fmax(pinb, tv))
+    return pinb_fail("compute_fmax");
+  /* the library returns this rank's share of Sum(delta^2)/Ntotal (src/collapse_times.c:656-670) */
+  MPI_Allreduce(tv, Smoothing.TrueVariance, Smoothing.Nsmooth, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+  free(tv);
+
+  pinb200_get_timers(pinb, &tm);
+  if (!ThisTask)
+    for (ismooth = 0; ismooth < Smoothing.Nsmooth; ismooth++)
+      printf("[%s] Completed, R=%6.3f, expected sigma: %7.4f, computed sigma: %7.4f, cpu time = %f s\n", fdate(),
+             Smoothing.Radius[ismooth], sqrt(Smoothing.Variance[ismooth]), sqrt(Smoothing.TrueVariance[ismooth]),
+             tm.per_radius[ismooth]);
+  cputime.deriv += tm.deriv;
+  cputime.coll += tm.coll;
+
+  if (compute_displacements(1, 0, ScaleDep.z[0]))
+    return 1;
+  if (Fmax_PDF())        /* histogram on the device, before the context can be released */
+    return 1;
+  if (finalize_fft())
+    return 1;
+
+  cputime.fmax = MPI_Wtime() - cputime.fmax;
+  if (!ThisTask)
+    printf("[%s] Finishing fmax, total fmax cpu time = %14.6f\n", fdate(), cputime.fmax);
+  return 0;
+}
+
+char *fdate(void)
+{
+  /* identical output format to src/fmax.c:261-289 */
+  time_t current_time = time(NULL);
+  char *string = ctime(&current_time);
+  int n;
+  for (n = 0; n < 10; n++) *(date_string + n) = *(string + n);
+  for (n = 10; n < 15; n++) *(date_string + n) = *(string + n + 9);
+  for (n = 10; n < 19; n++) *(date_string + n + 5) = *(string + n);
+  *(date_string + 24) = '\0';
+  return date_string;
+}
