@@ -4,50 +4,50 @@
 // InverseGrowingMode / my_spline_eval (src/cosmo.c:1822-1832, 2016-2027).
 // Host/device portable so tests/host can check it against the oracle on a CPU-only box.
 //
-// The kernel is bound by FP64 instruction issue, not by HBM (SURVEY.md section 7 "hard parts"),
-// so the arithmetic is restructured without changing the algorithm:
+// The kernel is bound by FP64 instruction issue and latency, not by HBM (ncu r01: FP64 pipe 41 %,
+// issue slots 54 %, DRAM 11 %), so the arithmetic is restructured without changing the algorithm:
 //   * cos(t/3), cos((t+2pi)/3), cos((t+4pi)/3) come from ONE sin/cos pair of t/3 in [0, pi/3]
 //     (no range reduction needed) and the angle-addition formulas;
 //   * pow(x, 0.333333333333333) -> cbrt(x);   1/pow(10, y) -> exp10(-y);
 //   * divisions by literal constants -> multiplications; a/b/c -> a/(b*c);
-//   * branch-free 8-step lower-bound search of the spline interval.
+//   * the spline interval comes from a uniform look-up table instead of a 10-step search;
+//   * the common path of ell_classic is branch free (both cubic cases are evaluated and
+//     selected) so that two cells can be interleaved per thread; the rare guarded cases
+//     (|l1| < SMALL, |den| < SMALL) fall back to the reference's nested branches.
 // Each substitution changes the result by a few ulps (1e-15 relative); the contract is 1e-6.
-// Branch structure, SMALL tests and NaN propagation are those of the reference (App. A.6).
+// SMALL tests and NaN propagation are those of the reference.
 #pragma once
 #include <math.h>
 #include "fft_core.cuh"
+#include "spline_pack.h"
 
 namespace pinb {
 
 #define PINB_PI 3.14159265358979323846 /* src/pinocchio.h:56 */
 #define PINB_SMALL 1.e-20              /* src/collapse_times.c:38 */
 
-// Natural cubic spline table [x | y | b | c | d], n knots each (b, d valid for n-1 intervals);
-// coefficients computed on the host exactly as gsl_interp_cspline does (engine.cu).
+// packed table of spline_pack.h (in shared memory on the device)
 struct SplineView {
-  const double* x;
-  const double* y;
-  const double* b;
-  const double* c;
-  const double* d;
+  const double* t;
   int n;
 };
 
 // my_spline_eval: linear (secant) extrapolation outside the knots, cspline inside.
 PINB_HD double spline_eval(const SplineView& s, double xq) {
+  const double* t = s.t;
+  if (xq < t[0]) return t[5] + (xq - t[0]) * t[3];
+  if (xq > t[1]) return t[6] + (xq - t[1]) * t[4];
   const int n = s.n;
-  if (xq < s.x[0]) return s.y[0] + (xq - s.x[0]) * (s.y[1] - s.y[0]) / (s.x[1] - s.x[0]);
-  if (xq > s.x[n - 1])
-    return s.y[n - 1] + (xq - s.x[n - 1]) * (s.y[n - 1] - s.y[n - 2]) / (s.x[n - 1] - s.x[n - 2]);
-  // gsl_interp_bsearch: largest i in [0, n-2] with x[i] <= xq  (branch-free lower bound)
-  int lo = 0;
-#pragma unroll
-  for (int step = 512; step >= 1; step >>= 1) {
-    const int m = lo + step;
-    if (m <= n - 2 && s.x[m] <= xq) lo = m;
-  }
-  const double dx = xq - s.x[lo];
-  return s.y[lo] + dx * (s.b[lo] + dx * (s.c[lo] + dx * s.d[lo]));
+  int j = (int)((xq - t[0]) * t[2]);
+  j = j < 0 ? 0 : (j > PINB_SPLINE_NLUT - 1 ? PINB_SPLINE_NLUT - 1 : j);
+  const unsigned short* lut = reinterpret_cast<const unsigned short*>(t + PINB_SPLINE_HDR + 5 * n);
+  int i = lut[j];
+  const double* k = t + PINB_SPLINE_HDR + 5 * i;
+  // gsl_interp_bsearch semantics: largest i in [0, n-2] with x[i] <= xq
+  while (i < n - 2 && k[5] <= xq) { i++; k += 5; }
+  if (i > 0 && xq < k[0]) k -= 5;  // rounding of the bin index at a bin edge
+  const double dx = xq - k[0];
+  return k[1] + dx * (k[2] + dx * (k[3] + dx * k[4]));
 }
 
 // InverseGrowingMode(D) = 1/10^spline(log10 D) - 1  (src/cosmo.c:1822-1832)
@@ -55,45 +55,50 @@ PINB_HD double inverse_growing_mode(const SplineView& s, double D) {
   return exp10(-spline_eval(s, log10(D))) - 1.0;
 }
 
-// sin and cos of a in [0, ~1.1] (a = t/3 with t = acos(.) in [0, pi]): Taylor series in a^2,
-// truncation < 1e-18 on the interval, no range reduction.
-PINB_HD void sincos_third(double a, double& s, double& c) {
-  const double z = a * a;
-  double ps = -8.2206352466243297e-18;              // -1/19!
-  ps = ps * z + 2.8114572543455208e-15;             //  1/17!
-  ps = ps * z - 7.6471637318198165e-13;             // -1/15!
-  ps = ps * z + 1.6059043836821613e-10;             //  1/13!
-  ps = ps * z - 2.5052108385441719e-08;             // -1/11!
-  ps = ps * z + 2.7557319223985893e-06;             //  1/9!
-  ps = ps * z - 1.9841269841269841e-04;             // -1/7!
-  ps = ps * z + 8.3333333333333332e-03;             //  1/5!
-  ps = ps * z - 1.6666666666666666e-01;             // -1/3!
-  s = a + a * (z * ps);
-  double pc = 4.1103176233121648e-19;               //  1/20!
-  pc = pc * z - 1.5619206968586225e-16;             // -1/18!
-  pc = pc * z + 4.7794773323873853e-14;             //  1/16!
-  pc = pc * z - 1.1470745597729725e-11;             // -1/14!
-  pc = pc * z + 2.0876756987868099e-09;             //  1/12!
-  pc = pc * z - 2.7557319223985888e-07;             // -1/10!
-  pc = pc * z + 2.4801587301587302e-05;             //  1/8!
-  pc = pc * z - 1.3888888888888889e-03;             // -1/6!
-  pc = pc * z + 4.1666666666666664e-02;             //  1/4!
-  pc = pc * z - 0.5;
-  c = 1.0 + z * pc;
+// Taylor coefficients of sin and cos in a^2 (descending order), kept in the constant bank on the
+// device: a literal double costs two UMOV issue slots per use (19 % of the r01 kernel).
+#define PINB_SINCOS_TABLE                                                                      \
+  {-8.2206352466243297e-18, 2.8114572543455208e-15, -7.6471637318198165e-13,                   \
+   1.6059043836821613e-10, -2.5052108385441719e-08, 2.7557319223985893e-06,                    \
+   -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01,                   \
+   4.1103176233121648e-19, -1.5619206968586225e-16, 4.7794773323873853e-14,                    \
+   -1.1470745597729725e-11, 2.0876756987868099e-09, -2.7557319223985888e-07,                   \
+   2.4801587301587302e-05, -1.3888888888888889e-03, 4.1666666666666664e-02, -0.5,              \
+   0.33333333333333333, 0.86602540378443864676}
+#if defined(__CUDACC__)
+static __constant__ double kSinCosDev[21] = PINB_SINCOS_TABLE;
+#endif
+static const double kSinCosHost[21] = PINB_SINCOS_TABLE;
+PINB_HD double sc_coef(int i) {
+#if defined(__CUDA_ARCH__)
+  return kSinCosDev[i];
+#else
+  return kSinCosHost[i];
+#endif
 }
 
-// the three values cos(t/3), cos((t+2pi)/3), cos((t+4pi)/3) for t in [0, pi]
+// the three values cos(t/3), cos((t+2pi)/3), cos((t+4pi)/3) for t in [0, pi]:
+// sin and cos of a = t/3 in [0, ~1.05] by Taylor series in a^2 (truncation < 1e-18), then
+// cos(a + 2pi/3) = -c/2 - (sqrt3/2) s,  cos(a + 4pi/3) = -c/2 + (sqrt3/2) s
 PINB_HD void cos_thirds(double t, double& c0, double& c1, double& c2) {
-  double s, c;
-  sincos_third(t * (1.0 / 3.0), s, c);
-  const double h = 0.86602540378443864676;  // sin(2pi/3)
+  const double a = t * sc_coef(19);
+  const double z = a * a;
+  double ps = sc_coef(0);
+#pragma unroll
+  for (int i = 1; i < 9; i++) ps = ps * z + sc_coef(i);
+  const double s = a + a * (z * ps);
+  double pc = sc_coef(9);
+#pragma unroll
+  for (int i = 10; i < 19; i++) pc = pc * z + sc_coef(i);
+  const double c = 1.0 + z * pc;
+  const double hs = sc_coef(20) * s;
   c0 = c;
-  c1 = -0.5 * c - h * s;
-  c2 = -0.5 * c + h * s;
+  c1 = -0.5 * c - hs;
+  c2 = -0.5 * c + hs;
 }
 
-// ell_classic, src/collapse_times.c:114-221 (branch structure kept so that NaNs and the SMALL
-// tests behave as in the reference)
+// ell_classic, src/collapse_times.c:114-221, with the reference's nested branches (used for the
+// rare guarded cases and as the plain scalar version)
 PINB_HD double ell_classic(double l1, double l2, double l3) {
   double ell;
   const double del = l1 + l2 + l3;
@@ -154,6 +159,49 @@ PINB_HD double ell_classic(double l1, double l2, double l3) {
   return ell;
 }
 
+// Same function with a branch-free common path: both cases of the 3rd-order cubic are evaluated
+// and selected with the reference's conditions, so that the compiler can interleave independent
+// cells.  `guard` lanes (|l1| < SMALL or |den| < SMALL) take the nested version above.
+PINB_HD double ell_classic_flat(double l1, double l2, double l3) {
+  const double del = l1 + l2 + l3;
+  const double det = l1 * l2 * l3;
+  const double den = det * (1. / 126.) + 5. * l1 * del * (del - l1) * (1. / 84.);
+  if (fabs(l1) < PINB_SMALL || fabs(den) < PINB_SMALL) return ell_classic(l1, l2, l3);
+  const double rden = 1.0 / den;
+  const double a1 = 3. * l1 * (del - l1) * (1. / 14.) * rden;
+  const double a1_2 = a1 * a1;
+  const double a2 = l1 * rden;
+  const double a3 = -1.0 * rden;
+  const double q = (a1_2 - 3. * a2) * (1. / 9.);
+  const double r = (2. * a1_2 * a1 - 9. * a1 * a2 + 27. * a3) * (1. / 54.);
+  const double r_2_q_3 = r * r - q * q * q;
+  const double a1_3 = a1 * (1. / 3.);
+  // case 1 (r^2 - q^3 > 0)
+  const double sqa = cbrt(sqrt(r_2_q_3) + fabs(r));
+  const double sg = (r > 0.) ? -1.0 : ((r < 0.) ? 1.0 : NAN);
+  double ella = sg * (sqa + q / sqa) - a1_3;
+  ella = (ella < 0.) ? -.1 : ella;
+  // case 2
+  const double sqb = 2 * sqrt(q);
+  const double t = acos(2 * r / (q * sqb));
+  double c0, c1, c2;
+  cos_thirds(t, c0, c1, c2);
+  double s1 = -sqb * c0 - a1_3;
+  double s2 = -sqb * c1 - a1_3;
+  double s3 = -sqb * c2 - a1_3;
+  s1 = (s1 < 0.) ? 1.e10 : s1;
+  s2 = (s2 < 0.) ? 1.e10 : s2;
+  s3 = (s3 < 0.) ? 1.e10 : s3;
+  double ellb = (s1 < s2 ? s1 : s2);
+  ellb = (s3 < ellb ? s3 : ellb);
+  ellb = (ellb == 1.e10) ? -.1 : ellb;
+  double ell = (r_2_q_3 > 0) ? ella : ellb;
+  const double inv_del = 1.0 / del;
+  const double corr = -.364 * inv_del * exp((-6.5 * (l1 - l2) - 2.8 * (l2 - l3)) * inv_del);
+  if (del > 0. && ell > 0.) ell += corr;
+  return ell;
+}
+
 // inverse_collapse_time with ELL_CLASSIC: returns F.  d = {xx, yy, zz, xy, xz, yz}
 PINB_HD double inverse_collapse_time(const double* d, const SplineView& sp) {
   const double mu1 = d[0] + d[1] + d[2];
@@ -164,29 +212,26 @@ PINB_HD double inverse_collapse_time(const double* d, const SplineView& sp) {
   mu2 -= add0 + add1 + add2;
   const double mu3 = d[0] * d[1] * d[2] + 2. * d[3] * d[4] * d[5] - d[0] * add2 - d[1] * add1 - d[2] * add0;
   const double q = (mu1_2 - 3.0 * mu2) * (1. / 9.);
-  double x1, x2, x3;
-  if (q == 0.) {
-    x1 = d[0]; x2 = d[1]; x3 = d[2];
-  } else {
-    const double r = -(2. * mu1_2 * mu1 - 9.0 * mu1 * mu2 + 27.0 * mu3) * (1. / 54.);
-    if (q * q * q < r * r || q < 0.0) return -10.0;
-    const double sq = 2 * sqrt(q);
-    const double t = acos(2 * r / (q * sq));
-    const double m3 = mu1 * (1. / 3.);
-    double c0, c1, c2;
-    cos_thirds(t, c0, c1, c2);
-    x1 = -sq * c0 + m3;
-    x2 = -sq * c1 + m3;
-    x3 = -sq * c2 + m3;
-  }
+  const double r = -(2. * mu1_2 * mu1 - 9.0 * mu1 * mu2 + 27.0 * mu3) * (1. / 54.);
+  const bool diag = (q == 0.);                                  // already diagonal (:724-728)
+  const bool bad = !diag && (q * q * q < r * r || q < 0.0);     // :734-736
+  const double sq = 2 * sqrt(q);
+  const double t = acos(2 * r / (q * sq));
+  const double m3 = mu1 * (1. / 3.);
+  double c0, c1, c2;
+  cos_thirds(t, c0, c1, c2);
+  const double x1 = diag ? d[0] : -sq * c0 + m3;
+  const double x2 = diag ? d[1] : -sq * c1 + m3;
+  const double x3 = diag ? d[2] : -sq * c2 + m3;
   // ord(): C macros, NaN behaviour of `a>b?a:b`
   const double m12 = (x1 > x2 ? x1 : x2), n12 = (x1 < x2 ? x1 : x2);
   const double hi = (m12 > x3 ? m12 : x3);
   const double lo = (n12 < x3 ? n12 : x3);
   const double mid = x1 + x2 + x3 - lo - hi;
-  const double bc = ell_classic(hi, mid, lo);
-  if (bc > 0.0) return 1. + inverse_growing_mode(sp, bc);
-  return 0.0;
+  const double bc = ell_classic_flat(hi, mid, lo);
+  double F = 0.0;
+  if (bc > 0.0) F = 1. + inverse_growing_mode(sp, bc);
+  return bad ? -10.0 : F;
 }
 
 }  // namespace pinb

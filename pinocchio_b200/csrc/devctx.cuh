@@ -8,6 +8,19 @@ struct DevCtx {
   __device__ __forceinline__ int bid() const { return blockIdx.x; }
   __device__ __forceinline__ int nthreads() const { return blockDim.x; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
+  // barrier among the n threads that own one z line: a warp-level sync when the line fits a warp
+  // (several small lines may share a warp: every lane executes the same instruction stream),
+  // else a named barrier (ids 1..15; n is a multiple of 32)
+  __device__ __forceinline__ void sync_line(int line_id, int n) const {
+    if (n <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + (line_id % 15)), "r"(n) : "memory");
+  }
+  // 16-byte asynchronous copy HBM -> shared memory (LDGSTS: no register staging) and its fence
+  __device__ __forceinline__ void async_copy16(void* smem_dst, const void* gsrc) const {
+    const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+  }
+  __device__ __forceinline__ void async_wait() const { asm volatile("cp.async.wait_all;" ::: "memory"); }
   __device__ __forceinline__ void atomic_add(double* p, double v) const { atomicAdd(p, v); }
 };
 

@@ -57,7 +57,7 @@ struct pinb200_ctx {
   double* pk = nullptr;
   std::vector<double> radius;
   std::vector<std::vector<double>> spl_host;  // index 0: global spline, 1+i: per radius
-  double* spl_dev = nullptr;                  // [(1+nsmooth)][5][nspl]
+  double* spl_dev = nullptr;                  // (1+nsmooth) packed tables (spline_pack.h)
   int nspl = 0;
   bool spl_dirty = true;
 
@@ -101,42 +101,6 @@ template <class T> static int dev_free(pinb200_ctx* ctx, T** p) {
   CK(cudaFreeAsync(*p, ctx->stream));
   *p = nullptr;
   return 0;
-}
-
-// ---- gsl_interp_cspline coefficients (natural spline) -------------------
-static void cspline_table(const double* x, const double* y, int n, std::vector<double>& t) {
-  t.assign((size_t)5 * n, 0.0);
-  std::vector<double> c(n, 0.0);
-  const int m = n - 2;
-  if (m > 0) {
-    std::vector<double> diag(m), off(m), rhs(m), cp(m, 0.0), dp(m, 0.0);
-    for (int i = 0; i < m; i++) {
-      const double h_i = x[i + 1] - x[i], h_ip1 = x[i + 2] - x[i + 1];
-      const double ydiff_i = y[i + 1] - y[i], ydiff_ip1 = y[i + 2] - y[i + 1];
-      off[i] = h_ip1;
-      diag[i] = 2.0 * (h_ip1 + h_i);
-      rhs[i] = 3.0 * (ydiff_ip1 / h_ip1 - ydiff_i / h_i);
-    }
-    cp[0] = m > 1 ? off[0] / diag[0] : 0.0;
-    dp[0] = rhs[0] / diag[0];
-    for (int i = 1; i < m; i++) {
-      const double den = diag[i] - off[i - 1] * cp[i - 1];
-      if (i < m - 1) cp[i] = off[i] / den;
-      dp[i] = (rhs[i] - off[i - 1] * dp[i - 1]) / den;
-    }
-    c[m] = dp[m - 1];
-    for (int i = m - 2; i >= 0; i--) c[i + 1] = dp[i] - cp[i] * c[i + 2];
-  }
-  for (int i = 0; i < n; i++) {
-    t[i] = x[i];
-    t[n + i] = y[i];
-    t[3 * n + i] = c[i];
-  }
-  for (int i = 0; i < n - 1; i++) {
-    const double dx = x[i + 1] - x[i], dy = y[i + 1] - y[i];
-    t[2 * n + i] = dy / dx - dx * (c[i + 1] + 2.0 * c[i]) / 3.0;
-    t[4 * n + i] = (c[i + 1] - c[i]) / (3.0 * dx);
-  }
 }
 
 // ---- seed plane (src/GenIC.c:482-990): MT19937 along the square spiral ---
@@ -386,7 +350,7 @@ extern "C" int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const d
   if (ctx->nspl && ctx->nspl != n) FAIL("all inverse-growth splines must have the same number of knots");
   const size_t slot = ismooth < 0 ? 0 : (size_t)ismooth + 1;
   if (ctx->spl_host.size() <= slot) ctx->spl_host.resize(slot + 1);
-  cspline_table(x, y, n, ctx->spl_host[slot]);
+  pack_spline(x, y, n, ctx->spl_host[slot]);
   ctx->nspl = n;
   ctx->spl_dirty = true;
   return 0;
@@ -395,7 +359,7 @@ extern "C" int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const d
 static int upload_splines(pinb200_ctx* ctx) {
   if (!ctx->spl_dirty) return 0;
   if (ctx->spl_host.empty() || ctx->nspl == 0) FAIL("inverse-growth spline not set (pinb200_set_invgrow_spline)");
-  const size_t per = (size_t)5 * ctx->nspl, ns = ctx->spl_host.size();
+  const size_t per = spline_table_doubles(ctx->nspl), ns = ctx->spl_host.size();
   std::vector<double> all(per * ns, 0.0);
   for (size_t s = 0; s < ns; s++) {
     const std::vector<double>& src = ctx->spl_host[s].empty() ? ctx->spl_host[0] : ctx->spl_host[s];
@@ -413,7 +377,7 @@ static int upload_splines(pinb200_ctx* ctx) {
 static const double* spline_for(pinb200_ctx* ctx, int ismooth) {
   size_t slot = (size_t)ismooth + 1;
   if (slot >= ctx->spl_host.size() || ctx->spl_host[slot].empty()) slot = 0;
-  return ctx->spl_dev + slot * (size_t)5 * ctx->nspl;
+  return ctx->spl_dev + slot * spline_table_doubles(ctx->nspl);
 }
 
 #define NEED_PEERS() do { if (!ctx->connected) FAIL("peer arenas not connected: exchange pinb200_ipc_handle() and call pinb200_connect()"); } while (0)
@@ -673,6 +637,7 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     c.tw = ctx->tw;
     c.spline = spline_for(ctx, is);
     c.nspl = ctx->nspl;
+    c.spl_doubles = (int)spline_table_doubles(ctx->nspl);
     c.ismooth = is;
     c.Fmax = ctx->fmax;
     c.Rmax = ctx->rmax;

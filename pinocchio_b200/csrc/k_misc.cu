@@ -85,9 +85,10 @@ cudaError_t launch_fmax_pdf(const float* fmax, size_t n, unsigned long long* cou
 __global__ void __launch_bounds__(128) collapse_cells_kernel(const double* __restrict__ h6, size_t n, const double* __restrict__ spline,
                                                              int nspl, double* __restrict__ F) {
   extern __shared__ double spl[];
-  for (int i = threadIdx.x; i < 5 * nspl; i += blockDim.x) spl[i] = spline[i];
+  const int nd = PINB_SPLINE_HDR + 5 * nspl + PINB_SPLINE_NLUT / 4;  // spline_table_doubles(nspl)
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) spl[i] = spline[i];
   __syncthreads();
-  SplineView sp{spl, spl + nspl, spl + 2 * nspl, spl + 3 * nspl, spl + 4 * nspl, nspl};
+  SplineView sp{spl, nspl};
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double h[6];
 #pragma unroll
@@ -100,7 +101,7 @@ cudaError_t launch_collapse_cells(const double* h6, size_t n, const double* spli
   size_t nb = (n + 127) / 128;
   if (nb > 148 * 16) nb = 148 * 16;
   if (nb < 1) nb = 1;
-  collapse_cells_kernel<<<(unsigned)nb, 128, 5 * nspl * sizeof(double), s>>>(h6, n, spline, nspl, F);
+  collapse_cells_kernel<<<(unsigned)nb, 128, spline_table_doubles(nspl) * sizeof(double), s>>>(h6, n, spline, nspl, F);
   return cudaGetLastError();
 }
 

@@ -12,16 +12,20 @@ __global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, (M >= 256 ? 3 : 1)) zpa
   extern __shared__ double2 smem[];
   using ZS = ZShape<M, TL, CG>;
   double* spl = reinterpret_cast<double*>(smem + ZS::fft_elems(6));
-  double* scratch = spl + 5 * p.nspl;
+  double* scratch = spl + p.spl_doubles;
   DevCtx ctx;
   zpass_collapse_body<M, TL, CG>(ctx, smem, spl, scratch, p);
 }
 
-template <int M, int TL>
-__global__ void __launch_bounds__(ZShape<M, TL, 1>::NT) zpass_out_kernel(const __grid_constant__ ZOutParams p) {
+// all components of a row are transformed concurrently (CG = ncomp): a 64-thread block per row
+// left the z epilogues latency bound (20.7 ms for the 39 GB float store at 1024^3)
+// register budget: keep >= 768 resident threads per SM (the compiler otherwise takes 168 registers)
+template <int NT> struct ZOutMinBlocks { static constexpr int V = NT >= 768 ? 1 : (768 / NT > 8 ? 8 : 768 / NT); };
+template <int M, int TL, int CG>
+__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, ZOutMinBlocks<ZShape<M, TL, CG>::NT>::V) zpass_out_kernel(const __grid_constant__ ZOutParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
-  zpass_out_body<M, TL, 1>(ctx, smem, p);
+  zpass_out_body<M, TL, CG>(ctx, smem, p);
 }
 
 template <int M, int TL>
@@ -34,25 +38,38 @@ __global__ void __launch_bounds__(ZShape<M, TL, 1>::NT) zpass_r2c_kernel(const _
 template <int N> static cudaError_t collapse_launch(const CollapseParams& p, size_t nrows, cudaStream_t s) {
   constexpr int M = N / 2, TL = ZCfg<M>::TL, CG = 6;
   using ZS = ZShape<M, TL, CG>;
-  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (size_t)5 * p.nspl * sizeof(double) + 2 * ZS::NT * sizeof(double);
+  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (size_t)p.spl_doubles * sizeof(double) + 2 * ZS::NT * sizeof(double);
   cudaError_t e = allow_smem(zpass_collapse_kernel<M, TL, CG>, smem);
   if (e != cudaSuccess) return e;
   zpass_collapse_kernel<M, TL, CG><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 
-template <int N> static cudaError_t out_launch(const ZOutParams& p, size_t nrows, cudaStream_t s) {
+template <int N, int CG> static cudaError_t out_launch_cg(const ZOutParams& p, size_t nrows, cudaStream_t s) {
   constexpr int M = N / 2, TL = ZCfg<M>::TL;
-  using ZS = ZShape<M, TL, 1>;
+  using ZS = ZShape<M, TL, CG>;
   const size_t smem = ZS::fft_elems(p.zs.ncomp) * sizeof(double2);
-  cudaError_t e = allow_smem(zpass_out_kernel<M, TL>, ZS::fft_elems(6) * sizeof(double2));
+  cudaError_t e = allow_smem(zpass_out_kernel<M, TL, CG>, ZS::fft_elems(6) * sizeof(double2));
   if (e != cudaSuccess) return e;
-  zpass_out_kernel<M, TL><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);
+  zpass_out_kernel<M, TL, CG><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 
+template <int N> static cudaError_t out_launch(const ZOutParams& p, size_t nrows, cudaStream_t s) {
+  switch (p.zs.ncomp) {
+    case 1: return out_launch_cg<N, 1>(p, nrows, s);
+    case 2: return out_launch_cg<N, 2>(p, nrows, s);
+    case 3: return out_launch_cg<N, 3>(p, nrows, s);
+    case 6: return out_launch_cg<N, 6>(p, nrows, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// rows per block of the forward z pass: four rows (256 threads) on the production grids
+template <int M> struct ZR2CCfg { static constexpr int TL = M >= 256 ? 4 : ZCfg<M>::TL; };
+
 template <int N> static cudaError_t r2c_launch(const ZR2CParams& p, size_t nrows, cudaStream_t s) {
-  constexpr int M = N / 2, TL = ZCfg<M>::TL;
+  constexpr int M = N / 2, TL = ZR2CCfg<M>::TL;
   using ZS = ZShape<M, TL, 1>;
   const size_t smem = ZS::fft_elems(1) * sizeof(double2);
   cudaError_t e = allow_smem(zpass_r2c_kernel<M, TL>, smem);

@@ -111,7 +111,9 @@ struct XPassParams {
   const double2* tw;    // N-th roots of unity
 };
 
-template <int L, int TK, int DIR, class Ctx>
+// MULTI = false: one rank; the owner look-up and the per-rank pointer table are compiled out
+// (they cost registers: the 1024-point kernel spilled 128 bytes with them).
+template <int L, int TK, int DIR, bool MULTI, class Ctx>
 PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   const Geom& g = p.g;
   const int yl = ctx.bid() / p.ntiles_z;
@@ -147,6 +149,8 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
     auto store = [&](int e, int tk, double2 val) {
       if (p.dst_klayout) {
         dp.r[0][(size_t)e * xstride + (size_t)yl * g.P + kz0 + tk] = val;
+      } else if (!MULTI) {
+        dp.r[0][(size_t)e * ((size_t)g.N * g.P) + roff + tk] = val;
       } else {
         const int owner = e >> p.lx_shift, xl = e & (g.lx - 1);
         dp.r[owner][(size_t)xl * ((size_t)g.N * g.P) + roff + tk] = val;
@@ -236,29 +240,41 @@ __device__ __forceinline__ void barrier_body(const BarrierParams& p) {
 #endif
 
 // ---------------------------------------------------------------------------------------
-// Contiguous (z) lines in shared memory.
+// Contiguous (z) lines in shared memory.  A line is owned by TPL threads (one or two warps, or a
+// fraction of a warp on the tiny test grids); the barriers between the Stockham stages only
+// involve those threads (`ctx.sync_line`: __syncwarp or a named bar.sync), so the components
+// and rows of a block proceed independently instead of meeting at block-wide barriers.
 // ---------------------------------------------------------------------------------------
-template <int M, int DIR, class Ctx>
-PINB_HD void zline_fft_smem(Ctx& ctx, double2* ln, int jl, const double2* __restrict__ tw) {
+// stages 1.. of a line whose stage-0 registers `v` are already loaded
+template <int M, int DIR, class Ctx, class In0>
+PINB_HD void zline_fft_stages(Ctx& ctx, double2* ln, int jl, int line_id, const double2* __restrict__ tw, In0 in0,
+                              bool in0_reads_smem) {
   using PL = Plan<M, true>;
   constexpr int TPL = PL::TPL, RMAX = PL::RMAX;
   double2 v[RMAX];
   auto s_in = [&](int e) { return ln[zpad(e)]; };
   auto s_out = [&](int e, double2 val) { ln[zpad(e)] = val; };
-  stage_load<M, PL::R0, TPL, RMAX>(jl, v, s_in);
-  ctx.sync();
+  stage_load<M, PL::R0, TPL, RMAX>(jl, v, in0);
+  if (in0_reads_smem) ctx.sync_line(line_id, TPL);
   stage_store<M, PL::R0, 1, DIR, TPL, RMAX>(jl, v, s_out, tw, 2);
-  ctx.sync();
+  ctx.sync_line(line_id, TPL);
   stage_load<M, PL::R1, TPL, RMAX>(jl, v, s_in);
-  ctx.sync();
+  ctx.sync_line(line_id, TPL);
   stage_store<M, PL::R1, PL::R0, DIR, TPL, RMAX>(jl, v, s_out, tw, 2);
-  ctx.sync();
+  ctx.sync_line(line_id, TPL);
   if constexpr (PL::NST == 3) {
     stage_load<M, PL::R2, TPL, RMAX>(jl, v, s_in);
-    ctx.sync();
+    ctx.sync_line(line_id, TPL);
     stage_store<M, PL::R2, PL::R0 * PL::R1, DIR, TPL, RMAX>(jl, v, s_out, tw, 2);
-    ctx.sync();
+    ctx.sync_line(line_id, TPL);
   }
+}
+
+// in-place FFT of a line that already sits in shared memory
+template <int M, int DIR, class Ctx>
+PINB_HD void zline_fft_smem(Ctx& ctx, double2* ln, int jl, const double2* __restrict__ tw, int line_id = 0) {
+  auto s_in = [&](int e) { return ln[zpad(e)]; };
+  zline_fft_stages<M, DIR>(ctx, ln, jl, line_id, tw, s_in, true);
 }
 
 struct ZSrc {
@@ -271,6 +287,10 @@ struct ZSrc {
 
 // c2r of a tile of TL rows x ncomp components into shared memory: on return
 // smem[(c*TL + line)*PITCH + zpad(m)] = (x[2m], x[2m+1]).  Block = TPL*TL*CG threads.
+// The row goes HBM -> shared memory with cp.async (no registers in flight, full memory-level
+// parallelism); stage 0 then reads X[e] and its mirror X[M-e] from shared memory and applies the
+// kz power and the half-complex -> packed-complex pre-twiddle on the fly.  Ends with a
+// block-wide barrier.
 template <int M, int TL, int CG, class Ctx>
 PINB_HD void zpass_c2r_tile(Ctx& ctx, double2* smem, const ZSrc& zs, const Geom& g, size_t row0,
                             const double2* __restrict__ tw) {
@@ -279,37 +299,39 @@ PINB_HD void zpass_c2r_tile(Ctx& ctx, double2* smem, const ZSrc& zs, const Geom&
   constexpr int PITCH = ZLine<M>::PITCH;
   const int tid = ctx.tid();
   const int jl = tid % TPL, line = (tid / TPL) % TL, cg = tid / (TPL * TL);
+  const int line_id = line + TL * cg;
+  // issue the copies of every component group first, then transform group by group
   for (int c0 = 0; c0 < zs.ncomp; c0 += CG) {
     const int c = c0 + cg;
     double2* ln = smem + ((size_t)c * TL + line) * PITCH;
     const double2* src = zs.src[c] + (row0 + line) * g.P;
-    const int pw = zs.kzpow[c];
-    for (int e = jl; e < M; e += TPL) {
-      double2 x = ld_ro(src + e);
-      if (pw) x = cscale(x, ipow(g.knorm * e, pw));
-      ln[zpad(e)] = x;
-    }
+    for (int e = jl; e < M; e += TPL) ctx.async_copy16(ln + zpad(e), src + e);
     if (jl == 0) {
-      double2 x = make_double2(0.0, 0.0);
-      if (zs.has_nyq) x = cscale(ld_ro(src + M), ipow(g.knorm * M, pw));
-      ln[zpad(M)] = x;
+      if (zs.has_nyq) ctx.async_copy16(ln + zpad(M), src + M);
+      else ln[zpad(M)] = make_double2(0.0, 0.0);
     }
-    ctx.sync();
-    for (int k = jl; k <= M / 2; k += TPL) {
-      if (k == 0) {
-        const double a = ln[zpad(0)].x, b = ln[zpad(M)].x;
-        ln[zpad(0)] = make_double2(a + b, a - b);
-      } else {
-        const double2 xk = ln[zpad(k)], xmk = ln[zpad(M - k)];
-        double2 zk, zmk;
-        c2r_pre_pair(xk, xmk, ld_ro(tw + k), zk, zmk);
-        ln[zpad(k)] = zk;
-        if (k != M / 2) ln[zpad(M - k)] = zmk;
-      }
-    }
-    ctx.sync();
-    zline_fft_smem<M, +1>(ctx, ln, jl, tw);
   }
+  ctx.async_wait();
+  for (int c0 = 0; c0 < zs.ncomp; c0 += CG) {
+    const int c = c0 + cg;
+    double2* ln = smem + ((size_t)c * TL + line) * PITCH;
+    const int pw = zs.kzpow[c];
+    auto s_in0 = [&](int e) {
+      double2 xk = ln[zpad(e)];
+      double2 xmk = ln[zpad(M - e)];
+      if (pw) {
+        xk = cscale(xk, ipow(g.knorm * e, pw));
+        xmk = cscale(xmk, ipow(g.knorm * (M - e), pw));
+      }
+      if (e == 0) return make_double2(xk.x + xmk.x, xk.x - xmk.x);  // only Re X[0], Re X[M] (App. A.5)
+      double2 zk, zmk;
+      c2r_pre_pair(xk, xmk, ld_ro(tw + e), zk, zmk);
+      return zk;
+    };
+    ctx.sync_line(line_id, TPL);  // the copies of this line have landed
+    zline_fft_stages<M, +1>(ctx, ln, jl, line_id, tw, s_in0, true);
+  }
+  ctx.sync();
 }
 
 template <int M, int TL, int CG> struct ZShape {
@@ -346,8 +368,9 @@ struct CollapseParams {
   ZSrc zs;
   Geom g;
   const double2* tw;
-  const double* spline;  // [5][nspl]: x,y,b,c,d (global); staged to shared memory
-  int nspl;
+  const double* spline;  // packed table of spline_pack.h (global); staged to shared memory
+  int nspl;              // knots
+  int spl_doubles;       // doubles of the packed table
   int ismooth;
   float* Fmax;           // [lx][N][N]
   int* Rmax;
@@ -355,41 +378,58 @@ struct CollapseParams {
   double2* hdst[6];      // if hdst[0] != nullptr: store the six real fields (in place allowed)
 };
 
-template <int M, int TL, int CG, class Ctx>
+template <int M, int TL, int CG, class Ctx, int CPT = 1>
 PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double* scratch, const CollapseParams& p) {
   using ZS = ZShape<M, TL, CG>;
   constexpr int N = 2 * M, NT = ZS::NT, PITCH = ZS::PITCH;
   const int tid = ctx.tid();
   const size_t row0 = (size_t)ctx.bid() * TL;
-  for (int i = tid; i < 5 * p.nspl; i += NT) spl_s[i] = ld_ro(p.spline + i);
+  for (int i = tid; i < p.spl_doubles; i += NT) spl_s[i] = ld_ro(p.spline + i);
   zpass_c2r_tile<M, TL, CG>(ctx, smem, p.zs, p.g, row0, p.tw);  // ends with a barrier
-  SplineView sp{spl_s, spl_s + p.nspl, spl_s + 2 * p.nspl, spl_s + 3 * p.nspl, spl_s + 4 * p.nspl, p.nspl};
+  SplineView sp{spl_s, p.nspl};
   const double dc = p.zs.dc_add ? ld_ro(p.zs.dc_add) : 0.0;
   double sd = 0.0, sd2 = 0.0;
-  for (int idx = tid; idx < TL * N; idx += NT) {
-    const int line = idx / N, z = idx % N, m = z >> 1;
-    double h[6];
+  // CPT independent cells per thread and iteration (instruction-level parallelism for the long
+  // FP64 dependency chains of the collapse arithmetic)
+  for (int base = tid; base < TL * N; base += CPT * NT) {
+    double F[CPT];
+    float fm[CPT];
+    size_t cell[CPT];
+    bool valid[CPT];
 #pragma unroll
-    for (int c = 0; c < 6; c++) {
-      const double2 v = smem[((size_t)c * TL + line) * PITCH + zpad(m)];
-      h[c] = ((z & 1) ? v.y : v.x) + dc;
+    for (int u = 0; u < CPT; u++) {
+      const int idx = base + u * NT;
+      valid[u] = idx < TL * N;
+      const int idc = valid[u] ? idx : base;
+      const int line = idc / N, z = idc % N, m = z >> 1;
+      double h[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        const double2 v = smem[((size_t)c * TL + line) * PITCH + zpad(m)];
+        h[c] = ((z & 1) ? v.y : v.x) + dc;
+      }
+      cell[u] = (row0 + line) * N + z;
+      // ismooth == 0 performs the -10 / -1 initialisation of src/collapse_times.c:468-469
+      fm[u] = -10.0f;
+      if (p.ismooth > 0) fm[u] = p.Fmax[cell[u]];
+      const double delta = h[0] + h[1] + h[2];
+      if (valid[u]) {
+        sd += delta;
+        sd2 += delta * delta;
+      }
+      F[u] = inverse_collapse_time(h, sp);
     }
-    const double delta = h[0] + h[1] + h[2];
-    sd += delta;
-    sd2 += delta * delta;
-    const double F = inverse_collapse_time(h, sp);
-    const size_t cell = (row0 + line) * N + z;
-    // running max, src/collapse_times.c:587-590 (float Fmax promoted to double for the test);
-    // ismooth == 0 also performs the -10 / -1 initialisation of :468-469
-    float fm = -10.0f;
-    int rm = -1;
-    if (p.ismooth > 0) fm = p.Fmax[cell];
-    if ((double)fm < F) {
-      p.Fmax[cell] = (float)F;
-      p.Rmax[cell] = p.ismooth;
-    } else if (p.ismooth == 0) {
-      p.Fmax[cell] = fm;
-      p.Rmax[cell] = rm;
+#pragma unroll
+    for (int u = 0; u < CPT; u++) {
+      if (!valid[u]) continue;
+      // running max, src/collapse_times.c:587-590 (float Fmax promoted to double for the test)
+      if ((double)fm[u] < F[u]) {
+        p.Fmax[cell[u]] = (float)F[u];
+        p.Rmax[cell[u]] = p.ismooth;
+      } else if (p.ismooth == 0) {
+        p.Fmax[cell[u]] = fm[u];
+        p.Rmax[cell[u]] = -1;
+      }
     }
   }
   block_sum2<NT>(ctx, scratch, sd, sd2);
@@ -488,9 +528,10 @@ PINB_HD void zpass_r2c_body(Ctx& ctx, double2* smem, const ZR2CParams& p) {
   const size_t row = (size_t)ctx.bid() * TL + line;
   double2* ln = smem + (size_t)line * PITCH;
   const double2* src = p.src + row * p.g.P;
-  for (int e = jl; e < M; e += TPL) ln[zpad(e)] = ld_ro(src + e);
-  ctx.sync();
-  zline_fft_smem<M, -1>(ctx, ln, jl, p.tw);
+  for (int e = jl; e < M; e += TPL) ctx.async_copy16(ln + zpad(e), src + e);
+  ctx.async_wait();
+  ctx.sync_line(line, TPL);
+  zline_fft_smem<M, -1>(ctx, ln, jl, p.tw, line);
   double2* dst = p.dst + row * p.g.P;
   for (int k = jl; k <= M / 2; k += TPL) {
     if (k == 0) {

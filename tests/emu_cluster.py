@@ -95,7 +95,7 @@ class EmuCluster:
             assert self.lib.emu_xpass(self.N, -1, r, self.P, ptr(kdst[r]), ptr_array(flat, 3 * self.P), 1, 1, 1, None,
                                       ctypes.c_double(1.0), 0, 0, ptr(self.tw)) == 0
 
-    def hessian_collapse(self, radius, cell, spline_packed, ismooth, store_h):
+    def hessian_collapse(self, radius, cell, spline_packed, nspl, ismooth, store_h):
         N, M = self.N, self.N // 2
         knorm = 2 * np.pi / N
         rs = radius / cell
@@ -103,7 +103,6 @@ class EmuCluster:
         dc = np.array([self.kdens[0][0, 0, 0].real * self.norm])
         self.xpass_inv(self.kdens, {0: self.A[0], 1: self.A[1], 2: self.A[2]}, 7, 0, gauss, self.norm, 1, 0)
         self.ypass_inv(self.A, self.B, HESS_JOBS, 0)
-        nspl = spline_packed.shape[1]
         for r in range(self.P):
             self.sums[r][:] = 0
             Br = [b[r] for b in self.B]

@@ -85,3 +85,13 @@ def real_view(c):
 def empty_field(N):
     # garbage-filled on purpose (pad columns must never leak into results)
     return np.full((N, N, pitch(N)), 1e300 + 0j, dtype=np.complex128)
+
+
+def packed_spline(lib, sp):
+    """Device table of a NaturalSpline, built by the engine's own packer (csrc/spline_pack.h)."""
+    lib.emu_spline_table_doubles.restype = ctypes.c_longlong
+    n = sp.size
+    out = np.zeros(lib.emu_spline_table_doubles(n))
+    x, y = np.ascontiguousarray(sp.x), np.ascontiguousarray(sp.y)
+    assert lib.emu_pack_spline(ptr(x), ptr(y), n, ptr(out)) == 0
+    return out

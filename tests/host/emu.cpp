@@ -30,6 +30,11 @@ struct HostCtx {
   int bid() const { return bid_; }
   int nthreads() const { return nt_; }
   void sync() const { pthread_barrier_wait(bar); }
+  // every line group calls sync_line the same number of times, so a block-wide barrier is a
+  // valid (stronger) stand-in on the host
+  void sync_line(int, int) const { pthread_barrier_wait(bar); }
+  void async_copy16(void* dst, const void* src) const { std::memcpy(dst, src, 16); }
+  void async_wait() const {}
   void atomic_add(double* p, double v) const {
     std::lock_guard<std::mutex> lk(g_atomic_mutex);
     *p += v;
@@ -134,7 +139,7 @@ template <int N, int DIR> static void xpass_run(const XPassParams& p) {
   constexpr int TK = StridedCfg<N>::TK;
   constexpr int NT = Plan<N, false>::TPL * TK;
   std::vector<double2> smem((size_t)N * TK);
-  run_blocks((long long)p.g.ly * p.ntiles_z, NT, [&](HostCtx& ctx) { xpass_body<N, TK, DIR>(ctx, smem.data(), p); });
+  run_blocks((long long)p.g.ly * p.ntiles_z, NT, [&](HostCtx& ctx) { xpass_body<N, TK, DIR, true>(ctx, smem.data(), p); });
 }
 
 // dsts: 3*nranks pointers, dsts[p*nranks + r] = destination field for power p on rank r
@@ -203,7 +208,7 @@ template <int N> static void collapse_run(const CollapseParams& p) {
   constexpr int M = N / 2, TL = ZCfg<M>::TL, CG = 6;
   using ZS = ZShape<M, TL, CG>;
   std::vector<double2> smem(ZS::fft_elems(6));
-  std::vector<double> spl((size_t)5 * p.nspl), scratch(2 * ZS::NT);
+  std::vector<double> spl((size_t)p.spl_doubles), scratch(2 * ZS::NT);
   run_blocks((long long)p.g.lx * N / TL, ZS::NT,
              [&](HostCtx& ctx) { zpass_collapse_body<M, TL, CG>(ctx, smem.data(), spl.data(), scratch.data(), p); });
 }
@@ -224,6 +229,7 @@ extern "C" int emu_zpass_collapse(int N, int nranks, double** srcs, const int* k
   p.tw = (const double2*)tw;
   p.spline = spline;
   p.nspl = nspl;
+  p.spl_doubles = (int)spline_table_doubles(nspl);
   p.ismooth = ismooth;
   p.Fmax = fmax;
   p.Rmax = rmax;
@@ -323,8 +329,17 @@ extern "C" int emu_genic(int N, int rank, int nranks, const unsigned int* seeds,
   return 0;
 }
 
+// the packed spline table, built by the same host code the engine uses (spline_pack.h)
+extern "C" long long emu_spline_table_doubles(int n) { return (long long)spline_table_doubles(n); }
+extern "C" int emu_pack_spline(const double* x, const double* y, int n, double* out) {
+  std::vector<double> t;
+  pack_spline(x, y, n, t);
+  std::memcpy(out, t.data(), t.size() * sizeof(double));
+  return 0;
+}
+
 extern "C" int emu_collapse_cells(const double* h6, long long n, const double* spline, int nspl, double* F) {
-  SplineView sp{spline, spline + nspl, spline + 2 * nspl, spline + 3 * nspl, spline + 4 * nspl, nspl};
+  SplineView sp{spline, nspl};
   for (long long i = 0; i < n; i++) {
     double h[6];
     for (int c = 0; c < 6; c++) h[c] = h6[c * n + i];

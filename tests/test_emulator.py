@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from emu_cluster import EmuCluster
-from emu_util import load_emulator, ptr, twiddles
+from emu_util import load_emulator, packed_spline, ptr, twiddles
 from oracle import pinocchio_oracle as po
 from pinocchio_b200.cosmology import Cosmology, pk_lattice_table
 
@@ -92,11 +92,12 @@ def test_genic_hessian_collapse_lpt(cosmo, P):
 
     # ---- radii loop
     radii = [6.0, 2.5, 0.0]
-    spl = cosmo.sp_invgrow.packed()
+    spl = packed_spline(cl.lib, cosmo.sp_invgrow)
+    nspl = cosmo.sp_invgrow.size
     Fo, Ro = po.init_products((N, N, N))
     unstable = np.zeros((N, N, N), dtype=bool)
     for ism, R in enumerate(radii):
-        s2 = cl.hessian_collapse(R, cell, spl, ism, store_h=(ism == len(radii) - 1))
+        s2 = cl.hessian_collapse(R, cell, spl, nspl, ism, store_h=(ism == len(radii) - 1))
         h = po.second_derivatives(kd_ref, R, cell)
         Fnew = po.inverse_collapse_time(h, cosmo.InverseGrowingMode)
         po.update_fmax(Fo, Ro, Fnew, ism)
@@ -146,8 +147,8 @@ def test_collapse_cells_branches(lib, cosmo):
     h[:, 3] = [-1.0, -2.0, -3.0, 0, 0, 0]
     h = np.ascontiguousarray(h)
     F = np.zeros(n)
-    spl = cosmo.sp_invgrow.packed()
-    assert lib.emu_collapse_cells(ptr(h), ctypes.c_longlong(n), ptr(spl), spl.shape[1], ptr(F)) == 0
+    spl = packed_spline(lib, cosmo.sp_invgrow)
+    assert lib.emu_collapse_cells(ptr(h), ctypes.c_longlong(n), ptr(spl), cosmo.sp_invgrow.size, ptr(F)) == 0
     hl = [h[i] for i in range(6)]
     ref = po.inverse_collapse_time(hl, cosmo.InverseGrowingMode)
     # cells where the reference algorithm itself is ill-conditioned are flagged, not compared

@@ -16,7 +16,7 @@ template <int L, int TK, int DIR, int MINB>
 __global__ void __launch_bounds__(Plan<L, false>::TPL* TK, MINB) xk(const __grid_constant__ XPassParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
-  xpass_body<L, TK, DIR>(ctx, smem, p);
+  xpass_body<L, TK, DIR, false>(ctx, smem, p);
 }
 template <int L, int TK, int DIR, int MINB>
 __global__ void __launch_bounds__(Plan<L, false>::TPL* TK, MINB) yk(const __grid_constant__ YPassParams p) {
@@ -24,20 +24,20 @@ __global__ void __launch_bounds__(Plan<L, false>::TPL* TK, MINB) yk(const __grid
   DevCtx ctx;
   ypass_body<L, TK, DIR>(ctx, smem, p);
 }
-template <int M, int TL, int CG, int MINB>
+template <int M, int TL, int CG, int MINB, int CPT>
 __global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, MINB) zck(const __grid_constant__ CollapseParams p) {
   extern __shared__ double2 smem[];
   using ZS = ZShape<M, TL, CG>;
   double* spl = reinterpret_cast<double*>(smem + ZS::fft_elems(6));
-  double* scratch = spl + 5 * p.nspl;
+  double* scratch = spl + p.spl_doubles;
   DevCtx ctx;
-  zpass_collapse_body<M, TL, CG>(ctx, smem, spl, scratch, p);
+  zpass_collapse_body<M, TL, CG, DevCtx, CPT>(ctx, smem, spl, scratch, p);
 }
-template <int M, int TL, int MINB>
-__global__ void __launch_bounds__(ZShape<M, TL, 1>::NT, MINB) zok(const __grid_constant__ ZOutParams p) {
+template <int M, int TL, int CG>
+__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, (768 / ZShape<M, TL, CG>::NT > 8 ? 8 : 768 / ZShape<M, TL, CG>::NT)) zok(const __grid_constant__ ZOutParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
-  zpass_out_body<M, TL, 1>(ctx, smem, p);
+  zpass_out_body<M, TL, CG>(ctx, smem, p);
 }
 
 struct Timer {
@@ -70,7 +70,7 @@ template <int N, int TK, int MINB> void bench_x(const Geom& g, double2* src, dou
   const size_t smem = (size_t)N * TK * sizeof(double2);
   CKE(cudaFuncSetAttribute(xk<N, TK, +1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   XPassParams p{};
-  p.src = src; p.dst[0] = A[0]; p.dst[1] = A[1]; p.dst[2] = A[2]; p.pmask = pmask; p.ntiles_z = g.M / TK;
+  p.src = src; p.dst[0].r[0] = A[0]; p.dst[1].r[0] = A[1]; p.dst[2].r[0] = A[2]; p.dst_klayout = 0; p.lx_shift = 10; p.pmask = pmask; p.ntiles_z = g.M / TK;
   p.kf.gauss = gauss; p.kf.scalar = 1e-9; p.kf.green = 1; p.kf.times_i = 0; p.g = g; p.tw = tw;
   Timer t;
   float ms = t.run([&] { xk<N, TK, +1, MINB><<<g.ly * p.ntiles_z, NT, smem>>>(p); });
@@ -90,7 +90,7 @@ template <int N, int TK, int MINB> void bench_y(const Geom& g, double2** A, doub
   for (int i = 0; i < 6; i++) p.dst[i] = B[i];
   static const YJob jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
   for (int i = 0; i < njobs; i++) p.job[i] = jobs[i];
-  p.njobs = njobs; p.ntiles_z = g.M / TK; p.g = g; p.tw = tw;
+  p.njobs = njobs; p.dst_klayout = 0; p.ly_shift = 10; p.ntiles_z = g.M / TK; p.g = g; p.tw = tw;
   Timer t;
   float ms = t.run([&] { yk<N, TK, +1, MINB><<<g.lx * p.ntiles_z, NT, smem>>>(p); });
   double gb = (njobs == 6 ? 9 : 2 * njobs) * 16.0 * g.N * g.N * g.M / 1e9;
@@ -99,22 +99,37 @@ template <int N, int TK, int MINB> void bench_y(const Geom& g, double2** A, doub
   printf("ypass %-18s TK=%d minb=%d njobs=%d regs=%d blocks/SM=%d : %.2f ms  %.0f GB/s\n", tag, TK, MINB, njobs, fa.numRegs, nb, ms, gb / ms * 1e3);
 }
 
-template <int N, int TL, int CG, int MINB> void bench_zc(const Geom& g, double2** B, const double2* tw, const double* spline, int nspl, float* fmax, int* rmax, double* sums, const char* tag) {
+template <int N, int TL, int CG, int MINB, int CPT> void bench_zc(const Geom& g, double2** B, const double2* tw, const double* spline, int nspl, float* fmax, int* rmax, double* sums, const char* tag) {
   constexpr int M = N / 2;
   using ZS = ZShape<M, TL, CG>;
-  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (size_t)5 * nspl * sizeof(double) + 2 * ZS::NT * sizeof(double);
-  CKE(cudaFuncSetAttribute(zck<M, TL, CG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + spline_table_doubles(nspl) * sizeof(double) + 2 * ZS::NT * sizeof(double);
+  CKE(cudaFuncSetAttribute(zck<M, TL, CG, MINB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CollapseParams p{};
   static const int kz[6] = {0, 0, 2, 0, 1, 1};
   for (int k = 0; k < 6; k++) { p.zs.src[k] = B[k]; p.zs.kzpow[k] = kz[k]; p.hdst[k] = nullptr; }
-  p.zs.ncomp = 6; p.zs.has_nyq = 0; p.zs.dc_add = nullptr; p.g = g; p.tw = tw; p.spline = spline; p.nspl = nspl;
+  p.zs.ncomp = 6; p.zs.has_nyq = 0; p.zs.dc_add = nullptr; p.g = g; p.tw = tw; p.spline = spline; p.nspl = nspl; p.spl_doubles = (int)spline_table_doubles(nspl);
   p.ismooth = 1; p.Fmax = fmax; p.Rmax = rmax; p.sums = sums;
   Timer t;
-  float ms = t.run([&] { zck<M, TL, CG, MINB><<<(unsigned)((size_t)g.lx * g.N / TL), ZS::NT, smem>>>(p); });
+  float ms = t.run([&] { zck<M, TL, CG, MINB, CPT><<<(unsigned)((size_t)g.lx * g.N / TL), ZS::NT, smem>>>(p); });
   double gb = (6 * 16.0 * g.N * g.N * g.M + 12.0 * g.N * g.N * g.N) / 1e9;
-  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, zck<M, TL, CG, MINB>);
-  int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, zck<M, TL, CG, MINB>, ZS::NT, smem);
-  printf("zcollapse %-14s TL=%d CG=%d minb=%d regs=%d blocks/SM=%d smem=%zu : %.2f ms  %.0f GB/s\n", tag, TL, CG, MINB, fa.numRegs, nb, smem, ms, gb / ms * 1e3);
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, zck<M, TL, CG, MINB, CPT>);
+  int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, zck<M, TL, CG, MINB, CPT>, ZS::NT, smem);
+  printf("zcollapse %-10s CPT=%d TL=%d CG=%d minb=%d regs=%d blocks/SM=%d smem=%zu : %.2f ms  %.0f GB/s\n", tag, CPT, TL, CG, MINB, fa.numRegs, nb, smem, ms, gb / ms * 1e3);
+}
+
+template <int N, int TL, int CG> void bench_zo(const Geom& g, double2** B, const double2* tw, float** fo, int mode, double* acc, const char* tag) {
+  constexpr int M = N / 2;
+  using ZS = ZShape<M, TL, CG>;
+  const int ncomp = 3;
+  const size_t smem = ZS::fft_elems(ncomp) * sizeof(double2);
+  CKE(cudaFuncSetAttribute(zok<M, TL, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZS::fft_elems(6) * sizeof(double2))));
+  ZOutParams p{};
+  for (int k = 0; k < ncomp; k++) { p.zs.src[k] = B[k]; p.zs.kzpow[k] = k == 2; p.fdst[k] = fo[k]; p.hsrc[k] = (const double*)B[3 + k]; p.weight[k] = 2.0; }
+  p.zs.ncomp = ncomp; p.zs.has_nyq = 1; p.zs.dc_add = nullptr; p.g = g; p.tw = tw; p.mode = mode; p.acc = acc;
+  Timer t;
+  float ms = t.run([&] { zok<M, TL, CG><<<(unsigned)((size_t)g.lx * g.N / TL), ZS::NT, smem>>>(p); });
+  int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, zok<M, TL, CG>, ZS::NT, smem);
+  printf("zout mode%d %-8s TL=%d CG=%d blocks/SM=%d : %.2f ms\n", mode, tag, TL, CG, nb, ms);
 }
 
 int main(int argc, char** argv) {
@@ -143,31 +158,27 @@ int main(int argc, char** argv) {
   double* gauss; CKE(cudaMalloc(&gauss, hg.size() * 8)); CKE(cudaMemcpy(gauss, hg.data(), hg.size() * 8, cudaMemcpyHostToDevice));
   // a plausible inverse-growth spline: x = log10 D in [-4, 0.12], y = log10 a
   const int nspl = 210;
-  std::vector<double> sx(nspl), sy(nspl), spl(5 * nspl, 0.0);
+  std::vector<double> sx(nspl), sy(nspl), spl;
   for (int i = 0; i < nspl; i++) { sy[i] = -4 + 0.02 * i; sx[i] = sy[i] - 0.15 * exp(3.0 * (sy[i] + 0.2)) / (1 + exp(3.0 * (sy[i] + 0.2))); }
-  for (int i = 0; i < nspl; i++) { spl[i] = sx[i]; spl[nspl + i] = sy[i]; }
-  for (int i = 0; i < nspl - 1; i++) spl[2 * nspl + i] = (sy[i + 1] - sy[i]) / (sx[i + 1] - sx[i]);
+  pack_spline(sx.data(), sy.data(), nspl, spl);
   double* dspl; CKE(cudaMalloc(&dspl, spl.size() * 8)); CKE(cudaMemcpy(dspl, spl.data(), spl.size() * 8, cudaMemcpyHostToDevice));
   float* fmax; int* rmax; double* sums;
   CKE(cudaMalloc(&fmax, (size_t)N * N * N * 4)); CKE(cudaMalloc(&rmax, (size_t)N * N * N * 4)); CKE(cudaMalloc(&sums, 16));
   CKE(cudaMemset(fmax, 0, (size_t)N * N * N * 4));
 
   bench_x<N, 8, 1>(g, src, A, tw, gauss, 7, "base");
-  bench_x<N, 4, 2>(g, src, A, tw, gauss, 7, "tk4");
-  bench_x<N, 4, 3>(g, src, A, tw, gauss, 7, "tk4");
-  bench_x<N, 8, 1>(g, src, A, tw, gauss, 1, "base");
-  bench_x<N, 4, 2>(g, src, A, tw, gauss, 1, "tk4");
-  bench_x<N, 4, 3>(g, src, A, tw, gauss, 1, "tk4");
   bench_y<N, 8, 1>(g, A, B, tw, 6, "base");
-  bench_y<N, 4, 2>(g, A, B, tw, 6, "tk4");
-  bench_y<N, 4, 3>(g, A, B, tw, 6, "tk4");
-  bench_y<N, 8, 1>(g, A, B, tw, 1, "base");
-  bench_y<N, 4, 2>(g, A, B, tw, 1, "tk4");
-  bench_y<N, 4, 3>(g, A, B, tw, 1, "tk4");
-  // make B small-amplitude so that the collapse math sees O(1) Hessians
-  bench_zc<N, 1, 6, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "base");
-  bench_zc<N, 1, 6, 3>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb3");
-  bench_zc<N, 1, 3, 4>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cg3");
-  bench_zc<N, 1, 2, 6>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cg2");
+  float* fo[3]; for (auto& f : fo) CKE(cudaMalloc(&f, (size_t)N * N * N * 4));
+  bench_zc<N, 1, 6, 3, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb3");
+  bench_zc<N, 1, 6, 2, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb2");
+  bench_zc<N, 1, 6, 3, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb3");
+  bench_zc<N, 1, 6, 2, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb2");
+  bench_zc<N, 1, 3, 3, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cg3");
+  bench_zc<N, 1, 3, 3, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cg3");
+  bench_zo<N, 1, 1>(g, B, tw, fo, 1, nullptr, "float");
+  bench_zo<N, 1, 3>(g, B, tw, fo, 1, nullptr, "float");
+  bench_zo<N, 2, 3>(g, B, tw, fo, 1, nullptr, "float");
+  bench_zo<N, 1, 1>(g, B, tw, fo, 2, (double*)A[0], "contract");
+  bench_zo<N, 1, 3>(g, B, tw, fo, 2, (double*)A[0], "contract");
   return 0;
 }
