@@ -18,6 +18,7 @@
 // SMALL tests and NaN propagation are those of the reference.
 #pragma once
 #include <math.h>
+#include "fastmath.cuh"
 #include "fft_core.cuh"
 #include "spline_pack.h"
 
@@ -52,7 +53,7 @@ PINB_HD double spline_eval(const SplineView& s, double xq) {
 
 // InverseGrowingMode(D) = 1/10^spline(log10 D) - 1  (src/cosmo.c:1822-1832)
 PINB_HD double inverse_growing_mode(const SplineView& s, double D) {
-  return exp10(-spline_eval(s, log10(D))) - 1.0;
+  return fm_exp10(-spline_eval(s, fm_log10(D))) - 1.0;
 }
 
 // Taylor coefficients of sin and cos in a^2 (descending order), kept in the constant bank on the
@@ -165,29 +166,35 @@ PINB_HD double ell_classic(double l1, double l2, double l3) {
 PINB_HD double ell_classic_flat(double l1, double l2, double l3) {
   const double del = l1 + l2 + l3;
   const double det = l1 * l2 * l3;
-  const double den = det * (1. / 126.) + 5. * l1 * del * (del - l1) * (1. / 84.);
+  const double den = det * mc(MC_1_126) + mc(MC_5_84) * l1 * del * (del - l1);
   if (fabs(l1) < PINB_SMALL || fabs(den) < PINB_SMALL) return ell_classic(l1, l2, l3);
   const double rden = 1.0 / den;
-  const double a1 = 3. * l1 * (del - l1) * (1. / 14.) * rden;
+  const double a1 = 3. * l1 * (del - l1) * mc(MC_1_14) * rden;
   const double a1_2 = a1 * a1;
   const double a2 = l1 * rden;
   const double a3 = -1.0 * rden;
-  const double q = (a1_2 - 3. * a2) * (1. / 9.);
-  const double r = (2. * a1_2 * a1 - 9. * a1 * a2 + 27. * a3) * (1. / 54.);
+  const double q = (a1_2 - 3. * a2) * mc(MC_1_9);
+  const double r = (2. * a1_2 * a1 - 9. * a1 * a2 + 27. * a3) * mc(MC_1_54);
   const double r_2_q_3 = r * r - q * q * q;
-  const double a1_3 = a1 * (1. / 3.);
+  const double a1_3 = a1 * mc(MC_1_3);
+  // Both cases are evaluated on every lane; the lane that will NOT be selected is fed benign
+  // operands (1, 0) instead of a negative radicand or an |argument| > 1: NaN operands send
+  // sqrt and division into their slow-path subroutines (r02 profile: 230 instructions per
+  // cell in __cuda_sm20_div_rn_f64_full / dsqrt_rn_f64_mediumpath before this guard).
+  const bool c1 = r_2_q_3 > 0;
   // case 1 (r^2 - q^3 > 0)
-  const double sqa = cbrt(sqrt(r_2_q_3) + fabs(r));
+  const double sqa = cbrt(sqrt(c1 ? r_2_q_3 : 1.0) + fabs(r));
   const double sg = (r > 0.) ? -1.0 : ((r < 0.) ? 1.0 : NAN);
   double ella = sg * (sqa + q / sqa) - a1_3;
   ella = (ella < 0.) ? -.1 : ella;
-  // case 2
-  const double sqb = 2 * sqrt(q);
-  const double t = acos(2 * r / (q * sqb));
-  double c0, c1, c2;
-  cos_thirds(t, c0, c1, c2);
+  // case 2 (r^2 <= q^3, hence q >= 0; a NaN discriminant lands here as in the reference)
+  const double q2 = c1 ? 1.0 : q;
+  const double sqb = 2 * sqrt(q2);
+  const double t = fm_acos(c1 ? 0.0 : 2 * r / (q2 * sqb));
+  double c0, c1c, c2;
+  cos_thirds(t, c0, c1c, c2);
   double s1 = -sqb * c0 - a1_3;
-  double s2 = -sqb * c1 - a1_3;
+  double s2 = -sqb * c1c - a1_3;
   double s3 = -sqb * c2 - a1_3;
   s1 = (s1 < 0.) ? 1.e10 : s1;
   s2 = (s2 < 0.) ? 1.e10 : s2;
@@ -195,9 +202,9 @@ PINB_HD double ell_classic_flat(double l1, double l2, double l3) {
   double ellb = (s1 < s2 ? s1 : s2);
   ellb = (s3 < ellb ? s3 : ellb);
   ellb = (ellb == 1.e10) ? -.1 : ellb;
-  double ell = (r_2_q_3 > 0) ? ella : ellb;
+  double ell = c1 ? ella : ellb;
   const double inv_del = 1.0 / del;
-  const double corr = -.364 * inv_del * exp((-6.5 * (l1 - l2) - 2.8 * (l2 - l3)) * inv_del);
+  const double corr = mc(MC_M0364) * inv_del * fm_exp_neg((mc(MC_M65) * (l1 - l2) + mc(MC_M28) * (l2 - l3)) * inv_del);
   if (del > 0. && ell > 0.) ell += corr;
   return ell;
 }
@@ -211,13 +218,16 @@ PINB_HD double inverse_collapse_time(const double* d, const SplineView& sp) {
   const double add0 = d[3] * d[3], add1 = d[4] * d[4], add2 = d[5] * d[5];
   mu2 -= add0 + add1 + add2;
   const double mu3 = d[0] * d[1] * d[2] + 2. * d[3] * d[4] * d[5] - d[0] * add2 - d[1] * add1 - d[2] * add0;
-  const double q = (mu1_2 - 3.0 * mu2) * (1. / 9.);
-  const double r = -(2. * mu1_2 * mu1 - 9.0 * mu1 * mu2 + 27.0 * mu3) * (1. / 54.);
+  const double q = (mu1_2 - 3.0 * mu2) * mc(MC_1_9);
+  const double r = -(2. * mu1_2 * mu1 - 9.0 * mu1 * mu2 + 27.0 * mu3) * mc(MC_1_54);
   const bool diag = (q == 0.);                                  // already diagonal (:724-728)
   const bool bad = !diag && (q * q * q < r * r || q < 0.0);     // :734-736
-  const double sq = 2 * sqrt(q);
-  const double t = acos(2 * r / (q * sq));
-  const double m3 = mu1 * (1. / 3.);
+  // benign operands on the lanes whose trigonometric solution is not used (see ell_classic_flat)
+  const bool unused = diag || bad;
+  const double qs = unused ? 1.0 : q;
+  const double sq = 2 * sqrt(qs);
+  const double t = fm_acos(unused ? 0.0 : 2 * r / (qs * sq));
+  const double m3 = mu1 * mc(MC_1_3);
   double c0, c1, c2;
   cos_thirds(t, c0, c1, c2);
   const double x1 = diag ? d[0] : -sq * c0 + m3;

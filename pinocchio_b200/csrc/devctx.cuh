@@ -1,6 +1,7 @@
 // Device execution context for the kernel bodies of kernels.cuh.
 #pragma once
 #include <cuda_runtime.h>
+#include "kernels.cuh"
 
 namespace pinb {
 struct DevCtx {
@@ -20,8 +21,33 @@ struct DevCtx {
     const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
   }
+  __device__ __forceinline__ void prefetch_l2(const void* g) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
   __device__ __forceinline__ void async_wait() const { asm volatile("cp.async.wait_all;" ::: "memory"); }
   __device__ __forceinline__ void atomic_add(double* p, double v) const { atomicAdd(p, v); }
+  // block-wide sum of two doubles (result valid in thread 0): warp shuffles + one barrier
+  template <int NT> __device__ __forceinline__ void block_sum2(double* scratch, double& a, double& b) const {
+    if constexpr (NT % 32 != 0) {
+      block_sum2_tree<NT>(*this, scratch, a, b);
+    } else {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+      }
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      if (l == 0) { scratch[w] = a; scratch[32 + w] = b; }
+      __syncthreads();
+      if (w == 0) {
+        a = l < NT / 32 ? scratch[l] : 0.0;
+        b = l < NT / 32 ? scratch[32 + l] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_down_sync(0xffffffffu, a, o);
+          b += __shfl_down_sync(0xffffffffu, b, o);
+        }
+      }
+    }
+  }
 };
 
 template <class K> inline cudaError_t allow_smem(K kernel, size_t bytes) {

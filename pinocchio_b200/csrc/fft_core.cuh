@@ -178,7 +178,25 @@ PINB_HD void stage_load(int jl, double2* v, In in) {
   }
 }
 
-template <int L, int R, int NS, int DIR, int TPL, int RMAX, class Out>
+// same, the functor also receives s = (e - jl)/TPL = m + r*NB (a compile-time constant after
+// unrolling): element e = jl + s*TPL, so exp(i*phi*e) = exp(i*phi*jl) * exp(i*phi*TPL)^s
+template <int L, int R, int TPL, int RMAX, class In>
+PINB_HD void stage_load_s(int jl, double2* v, In in) {
+  constexpr int T = L / R;
+  constexpr int NB = T / TPL;
+  static_assert(NB * R == RMAX && NB * TPL == T, "bad stage shape");
+#pragma unroll
+  for (int m = 0; m < NB; m++) {
+    const int j = jl + m * TPL;
+#pragma unroll
+    for (int r = 0; r < R; r++) v[m * R + r] = in(j + r * T, m + r * NB);
+  }
+}
+
+// TWPOW: fetch only w^k and build w^(rk) by (shallow) repeated multiplication.  Used by the z
+// passes, whose shared-memory footprint leaves no L1 for the twiddle table: every table read
+// is an L2 round trip there (r02 profile: the twiddle multiply was the top stall of the FFT part).
+template <int L, int R, int NS, int DIR, int TPL, int RMAX, class Out, bool TWPOW = false>
 PINB_HD void stage_store(int jl, double2* v, Out out, const double2* __restrict__ tw, int twscale) {
   constexpr int T = L / R;
   constexpr int NB = T / TPL;
@@ -188,8 +206,17 @@ PINB_HD void stage_store(int jl, double2* v, Out out, const double2* __restrict_
     const int k = j & (NS - 1);
     if (NS > 1) {
       const int base = k * (L / (NS * R)) * twscale;
+      if (TWPOW) {
+        double2 w[R];
+        w[1] = twiddle<DIR>(tw, base);
 #pragma unroll
-      for (int r = 1; r < R; r++) v[m * R + r] = cmul(v[m * R + r], twiddle<DIR>(tw, r * base));
+        for (int r = 2; r < R; r++) w[r] = (r & 1) ? cmul(w[r - 1], w[1]) : cmul(w[r / 2], w[r / 2]);
+#pragma unroll
+        for (int r = 1; r < R; r++) v[m * R + r] = cmul(v[m * R + r], w[r]);
+      } else {
+#pragma unroll
+        for (int r = 1; r < R; r++) v[m * R + r] = cmul(v[m * R + r], twiddle<DIR>(tw, r * base));
+      }
     }
     Radix<R, DIR>::run(v + m * R);
     const int j0 = (j - k) * R + k;

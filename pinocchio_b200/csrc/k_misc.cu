@@ -85,7 +85,7 @@ cudaError_t launch_fmax_pdf(const float* fmax, size_t n, unsigned long long* cou
 __global__ void __launch_bounds__(128) collapse_cells_kernel(const double* __restrict__ h6, size_t n, const double* __restrict__ spline,
                                                              int nspl, double* __restrict__ F) {
   extern __shared__ double spl[];
-  const int nd = PINB_SPLINE_HDR + 5 * nspl + PINB_SPLINE_NLUT / 4;  // spline_table_doubles(nspl)
+  const int nd = (PINB_SPLINE_HDR + 5 * nspl + PINB_SPLINE_NLUT / 4 + 1) & ~1;  // spline_table_doubles(nspl)
   for (int i = threadIdx.x; i < nd; i += blockDim.x) spl[i] = spline[i];
   __syncthreads();
   SplineView sp{spl, nspl};

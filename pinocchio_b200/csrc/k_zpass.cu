@@ -35,7 +35,19 @@ __global__ void __launch_bounds__(ZShape<M, TL, 1>::NT) zpass_r2c_kernel(const _
   zpass_r2c_body<M, TL>(ctx, smem, p);
 }
 
-template <int N> static cudaError_t collapse_launch(const CollapseParams& p, size_t nrows, cudaStream_t s) {
+// pre-twiddle factors exp(2 pi i TPL s / N), s < RMAX (see ZSrc::pretw)
+template <int M> static void fill_pretw(ZSrc& zs) {
+  constexpr int TPL = Plan<M, true>::TPL, RMAX = Plan<M, true>::RMAX;
+  static_assert(RMAX <= 32, "pretw too small");
+  for (int s = 0; s < RMAX; s++) {
+    const long double a = 2.0L * 3.141592653589793238462643383279502884L * (long double)TPL * s / (2.0L * M);
+    zs.pretw[s] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+}
+
+template <int N> static cudaError_t collapse_launch(const CollapseParams& p_in, size_t nrows, cudaStream_t s) {
+  CollapseParams p = p_in;
+  fill_pretw<N / 2>(p.zs);
   constexpr int M = N / 2, TL = ZCfg<M>::TL, CG = 6;
   using ZS = ZShape<M, TL, CG>;
   const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (size_t)p.spl_doubles * sizeof(double) + 2 * ZS::NT * sizeof(double);
@@ -45,7 +57,9 @@ template <int N> static cudaError_t collapse_launch(const CollapseParams& p, siz
   return cudaGetLastError();
 }
 
-template <int N, int CG> static cudaError_t out_launch_cg(const ZOutParams& p, size_t nrows, cudaStream_t s) {
+template <int N, int CG> static cudaError_t out_launch_cg(const ZOutParams& p_in, size_t nrows, cudaStream_t s) {
+  ZOutParams p = p_in;
+  fill_pretw<N / 2>(p.zs);
   constexpr int M = N / 2, TL = ZCfg<M>::TL;
   using ZS = ZShape<M, TL, CG>;
   const size_t smem = ZS::fft_elems(p.zs.ncomp) * sizeof(double2);

@@ -106,6 +106,8 @@ struct XPassParams {
   int lx_shift;         // log2(lx)
   int pmask;            // bit p set -> compute job p
   int ntiles_z;         // kz tiles per row that are processed (M/TK, +1 with the Nyquist tile)
+  int prefetch;         // > 0: pull the source tile of block (bid + prefetch) into L2 while this one computes
+  int nblocks;
   KFactor kf;
   Geom g;
   const double2* tw;    // N-th roots of unity
@@ -122,6 +124,14 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   const double ky = g.knorm * ny;
   const size_t xstride = (size_t)g.ly * g.P;
   const double2* src = p.src + (size_t)yl * g.P + kz0;
+  // With one 128 KB tile per SM the load, compute and store phases of a block do not overlap
+  // (tools/bwtest: the same access pattern without FFT runs at 4.0-6.7 TB/s).  Pulling the tile
+  // of the block that will run next on some SM into L2 now lets DRAM work during our FFT.
+  if (p.prefetch > 0 && ctx.bid() + p.prefetch < p.nblocks) {
+    const int nb = ctx.bid() + p.prefetch;
+    const double2* nsrc = p.src + (size_t)(nb / p.ntiles_z) * g.P + (size_t)(nb % p.ntiles_z) * TK;
+    for (int e = ctx.tid(); e < L; e += ctx.nthreads()) ctx.prefetch_l2(nsrc + (size_t)e * xstride);
+  }
   for (int pw = 0; pw < 3; pw++) {
     if (!((p.pmask >> pw) & 1)) continue;
     const PeerPtrs& dp = p.dst[pw];
@@ -173,6 +183,9 @@ struct YPassParams {
   YJob job[6];
   int njobs;
   int ntiles_z;
+  int prefetch;           // as in XPassParams
+  int nblocks;
+  int nsrc;               // distinct source fields (prefetched)
   Geom g;
   const double2* tw;
 };
@@ -183,6 +196,12 @@ PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
   const int xl = ctx.bid() / p.ntiles_z;
   const int kz0 = (ctx.bid() % p.ntiles_z) * TK;
   const size_t base = (size_t)xl * g.N * g.P + kz0;
+  if (p.prefetch > 0 && ctx.bid() + p.prefetch < p.nblocks) {
+    const int nb = ctx.bid() + p.prefetch;
+    const size_t nbase = (size_t)(nb / p.ntiles_z) * g.N * g.P + (size_t)(nb % p.ntiles_z) * TK;
+    for (int sidx = 0; sidx < p.nsrc; sidx++)
+      for (int e = ctx.tid(); e < L; e += ctx.nthreads()) ctx.prefetch_l2(p.src[sidx] + nbase + (size_t)e * g.P);
+  }
   for (int j = 0; j < p.njobs; j++) {
     const double2* src = p.src[p.job[j].src] + base;
     double2* dst = p.dst_klayout ? nullptr : p.dst[p.job[j].dst] + base;
@@ -245,7 +264,7 @@ __device__ __forceinline__ void barrier_body(const BarrierParams& p) {
 // involve those threads (`ctx.sync_line`: __syncwarp or a named bar.sync), so the components
 // and rows of a block proceed independently instead of meeting at block-wide barriers.
 // ---------------------------------------------------------------------------------------
-// stages 1.. of a line whose stage-0 registers `v` are already loaded
+// all stages of one line; `in0(e, s)` supplies the stage-0 inputs (s: see stage_load_s)
 template <int M, int DIR, class Ctx, class In0>
 PINB_HD void zline_fft_stages(Ctx& ctx, double2* ln, int jl, int line_id, const double2* __restrict__ tw, In0 in0,
                               bool in0_reads_smem) {
@@ -254,18 +273,18 @@ PINB_HD void zline_fft_stages(Ctx& ctx, double2* ln, int jl, int line_id, const 
   double2 v[RMAX];
   auto s_in = [&](int e) { return ln[zpad(e)]; };
   auto s_out = [&](int e, double2 val) { ln[zpad(e)] = val; };
-  stage_load<M, PL::R0, TPL, RMAX>(jl, v, in0);
+  stage_load_s<M, PL::R0, TPL, RMAX>(jl, v, in0);
   if (in0_reads_smem) ctx.sync_line(line_id, TPL);
-  stage_store<M, PL::R0, 1, DIR, TPL, RMAX>(jl, v, s_out, tw, 2);
+  stage_store<M, PL::R0, 1, DIR, TPL, RMAX, decltype(s_out), true>(jl, v, s_out, tw, 2);
   ctx.sync_line(line_id, TPL);
   stage_load<M, PL::R1, TPL, RMAX>(jl, v, s_in);
   ctx.sync_line(line_id, TPL);
-  stage_store<M, PL::R1, PL::R0, DIR, TPL, RMAX>(jl, v, s_out, tw, 2);
+  stage_store<M, PL::R1, PL::R0, DIR, TPL, RMAX, decltype(s_out), true>(jl, v, s_out, tw, 2);
   ctx.sync_line(line_id, TPL);
   if constexpr (PL::NST == 3) {
     stage_load<M, PL::R2, TPL, RMAX>(jl, v, s_in);
     ctx.sync_line(line_id, TPL);
-    stage_store<M, PL::R2, PL::R0 * PL::R1, DIR, TPL, RMAX>(jl, v, s_out, tw, 2);
+    stage_store<M, PL::R2, PL::R0 * PL::R1, DIR, TPL, RMAX, decltype(s_out), true>(jl, v, s_out, tw, 2);
     ctx.sync_line(line_id, TPL);
   }
 }
@@ -273,7 +292,7 @@ PINB_HD void zline_fft_stages(Ctx& ctx, double2* ln, int jl, int line_id, const 
 // in-place FFT of a line that already sits in shared memory
 template <int M, int DIR, class Ctx>
 PINB_HD void zline_fft_smem(Ctx& ctx, double2* ln, int jl, const double2* __restrict__ tw, int line_id = 0) {
-  auto s_in = [&](int e) { return ln[zpad(e)]; };
+  auto s_in = [&](int e, int) { return ln[zpad(e)]; };
   zline_fft_stages<M, DIR>(ctx, ln, jl, line_id, tw, s_in, true);
 }
 
@@ -283,6 +302,8 @@ struct ZSrc {
   int ncomp;
   int has_nyq;            // 0: the kz = N/2 plane is known to be zero (delta_k-derived fields)
   const double* dc_add;   // device scalar added to every component in real space (or nullptr)
+  double2 pretw[32];      // exp(2 pi i * TPL * s / N), s < RMAX (filled by the launcher): pre-twiddle
+                          // w^e = w^jl * pretw[s] for the element e = jl + s*TPL of a thread
 };
 
 // c2r of a tile of TL rows x ncomp components into shared memory: on return
@@ -316,7 +337,8 @@ PINB_HD void zpass_c2r_tile(Ctx& ctx, double2* smem, const ZSrc& zs, const Geom&
     const int c = c0 + cg;
     double2* ln = smem + ((size_t)c * TL + line) * PITCH;
     const int pw = zs.kzpow[c];
-    auto s_in0 = [&](int e) {
+    const double2 wj = ld_ro(tw + jl);
+    auto s_in0 = [&](int e, int s) {
       double2 xk = ln[zpad(e)];
       double2 xmk = ln[zpad(M - e)];
       if (pw) {
@@ -325,7 +347,7 @@ PINB_HD void zpass_c2r_tile(Ctx& ctx, double2* smem, const ZSrc& zs, const Geom&
       }
       if (e == 0) return make_double2(xk.x + xmk.x, xk.x - xmk.x);  // only Re X[0], Re X[M] (App. A.5)
       double2 zk, zmk;
-      c2r_pre_pair(xk, xmk, ld_ro(tw + e), zk, zmk);
+      c2r_pre_pair(xk, xmk, cmul(wj, zs.pretw[s]), zk, zmk);
       return zk;
     };
     ctx.sync_line(line_id, TPL);  // the copies of this line have landed
@@ -341,8 +363,9 @@ template <int M, int TL, int CG> struct ZShape {
   static constexpr size_t fft_elems(int ncomp) { return (size_t)ncomp * TL * PITCH; }
 };
 
-// block-wide sum of two doubles through shared scratch (2*NT doubles)
-template <int NT, class Ctx> PINB_HD void block_sum2(Ctx& ctx, double* scratch, double& a, double& b) {
+// block-wide sum of two doubles through shared scratch (2*NT doubles): portable tree version
+// (the device context uses warp shuffles when NT is a multiple of 32)
+template <int NT, class Ctx> PINB_HD void block_sum2_tree(Ctx& ctx, double* scratch, double& a, double& b) {
   const int tid = ctx.tid();
   scratch[tid] = a;
   scratch[NT + tid] = b;
@@ -384,8 +407,8 @@ PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double*
   constexpr int N = 2 * M, NT = ZS::NT, PITCH = ZS::PITCH;
   const int tid = ctx.tid();
   const size_t row0 = (size_t)ctx.bid() * TL;
-  for (int i = tid; i < p.spl_doubles; i += NT) spl_s[i] = ld_ro(p.spline + i);
-  zpass_c2r_tile<M, TL, CG>(ctx, smem, p.zs, p.g, row0, p.tw);  // ends with a barrier
+  for (int i = 2 * tid; i < p.spl_doubles; i += 2 * NT) ctx.async_copy16(spl_s + i, p.spline + i);  // even count
+  zpass_c2r_tile<M, TL, CG>(ctx, smem, p.zs, p.g, row0, p.tw);  // waits for the copies, ends with a barrier
   SplineView sp{spl_s, p.nspl};
   const double dc = p.zs.dc_add ? ld_ro(p.zs.dc_add) : 0.0;
   double sd = 0.0, sd2 = 0.0;
@@ -432,7 +455,7 @@ PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double*
       }
     }
   }
-  block_sum2<NT>(ctx, scratch, sd, sd2);
+  ctx.template block_sum2<NT>(scratch, sd, sd2);
   if (tid == 0) {
     ctx.atomic_add(p.sums + 0, sd);
     ctx.atomic_add(p.sums + 1, sd2);

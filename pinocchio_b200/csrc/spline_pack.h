@@ -20,7 +20,8 @@
 
 namespace pinb {
 
-inline size_t spline_table_doubles(int n) { return (size_t)PINB_SPLINE_HDR + 5 * (size_t)n + PINB_SPLINE_NLUT / 4; }
+// rounded up to an even count: the table is staged with 16-byte asynchronous copies
+inline size_t spline_table_doubles(int n) { return ((size_t)PINB_SPLINE_HDR + 5 * (size_t)n + PINB_SPLINE_NLUT / 4 + 1) & ~(size_t)1; }
 
 inline void pack_spline(const double* x, const double* y, int n, std::vector<double>& t) {
   t.assign(spline_table_doubles(n), 0.0);

@@ -35,6 +35,8 @@ struct HostCtx {
   void sync_line(int, int) const { pthread_barrier_wait(bar); }
   void async_copy16(void* dst, const void* src) const { std::memcpy(dst, src, 16); }
   void async_wait() const {}
+  void prefetch_l2(const void*) const {}
+  template <int NT> void block_sum2(double* scratch, double& a, double& b) const { block_sum2_tree<NT>(*this, scratch, a, b); }
   void atomic_add(double* p, double v) const {
     std::lock_guard<std::mutex> lk(g_atomic_mutex);
     *p += v;
@@ -204,7 +206,16 @@ extern "C" int emu_ypass(int N, int dir, int rank, int nranks, double** srcs, do
   return 1;
 }
 
-template <int N> static void collapse_run(const CollapseParams& p) {
+template <int M> static void fill_pretw(ZSrc& zs) {
+  constexpr int TPL = Plan<M, true>::TPL, RMAX = Plan<M, true>::RMAX;
+  for (int s = 0; s < RMAX; s++) {
+    const double a = 2.0 * PINB_PI * (double)TPL * s / (2.0 * M);
+    zs.pretw[s] = make_double2(cos(a), sin(a));
+  }
+}
+
+template <int N> static void collapse_run(CollapseParams p) {
+  fill_pretw<N / 2>(p.zs);
   constexpr int M = N / 2, TL = ZCfg<M>::TL, CG = 6;
   using ZS = ZShape<M, TL, CG>;
   std::vector<double2> smem(ZS::fft_elems(6));
@@ -242,7 +253,8 @@ extern "C" int emu_zpass_collapse(int N, int nranks, double** srcs, const int* k
   return 1;
 }
 
-template <int N> static void zout_run(const ZOutParams& p) {
+template <int N> static void zout_run(ZOutParams p) {
+  fill_pretw<N / 2>(p.zs);
   constexpr int M = N / 2, TL = ZCfg<M>::TL;
   using ZS = ZShape<M, TL, 1>;
   std::vector<double2> smem(ZS::fft_elems(6));
@@ -344,6 +356,20 @@ extern "C" int emu_collapse_cells(const double* h6, long long n, const double* s
     double h[6];
     for (int c = 0; c < 6; c++) h[c] = h6[c * n + i];
     F[i] = inverse_collapse_time(h, sp);
+  }
+  return 0;
+}
+
+// elementary functions of fastmath.cuh, exposed for direct comparison with libm
+extern "C" int emu_fastmath(int which, const double* x, long long n, double* y) {
+  for (long long i = 0; i < n; i++) {
+    switch (which) {
+      case 0: y[i] = fm_acos(x[i]); break;
+      case 1: y[i] = fm_log10(x[i]); break;
+      case 2: y[i] = fm_exp_neg(x[i]); break;
+      case 3: y[i] = fm_exp10(x[i]); break;
+      default: return 1;
+    }
   }
   return 0;
 }

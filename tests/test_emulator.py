@@ -159,3 +159,28 @@ def test_collapse_cells_branches(lib, cosmo):
     assert (np.abs(F[ok] - ref[ok]) <= 1e-6 * np.maximum(1.0, np.abs(ref[ok]))).all()   # the 1e-6 contract
     assert np.median(np.abs(F[ok] - ref[ok])) < 1e-14
     assert (ref == 0).sum() > 100 and (ref > 1).sum() > 100
+
+
+def test_fastmath(lib):
+    """fastmath.cuh (constant-bank elementary functions of the collapse epilogue) against libm."""
+    rng = np.random.default_rng(5)
+
+    def run(which, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        assert lib.emu_fastmath(which, ptr(x), ctypes.c_longlong(x.size), ptr(y)) == 0
+        return y
+
+    x = np.concatenate([rng.uniform(-1, 1, 200000), [1.0, -1.0, 0.0, 0.5, -0.5, 1 - 1e-16, -1 + 1e-16, 1e-300]])
+    assert np.abs(run(0, x) - np.arccos(x)).max() < 1e-15
+    with np.errstate(invalid="ignore"):
+        assert np.isnan(run(0, np.array([1.0000001, -1.5, np.nan]))).all()
+    x = np.concatenate([10.0 ** rng.uniform(-300, 300, 200000), rng.uniform(0.5, 2.0, 100000), [1.0, 2.0, 0.1, 1e-310]])
+    ref = np.log10(x)
+    assert (np.abs(run(1, x) - ref) <= 4e-16 * np.maximum(1.0, np.abs(ref))).all()
+    x = np.concatenate([-(10.0 ** rng.uniform(-8, 2.84, 200000)), [0.0, -1e-300, -699.9, -800.0, -1e10]])
+    ref = np.exp(x)
+    assert (np.abs(run(2, x) - ref) <= 5e-16 * ref + 1e-300).all()
+    x = np.concatenate([rng.uniform(-20, 20, 200000), [0.0, 1.0, -1.0, 0.30102999566, 299.9, -299.9]])
+    ref = 10.0 ** x
+    assert (np.abs(run(3, x) - ref) <= 3e-15 * ref).all()

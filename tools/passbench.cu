@@ -40,6 +40,11 @@ __global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, (768 / ZShape<M, TL, CG
   zpass_out_body<M, TL, CG>(ctx, smem, p);
 }
 
+template <int M> static void fill_pretw(ZSrc& zs) {
+  constexpr int TPL = Plan<M, true>::TPL, RMAX = Plan<M, true>::RMAX;
+  for (int s = 0; s < RMAX; s++) { const double a = 2.0 * M_PI * TPL * s / (2.0 * M); zs.pretw[s] = make_double2(cos(a), sin(a)); }
+}
+
 struct Timer {
   cudaEvent_t a, b;
   Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -65,23 +70,23 @@ static Geom geom(int N) {
   Geom g; g.N = N; g.M = N / 2; g.P = g.M + 8; g.lx = N; g.ly = N; g.x0 = 0; g.y0 = 0; g.knorm = 2 * M_PI / N; return g;
 }
 
-template <int N, int TK, int MINB> void bench_x(const Geom& g, double2* src, double2** A, const double2* tw, const double* gauss, int pmask, const char* tag) {
+template <int N, int TK, int MINB> void bench_x(const Geom& g, double2* src, double2** A, const double2* tw, const double* gauss, int pmask, const char* tag, int pf = 0) {
   constexpr int NT = Plan<N, false>::TPL * TK;
   const size_t smem = (size_t)N * TK * sizeof(double2);
   CKE(cudaFuncSetAttribute(xk<N, TK, +1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   XPassParams p{};
   p.src = src; p.dst[0].r[0] = A[0]; p.dst[1].r[0] = A[1]; p.dst[2].r[0] = A[2]; p.dst_klayout = 0; p.lx_shift = 10; p.pmask = pmask; p.ntiles_z = g.M / TK;
-  p.kf.gauss = gauss; p.kf.scalar = 1e-9; p.kf.green = 1; p.kf.times_i = 0; p.g = g; p.tw = tw;
+  p.kf.gauss = gauss; p.kf.scalar = 1e-9; p.kf.green = 1; p.kf.times_i = 0; p.g = g; p.tw = tw; p.prefetch = pf; p.nblocks = g.ly * p.ntiles_z;
   Timer t;
   float ms = t.run([&] { xk<N, TK, +1, MINB><<<g.ly * p.ntiles_z, NT, smem>>>(p); });
   int nout = __builtin_popcount(pmask);
   double gb = (1 + nout) * 16.0 * g.N * g.N * g.M / 1e9;
   cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, xk<N, TK, +1, MINB>);
   int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xk<N, TK, +1, MINB>, NT, smem);
-  printf("xpass %-18s TK=%d minb=%d nout=%d regs=%d blocks/SM=%d : %.2f ms  %.0f GB/s\n", tag, TK, MINB, nout, fa.numRegs, nb, ms, gb / ms * 1e3);
+  printf("xpass %-10s pf=%4d TK=%d minb=%d nout=%d regs=%d blocks/SM=%d : %.2f ms  %.0f GB/s\n", tag, pf, TK, MINB, nout, fa.numRegs, nb, ms, gb / ms * 1e3);
 }
 
-template <int N, int TK, int MINB> void bench_y(const Geom& g, double2** A, double2** B, const double2* tw, int njobs, const char* tag) {
+template <int N, int TK, int MINB> void bench_y(const Geom& g, double2** A, double2** B, const double2* tw, int njobs, const char* tag, int pf = 0) {
   constexpr int NT = Plan<N, false>::TPL * TK;
   const size_t smem = (size_t)N * TK * sizeof(double2);
   CKE(cudaFuncSetAttribute(yk<N, TK, +1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -90,13 +95,13 @@ template <int N, int TK, int MINB> void bench_y(const Geom& g, double2** A, doub
   for (int i = 0; i < 6; i++) p.dst[i] = B[i];
   static const YJob jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
   for (int i = 0; i < njobs; i++) p.job[i] = jobs[i];
-  p.njobs = njobs; p.dst_klayout = 0; p.ly_shift = 10; p.ntiles_z = g.M / TK; p.g = g; p.tw = tw;
+  p.njobs = njobs; p.dst_klayout = 0; p.ly_shift = 10; p.ntiles_z = g.M / TK; p.g = g; p.tw = tw; p.prefetch = pf; p.nblocks = g.lx * p.ntiles_z; p.nsrc = njobs == 6 ? 3 : 1; if (njobs == 1) p.job[0] = YJob{0, 0, 0};
   Timer t;
   float ms = t.run([&] { yk<N, TK, +1, MINB><<<g.lx * p.ntiles_z, NT, smem>>>(p); });
   double gb = (njobs == 6 ? 9 : 2 * njobs) * 16.0 * g.N * g.N * g.M / 1e9;
   cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, yk<N, TK, +1, MINB>);
   int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yk<N, TK, +1, MINB>, NT, smem);
-  printf("ypass %-18s TK=%d minb=%d njobs=%d regs=%d blocks/SM=%d : %.2f ms  %.0f GB/s\n", tag, TK, MINB, njobs, fa.numRegs, nb, ms, gb / ms * 1e3);
+  printf("ypass %-10s pf=%4d TK=%d minb=%d njobs=%d regs=%d blocks/SM=%d : %.2f ms  %.0f GB/s\n", tag, pf, TK, MINB, njobs, fa.numRegs, nb, ms, gb / ms * 1e3);
 }
 
 template <int N, int TL, int CG, int MINB, int CPT> void bench_zc(const Geom& g, double2** B, const double2* tw, const double* spline, int nspl, float* fmax, int* rmax, double* sums, const char* tag) {
@@ -108,7 +113,7 @@ template <int N, int TL, int CG, int MINB, int CPT> void bench_zc(const Geom& g,
   static const int kz[6] = {0, 0, 2, 0, 1, 1};
   for (int k = 0; k < 6; k++) { p.zs.src[k] = B[k]; p.zs.kzpow[k] = kz[k]; p.hdst[k] = nullptr; }
   p.zs.ncomp = 6; p.zs.has_nyq = 0; p.zs.dc_add = nullptr; p.g = g; p.tw = tw; p.spline = spline; p.nspl = nspl; p.spl_doubles = (int)spline_table_doubles(nspl);
-  p.ismooth = 1; p.Fmax = fmax; p.Rmax = rmax; p.sums = sums;
+  p.ismooth = 1; p.Fmax = fmax; p.Rmax = rmax; p.sums = sums; fill_pretw<M>(p.zs);
   Timer t;
   float ms = t.run([&] { zck<M, TL, CG, MINB, CPT><<<(unsigned)((size_t)g.lx * g.N / TL), ZS::NT, smem>>>(p); });
   double gb = (6 * 16.0 * g.N * g.N * g.M + 12.0 * g.N * g.N * g.N) / 1e9;
@@ -125,7 +130,7 @@ template <int N, int TL, int CG> void bench_zo(const Geom& g, double2** B, const
   CKE(cudaFuncSetAttribute(zok<M, TL, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZS::fft_elems(6) * sizeof(double2))));
   ZOutParams p{};
   for (int k = 0; k < ncomp; k++) { p.zs.src[k] = B[k]; p.zs.kzpow[k] = k == 2; p.fdst[k] = fo[k]; p.hsrc[k] = (const double*)B[3 + k]; p.weight[k] = 2.0; }
-  p.zs.ncomp = ncomp; p.zs.has_nyq = 1; p.zs.dc_add = nullptr; p.g = g; p.tw = tw; p.mode = mode; p.acc = acc;
+  p.zs.ncomp = ncomp; p.zs.has_nyq = 1; p.zs.dc_add = nullptr; p.g = g; p.tw = tw; p.mode = mode; p.acc = acc; fill_pretw<M>(p.zs);
   Timer t;
   float ms = t.run([&] { zok<M, TL, CG><<<(unsigned)((size_t)g.lx * g.N / TL), ZS::NT, smem>>>(p); });
   int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, zok<M, TL, CG>, ZS::NT, smem);
@@ -166,19 +171,14 @@ int main(int argc, char** argv) {
   CKE(cudaMalloc(&fmax, (size_t)N * N * N * 4)); CKE(cudaMalloc(&rmax, (size_t)N * N * N * 4)); CKE(cudaMalloc(&sums, 16));
   CKE(cudaMemset(fmax, 0, (size_t)N * N * N * 4));
 
-  bench_x<N, 8, 1>(g, src, A, tw, gauss, 7, "base");
-  bench_y<N, 8, 1>(g, A, B, tw, 6, "base");
+  bench_x<N, 8, 1>(g, src, A, tw, gauss, 7, "base", 0);
+  bench_y<N, 8, 1>(g, A, B, tw, 6, "base", 0);
   float* fo[3]; for (auto& f : fo) CKE(cudaMalloc(&f, (size_t)N * N * N * 4));
   bench_zc<N, 1, 6, 3, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb3");
   bench_zc<N, 1, 6, 2, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb2");
   bench_zc<N, 1, 6, 3, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb3");
   bench_zc<N, 1, 6, 2, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb2");
-  bench_zc<N, 1, 3, 3, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cg3");
-  bench_zc<N, 1, 3, 3, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cg3");
-  bench_zo<N, 1, 1>(g, B, tw, fo, 1, nullptr, "float");
   bench_zo<N, 1, 3>(g, B, tw, fo, 1, nullptr, "float");
-  bench_zo<N, 2, 3>(g, B, tw, fo, 1, nullptr, "float");
-  bench_zo<N, 1, 1>(g, B, tw, fo, 2, (double*)A[0], "contract");
   bench_zo<N, 1, 3>(g, B, tw, fo, 2, (double*)A[0], "contract");
   return 0;
 }
