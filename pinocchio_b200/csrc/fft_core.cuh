@@ -118,6 +118,46 @@ template <int DIR> struct Radix<16, DIR> {
   }
 };
 
+// Radix 32 = 4 x 8: n = 8*n1 + n2, k = k1 + 4*k2.  Used by the strided passes of the 512- and
+// 1024-point lines: two stages instead of three means two trips through shared memory per
+// element instead of four (r02 timeline: the 16x8x8 plan was shared-memory-bandwidth bound).
+template <int DIR> struct Radix<32, DIR> {
+  static PINB_HD void run(double2* v) {
+    constexpr double C[22] = {1.0, 0.98078528040323043, 0.92387953251128674, 0.83146961230254524, 0.70710678118654752,
+                              0.55557023301960218, 0.38268343236508977, 0.19509032201612825, 0.0, -0.19509032201612825,
+                              -0.38268343236508977, -0.55557023301960218, -0.70710678118654752, -0.83146961230254524,
+                              -0.92387953251128674, -0.98078528040323043, -1.0, -0.98078528040323043,
+                              -0.92387953251128674, -0.83146961230254524, -0.70710678118654752, -0.55557023301960218};
+    constexpr double S[22] = {0.0, 0.19509032201612825, 0.38268343236508977, 0.55557023301960218, 0.70710678118654752,
+                              0.83146961230254524, 0.92387953251128674, 0.98078528040323043, 1.0, 0.98078528040323043,
+                              0.92387953251128674, 0.83146961230254524, 0.70710678118654752, 0.55557023301960218,
+                              0.38268343236508977, 0.19509032201612825, 0.0, -0.19509032201612825,
+                              -0.38268343236508977, -0.55557023301960218, -0.70710678118654752, -0.83146961230254524};
+    // step 1: for each n2, 4-point DFT over n1 of v[8*n1 + n2] -> b[n2][k1] left in v[8*k1 + n2]
+#pragma unroll
+    for (int n2 = 0; n2 < 8; n2++) Radix<4, DIR>::run4(v[n2], v[8 + n2], v[16 + n2], v[24 + n2]);
+    // step 2: twiddle by w32^(n2*k1)
+#pragma unroll
+    for (int k1 = 1; k1 < 4; k1++)
+#pragma unroll
+      for (int n2 = 1; n2 < 8; n2++) {
+        const int m = n2 * k1;
+        v[8 * k1 + n2] = cmul(v[8 * k1 + n2], make_double2(C[m], DIR > 0 ? S[m] : -S[m]));
+      }
+    // step 3: for each k1, 8-point DFT over n2 -> X[k1 + 4*k2] left in v[8*k1 + k2]
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) Radix<8, DIR>::run(v + 8 * k1);
+    // step 4: natural order
+    double2 t[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) t[i] = v[i];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++)
+#pragma unroll
+      for (int k2 = 0; k2 < 8; k2++) v[k1 + 4 * k2] = t[8 * k1 + k2];
+  }
+};
+
 // ---------------------------------------------------------------------------------------
 // Plans: radices per line length.  ZFIRST8 plans (used by the contiguous z pass) start with
 // radix 8 so that the padded shared-memory layout e + (e >> 3) is bank-conflict free.
@@ -134,8 +174,8 @@ PINB_PLAN(32, false, 2, 8, 4, 1)
 PINB_PLAN(64, false, 2, 8, 8, 1)
 PINB_PLAN(128, false, 2, 16, 8, 1)
 PINB_PLAN(256, false, 2, 16, 16, 1)
-PINB_PLAN(512, false, 3, 8, 8, 8)
-PINB_PLAN(1024, false, 3, 16, 8, 8)
+PINB_PLAN(512, false, 2, 32, 16, 1)
+PINB_PLAN(1024, false, 2, 32, 32, 1)
 PINB_PLAN(2048, false, 3, 16, 16, 8)
 PINB_PLAN(4096, false, 3, 16, 16, 16)
 PINB_PLAN(16, true, 2, 8, 2, 1)
@@ -147,6 +187,17 @@ PINB_PLAN(512, true, 3, 8, 8, 8)
 PINB_PLAN(1024, true, 3, 8, 8, 16)
 PINB_PLAN(2048, true, 3, 8, 16, 16)
 #undef PINB_PLAN
+
+// The x pass keeps three-stage plans with <= 16 values per thread: its loader (the fused k-space
+// Green/window factor) is heavy, and unrolled 32x it overflowed the instruction cache
+// (r02: "no_instructions" was the top stall, 43 ms instead of 15 ms).
+template <int L> struct XPlan : Plan<L, false> {};
+template <> struct XPlan<512> {
+  static constexpr int NST = 3, R0 = 8, R1 = 8, R2 = 8, RMAX = 8, TPL = 64;
+};
+template <> struct XPlan<1024> {
+  static constexpr int NST = 3, R0 = 16, R1 = 8, R2 = 8, RMAX = 16, TPL = 64;
+};
 
 // Twiddle table: tw[k] = exp(+2*pi*i*k/NROOT), k in [0, NROOT).  A line of length L uses
 // every (NROOT/L)-th entry; DIR=-1 conjugates.

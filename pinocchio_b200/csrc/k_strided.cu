@@ -5,7 +5,7 @@
 namespace pinb {
 
 template <int L, int TK, int DIR, bool MULTI>
-__global__ void __launch_bounds__(Plan<L, false>::TPL* TK) xpass_kernel(const __grid_constant__ XPassParams p) {
+__global__ void __launch_bounds__(XPlan<L>::TPL* TK) xpass_kernel(const __grid_constant__ XPassParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
   xpass_body<L, TK, DIR, MULTI>(ctx, smem, p);
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(Plan<L, false>::TPL* TK) ypass_kernel(const __
 
 template <int L, int DIR, bool MULTI> static cudaError_t xpass_launch_m(const XPassParams& p, int nblocks_y, cudaStream_t s) {
   constexpr int TK = StridedCfg<L>::TK;
-  constexpr int NT = Plan<L, false>::TPL * TK;
+  constexpr int NT = XPlan<L>::TPL * TK;
   const size_t smem = (size_t)L * TK * sizeof(double2);
   cudaError_t e = allow_smem(xpass_kernel<L, TK, DIR, MULTI>, smem);
   if (e != cudaSuccess) return e;

@@ -36,6 +36,7 @@ struct HostCtx {
   void async_copy16(void* dst, const void* src) const { std::memcpy(dst, src, 16); }
   void async_wait() const {}
   void prefetch_l2(const void*) const {}
+  void mark(int) const {}
   template <int NT> void block_sum2(double* scratch, double& a, double& b) const { block_sum2_tree<NT>(*this, scratch, a, b); }
   void atomic_add(double* p, double v) const {
     std::lock_guard<std::mutex> lk(g_atomic_mutex);
@@ -139,7 +140,7 @@ extern "C" int emu_zline_fft(int M, int dir, const double* in, double* out, cons
 // ---- whole kernels on pitched arrays (K layout [N][ly][P], R layout [lx][N][P]) ---------------
 template <int N, int DIR> static void xpass_run(const XPassParams& p) {
   constexpr int TK = StridedCfg<N>::TK;
-  constexpr int NT = Plan<N, false>::TPL * TK;
+  constexpr int NT = XPlan<N>::TPL * TK;
   std::vector<double2> smem((size_t)N * TK);
   run_blocks((long long)p.g.ly * p.ntiles_z, NT, [&](HostCtx& ctx) { xpass_body<N, TK, DIR, true>(ctx, smem.data(), p); });
 }

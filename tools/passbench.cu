@@ -13,10 +13,22 @@ using namespace pinb;
 #define CKE(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 template <int L, int TK, int DIR, int MINB>
-__global__ void __launch_bounds__(Plan<L, false>::TPL* TK, MINB) xk(const __grid_constant__ XPassParams p) {
+__global__ void __launch_bounds__(XPlan<L>::TPL* TK, MINB) xk(const __grid_constant__ XPassParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
   xpass_body<L, TK, DIR, false>(ctx, smem, p);
+}
+__device__ long long* g_dbg;
+struct TimedCtx : DevCtx {
+  __device__ __forceinline__ void mark(int k) const {
+    if (threadIdx.x == 0 && blockIdx.x % 997 == 3) g_dbg[(blockIdx.x / 997) * 32 + k] = clock64();
+  }
+};
+template <int L, int TK>
+__global__ void __launch_bounds__(Plan<L, false>::TPL* TK, 1) yk_timed(const __grid_constant__ YPassParams p) {
+  extern __shared__ double2 smem[];
+  TimedCtx ctx;
+  ypass_body<L, TK, +1>(ctx, smem, p);
 }
 template <int L, int TK, int DIR, int MINB>
 __global__ void __launch_bounds__(Plan<L, false>::TPL* TK, MINB) yk(const __grid_constant__ YPassParams p) {
@@ -71,7 +83,7 @@ static Geom geom(int N) {
 }
 
 template <int N, int TK, int MINB> void bench_x(const Geom& g, double2* src, double2** A, const double2* tw, const double* gauss, int pmask, const char* tag, int pf = 0) {
-  constexpr int NT = Plan<N, false>::TPL * TK;
+  constexpr int NT = XPlan<N>::TPL * TK;
   const size_t smem = (size_t)N * TK * sizeof(double2);
   CKE(cudaFuncSetAttribute(xk<N, TK, +1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   XPassParams p{};
@@ -101,6 +113,19 @@ template <int N, int TK, int MINB> void bench_y(const Geom& g, double2** A, doub
   double gb = (njobs == 6 ? 9 : 2 * njobs) * 16.0 * g.N * g.N * g.M / 1e9;
   cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, yk<N, TK, +1, MINB>);
   int nb; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, yk<N, TK, +1, MINB>, NT, smem);
+  if (njobs == 6 && TK == 8) {
+    long long* dbg; CKE(cudaMalloc(&dbg, 80 * 32 * 8)); CKE(cudaMemset(dbg, 0, 80 * 32 * 8));
+    CKE(cudaMemcpyToSymbol(g_dbg, &dbg, sizeof(dbg)));
+    CKE(cudaFuncSetAttribute(yk_timed<N, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    yk_timed<N, 8><<<g.lx * p.ntiles_z, NT, smem>>>(p);
+    CKE(cudaDeviceSynchronize());
+    std::vector<long long> h(80 * 32);
+    CKE(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+    double acc[24] = {0}; int nb = 0;
+    for (int b = 5; b < 60; b++) { if (!h[b * 32]) continue; nb++; for (int k = 1; k < 24; k++) acc[k] += (double)(h[b * 32 + k] - h[b * 32 + k - 1]); }
+    printf("y-pass timeline (cycles, mean of %d blocks): per job [wait copies | stage0..last-load | issue+last stage+stores]\n", nb);
+    for (int j = 0; j < 6; j++) printf("  job %d: gap %.0f | wait %.0f | stages %.0f | tail %.0f\n", j, j ? acc[4 * j] / nb : 0.0, acc[4 * j + 1] / nb, acc[4 * j + 2] / nb, acc[4 * j + 3] / nb);
+  }
   printf("ypass %-10s pf=%4d TK=%d minb=%d njobs=%d regs=%d blocks/SM=%d : %.2f ms  %.0f GB/s\n", tag, pf, TK, MINB, njobs, fa.numRegs, nb, ms, gb / ms * 1e3);
 }
 
@@ -172,13 +197,8 @@ int main(int argc, char** argv) {
   CKE(cudaMemset(fmax, 0, (size_t)N * N * N * 4));
 
   bench_x<N, 8, 1>(g, src, A, tw, gauss, 7, "base", 0);
+  bench_x<N, 8, 1>(g, src, A, tw, gauss, 1, "base", 0);
   bench_y<N, 8, 1>(g, A, B, tw, 6, "base", 0);
-  float* fo[3]; for (auto& f : fo) CKE(cudaMalloc(&f, (size_t)N * N * N * 4));
-  bench_zc<N, 1, 6, 3, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb3");
-  bench_zc<N, 1, 6, 2, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb2");
-  bench_zc<N, 1, 6, 3, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb3");
-  bench_zc<N, 1, 6, 2, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "minb2");
-  bench_zo<N, 1, 3>(g, B, tw, fo, 1, nullptr, "float");
-  bench_zo<N, 1, 3>(g, B, tw, fo, 2, (double*)A[0], "contract");
+  bench_y<N, 8, 1>(g, A, B, tw, 1, "base", 0);
   return 0;
 }
