@@ -8,7 +8,7 @@ namespace pinb {
 // bound and gains from occupancy (passbench: 1 block/SM 108 ms, 2 blocks 72 ms, 3 blocks 57 ms at
 // 1024^3), so the register budget is capped to fit three 384-thread blocks per SM.
 template <int M, int TL, int CG>
-__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, (M >= 256 ? 3 : 1)) zpass_collapse_kernel(const __grid_constant__ CollapseParams p) {
+__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, ((M >= 256 && M <= 512) ? 3 : 1)) zpass_collapse_kernel(const __grid_constant__ CollapseParams p) {
   extern __shared__ double2 smem[];
   using ZS = ZShape<M, TL, CG>;
   double* spl = reinterpret_cast<double*>(smem + ZS::fft_elems(6));
@@ -57,10 +57,17 @@ template <int N> static cudaError_t collapse_launch(const CollapseParams& p_in, 
   return cudaGetLastError();
 }
 
+// rows per block of the generic z epilogues: keep >= 256 threads per block when few components
+// are transformed (a 64-thread block per row ran the 1-component contraction at 1.5 TB/s)
+template <int M, int CG> struct ZOutCfg {
+  static constexpr int T0 = ZCfg<M>::TL;
+  static constexpr int TL = (M >= 256 && CG <= 2) ? 4 / CG : T0;
+};
+
 template <int N, int CG> static cudaError_t out_launch_cg(const ZOutParams& p_in, size_t nrows, cudaStream_t s) {
   ZOutParams p = p_in;
   fill_pretw<N / 2>(p.zs);
-  constexpr int M = N / 2, TL = ZCfg<M>::TL;
+  constexpr int M = N / 2, TL = ZOutCfg<M, CG>::TL;
   using ZS = ZShape<M, TL, CG>;
   const size_t smem = ZS::fft_elems(p.zs.ncomp) * sizeof(double2);
   cudaError_t e = allow_smem(zpass_out_kernel<M, TL, CG>, ZS::fft_elems(6) * sizeof(double2));
