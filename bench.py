@@ -171,6 +171,13 @@ def run_b200(args):
     cells = float(N) ** 3              # one box, slab-decomposed over the ranks
     value = cells / (ms_per_step * 1e-3) / 1e6
 
+    # ---- size-independent sanity of the timed result (not timed; Fmax_PDF all-reduces over the ranks)
+    pdf = pin.Fmax_PDF()
+    tvar = np.asarray(pin.TrueVariance, dtype=np.float64)
+    checks = {"pdf_total_is_ncells": bool(int(pdf.sum()) == N ** 3),
+              "variance_ladder_monotone": bool(np.isfinite(tvar).all() and (np.diff(tvar) > 0).all()),
+              "collapsed_fraction": round(float(pdf[10:].sum()) / float(N) ** 3, 6)}
+
     # ---- per-kernel device times measured live (CUDA events inside the engine, same stream)
     K = args.steps
     per_launch_ms = {"xpass_kernel": (tm1.hess_x - tm0.hess_x) / (K * S) * 1e3,
@@ -259,7 +266,7 @@ def run_b200(args):
                           "seed": 486604, "parallelism": f"slab{world}" if world > 1 else "single GPU",
                           "l2_policy": "inputs larger than L2 (each field 8.7 GB at 1024^3)"},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-               "cpu_baseline": cpu_baseline, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
+               "cpu_baseline": cpu_baseline, "checks": checks, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
         print(json.dumps(out))
     pin.close()
     if world > 1:

@@ -386,11 +386,17 @@ def ill_conditioned_mask(h, inverse_growing_mode, eps=1e-13, ntrial=2, tol=1e-7,
     rng = np.random.default_rng(seed)
     F0 = inverse_collapse_time(h, inverse_growing_mode)
     mask = np.zeros(F0.shape, dtype=bool)
+    # FFT round-off is absolute (~1e-16 of the field's largest value), not relative to each
+    # entry, and most of the jumps are branch switches of ell_classic: a one-sided random
+    # trial crosses a nearby switch only half of the time, so every trial is applied with both
+    # signs (antithetic pair) and carries an absolute as well as a relative part.
+    scale = max(float(np.abs(a).max()) for a in h)
     for _ in range(ntrial):
-        hp = [a * (1.0 + eps * rng.standard_normal(a.shape)) for a in h]
-        Fp = inverse_collapse_time(hp, inverse_growing_mode)
-        with np.errstate(invalid="ignore"):
-            mask |= ~(np.abs(Fp - F0) <= tol * np.maximum(1.0, np.abs(F0)))
+        noise = [eps * (a * rng.standard_normal(a.shape) + scale * rng.standard_normal(a.shape)) for a in h]
+        for sgn in (1.0, -1.0):
+            Fp = inverse_collapse_time([a + sgn * d for a, d in zip(h, noise)], inverse_growing_mode)
+            with np.errstate(invalid="ignore"):
+                mask |= ~(np.abs(Fp - F0) <= tol * np.maximum(1.0, np.abs(F0)))
     return mask
 
 

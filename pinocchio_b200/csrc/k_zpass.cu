@@ -70,7 +70,7 @@ template <int N, int CG> static cudaError_t out_launch_cg(const ZOutParams& p_in
   constexpr int M = N / 2, TL = ZOutCfg<M, CG>::TL;
   using ZS = ZShape<M, TL, CG>;
   const size_t smem = ZS::fft_elems(p.zs.ncomp) * sizeof(double2);
-  cudaError_t e = allow_smem(zpass_out_kernel<M, TL, CG>, ZS::fft_elems(6) * sizeof(double2));
+  cudaError_t e = allow_smem(zpass_out_kernel<M, TL, CG>, smem);  // ncomp == CG in this dispatch
   if (e != cudaSuccess) return e;
   zpass_out_kernel<M, TL, CG><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);
   return cudaGetLastError();

@@ -226,7 +226,7 @@ def test_error_paths(cosmo):
     p.close()
 
 
-@pytest.mark.parametrize("N", [512])
+@pytest.mark.parametrize("N", [512, 1024])
 def test_large_grid_properties(N, cosmo):
     """Size-independent properties at a grid the oracle cannot afford: histogram total,
     monotone variance ladder, zero-mean displacements, Parseval for the R=0 variance."""
