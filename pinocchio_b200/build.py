@@ -29,47 +29,60 @@ NVCC_FLAGS = [
 SOURCES = ["engine.cu", "k_strided.cu", "k_zpass.cu", "k_misc.cu"]
 
 
-def _digest() -> str:
+# Test-only variant: the long-line (decimation-in-frequency) strided passes that the product
+# uses for N = 2048 (8 GPUs) are compiled in for every N > 32, so that single-GPU parity tests
+# at 64^3 / 128^3 exercise them on real hardware (PINB200_LIB selects the library).
+VARIANTS = {"": [], "split": ["-DPINB_SPLIT_ABOVE=32"]}
+
+
+def _digest(extra=()) -> str:
     h = hashlib.sha256()
     for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))
                     + [HERE.parent / "include" / "pinb200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join([*NVCC_FLAGS, *extra]).encode())
     return h.hexdigest()
 
 
-def _compile(src: str) -> tuple[str, str]:
-    obj = OBJ / (src + ".o")
-    cmd = [NVCC, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+def _compile(src: str, objdir: Path = OBJ, extra=()) -> tuple[str, str]:
+    obj = objdir / (src + ".o")
+    cmd = [NVCC, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
     return src, r.stderr
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile (if sources changed) and return the path of libpinb200.so."""
-    OBJ.mkdir(exist_ok=True)
-    stamp = OBJ / "digest.txt"
-    dig = _digest()
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
-        return LIB
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> Path:
+    """Compile (if sources changed) and return the path of libpinb200.so (or of a test variant)."""
+    extra = VARIANTS[variant]
+    objdir = OBJ / variant if variant else OBJ
+    lib = HERE / f"libpinb200_{variant}.so" if variant else LIB
+    objdir.mkdir(parents=True, exist_ok=True)
+    stamp = objdir / "digest.txt"
+    dig = _digest(extra)
+    if not force and lib.exists() and stamp.exists() and stamp.read_text() == dig:
+        return lib
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        logs = list(ex.map(_compile, SOURCES))
-    (OBJ / "ptxas.log").write_text("\n".join(f"==== {s}\n{l}" for s, l in logs))
+        logs = list(ex.map(lambda src: _compile(src, objdir, extra), SOURCES))
+    (objdir / "ptxas.log").write_text("\n".join(f"==== {s}\n{l}" for s, l in logs))
     if verbose:
         for s, l in logs:
             print(f"==== {s}\n{l}")
-    cmd = [NVCC, "-shared", "-o", str(LIB), *[str(OBJ / (s + ".o")) for s in SOURCES],
+    cmd = [NVCC, "-shared", "-o", str(lib), *[str(objdir / (s + ".o")) for s in SOURCES],
            "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     stamp.write_text(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(p)
+    if "--variants" in sys.argv:
+        for v in VARIANTS:
+            if v:
+                print(build(force="--force" in sys.argv, variant=v))

@@ -22,6 +22,8 @@ struct DevCtx {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
   }
   __device__ __forceinline__ void mark(int) const {}  // timeline hook (tools/passbench only)
+  // compiler scheduling fence: memory operations are not moved across it (bounds loads in flight)
+  __device__ __forceinline__ void sched_fence() const { asm volatile("" ::: "memory"); }
   __device__ __forceinline__ void prefetch_l2(const void* g) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
   __device__ __forceinline__ void async_wait() const { asm volatile("cp.async.wait_all;" ::: "memory"); }
   __device__ __forceinline__ void atomic_add(double* p, double v) const { atomicAdd(p, v); }

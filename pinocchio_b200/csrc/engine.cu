@@ -486,10 +486,7 @@ extern "C" int pinb200_download_kdensity(pinb200_ctx* ctx, double* kd) {
 }
 
 // ---- pass helpers --------------------------------------------------------------------------
-static int ntiles(const pinb200_ctx* ctx, bool with_nyq) {
-  const int tk = xpass_tk(ctx->g.N);
-  return ctx->g.M / tk + (with_nyq ? 1 : 0);
-}
+static int ntiles(const pinb200_ctx* ctx, int tk, bool with_nyq) { return ctx->g.M / tk + (with_nyq ? 1 : 0); }
 
 // inverse x pass of the local K-layout field `src`; the output for power p of kx is scattered
 // into the arena buffer dst[p] (R layout) of the rank owning each x.  Barriers on both sides:
@@ -503,7 +500,7 @@ static int run_xpass_inv(pinb200_ctx* ctx, const double2* src, double2* const ds
   p.dst_klayout = 0;
   p.lx_shift = ctx->lx_shift;
   p.pmask = pmask;
-  p.ntiles_z = ntiles(ctx, with_nyq);
+  p.ntiles_z = ntiles(ctx, xpass_tk(ctx->g.N, +1), with_nyq);
   p.kf.gauss = gauss ? ctx->gauss : nullptr;
   p.kf.scalar = scalar;
   p.kf.green = green;
@@ -525,7 +522,7 @@ static int run_ypass_inv(pinb200_ctx* ctx, const double2* const src[3], double2*
   p.njobs = njobs;
   p.dst_klayout = 0;
   p.ly_shift = ctx->ly_shift;
-  p.ntiles_z = ntiles(ctx, with_nyq);
+  p.ntiles_z = ntiles(ctx, ypass_tk(ctx->g.N), with_nyq);
   p.g = ctx->g;
   p.tw = ctx->tw;
   LAUNCH(launch_ypass(ctx->g.N, +1, p, ctx->g.lx, ctx->stream));
@@ -550,7 +547,7 @@ static int run_r2c(pinb200_ctx* ctx, double2* src, double2* kdst) {
   y.ly_shift = ctx->ly_shift;
   y.job[0] = YJob{0, 0, 0};
   y.njobs = 1;
-  y.ntiles_z = ntiles(ctx, true);
+  y.ntiles_z = ntiles(ctx, ypass_tk(g.N), true);
   y.g = g;
   y.tw = ctx->tw;
   TRY(peer_barrier(ctx));
@@ -562,7 +559,7 @@ static int run_r2c(pinb200_ctx* ctx, double2* src, double2* kdst) {
   p.dst_klayout = 1;
   p.lx_shift = ctx->lx_shift;
   p.pmask = 1;
-  p.ntiles_z = ntiles(ctx, true);
+  p.ntiles_z = ntiles(ctx, xpass_tk(g.N, -1), true);
   p.kf.gauss = nullptr;
   p.kf.scalar = 1.0;
   p.kf.green = 0;
@@ -870,17 +867,18 @@ extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* 
   CK(cudaSetDevice(ctx->d.device));
   const Geom& g = ctx->g;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
-  // K-layout input in A0, x pass into A1 (R layout), y and z passes in place
+  // K-layout input in A0, x pass into A1 (R layout), y pass into A2 (the long-line y pass is
+  // not usable in place, see YCfg), z pass in place
   ctx->hessian_valid = false;
   TRY(upload_cplx(ctx, cplx_in, ctx->A[0]));
   double2* xdst[3] = {ctx->A[1], nullptr, nullptr};
   TRY(run_xpass_inv(ctx, ctx->A[0], xdst, 1, false, 0, 0, norm, true));
   const double2* ysrc[3] = {ctx->A[1], nullptr, nullptr};
-  double2* ydst[6] = {ctx->A[1], nullptr, nullptr, nullptr, nullptr, nullptr};
+  double2* ydst[6] = {ctx->A[2], nullptr, nullptr, nullptr, nullptr, nullptr};
   YJob job{0, 0, 0};
   TRY(run_ypass_inv(ctx, ysrc, ydst, &job, 1, true));
   ZOutParams z{};
-  z.zs.src[0] = ctx->A[1];
+  z.zs.src[0] = ctx->A[2];
   z.zs.kzpow[0] = 0;
   z.zs.ncomp = 1;
   z.zs.has_nyq = 1;
@@ -888,9 +886,9 @@ extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* 
   z.g = g;
   z.tw = ctx->tw;
   z.mode = 0;
-  z.rdst[0] = ctx->A[1];
+  z.rdst[0] = ctx->A[2];
   LAUNCH(launch_zpass_out(g.N, z, (size_t)g.lx * g.N, ctx->stream));
-  TRY(download_real(ctx, ctx->A[1], real_out));
+  TRY(download_real(ctx, ctx->A[2], real_out));
   return 0;
 }
 

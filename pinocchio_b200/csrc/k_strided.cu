@@ -4,27 +4,34 @@
 
 namespace pinb {
 
-template <int L, int TK, int DIR, bool MULTI>
-__global__ void __launch_bounds__(XPlan<L>::TPL* TK) xpass_kernel(const __grid_constant__ XPassParams p) {
+template <int L, int DIR, bool MULTI, int CHUNK = 0>
+__global__ void __launch_bounds__(XCfg<L, DIR>::NT) xpass_kernel(const __grid_constant__ XPassParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
-  xpass_body<L, TK, DIR, MULTI>(ctx, smem, p);
+  xpass_body<L, DIR, MULTI, CHUNK>(ctx, smem, p);
 }
 
-template <int L, int TK, int DIR>
-__global__ void __launch_bounds__(Plan<L, false>::TPL* TK) ypass_kernel(const __grid_constant__ YPassParams p) {
+template <int L, int DIR>
+__global__ void __launch_bounds__(YCfg<L>::NT) ypass_kernel(const __grid_constant__ YPassParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
-  ypass_body<L, TK, DIR>(ctx, smem, p);
+  ypass_body<L, DIR>(ctx, smem, p);
 }
 
 template <int L, int DIR, bool MULTI> static cudaError_t xpass_launch_m(const XPassParams& p, int nblocks_y, cudaStream_t s) {
-  constexpr int TK = StridedCfg<L>::TK;
-  constexpr int NT = XPlan<L>::TPL * TK;
-  const size_t smem = (size_t)L * TK * sizeof(double2);
-  cudaError_t e = allow_smem(xpass_kernel<L, TK, DIR, MULTI>, smem);
+  using C = XCfg<L, DIR>;
+  const size_t smem = (size_t)C::LT * C::TK * sizeof(double2);
+  if constexpr (C::SPLIT) {
+    if (p.variant == 1) {
+      cudaError_t e = allow_smem(xpass_kernel<L, DIR, MULTI, 4>, smem);
+      if (e != cudaSuccess) return e;
+      xpass_kernel<L, DIR, MULTI, 4><<<(unsigned)(nblocks_y * p.ntiles_z), C::NT, smem, s>>>(p);
+      return cudaGetLastError();
+    }
+  }
+  cudaError_t e = allow_smem(xpass_kernel<L, DIR, MULTI>, smem);
   if (e != cudaSuccess) return e;
-  xpass_kernel<L, TK, DIR, MULTI><<<(unsigned)(nblocks_y * p.ntiles_z), NT, smem, s>>>(p);
+  xpass_kernel<L, DIR, MULTI><<<(unsigned)(nblocks_y * p.ntiles_z), C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 template <int L, int DIR> static cudaError_t xpass_launch(const XPassParams& p, int nblocks_y, cudaStream_t s) {
@@ -34,25 +41,34 @@ template <int L, int DIR> static cudaError_t xpass_launch(const XPassParams& p, 
 }
 
 template <int L, int DIR> static cudaError_t ypass_launch(const YPassParams& p, int nblocks_x, cudaStream_t s) {
-  constexpr int TK = StridedCfg<L>::TK;
-  constexpr int NT = Plan<L, false>::TPL * TK;
-  const size_t smem = (size_t)L * TK * sizeof(double2);
-  cudaError_t e = allow_smem(ypass_kernel<L, TK, DIR>, smem);
+  using C = YCfg<L>;
+  const size_t smem = (size_t)C::LT * C::TK * sizeof(double2);
+  cudaError_t e = allow_smem(ypass_kernel<L, DIR>, smem);
   if (e != cudaSuccess) return e;
-  ypass_kernel<L, TK, DIR><<<(unsigned)(nblocks_x * p.ntiles_z), NT, smem, s>>>(p);
+  ypass_kernel<L, DIR><<<(unsigned)(nblocks_x * p.ntiles_z), C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 
-int xpass_tk(int N) {
+// kz-tile width of the x pass in direction dir and of the y pass (they differ for N > 1024)
+int xpass_tk(int N, int dir) {
   switch (N) {
-#define X(L) case L: return StridedCfg<L>::TK;
+#define X(L) case L: return dir > 0 ? XCfg<L, +1>::TK : XCfg<L, -1>::TK;
     PINB_FOR_EACH_GRID(X)
 #undef X
   }
   return 0;
 }
 
-bool grid_supported(int N) { return xpass_tk(N) != 0; }
+int ypass_tk(int N) {
+  switch (N) {
+#define X(L) case L: return YCfg<L>::TK;
+    PINB_FOR_EACH_GRID(X)
+#undef X
+  }
+  return 0;
+}
+
+bool grid_supported(int N) { return ypass_tk(N) != 0; }
 
 cudaError_t launch_xpass(int N, int dir, const XPassParams& p, int nblocks_y, cudaStream_t s) {
   switch (N) {

@@ -40,6 +40,29 @@ struct KFactor {
 // kz-tile width of the strided passes: 8 complex (128 B contiguous per line element) while the
 // tile fits 128 KB of shared memory.
 template <int L> struct StridedCfg { static constexpr int TK = (L <= 1024) ? 8 : 4; };
+// Lines longer than PINB_SPLIT_ABOVE do not fit a TK = 8 tile.  With TK = 4 every line element
+// is a 64-byte piece: the 2048^3 run on 8 GPUs scattered its x pass over NVLink at 280 GB/s (r01).
+// Such passes run one decimation-in-frequency step while loading instead:
+//   X[2k]   = FFT_{L/2}[ a[n] + a[n+L/2] ],   X[2k+1] = FFT_{L/2}[ (a[n] - a[n+L/2]) w_L^n ]
+// i.e. two half-length jobs per output field on a TK = 8 tile (128-byte pieces on both sides);
+// the second reading of the source tile comes from L2.  Not usable in place.
+#ifndef PINB_SPLIT_ABOVE
+#define PINB_SPLIT_ABOVE 1024
+#endif
+template <int L, int DIR> struct XCfg {
+  static constexpr bool SPLIT = (L > PINB_SPLIT_ABOVE) && DIR > 0;  // the forward x pass is in place (and local)
+  static constexpr int LT = SPLIT ? L / 2 : L;
+  static constexpr int TK = LT <= 1024 ? 8 : 4;
+  using PL = XPlan<LT>;
+  static constexpr int NT = PL::TPL * TK;
+};
+template <int L> struct YCfg {
+  static constexpr bool SPLIT = (L > PINB_SPLIT_ABOVE);
+  static constexpr int LT = SPLIT ? L / 2 : L;
+  static constexpr int TK = LT <= 1024 ? 8 : 4;
+  using PL = Plan<LT, false>;
+  static constexpr int NT = PL::TPL * TK;
+};
 // rows per block of the z passes: >= 16 threads per component group on the tiny test grids,
 // one row per block (three resident blocks per SM at N = 1024) for the production sizes.
 template <int M> struct ZCfg { static constexpr int TL = M <= 32 ? 4 : (M <= 128 ? 2 : 1); };
@@ -94,7 +117,9 @@ PINB_HD void strided_tile_fft(Ctx& ctx, double2* s, const double2* __restrict__ 
 // As soon as the last stage of job j has pulled its operands into registers the shared-memory
 // tile is free again and the copies of job j+1 are issued: they overlap the last butterflies and
 // the global stores of job j (with one 128 KB tile per SM nothing else can hide that latency).
-template <int L, int TK, int DIR, class PL, class Ctx, class SrcF, class XformF, class StoreF>
+// CHUNK > 0: a scheduling fence after every CHUNK stage-0 elements (for xform functors that
+// load from global memory: bounds the registers the compiler spends on loads in flight).
+template <int L, int TK, int DIR, class PL, int TWS, int CHUNK = 0, class Ctx, class SrcF, class XformF, class StoreF>
 PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__ tw, int njobs, SrcF src, XformF xform,
                                StoreF store) {
   constexpr int TPL = PL::TPL, RMAX = PL::RMAX;
@@ -119,27 +144,37 @@ PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__
     ctx.mark(4 * job + 0);
     ctx.async_wait();  // my own elements have landed
     ctx.mark(4 * job + 1);
-    stage_load<L, PL::R0, TPL, RMAX>(jl, v, raw_in);
+    if constexpr (CHUNK == 0) {
+      stage_load<L, PL::R0, TPL, RMAX>(jl, v, raw_in);
+    } else {
+#pragma unroll
+      for (int m = 0; m < NB0; m++)
+#pragma unroll
+        for (int r = 0; r < PL::R0; r++) {
+          v[m * PL::R0 + r] = raw_in(jl + m * TPL + r * T0);
+          if ((m * PL::R0 + r) % CHUNK == CHUNK - 1) ctx.sched_fence();
+        }
+    }
     ctx.sync();  // every thread holds its raw elements: the tile may be overwritten
-    stage_store<L, PL::R0, 1, DIR, TPL, RMAX>(jl, v, s_out, tw, 1);
+    stage_store<L, PL::R0, 1, DIR, TPL, RMAX>(jl, v, s_out, tw, TWS);
     ctx.sync();
     if constexpr (PL::NST == 3) {
       stage_load<L, PL::R1, TPL, RMAX>(jl, v, s_in);
       ctx.sync();
-      stage_store<L, PL::R1, PL::R0, DIR, TPL, RMAX>(jl, v, s_out, tw, 1);
+      stage_store<L, PL::R1, PL::R0, DIR, TPL, RMAX>(jl, v, s_out, tw, TWS);
       ctx.sync();
       stage_load<L, PL::R2, TPL, RMAX>(jl, v, s_in);
       ctx.sync();  // tile free
       ctx.mark(4 * job + 2);
       if (job + 1 < njobs) issue(job + 1);
-      stage_store<L, PL::R2, PL::R0 * PL::R1, DIR, TPL, RMAX>(jl, v, g_out, tw, 1);
+      stage_store<L, PL::R2, PL::R0 * PL::R1, DIR, TPL, RMAX>(jl, v, g_out, tw, TWS);
       ctx.mark(4 * job + 3);
     } else {
       stage_load<L, PL::R1, TPL, RMAX>(jl, v, s_in);
       ctx.sync();  // tile free
       ctx.mark(4 * job + 2);
       if (job + 1 < njobs) issue(job + 1);
-      stage_store<L, PL::R1, PL::R0, DIR, TPL, RMAX, decltype(g_out), (PL::R1 >= 16)>(jl, v, g_out, tw, 1);
+      stage_store<L, PL::R1, PL::R0, DIR, TPL, RMAX, decltype(g_out), (PL::R1 >= 16)>(jl, v, g_out, tw, TWS);
       ctx.mark(4 * job + 3);
     }
   }
@@ -166,6 +201,7 @@ struct XPassParams {
   int ntiles_z;         // kz tiles per row that are processed (M/TK, +1 with the Nyquist tile)
   int prefetch;         // > 0: pull the source tile of block (bid + prefetch) into L2 while this one computes
   int nblocks;
+  int variant;          // experiments (tools/slabbench): 1 = chunked stage-0 loads of the split path
   KFactor kf;
   Geom g;
   const double2* tw;    // N-th roots of unity
@@ -173,8 +209,11 @@ struct XPassParams {
 
 // MULTI = false: one rank; the owner look-up and the per-rank pointer table are compiled out
 // (they cost registers: the 1024-point kernel spilled 128 bytes with them).
-template <int L, int TK, int DIR, bool MULTI, class Ctx>
+template <int L, int DIR, bool MULTI, int CHUNK = 0, class Ctx>
 PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
+  using C = XCfg<L, DIR>;
+  constexpr int TK = C::TK, LT = C::LT;
+  constexpr bool SPLIT = C::SPLIT;
   const Geom& g = p.g;
   const int yl = ctx.bid() / p.ntiles_z;
   const int kz0 = (ctx.bid() % p.ntiles_z) * TK;
@@ -190,9 +229,9 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
     const double2* nsrc = p.src + (size_t)(nb / p.ntiles_z) * g.P + (size_t)(nb % p.ntiles_z) * TK;
     for (int e = ctx.tid(); e < L; e += ctx.nthreads()) ctx.prefetch_l2(nsrc + (size_t)e * xstride);
   }
-  int jobs[3], njobs = 0;
+  int jobs[3], npw = 0;
   for (int pw = 0; pw < 3; pw++)
-    if ((p.pmask >> pw) & 1) jobs[njobs++] = pw;
+    if ((p.pmask >> pw) & 1) jobs[npw++] = pw;
   const size_t roff = (size_t)(g.y0 + yl) * g.P + kz0;  // offset of (y, kz0) inside an R-layout x plane
   auto srcf = [&](int, int e, int tk) { return src + (size_t)e * xstride + tk; };
   // per-thread invariants of the mode factor: everything that does not depend on x
@@ -201,8 +240,7 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   const double kyz2 = ky * ky + kz_t * kz_t;
   double fyz = p.kf.scalar;
   if (p.kf.gauss) fyz *= ld_ro(p.kf.gauss + (ny < 0 ? -ny : ny)) * ld_ro(p.kf.gauss + kz0 + tk0);
-  auto xform = [&](int job, int e, int, double2 c) {
-    const int pw = jobs[job];
+  auto mode = [&](int pw, int e, double2 c) {
     const int nx = fold(e, g.N, g.M);
     const double kx = g.knorm * nx;
     double f = fyz;
@@ -216,8 +254,21 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
     if (p.kf.times_i) c = make_double2(-c.y, c.x);
     return c;
   };
-  auto storef = [&](int job, int e, int tk, double2 val) {
-    const PeerPtrs& dp = p.dst[jobs[job]];
+  // SPLIT: job = 2*(index of the power) + h; h selects the even or the odd outputs
+  auto xform = [&](int job, int e, int tk, double2 c) {
+    if constexpr (!SPLIT) {
+      return mode(jobs[job], e, c);
+    } else {
+      const int pw = jobs[job >> 1];
+      const double2 a = mode(pw, e, c);
+      const double2 b = mode(pw, e + LT, ld_ro(src + (size_t)(e + LT) * xstride + tk));
+      if (!(job & 1)) return cadd(a, b);
+      return cmul(csub(a, b), twiddle<DIR>(p.tw, e));
+    }
+  };
+  auto storef = [&](int job, int k, int tk, double2 val) {
+    const int e = SPLIT ? 2 * k + (job & 1) : k;
+    const PeerPtrs& dp = p.dst[jobs[SPLIT ? (job >> 1) : job]];
     if (p.dst_klayout) {
       dp.r[0][(size_t)e * xstride + (size_t)yl * g.P + kz0 + tk] = val;
     } else if (!MULTI) {
@@ -227,7 +278,7 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
       dp.r[owner][(size_t)xl * ((size_t)g.N * g.P) + roff + tk] = val;
     }
   };
-  strided_tile_jobs<L, TK, DIR, XPlan<L>>(ctx, smem, p.tw, njobs, srcf, xform, storef);
+  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * npw : npw, srcf, xform, storef);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -250,8 +301,11 @@ struct YPassParams {
   const double2* tw;
 };
 
-template <int L, int TK, int DIR, class Ctx>
+template <int L, int DIR, class Ctx>
 PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
+  using C = YCfg<L>;
+  constexpr int TK = C::TK, LT = C::LT;
+  constexpr bool SPLIT = C::SPLIT;
   const Geom& g = p.g;
   const int xl = ctx.bid() / p.ntiles_z;
   const int kz0 = (ctx.bid() % p.ntiles_z) * TK;
@@ -262,13 +316,26 @@ PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
     for (int sidx = 0; sidx < p.nsrc; sidx++)
       for (int e = ctx.tid(); e < L; e += ctx.nthreads()) ctx.prefetch_l2(p.src[sidx] + nbase + (size_t)e * g.P);
   }
-  auto srcf = [&](int j, int e, int tk) { return p.src[p.job[j].src] + base + (size_t)e * g.P + tk; };
-  auto xform = [&](int j, int e, int, double2 c) {
-    const int q = p.job[j].q;
+  // SPLIT: job = 2*j + h, see XCfg
+  auto srcf = [&](int job, int e, int tk) { return p.src[p.job[SPLIT ? (job >> 1) : job].src] + base + (size_t)e * g.P + tk; };
+  auto mode = [&](int q, int e, double2 c) {
     if (q) c = cscale(c, ipow(g.knorm * fold(e, g.N, g.M), q));
     return c;
   };
-  auto storef = [&](int j, int e, int tk, double2 val) {
+  auto xform = [&](int job, int e, int tk, double2 c) {
+    if constexpr (!SPLIT) {
+      return mode(p.job[job].q, e, c);
+    } else {
+      const YJob& yj = p.job[job >> 1];
+      const double2 a = mode(yj.q, e, c);
+      const double2 b = mode(yj.q, e + LT, ld_ro(p.src[yj.src] + base + (size_t)(e + LT) * g.P + tk));
+      if (!(job & 1)) return cadd(a, b);
+      return cmul(csub(a, b), twiddle<DIR>(p.tw, e));
+    }
+  };
+  auto storef = [&](int job, int k, int tk, double2 val) {
+    const int e = SPLIT ? 2 * k + (job & 1) : k;
+    const int j = SPLIT ? (job >> 1) : job;
     if (p.dst_klayout) {
       const int owner = e >> p.ly_shift, yl = e & (g.ly - 1);
       p.kdst.r[owner][((size_t)(g.x0 + xl) * g.ly + yl) * g.P + kz0 + tk] = val;
@@ -276,7 +343,7 @@ PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
       p.dst[p.job[j].dst][base + (size_t)e * g.P + tk] = val;
     }
   };
-  strided_tile_jobs<L, TK, DIR, Plan<L, false>>(ctx, smem, p.tw, p.njobs, srcf, xform, storef);
+  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT>(ctx, smem, p.tw, SPLIT ? 2 * p.njobs : p.njobs, srcf, xform, storef);
 }
 
 // ---------------------------------------------------------------------------------------

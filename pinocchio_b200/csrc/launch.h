@@ -12,7 +12,8 @@ cudaError_t launch_ypass(int N, int dir, const YPassParams& p, int nblocks_x, cu
 cudaError_t launch_zpass_collapse(int N, const CollapseParams& p, size_t nrows, cudaStream_t s);
 cudaError_t launch_zpass_out(int N, const ZOutParams& p, size_t nrows, cudaStream_t s);
 cudaError_t launch_zpass_r2c(int N, const ZR2CParams& p, size_t nrows, cudaStream_t s);
-int xpass_tk(int N);  // kz-tile width used by the strided passes for this grid
+int xpass_tk(int N, int dir);  // kz-tile width of the x pass (dir +1 inverse, -1 forward) ...
+int ypass_tk(int N);           // ... and of the y pass for this grid
 
 cudaError_t launch_sources(const SourcesParams& p, cudaStream_t s);
 cudaError_t launch_genic(const GenicParams& p, cudaStream_t s);

@@ -10,6 +10,7 @@ if the library is missing, and every call fails if no B200 is visible.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from pathlib import Path
 
@@ -64,10 +65,12 @@ def load_library() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m pinocchio_b200.build` "
+    # PINB200_LIB: a build of the same sources with other compile-time options (tests only)
+    path = Path(os.environ["PINB200_LIB"]) if os.environ.get("PINB200_LIB") else LIB_PATH
+    if not path.exists():
+        raise RuntimeError(f"{path} is missing: run `python -m pinocchio_b200.build` "
                            "(there is no CPU fallback for the collapse-time path)")
-    lib = ctypes.CDLL(str(LIB_PATH))
+    lib = ctypes.CDLL(str(path))
     lib.pinb200_last_error.restype = ctypes.c_char_p
     lib.pinb200_last_error.argtypes = [ctypes.c_void_p]
     lib.pinb200_create.argtypes = [ctypes.POINTER(Desc), ctypes.POINTER(ctypes.c_void_p)]

@@ -18,8 +18,8 @@ HESS_KZ = np.array([0, 0, 2, 0, 1, 1], dtype=np.int32)
 
 
 class EmuCluster:
-    def __init__(self, N: int, nranks: int):
-        self.lib = load_emulator()
+    def __init__(self, N: int, nranks: int, split: bool = False):
+        self.lib = load_emulator(split)   # split: long-line (N = 2048) code path on the small grids
         self.N, self.P = N, nranks
         self.lx = N // nranks
         self.Pc = pitch(N)
@@ -154,11 +154,11 @@ class EmuCluster:
         return [np.concatenate([out[r][a] for r in range(self.P)], axis=0) for a in range(3)]
 
     def c2r_plain(self, kvec):
-        """plain c2r of K-layout kvec[rank] -> global real field (x dest A[0], in place y/z)."""
+        """plain c2r of K-layout kvec[rank] -> global real field (x dest A[0], y dest A[1], z in place)."""
         self.xpass_inv(kvec, {0: self.A[0]}, 1, 1, None, self.norm, 0, 0)
-        self.ypass_inv([self.A[0]], [self.A[0]], [(0, 0, 0)], 1)
+        self.ypass_inv([self.A[0]], [self.A[1]], [(0, 0, 0)], 1)
         kz = np.zeros(6, dtype=np.int32)
         for r in range(self.P):
-            assert self.lib.emu_zpass_out(self.N, self.P, 1, ptr_array([self.A[0][r]], 6), ptr(kz, PI32), 1, None, 0,
-                                          ptr_array([self.A[0][r]], 6), None, None, None, None, ptr(self.tw)) == 0
-        return self.gather_real(self.A[0])
+            assert self.lib.emu_zpass_out(self.N, self.P, 1, ptr_array([self.A[1][r]], 6), ptr(kz, PI32), 1, None, 0,
+                                          ptr_array([self.A[1][r]], 6), None, None, None, None, ptr(self.tw)) == 0
+        return self.gather_real(self.A[1])

@@ -18,18 +18,25 @@ PI32 = ctypes.POINTER(ctypes.c_int)
 PU32 = ctypes.POINTER(ctypes.c_uint)
 
 
-def build_emulator() -> Path:
-    deps = [SRC] + list((ROOT / "pinocchio_b200" / "csrc").glob("*.cuh"))
-    if LIB.exists() and all(LIB.stat().st_mtime > d.stat().st_mtime for d in deps):
-        return LIB
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas",
-           "-o", str(LIB), str(SRC)]
-    subprocess.run(cmd, check=True)
-    return LIB
+LIB_SPLIT = HERE / "host" / "libpinb_emu_split.so"
 
 
-def load_emulator():
-    lib = ctypes.CDLL(str(build_emulator()))
+def build_emulator(split: bool = False) -> Path:
+    """split=True lowers PINB_SPLIT_ABOVE to 16, so that the 32^3 and 64^3 emulator grids take the
+    decimation-in-frequency path that the product only uses for N = 2048."""
+    lib = LIB_SPLIT if split else LIB
+    deps = [SRC] + list((ROOT / "pinocchio_b200" / "csrc").glob("*.cuh")) + list((ROOT / "pinocchio_b200" / "csrc").glob("*.h"))
+    if lib.exists() and all(lib.stat().st_mtime > d.stat().st_mtime for d in deps):
+        return lib
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas"]
+    if split:
+        cmd.append("-DPINB_SPLIT_ABOVE=16")
+    subprocess.run(cmd + ["-o", str(lib), str(SRC)], check=True)
+    return lib
+
+
+def load_emulator(split: bool = False):
+    lib = ctypes.CDLL(str(build_emulator(split)))
     return lib
 
 

@@ -37,6 +37,7 @@ struct HostCtx {
   void async_wait() const {}
   void prefetch_l2(const void*) const {}
   void mark(int) const {}
+  void sched_fence() const {}
   template <int NT> void block_sum2(double* scratch, double& a, double& b) const { block_sum2_tree<NT>(*this, scratch, a, b); }
   void atomic_add(double* p, double v) const {
     std::lock_guard<std::mutex> lk(g_atomic_mutex);
@@ -138,11 +139,11 @@ extern "C" int emu_zline_fft(int M, int dir, const double* in, double* out, cons
 }
 
 // ---- whole kernels on pitched arrays (K layout [N][ly][P], R layout [lx][N][P]) ---------------
-template <int N, int DIR> static void xpass_run(const XPassParams& p) {
-  constexpr int TK = StridedCfg<N>::TK;
-  constexpr int NT = XPlan<N>::TPL * TK;
-  std::vector<double2> smem((size_t)N * TK);
-  run_blocks((long long)p.g.ly * p.ntiles_z, NT, [&](HostCtx& ctx) { xpass_body<N, TK, DIR, true>(ctx, smem.data(), p); });
+template <int N, int DIR> static void xpass_run(XPassParams& p, int with_nyq) {
+  using C = XCfg<N, DIR>;
+  p.ntiles_z = (N / 2) / C::TK + (with_nyq ? 1 : 0);
+  std::vector<double2> smem((size_t)C::LT * C::TK);
+  run_blocks((long long)p.g.ly * p.ntiles_z, C::NT, [&](HostCtx& ctx) { xpass_body<N, DIR, true>(ctx, smem.data(), p); });
 }
 
 // dsts: 3*nranks pointers, dsts[p*nranks + r] = destination field for power p on rank r
@@ -165,8 +166,7 @@ extern "C" int emu_xpass(int N, int dir, int rank, int nranks, const double* src
   switch (N) {
 #define X(LL)                                                         \
   case LL:                                                            \
-    p.ntiles_z = (LL / 2) / StridedCfg<LL>::TK + (with_nyq ? 1 : 0);  \
-    if (dir > 0) xpass_run<LL, +1>(p); else xpass_run<LL, -1>(p);     \
+    if (dir > 0) xpass_run<LL, +1>(p, with_nyq); else xpass_run<LL, -1>(p, with_nyq); \
     return 0;
     EMU_GRIDS(X)
 #undef X
@@ -174,11 +174,11 @@ extern "C" int emu_xpass(int N, int dir, int rank, int nranks, const double* src
   return 1;
 }
 
-template <int N, int DIR> static void ypass_run(const YPassParams& p) {
-  constexpr int TK = StridedCfg<N>::TK;
-  constexpr int NT = Plan<N, false>::TPL * TK;
-  std::vector<double2> smem((size_t)N * TK);
-  run_blocks((long long)p.g.lx * p.ntiles_z, NT, [&](HostCtx& ctx) { ypass_body<N, TK, DIR>(ctx, smem.data(), p); });
+template <int N, int DIR> static void ypass_run(YPassParams& p, int with_nyq) {
+  using C = YCfg<N>;
+  p.ntiles_z = (N / 2) / C::TK + (with_nyq ? 1 : 0);
+  std::vector<double2> smem((size_t)C::LT * C::TK);
+  run_blocks((long long)p.g.lx * p.ntiles_z, C::NT, [&](HostCtx& ctx) { ypass_body<N, DIR>(ctx, smem.data(), p); });
 }
 
 // srcs[3], dsts[6]: pointers (may be null); kdsts[nranks] (forward scatter); jobs: njobs x (src, q, dst)
@@ -198,8 +198,7 @@ extern "C" int emu_ypass(int N, int dir, int rank, int nranks, double** srcs, do
   switch (N) {
 #define X(LL)                                                         \
   case LL:                                                            \
-    p.ntiles_z = (LL / 2) / StridedCfg<LL>::TK + (with_nyq ? 1 : 0);  \
-    if (dir > 0) ypass_run<LL, +1>(p); else ypass_run<LL, -1>(p);     \
+    if (dir > 0) ypass_run<LL, +1>(p, with_nyq); else ypass_run<LL, -1>(p, with_nyq); \
     return 0;
     EMU_GRIDS(X)
 #undef X

@@ -57,10 +57,12 @@ def test_contiguous_line_fft(lib, M):
         assert rel(out, ref) < 2e-15
 
 
-@pytest.mark.parametrize("N,P", [(32, 1), (64, 1), (32, 2), (32, 4)])
-def test_fft3d_forward_and_nonhermitian_c2r(N, P):
-    """r2c and c2r through the three passes, on 1, 2 and 4 emulated ranks."""
-    cl = EmuCluster(N, P)
+@pytest.mark.parametrize("N,P,split", [(32, 1, False), (64, 1, False), (32, 2, False), (32, 4, False),
+                                       (32, 1, True), (64, 2, True), (32, 4, True)])
+def test_fft3d_forward_and_nonhermitian_c2r(N, P, split):
+    """r2c and c2r through the three passes, on 1, 2 and 4 emulated ranks; split = the
+    decimation-in-frequency long-line path (XCfg/YCfg in kernels.cuh)."""
+    cl = EmuCluster(N, P, split)
     rng = np.random.default_rng(7)
     r = rng.standard_normal((N, N, N))
     for k in range(P):
@@ -73,15 +75,15 @@ def test_fft3d_forward_and_nonhermitian_c2r(N, P):
     assert rel(cl.c2r_plain(cl.KV[1]), po.reverse_transform(c)) < 5e-15
 
 
-@pytest.mark.parametrize("P", [1, 2, 4])
-def test_genic_hessian_collapse_lpt(cosmo, P):
+@pytest.mark.parametrize("P,split", [(1, False), (2, False), (4, False), (2, True)])
+def test_genic_hessian_collapse_lpt(cosmo, P, split):
     """The engine's whole schedule at 32^3 on P emulated ranks: GenIC -> 3 radii -> Fmax/Rmax ->
     sources -> r2c -> contraction -> r2c -> displacements, each stage against the oracle."""
     N = 32
     box = 64.0 / 0.7
     cell = box / N
     seed = 486604
-    cl = EmuCluster(N, P)
+    cl = EmuCluster(N, P, split)
     # ---- GenIC
     cl.genic(po.seed_table(N, seed), pk_lattice_table(cosmo, N, box), box)
     kd = cl.gather_k(cl.kdens)

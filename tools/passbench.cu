@@ -16,7 +16,7 @@ template <int L, int TK, int DIR, int MINB>
 __global__ void __launch_bounds__(XPlan<L>::TPL* TK, MINB) xk(const __grid_constant__ XPassParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
-  xpass_body<L, TK, DIR, false>(ctx, smem, p);
+  xpass_body<L, DIR, false>(ctx, smem, p);  // TK must equal XCfg<L, DIR>::TK
 }
 __device__ long long* g_dbg;
 struct TimedCtx : DevCtx {
@@ -28,13 +28,13 @@ template <int L, int TK>
 __global__ void __launch_bounds__(Plan<L, false>::TPL* TK, 1) yk_timed(const __grid_constant__ YPassParams p) {
   extern __shared__ double2 smem[];
   TimedCtx ctx;
-  ypass_body<L, TK, +1>(ctx, smem, p);
+  ypass_body<L, +1>(ctx, smem, p);
 }
 template <int L, int TK, int DIR, int MINB>
 __global__ void __launch_bounds__(Plan<L, false>::TPL* TK, MINB) yk(const __grid_constant__ YPassParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
-  ypass_body<L, TK, DIR>(ctx, smem, p);
+  ypass_body<L, DIR>(ctx, smem, p);
 }
 template <int M, int TL, int CG, int MINB, int CPT>
 __global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, MINB) zck(const __grid_constant__ CollapseParams p) {
