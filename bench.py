@@ -273,13 +273,36 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def cpu_reference_sample(grid: int, steps: int):
-    """The oracle port (NumPy, one host thread for the collapse math, pocketfft FFTs) timed on a
-    bounded sample of the same workload: the full S-radius sweep + 3LPT on a `grid`^3 box."""
+def cpu_reference_sample(grid: int, steps: int, warmup: int = 0):
+    """CPU baseline on a bounded sample of the same workload (full S-radius sweep + 3LPT on a
+    `grid`^3 box), on all host cores.
+
+    kind "reference": oracle/_ref, i.e. the reference's own src/{fmax,fmax-pfft,LPT,collapse_times}.c
+    compiled verbatim (gcc -O3 -fopenmp) over one-task stand-ins for MPI/PFFT/GSL -- the FFT
+    underneath is the in-repo Stockham of oracle/ref_fft.c, not FFTW.  Run in a fresh process
+    (oracle/reference_runner.py) with OMP_NUM_THREADS = host cores.
+    kind "port": the NumPy oracle, when oracle/_ref was never built."""
+    N = grid
+    cores = os.cpu_count() or 1
+    runner = ROOT / "oracle" / "reference_runner.py"
+    if (ROOT / "oracle" / "_ref" / "libpinocchio_ref.so").exists():
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="false")
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        r = subprocess.run([sys.executable, str(runner), "--grid", str(N), "--steps", str(steps), "--warmup", str(warmup),
+                            "--threads", str(cores)], capture_output=True, text=True, env=env, timeout=3000)
+        if r.returncode == 0:
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            t = j["seconds_per_step"]
+            return {"value": round(N ** 3 / t / 1e6, 4), "unit": "Mcells/s", "cores": cores, "kind": "reference",
+                    "sample": f"{N}^3 box, same 9-radius sweep + 3LPT, the reference's own C sources (oracle/_ref: gcc -O3 "
+                              f"-fopenmp, OpenMP on {cores} threads, one task; MPI/PFFT/GSL replaced by in-repo stand-ins, "
+                              f"FFT = oracle/ref_fft.c not FFTW), {steps} step(s), {t:.2f} s/step",
+                    "ms_per_step": round(t * 1e3, 1), "reference_timers_s": j["timers_last_step"]}
+        sys.stderr.write(f"oracle/_ref run failed, falling back to the NumPy port:\n{r.stderr[-2000:]}\n")
     from oracle import pinocchio_oracle as po
     from pinocchio_b200.cosmology import Cosmology
     cosmo = Cosmology(pk_norm_override=2.03146e7)
-    N = grid
     kd = po.genic(N, N / 0.7, 486604, cosmo.PowerSpectrum)
     g = (cosmo.GrowingMode(0.0), cosmo.GrowingMode_2LPT(0.0), cosmo.GrowingMode_3LPT_1(0.0), cosmo.GrowingMode_3LPT_2(0.0))
     ts = []
@@ -300,10 +323,7 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     N = args.cpu_grid
-    # warmup
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_sample(min(N, 64), 1)
-    cb = cpu_reference_sample(N, max(1, min(args.steps, 3)))
+    cb = cpu_reference_sample(N, max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
     S = len(HMF_RADII)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Mcells/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
@@ -323,7 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=0, help="override the grid side (default 1024)")
-    ap.add_argument("--cpu-grid", type=int, default=128, help="grid of the bounded CPU sample")
+    ap.add_argument("--cpu-grid", type=int, default=256, help="grid of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

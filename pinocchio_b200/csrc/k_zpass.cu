@@ -7,14 +7,27 @@ namespace pinb {
 // The collapse epilogue is a long serial FP64 dependency chain per cell: the kernel is latency
 // bound and gains from occupancy (passbench: 1 block/SM 108 ms, 2 blocks 72 ms, 3 blocks 57 ms at
 // 1024^3), so the register budget is capped to fit three 384-thread blocks per SM.
-template <int M, int TL, int CG>
-__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, ((M >= 256 && M <= 512) ? 3 : 1)) zpass_collapse_kernel(const __grid_constant__ CollapseParams p) {
+// M = 1024 (N = 2048): the six padded rows take 108 KB; with the spline table (10.5 KB) next to
+// them only one block fits an SM (r01: 80 ms against 50 ms for the same cell count at M = 512).
+// There the table stays in global memory (L1/L2 resident) and two blocks fit.
+template <int M> struct CollapseCfg {
+  static constexpr bool SPLINE_GLOBAL = (M >= 1024);
+  static constexpr int MINB = (M >= 256 && M <= 512) ? 3 : (M == 1024 ? 2 : 1);
+};
+template <int NT> constexpr size_t sum_scratch_bytes() { return (NT % 32 == 0 ? 64 : 2 * NT) * sizeof(double); }
+
+int g_tune_zc = 0;  // tools/slabbench: 1 = one block per SM, full register budget (M = 1024 only)
+
+template <int M, int TL, int CG, int MINB = CollapseCfg<M>::MINB>
+__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, MINB) zpass_collapse_kernel(const __grid_constant__ CollapseParams p) {
   extern __shared__ double2 smem[];
   using ZS = ZShape<M, TL, CG>;
-  double* spl = reinterpret_cast<double*>(smem + ZS::fft_elems(6));
-  double* scratch = spl + p.spl_doubles;
+  constexpr bool SG = CollapseCfg<M>::SPLINE_GLOBAL;
+  double* after = reinterpret_cast<double*>(smem + ZS::fft_elems(6));
+  double* spl = SG ? nullptr : after;
+  double* scratch = SG ? after : after + p.spl_doubles;
   DevCtx ctx;
-  zpass_collapse_body<M, TL, CG>(ctx, smem, spl, scratch, p);
+  zpass_collapse_body<M, TL, CG>(ctx, smem, spl, scratch, p, SG);
 }
 
 // all components of a row are transformed concurrently (CG = ncomp): a 64-thread block per row
@@ -50,7 +63,16 @@ template <int N> static cudaError_t collapse_launch(const CollapseParams& p_in, 
   fill_pretw<N / 2>(p.zs);
   constexpr int M = N / 2, TL = ZCfg<M>::TL, CG = 6;
   using ZS = ZShape<M, TL, CG>;
-  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (size_t)p.spl_doubles * sizeof(double) + 2 * ZS::NT * sizeof(double);
+  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (CollapseCfg<M>::SPLINE_GLOBAL ? 0 : (size_t)p.spl_doubles * sizeof(double)) +
+                      sum_scratch_bytes<ZS::NT>();
+  if constexpr (M == 1024) {
+    if (g_tune_zc == 1) {
+      cudaError_t e1 = allow_smem(zpass_collapse_kernel<M, TL, CG, 1>, smem);
+      if (e1 != cudaSuccess) return e1;
+      zpass_collapse_kernel<M, TL, CG, 1><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);
+      return cudaGetLastError();
+    }
+  }
   cudaError_t e = allow_smem(zpass_collapse_kernel<M, TL, CG>, smem);
   if (e != cudaSuccess) return e;
   zpass_collapse_kernel<M, TL, CG><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);

@@ -525,14 +525,17 @@ struct CollapseParams {
 };
 
 template <int M, int TL, int CG, class Ctx, int CPT = 1>
-PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double* scratch, const CollapseParams& p) {
+PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double* scratch, const CollapseParams& p,
+                                 const bool spline_global = false) {
   using ZS = ZShape<M, TL, CG>;
   constexpr int N = 2 * M, NT = ZS::NT, PITCH = ZS::PITCH;
   const int tid = ctx.tid();
   const size_t row0 = (size_t)ctx.bid() * TL;
-  for (int i = 2 * tid; i < p.spl_doubles; i += 2 * NT) ctx.async_copy16(spl_s + i, p.spline + i);  // even count
+  // spline_global (a compile-time constant at the call site): evaluate the table where it lies
+  if (!spline_global)
+    for (int i = 2 * tid; i < p.spl_doubles; i += 2 * NT) ctx.async_copy16(spl_s + i, p.spline + i);  // even count
   zpass_c2r_tile<M, TL, CG>(ctx, smem, p.zs, p.g, row0, p.tw);  // waits for the copies, ends with a barrier
-  SplineView sp{spl_s, p.nspl};
+  SplineView sp{spline_global ? p.spline : spl_s, p.nspl};
   const double dc = p.zs.dc_add ? ld_ro(p.zs.dc_add) : 0.0;
   double sd = 0.0, sd2 = 0.0;
   // CPT independent cells per thread and iteration (instruction-level parallelism for the long

@@ -178,6 +178,39 @@ def test_fmax_and_displacements(N, cosmo):
     p.close()
 
 
+def test_against_reference_code_golden(cosmo):
+    """CUDA path against the outputs of the REFERENCE'S OWN compute_fmax() (compiled verbatim into
+    oracle/_ref; fixture tests/golden/reference_fmax_32.npz made by make_reference_golden.py)."""
+    gold = dict(np.load(Path(__file__).resolve().parent / "golden" / "reference_fmax_32.npz"))
+    gp = gold["products"].view(po.PRODUCT_DTYPE_3LPT)
+    N = int(gold["N"])
+    radii = list(gold["radii"])
+    p = make(N, cosmo, radii=radii, box=float(gold["box"]))
+    assert np.allclose(p.growth_rates(0.0), gold["growth"], rtol=1e-14, atol=0)
+    p.write_kdensity(gold["kdensity"])
+    p.compute_fmax()
+    assert np.abs(p.TrueVariance / gold["true_variance"] - 1).max() < 1e-12
+    # cells the reference itself cannot pin to 1e-6 (see test_fmax_and_displacements) and near-ties
+    h_masks = po.compute_fmax(gold["kdensity"], radii, float(gold["box"]) / N, cosmo.InverseGrowingMode,
+                              growth=tuple(gold["growth"]), keep=True)
+    ok = ~h_masks["unstable"]
+    assert (~ok).mean() < 1e-3
+    Fref = gp["Fmax"].reshape(N, N, N).astype(np.float64)
+    dF = np.abs(p.field("Fmax").astype(np.float64) - Fref)
+    assert (dF[ok] <= 1e-6 * np.maximum(1.0, np.abs(Fref[ok]))).all()
+    bad = (p.field("Rmax") != gp["Rmax"].reshape(N, N, N)) & ok & ~_near_tie_mask(h_masks["F"])
+    assert not bad.any()
+    for name in ("Vel", "Vel_2LPT", "Vel_3LPT_1", "Vel_3LPT_2"):
+        for a in range(3):
+            r = gp[name][:, a].reshape(N, N, N).astype(np.float64)
+            assert np.abs(p.field(name, a).astype(np.float64) - r).max() <= 1e-6 * np.abs(r).max(), (name, a)
+    for which, name in enumerate(("kvector_2LPT", "kvector_3LPT_1", "kvector_3LPT_2")):
+        assert rel(p.read_kvector(which), gold[name]) < 1e-11, name
+    pdf_ref = gold["fmax_pdf_file"][:, 2].astype(np.int64)
+    assert np.abs(p.Fmax_PDF().astype(np.int64) - pdf_ref).sum() <= 2 + 2 * int((~ok).sum())
+    p.close()
+
+
 def test_hmf_validation_golden(cosmo):
     """The reference's own shipped run (HMF_Validation/, 128^3, seed 486604): sigma per radius
     to the 4 printed digits, the FmaxPDF histogram and the collapsed count."""

@@ -1,0 +1,160 @@
+"""The oracle against the REFERENCE'S OWN CODE.
+
+tests/golden/reference_fmax_32.npz holds the outputs of the reference's compute_fmax()
+(src/fmax.c + fmax-pfft.c + LPT.c + collapse_times.c compiled verbatim, oracle/Makefile) for a
+seeded 32^3 box; tests/golden/make_reference_golden.py generated it.  Where oracle/_ref is
+available (this container, or the prebuilt library on the GPU box) the reference is also run
+live.  Tolerances: float products bit-equal except where a 1e-16 difference in double flips the
+float rounding or the reference's own cubic solver is ill-conditioned (po.ill_conditioned_mask);
+double k-vectors to 1e-13 of their maximum.
+"""
+import ctypes
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import pinocchio_oracle as po  # noqa: E402
+from oracle import reference_runner as rr  # noqa: E402
+from pinocchio_b200.cosmology import Cosmology  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden" / "reference_fmax_32.npz"
+VELS = ("Vel", "Vel_2LPT", "Vel_3LPT_1", "Vel_3LPT_2")
+
+
+@pytest.fixture(scope="module")
+def cosmo():
+    return Cosmology(pk_norm_override=2.03146e7)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = dict(np.load(GOLD))
+    g["products"] = g["products"].view(po.PRODUCT_DTYPE_3LPT)
+    return g
+
+
+def compare_products(prod, res, N):
+    """reference products[] (AoS) against an oracle result dict; returns statistics"""
+    good = ~res["unstable"]
+    Fm = prod["Fmax"].reshape(N, N, N)
+    Rm = prod["Rmax"].reshape(N, N, N)
+    dF = np.abs(Fm.astype(np.float64) - res["Fmax"])
+    assert (dF[good] <= 1e-6 * np.maximum(1.0, np.abs(res["Fmax"][good]))).all()
+    assert (Fm == res["Fmax"])[good].mean() > 0.9995          # the rest: float rounding flips
+    top2 = np.sort(np.stack(res["F"]), axis=0)[-2:]
+    ties = np.abs(top2[1] - top2[0]) <= 1e-6 * np.maximum(1.0, np.abs(top2[1]))
+    assert ((Rm != res["Rmax"]) & good & ~ties).sum() == 0
+    for name in VELS:
+        for a in range(3):
+            v = prod[name][:, a].reshape(N, N, N)
+            o = res[name][a]
+            assert np.abs(v.astype(np.float64) - o).max() <= 2e-7 * np.abs(o).max(), (name, a)
+            assert (v == o).mean() > 0.999, (name, a)
+    return int((~good).sum())
+
+
+def test_oracle_against_reference_golden(gold, cosmo):
+    N = int(gold["N"])
+    # the fixture was made with the same growth tables as today's cosmology module
+    assert np.array_equal(gold["invgrow_x"], np.asarray(cosmo.sp_invgrow.x))
+    assert np.array_equal(gold["invgrow_y"], np.asarray(cosmo.sp_invgrow.y))
+    kd = po.genic(N, float(gold["box"]), int(gold["seed"]), cosmo.PowerSpectrum)
+    assert np.array_equal(kd, gold["kdensity"])
+    res = po.compute_fmax(gold["kdensity"], list(gold["radii"]), float(gold["box"]) / N, cosmo.InverseGrowingMode,
+                          growth=tuple(gold["growth"]), keep=True)
+    assert np.abs(res["TrueVariance"] / gold["true_variance"] - 1).max() < 1e-12
+    nbad = compare_products(gold["products"], res, N)
+    assert nbad < 1e-3 * N ** 3
+    for name in ("kvector_2LPT", "kvector_3LPT_1", "kvector_3LPT_2"):
+        assert np.abs(res[name] - gold[name]).max() <= 1e-13 * np.abs(gold[name]).max()
+    # Fmax_PDF as the reference wrote it to pinocchio.ref.FmaxPDF.out (src/fmax.c:509-550)
+    pdf_ref = gold["fmax_pdf_file"][:, 2].astype(np.int64)
+    assert pdf_ref.sum() == N ** 3
+    assert np.abs(po.fmax_pdf(res["Fmax"]).astype(np.int64) - pdf_ref).sum() <= 2 * nbad + 2
+    assert np.array_equal(po.fmax_pdf(gold["products"]["Fmax"]).astype(np.int64), pdf_ref)
+
+
+def test_product_record_layout(gold):
+    """sizeof(product_data) = 56 and the offsets of src/pinocchio.h:233-259, as the reference's
+    compiler laid them out (the fixture stores the raw records)."""
+    assert po.PRODUCT_DTYPE_3LPT.itemsize == 56
+    assert gold["products"].size == int(gold["N"]) ** 3
+    assert gold["products"]["Rmax"].min() >= 0 and gold["products"]["Rmax"].max() <= len(gold["radii"]) - 1
+
+
+needs_ref = pytest.mark.skipif(not rr.available(), reason="oracle/_ref not built (needs /root/reference once: make -C oracle)")
+
+
+@needs_ref
+def test_reference_fft_standin_against_numpy():
+    """oracle/ref_fft.c (the one-task PFFT stand-in) has FFTW's r2c/c2r semantics"""
+    lib = ctypes.CDLL(str(rr.LIB))
+    PD = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(3)
+    for N in (16, 32, 64):
+        r = rng.standard_normal((N, N, N))
+        out = np.empty((N, N, N // 2 + 1), dtype=np.complex128)
+        lib.ref_fft_r2c(N, r.ctypes.data_as(PD), out.view(np.float64).ctypes.data_as(PD))
+        ref = np.fft.rfftn(r)
+        assert np.abs(out - ref).max() <= 1e-14 * np.abs(ref).max()
+        c = rng.standard_normal((N, N, N // 2 + 1)) + 1j * rng.standard_normal((N, N, N // 2 + 1))   # not Hermitian
+        want = po.reverse_transform(c) * N ** 3
+        o = np.empty((N, N, N))
+        cc = c.copy()
+        lib.ref_fft_c2r(N, cc.view(np.float64).ctypes.data_as(PD), o.ctypes.data_as(PD))
+        assert np.abs(o - want).max() <= 1e-14 * np.abs(want).max()
+
+
+@needs_ref
+def test_reference_collapse_solver_against_oracle(cosmo):
+    """the reference's inverse_collapse_time()/ell_classic() (src/collapse_times.c:114-221,679-776)
+    cell by cell on random Hessians, including exactly diagonal and degenerate ones"""
+    lib = ctypes.CDLL(str(rr.LIB))
+    PD = ctypes.POINTER(ctypes.c_double)
+    x = np.ascontiguousarray(cosmo.sp_invgrow.x)
+    y = np.ascontiguousarray(cosmo.sp_invgrow.y)
+    lib.ref_set_invgrow(len(x), x.ctypes.data_as(PD), y.ctypes.data_as(PD))
+    lib.ref_inverse_collapse_time.argtypes = [ctypes.c_long, PD, PD, PD]
+    rng = np.random.default_rng(11)
+    n = 200000
+    h = rng.standard_normal((6, n)) * np.array([1.5, 1.5, 1.5, 0.8, 0.8, 0.8])[:, None]
+    h[:3] += 0.6
+    h[3:, :1000] = 0.0                      # diagonal tensors
+    h[:, 1000:1100] = 0.0                   # null tensors
+    h[1, 1100:1200] = h[0, 1100:1200]       # two equal diagonal entries
+    F = np.empty(n)
+    lam = np.empty(3 * n)
+    fails = lib.ref_inverse_collapse_time(n, np.ascontiguousarray(h).ctypes.data_as(PD), F.ctypes.data_as(PD), lam.ctypes.data_as(PD))
+    assert fails == 0
+    hs = [h[i] for i in range(6)]
+    Fo = po.inverse_collapse_time(hs, cosmo.InverseGrowingMode)
+    good = ~po.ill_conditioned_mask(hs, cosmo.InverseGrowingMode)
+    assert good.mean() > 0.999
+    assert np.array_equal(np.isfinite(F), np.isfinite(Fo))
+    d = np.abs(F - Fo)[good]
+    assert d.max() <= 1e-9 * max(1.0, np.abs(Fo[good]).max()), d.max()
+    assert np.median(d) < 1e-14
+
+
+@needs_ref
+def test_reference_compute_fmax_live_against_golden_and_oracle(gold, cosmo):
+    """run the compiled reference now: it reproduces the committed fixture bit for bit"""
+    N = int(gold["N"])
+    run = rr.ReferenceRun(N, float(gold["box"]), gold["radii"], gold["growth"], gold["invgrow_x"], gold["invgrow_y"], threads=4)
+    run.set_kdensity(gold["kdensity"])
+    _, tv = run.compute_fmax()
+    prod = run.products(po.PRODUCT_DTYPE_3LPT)
+    assert np.array_equal(prod["Rmax"], gold["products"]["Rmax"])
+    assert np.array_equal(prod["Fmax"], gold["products"]["Fmax"])
+    for name in VELS:
+        assert np.array_equal(prod[name], gold["products"][name])
+    assert np.abs(tv / gold["true_variance"] - 1).max() < 1e-13      # OpenMP reduction order
+    assert np.array_equal(run.fmax_pdf_file()[:, 2], gold["fmax_pdf_file"][:, 2])
+    # a second call on the same field: compute_fmax re-initialises products at ismooth == 0
+    run.compute_fmax()
+    assert np.array_equal(run.products(po.PRODUCT_DTYPE_3LPT)["Fmax"], gold["products"]["Fmax"])

@@ -14,6 +14,7 @@
 #include "launch.h"
 #include "spline_pack.h"
 
+namespace pinb { extern int g_tune_zc; }
 using namespace pinb;
 
 #define CKE(x)                                                                              \
@@ -135,9 +136,12 @@ int main(int argc, char** argv) {
     c.zs.ncomp = 6; c.zs.has_nyq = 0; c.zs.dc_add = nullptr;
     c.g = g; c.tw = tw; c.spline = dspl; c.nspl = nspl; c.spl_doubles = (int)spl.size(); c.ismooth = 1;
     c.Fmax = fmax; c.Rmax = rmax; c.sums = sums;
+    for (int v = 0; v < (N == 2048 ? 2 : 1); v++) {
+    g_tune_zc = v;
     const float ms = timed(reps, [&] { CKE(launch_zpass_collapse(N, c, (size_t)g.lx * N, 0)); });
-    printf("zpass collapse: %.2f ms  (%.0f GB/s algorithmic: 6 half-complex reads + 8 B/cell)\n", ms,
-           (6 * gb + ncell * 8 / 1e9) / ms * 1e3);
+    printf("zpass collapse (tune %d): %.2f ms  (%.0f GB/s algorithmic: 6 half-complex reads + 8 B/cell)\n", ms,
+           v, (6 * gb + ncell * 8 / 1e9) / ms * 1e3);
+    }
   }
   // ---- forward x pass (in place, local)
   {
