@@ -29,10 +29,11 @@ NVCC_FLAGS = [
 SOURCES = ["engine.cu", "k_strided.cu", "k_zpass.cu", "k_misc.cu"]
 
 
-# Test-only variant: the long-line (decimation-in-frequency) strided passes that the product
-# uses for N = 2048 (8 GPUs) are compiled in for every N > 32, so that single-GPU parity tests
-# at 64^3 / 128^3 exercise them on real hardware (PINB200_LIB selects the library).
-VARIANTS = {"": [], "split": ["-DPINB_SPLIT_ABOVE=32"]}
+# Test-only variant: the code paths the product only takes at N = 2048 (8 GPUs) -- the
+# decimation-in-frequency strided passes and the collapse kernel that reads its spline from
+# global memory -- are compiled in for the small grids, so that single-GPU parity tests at
+# 64^3 / 128^3 exercise them on real hardware (PINB200_LIB selects the library).
+VARIANTS = {"": [], "split": ["-DPINB_SPLIT_ABOVE=32", "-DPINB_SPLIT_ABOVE_Y=32", "-DPINB_SPLINE_GLOBAL_FROM=16"]}
 
 
 def _digest(extra=()) -> str:

@@ -4,11 +4,11 @@
 
 namespace pinb {
 
-template <int L, int DIR, bool MULTI, int CHUNK = 0>
+template <int L, int DIR, bool MULTI>
 __global__ void __launch_bounds__(XCfg<L, DIR>::NT) xpass_kernel(const __grid_constant__ XPassParams p) {
   extern __shared__ double2 smem[];
   DevCtx ctx;
-  xpass_body<L, DIR, MULTI, CHUNK>(ctx, smem, p);
+  xpass_body<L, DIR, MULTI>(ctx, smem, p);
 }
 
 template <int L, int DIR>
@@ -21,14 +21,6 @@ __global__ void __launch_bounds__(YCfg<L>::NT) ypass_kernel(const __grid_constan
 template <int L, int DIR, bool MULTI> static cudaError_t xpass_launch_m(const XPassParams& p, int nblocks_y, cudaStream_t s) {
   using C = XCfg<L, DIR>;
   const size_t smem = (size_t)C::LT * C::TK * sizeof(double2);
-  if constexpr (C::SPLIT) {
-    if (p.variant == 1) {
-      cudaError_t e = allow_smem(xpass_kernel<L, DIR, MULTI, 4>, smem);
-      if (e != cudaSuccess) return e;
-      xpass_kernel<L, DIR, MULTI, 4><<<(unsigned)(nblocks_y * p.ntiles_z), C::NT, smem, s>>>(p);
-      return cudaGetLastError();
-    }
-  }
   cudaError_t e = allow_smem(xpass_kernel<L, DIR, MULTI>, smem);
   if (e != cudaSuccess) return e;
   xpass_kernel<L, DIR, MULTI><<<(unsigned)(nblocks_y * p.ntiles_z), C::NT, smem, s>>>(p);

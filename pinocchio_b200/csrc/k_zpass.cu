@@ -9,17 +9,19 @@ namespace pinb {
 // 1024^3), so the register budget is capped to fit three 384-thread blocks per SM.
 // M = 1024 (N = 2048): the six padded rows take 108 KB; with the spline table (10.5 KB) next to
 // them only one block fits an SM (r01: 80 ms against 50 ms for the same cell count at M = 512).
-// There the table stays in global memory (L1/L2 resident) and two blocks fit.
+// There the table stays in global memory (L1/L2 resident) and two blocks fit: 58.5 ms (80 registers,
+// some spills in the FFT part) against 80.5 ms with one 162-register block.
+#ifndef PINB_SPLINE_GLOBAL_FROM
+#define PINB_SPLINE_GLOBAL_FROM 1024  // the "split" test build lowers it so that small grids cover the path
+#endif
 template <int M> struct CollapseCfg {
-  static constexpr bool SPLINE_GLOBAL = (M >= 1024);
+  static constexpr bool SPLINE_GLOBAL = (M >= PINB_SPLINE_GLOBAL_FROM);
   static constexpr int MINB = (M >= 256 && M <= 512) ? 3 : (M == 1024 ? 2 : 1);
 };
 template <int NT> constexpr size_t sum_scratch_bytes() { return (NT % 32 == 0 ? 64 : 2 * NT) * sizeof(double); }
 
-int g_tune_zc = 0;  // tools/slabbench: 1 = one block per SM, full register budget (M = 1024 only)
-
-template <int M, int TL, int CG, int MINB = CollapseCfg<M>::MINB>
-__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, MINB) zpass_collapse_kernel(const __grid_constant__ CollapseParams p) {
+template <int M, int TL, int CG>
+__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, CollapseCfg<M>::MINB) zpass_collapse_kernel(const __grid_constant__ CollapseParams p) {
   extern __shared__ double2 smem[];
   using ZS = ZShape<M, TL, CG>;
   constexpr bool SG = CollapseCfg<M>::SPLINE_GLOBAL;
@@ -65,14 +67,6 @@ template <int N> static cudaError_t collapse_launch(const CollapseParams& p_in, 
   using ZS = ZShape<M, TL, CG>;
   const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (CollapseCfg<M>::SPLINE_GLOBAL ? 0 : (size_t)p.spl_doubles * sizeof(double)) +
                       sum_scratch_bytes<ZS::NT>();
-  if constexpr (M == 1024) {
-    if (g_tune_zc == 1) {
-      cudaError_t e1 = allow_smem(zpass_collapse_kernel<M, TL, CG, 1>, smem);
-      if (e1 != cudaSuccess) return e1;
-      zpass_collapse_kernel<M, TL, CG, 1><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);
-      return cudaGetLastError();
-    }
-  }
   cudaError_t e = allow_smem(zpass_collapse_kernel<M, TL, CG>, smem);
   if (e != cudaSuccess) return e;
   zpass_collapse_kernel<M, TL, CG><<<(unsigned)(nrows / TL), ZS::NT, smem, s>>>(p);

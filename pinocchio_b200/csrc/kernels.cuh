@@ -53,13 +53,21 @@ template <int L, int DIR> struct XCfg {
   static constexpr bool SPLIT = (L > PINB_SPLIT_ABOVE) && DIR > 0;  // the forward x pass is in place (and local)
   static constexpr int LT = SPLIT ? L / 2 : L;
   static constexpr int TK = LT <= 1024 ? 8 : 4;
+  static constexpr int CHUNK = SPLIT ? 4 : 0;  // see strided_tile_jobs (r01 slab benchmark: 41 -> 32 ms)
   using PL = XPlan<LT>;
   static constexpr int NT = PL::TPL * TK;
 };
+// The y pass stays local (no NVLink stores) and measured faster unsplit at N = 2048 (r01 slab
+// benchmark: 26 ms with TK = 4 against 52 ms split), so its threshold is separate; the split y
+// code is kept compiled and tested through the PINB_SPLIT_ABOVE_Y = 32 test build.
+#ifndef PINB_SPLIT_ABOVE_Y
+#define PINB_SPLIT_ABOVE_Y 4096
+#endif
 template <int L> struct YCfg {
-  static constexpr bool SPLIT = (L > PINB_SPLIT_ABOVE);
+  static constexpr bool SPLIT = (L > PINB_SPLIT_ABOVE_Y);
   static constexpr int LT = SPLIT ? L / 2 : L;
   static constexpr int TK = LT <= 1024 ? 8 : 4;
+  static constexpr int CHUNK = SPLIT ? 4 : 0;
   using PL = Plan<LT, false>;
   static constexpr int NT = PL::TPL * TK;
 };
@@ -117,8 +125,7 @@ PINB_HD void strided_tile_fft(Ctx& ctx, double2* s, const double2* __restrict__ 
 // As soon as the last stage of job j has pulled its operands into registers the shared-memory
 // tile is free again and the copies of job j+1 are issued: they overlap the last butterflies and
 // the global stores of job j (with one 128 KB tile per SM nothing else can hide that latency).
-// CHUNK > 0: a scheduling fence after every CHUNK stage-0 elements (for xform functors that
-// load from global memory: bounds the registers the compiler spends on loads in flight).
+// CHUNK > 0: xform is applied in a separate rolled loop, CHUNK elements per iteration.
 template <int L, int TK, int DIR, class PL, int TWS, int CHUNK = 0, class Ctx, class SrcF, class XformF, class StoreF>
 PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__ tw, int njobs, SrcF src, XformF xform,
                                StoreF store) {
@@ -147,13 +154,15 @@ PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__
     if constexpr (CHUNK == 0) {
       stage_load<L, PL::R0, TPL, RMAX>(jl, v, raw_in);
     } else {
-#pragma unroll
-      for (int m = 0; m < NB0; m++)
-#pragma unroll
-        for (int r = 0; r < PL::R0; r++) {
-          v[m * PL::R0 + r] = raw_in(jl + m * TPL + r * T0);
-          if ((m * PL::R0 + r) % CHUNK == CHUNK - 1) ctx.sched_fence();
-        }
+      // transform my own elements in place first, CHUNK at a time in a rolled loop, then load
+      // them plainly: for xform functors that read global memory (the split passes) the fully
+      // unrolled form spilled 256 B/thread to L2 and overflowed the instruction cache (r01 ncu)
+#pragma unroll CHUNK
+      for (int i = 0; i < NB0 * PL::R0; i++) {
+        const int e = jl + (i / PL::R0) * TPL + (i % PL::R0) * T0;
+        s[e * TK + tk] = xform(job, e, tk, s[e * TK + tk]);
+      }
+      stage_load<L, PL::R0, TPL, RMAX>(jl, v, s_in);
     }
     ctx.sync();  // every thread holds its raw elements: the tile may be overwritten
     stage_store<L, PL::R0, 1, DIR, TPL, RMAX>(jl, v, s_out, tw, TWS);
@@ -201,7 +210,6 @@ struct XPassParams {
   int ntiles_z;         // kz tiles per row that are processed (M/TK, +1 with the Nyquist tile)
   int prefetch;         // > 0: pull the source tile of block (bid + prefetch) into L2 while this one computes
   int nblocks;
-  int variant;          // experiments (tools/slabbench): 1 = chunked stage-0 loads of the split path
   KFactor kf;
   Geom g;
   const double2* tw;    // N-th roots of unity
@@ -209,7 +217,7 @@ struct XPassParams {
 
 // MULTI = false: one rank; the owner look-up and the per-rank pointer table are compiled out
 // (they cost registers: the 1024-point kernel spilled 128 bytes with them).
-template <int L, int DIR, bool MULTI, int CHUNK = 0, class Ctx>
+template <int L, int DIR, bool MULTI, class Ctx>
 PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   using C = XCfg<L, DIR>;
   constexpr int TK = C::TK, LT = C::LT;
@@ -278,7 +286,7 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
       dp.r[owner][(size_t)xl * ((size_t)g.N * g.P) + roff + tk] = val;
     }
   };
-  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * npw : npw, srcf, xform, storef);
+  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, C::CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * npw : npw, srcf, xform, storef);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -343,7 +351,7 @@ PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
       p.dst[p.job[j].dst][base + (size_t)e * g.P + tk] = val;
     }
   };
-  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT>(ctx, smem, p.tw, SPLIT ? 2 * p.njobs : p.njobs, srcf, xform, storef);
+  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, C::CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * p.njobs : p.njobs, srcf, xform, storef);
 }
 
 // ---------------------------------------------------------------------------------------

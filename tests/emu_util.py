@@ -30,7 +30,7 @@ def build_emulator(split: bool = False) -> Path:
         return lib
     cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas"]
     if split:
-        cmd.append("-DPINB_SPLIT_ABOVE=16")
+        cmd += ["-DPINB_SPLIT_ABOVE=16", "-DPINB_SPLIT_ABOVE_Y=16"]
     subprocess.run(cmd + ["-o", str(lib), str(SRC)], check=True)
     return lib
 

@@ -14,7 +14,6 @@
 #include "launch.h"
 #include "spline_pack.h"
 
-namespace pinb { extern int g_tune_zc; }
 using namespace pinb;
 
 #define CKE(x)                                                                              \
@@ -92,10 +91,8 @@ int main(int argc, char** argv) {
   printf("slab of %d^3 over %d ranks: lx=%d, %.2f GB per field\n", N, P, g.lx, gb);
 
   // ---- inverse x pass, 3 powers; "owner o" = y-block o of the local R-layout field (disjoint stores)
-  for (int pmask : {7, 1, 7 + 8}) {
+  for (int pmask : {7, 1}) {
     XPassParams p{};
-    p.variant = pmask >> 3;
-    pmask &= 7;
     p.src = src;
     for (int pw = 0; pw < 3; pw++)
       for (int o = 0; o < P; o++) p.dst[pw].r[o] = A[pw] + (size_t)o * g.ly * g.P;
@@ -105,7 +102,7 @@ int main(int argc, char** argv) {
     p.nblocks = g.ly * p.ntiles_z;
     const float ms = timed(reps, [&] { CKE(launch_xpass(N, +1, p, g.ly, 0)); });
     const int nj = pmask == 7 ? 3 : 1;
-    printf("xpass inv variant=%d pmask=%d tk=%d: %.2f ms  (%.0f GB/s algorithmic: 1 read + %d writes)\n", p.variant, pmask, xpass_tk(N, +1), ms,
+    printf("xpass inv pmask=%d tk=%d: %.2f ms  (%.0f GB/s algorithmic: 1 read + %d writes)\n", pmask, xpass_tk(N, +1), ms,
            (1 + nj) * gb / ms * 1e3, nj);
   }
   // ---- inverse y pass, 6 jobs from 3 sources
@@ -136,12 +133,9 @@ int main(int argc, char** argv) {
     c.zs.ncomp = 6; c.zs.has_nyq = 0; c.zs.dc_add = nullptr;
     c.g = g; c.tw = tw; c.spline = dspl; c.nspl = nspl; c.spl_doubles = (int)spl.size(); c.ismooth = 1;
     c.Fmax = fmax; c.Rmax = rmax; c.sums = sums;
-    for (int v = 0; v < (N == 2048 ? 2 : 1); v++) {
-    g_tune_zc = v;
     const float ms = timed(reps, [&] { CKE(launch_zpass_collapse(N, c, (size_t)g.lx * N, 0)); });
-    printf("zpass collapse (tune %d): %.2f ms  (%.0f GB/s algorithmic: 6 half-complex reads + 8 B/cell)\n", ms,
-           v, (6 * gb + ncell * 8 / 1e9) / ms * 1e3);
-    }
+    printf("zpass collapse: %.2f ms  (%.0f GB/s algorithmic: 6 half-complex reads + 8 B/cell)\n", ms,
+           (6 * gb + ncell * 8 / 1e9) / ms * 1e3);
   }
   // ---- forward x pass (in place, local)
   {
