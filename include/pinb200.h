@@ -99,6 +99,17 @@ int pinb200_fmax(pinb200_ctx* ctx, double* true_variance);
  * src/fmax-pfft.c:344-364 for ScaleDep.order 1..4 at the segment redshift, i.e.
  * {GrowingMode, GrowingMode_2LPT, GrowingMode_3LPT_1 (negative), GrowingMode_3LPT_2}. */
 int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, const double growth[4]);
+/* The same for -DSCALE_DEPENDENT builds, where growth_rate depends on |k| (src/fmax-pfft.c:340-364,
+ * InterpolateGrowth src/cosmo.c:1728-1757).  log10_growth[o*nk + j], o = ScaleDep.order-1 = 0..3,
+ * j = 0..nk-1, is my_spline_eval(SPLINE[SP_GROW1|SP_GROW2|SP_GROW31|SP_GROW32 + j], -log10(1+z))
+ * at the segment redshift z (evaluated by the unchanged host cosmology); nk = NkBINS,
+ * logkmin = LOGKMIN, dlogk = DELTALOGK (src/def_splines.h:40-42).  The device interpolates
+ * linearly in log10|k| (|k| in grid units, as the reference passes it), clamps below kmin and
+ * above kmax, takes 10^ and applies the minus sign of GrowingMode_3LPT_1 (src/cosmo.c:1810).
+ * The sources (compute_sources = 1) are computed with growth 1 as in the reference
+ * (ScaleDep.order = 0, src/fmax.c:308-309, src/LPT.c:53-54). */
+int pinb200_displacements_scaledep(pinb200_ctx* ctx, int compute_sources, int nk, double logkmin, double dlogk,
+                                   const double* log10_growth);
 /* Fmax_PDF (src/fmax.c:509-550): local histogram, counts[PINB200_NBINS]. */
 int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts);
 
@@ -114,7 +125,8 @@ int pinb200_get_timers(pinb200_ctx* ctx, pinb200_timers* t);
 
 /* ---- finer-grained entry points (reference function granularity; used by the parity tests) */
 /* forward_transform / reverse_transform (src/fmax-pfft.c:191-228) on host arrays:
- * real [N][N][N] doubles <-> half-complex [N][N][N/2+1]; reverse includes the 1/N^3. */
+ * real [N/nranks (local x)][N][N] doubles <-> half-complex [N][N/nranks (local y)][N/2+1];
+ * reverse includes the 1/N^3.  Collective when nranks > 1 (every rank passes its slab). */
 int pinb200_fft_r2c(pinb200_ctx* ctx, const double* real_in, double* cplx_out);
 int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* real_out);
 /* compute_second_derivatives(R) (src/fmax.c:225-258) of the resident kdensity: six real

@@ -248,6 +248,36 @@ def derivative_kspace(ck: np.ndarray, d1: int, d2: int, rsmooth: float, growth: 
     return out
 
 
+def interpolate_growth(k, tab, logkmin=-3.0, dlogk=0.5):
+    """InterpolateGrowth (src/cosmo.c:1728-1757, -DSCALE_DEPENDENT) at a fixed redshift:
+    ``tab[j]`` = my_spline_eval(SPLINE[pointer + j], -log10(1+z)), j = 0..NkBINS-1; linear
+    interpolation in log10 k between the k bins, the first / last bin below kmin / above kmax
+    (kmin, kmax as src/cosmo.c:169-170; LOGKMIN, DELTALOGK src/def_splines.h:41-42)."""
+    tab = np.asarray(tab, dtype=np.float64)
+    nk = tab.size
+    k = np.asarray(k, dtype=np.float64)
+    kmin = 10.0 ** logkmin
+    kmax = 10.0 ** (logkmin + (nk - 1) * dlogk)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dk = (np.log10(np.where(k > 0, k, 1.0)) - logkmin) / dlogk
+    kk = np.clip(dk.astype(np.int64), 0, nk - 1)      # (int)dk; only used inside [kmin, kmax]
+    frac = dk - kk
+    hi = tab[np.minimum(kk + 1, nk - 1)]              # k == kmax: weight 0 on the entry past the end
+    mid = frac * hi + (1 - frac) * tab[kk]
+    return np.where(k < kmin, tab[0], np.where(k > kmax, tab[nk - 1], mid))
+
+
+def growth_rate_of_k(N, order, log10_growth, logkmin=-3.0, dlogk=0.5):
+    """growth_rate of src/fmax-pfft.c:340-364 on the whole k grid for ScaleDep.order = 1..4:
+    GrowingMode*(z, k_module) = +-10^InterpolateGrowth (src/cosmo.c:1786-1819; the minus sign
+    is GrowingMode_3LPT_1's, :1810).  k_module is in GRID units, as the reference passes it.
+    ``log10_growth`` is the [4][NkBINS] table at the segment redshift."""
+    kx, ky, kz = _kgrid(N)
+    kmod = np.sqrt((kx * kx + ky * ky) + kz * kz)
+    g = 10.0 ** interpolate_growth(kmod, np.asarray(log10_growth)[order - 1], logkmin, dlogk)
+    return -g if order == 3 else g
+
+
 def reverse_transform(ck: np.ndarray) -> np.ndarray:
     """c2r with the 1/N^3 normalisation (src/fmax-pfft.c:203-228).  numpy.fft.irfftn has
     FFTW's literal half-complex semantics (App. A.5) and includes 1/N^3."""
@@ -456,7 +486,8 @@ def lpt_kvectors(h):
 
 def first_derivatives(kvec, growth):
     """compute_first_derivatives (src/fmax.c:193-222): three real fields, Rsmooth = 0, then
-    cast to PRODFLOAT=float by write_from_rvector_to_products (src/fmax-pfft.c:563-631)."""
+    cast to PRODFLOAT=float by write_from_rvector_to_products (src/fmax-pfft.c:563-631).
+    ``growth``: a scalar, or the per-mode array of growth_rate_of_k (-DSCALE_DEPENDENT)."""
     return [compute_derivative(kvec, ia, 0, 0.0, growth).astype(np.float32) for ia in (1, 2, 3)]
 
 
@@ -467,7 +498,8 @@ def compute_fmax(kdensity, radii, cell_size, inverse_growing_mode, growth=None,
                  lpt_order=3, keep=False):
     """Returns dict with Fmax (f32), Rmax (i32), TrueVariance[], Vel, Vel_2LPT, Vel_3LPT_1,
     Vel_3LPT_2 (each [3] list of f32 fields).  ``growth`` = (D, D2, D31, D32) at the segment
-    redshift (growth_rate of src/fmax-pfft.c:344-364); default all ones."""
+    redshift (growth_rate of src/fmax-pfft.c:344-364), scalars or per-mode arrays
+    (growth_rate_of_k); default all ones."""
     N = kdensity.shape[0]
     if growth is None:
         growth = (1.0, 1.0, 1.0, 1.0)

@@ -121,10 +121,38 @@ static void trap(const char* what) {
  * reference evaluates one spline of z and ignores k, src/cosmo.c:1728-1819).  Sign conventions
  * are those of the reference's return values (GrowingMode_3LPT_1 is negative, :1810). */
 static double ref_growth[4] = {1.0, 1.0, 1.0, 1.0};
-double GrowingMode(double z, double k) { (void)z; (void)k; return ref_growth[0]; }
-double GrowingMode_2LPT(double z, double k) { (void)z; (void)k; return ref_growth[1]; }
-double GrowingMode_3LPT_1(double z, double k) { (void)z; (void)k; return ref_growth[2]; }
-double GrowingMode_3LPT_2(double z, double k) { (void)z; (void)k; return ref_growth[3]; }
+/* -DSCALE_DEPENDENT stand-in: src/cosmo.c cannot be compiled here (GSL integrators), so the k
+ * interpolation of InterpolateGrowth (src/cosmo.c:1728-1757) is restated on caller-supplied
+ * tables tab[o*nk + j] = value of the j-th k-bin spline of order o+1 at the segment redshift.
+ * The k loop that calls it -- which k is passed, which modes are scaled -- is the reference's own
+ * compute_derivative (src/fmax-pfft.c:306-397). */
+static int gk_n = 0;
+static double gk_logkmin = -3.0, gk_dlogk = 0.5, *gk_tab = NULL;
+int ref_set_growth_tables(int nk, double logkmin, double dlogk, const double* tab) {
+  free(gk_tab);
+  gk_tab = NULL;
+  gk_n = nk;
+  if (nk <= 0) return 0;
+  gk_logkmin = logkmin;
+  gk_dlogk = dlogk;
+  gk_tab = malloc((size_t)4 * nk * sizeof(double));
+  memcpy(gk_tab, tab, (size_t)4 * nk * sizeof(double));
+  return 0;
+}
+static double interpolate_growth(double k, int o) {
+  const double* t = gk_tab + (size_t)o * gk_n;
+  const double kmin = pow(10., gk_logkmin), kmax = pow(10., gk_logkmin + (gk_n - 1) * gk_dlogk);
+  if (k < kmin) return t[0];
+  if (k > kmax) return t[gk_n - 1];
+  double dk = (log10(k) - gk_logkmin) / gk_dlogk;
+  const int kk = (int)dk;
+  dk -= kk;
+  return (kk + 1 < gk_n) ? dk * t[kk + 1] + (1 - dk) * t[kk] : t[kk];
+}
+double GrowingMode(double z, double k) { (void)z; return gk_n ? pow(10., interpolate_growth(k, 0)) : ref_growth[0]; }
+double GrowingMode_2LPT(double z, double k) { (void)z; return gk_n ? pow(10., interpolate_growth(k, 1)) : ref_growth[1]; }
+double GrowingMode_3LPT_1(double z, double k) { (void)z; return gk_n ? -pow(10., interpolate_growth(k, 2)) : ref_growth[2]; }
+double GrowingMode_3LPT_2(double z, double k) { (void)z; return gk_n ? pow(10., interpolate_growth(k, 3)) : ref_growth[3]; }
 double OmegaMatter(double z) { (void)z; trap("OmegaMatter"); return 0; }
 double OmegaLambda(double z) { (void)z; trap("OmegaLambda"); return 0; }
 int jac(double t, const double y[], double* dfdy, double dfdt[], void* p) { (void)t; (void)y; (void)dfdy; (void)dfdt; (void)p; trap("jac"); return 0; }
@@ -303,6 +331,26 @@ int ref_fetch_products(void* out) {
 int ref_fetch_kvector(int which, double* out) {
   const double* src = which == 0 ? kvector_2LPT : (which == 1 ? kvector_3LPT_1 : kvector_3LPT_2);
   memcpy(out, src, (size_t)MyGrids[0].total_local_size_fft * sizeof(double));
+  return 0;
+}
+
+/* the reference's DumpProducts file boundary (src/fmax.c:372-506) on the arrays of ref_setup */
+int dump_products(void);
+int read_dumps(void);
+int ref_dump_setup(const char* dumpdir, int seed) {
+  snprintf(params.DumpDir, SBLENGTH, "%s", dumpdir);
+  params.RandomSeed = seed;
+  return 0;
+}
+int ref_dump_products(void) { return dump_products(); }
+int ref_read_dumps(double* true_variance) {
+  const int rc = read_dumps();
+  if (true_variance) memcpy(true_variance, Smoothing.TrueVariance, Smoothing.Nsmooth * sizeof(double));
+  return rc;
+}
+int ref_set_products(const void* rec, const double* true_variance) {
+  memcpy(products, rec, (size_t)ref_n * sizeof(product_data));
+  if (true_variance) memcpy(Smoothing.TrueVariance, true_variance, Smoothing.Nsmooth * sizeof(double));
   return 0;
 }
 

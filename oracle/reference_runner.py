@@ -25,6 +25,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "_ref" / "libpinocchio_ref.so"
+SHIM_HOST_LIB = HERE / "_ref" / "libshim_host.so"
 REFERENCE_SRC = Path("/root/reference/src")
 HMF_RADII = [20.635922, 13.996056, 9.026099, 5.465945, 3.058354, 1.548258, 0.689079, 0.258729, 0.0]
 _PD = ctypes.POINTER(ctypes.c_double)
@@ -40,7 +41,10 @@ def build(force: bool = False) -> Path | None:
     if REFERENCE_SRC.exists():
         if force and LIB.exists():
             LIB.unlink()
-        r = subprocess.run(["make", "-C", str(HERE)], capture_output=True, text=True)
+        # `all` also links oracle/_ref/libshim_host.so (the drop-in shim's host side) against the
+        # in-tree libpinb200.so when that has been built
+        target = "all" if (HERE.parent / "pinocchio_b200" / "libpinb200.so").exists() else "_ref/libpinocchio_ref.so"
+        r = subprocess.run(["make", "-C", str(HERE), target], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"oracle/_ref build failed:\n{r.stdout}\n{r.stderr}")
     return LIB if LIB.exists() else None
@@ -106,6 +110,16 @@ class ReferenceRun:
         a = np.ascontiguousarray(kd, dtype=np.complex128)
         assert a.shape == (self.N, self.N, self.N // 2 + 1)
         self.lib.ref_set_kdensity(_p(a.view(np.float64)))
+
+    def set_growth_tables(self, log10_growth, logkmin: float = -3.0, dlogk: float = 0.5):
+        """-DSCALE_DEPENDENT: [4][NkBINS] tables for GrowingMode*(z, k) (ref_harness.c); None = off."""
+        self.lib.ref_set_growth_tables.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, _PD]
+        if log10_growth is None:
+            self.lib.ref_set_growth_tables(0, 0.0, 1.0, None)
+            return
+        t = np.ascontiguousarray(log10_growth, dtype=np.float64)
+        assert t.ndim == 2 and t.shape[0] == 4
+        self.lib.ref_set_growth_tables(t.shape[1], float(logkmin), float(dlogk), _p(t))
 
     def compute_fmax(self):
         """The reference's compute_fmax(): returns (seconds by its own cputime.fmax, TrueVariance[])."""

@@ -52,6 +52,7 @@ struct pinb200_ctx {
   double2* tw = nullptr;
   double* gauss = nullptr;
   double* dc = nullptr;
+  double* growthk = nullptr;  // [4][nk] log10 growth tables of a scale-dependent displacement call
   double* sums = nullptr;  // [2*64]
   unsigned int* seeds = nullptr;
   double* pk = nullptr;
@@ -288,7 +289,7 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
   for (int r = 0; r < ctx->P; r++)
     if (r != ctx->d.rank && ctx->peer_arena[r]) cudaIpcCloseMemHandle(ctx->peer_arena[r]);
   auto fr = [&](void* p) { if (p) cudaFree(p); };
-  fr(ctx->tw); fr(ctx->gauss); fr(ctx->dc); fr(ctx->sums); fr(ctx->seeds); fr(ctx->pk); fr(ctx->spl_dev);
+  fr(ctx->tw); fr(ctx->gauss); fr(ctx->dc); fr(ctx->growthk); fr(ctx->sums); fr(ctx->seeds); fr(ctx->pk); fr(ctx->spl_dev);
   fr(ctx->d_error);
   for (auto p : ctx->B) fr(p);
   for (auto p : ctx->D) fr(p);
@@ -491,8 +492,13 @@ static int ntiles(const pinb200_ctx* ctx, int tk, bool with_nyq) { return ctx->g
 // inverse x pass of the local K-layout field `src`; the output for power p of kx is scattered
 // into the arena buffer dst[p] (R layout) of the rank owning each x.  Barriers on both sides:
 // before, so that no peer still reads the destinations; after, so that readers see all stores.
+struct GrowthK {        // one row of the scale-dependent growth tables (KFactor::gk*), device pointer
+  const double* tab = nullptr;
+  int n = 0;
+  double logkmin = 0, dlogk = 1, sign = 1;
+};
 static int run_xpass_inv(pinb200_ctx* ctx, const double2* src, double2* const dst[3], int pmask, bool gauss, int green,
-                         int times_i, double scalar, bool with_nyq) {
+                         int times_i, double scalar, bool with_nyq, const GrowthK* gk = nullptr) {
   XPassParams p{};
   p.src = src;
   for (int i = 0; i < 3; i++)
@@ -505,6 +511,13 @@ static int run_xpass_inv(pinb200_ctx* ctx, const double2* src, double2* const ds
   p.kf.scalar = scalar;
   p.kf.green = green;
   p.kf.times_i = times_i;
+  if (gk && gk->tab) {
+    p.kf.gk = gk->tab;
+    p.kf.gk_n = gk->n;
+    p.kf.gk_logkmin = gk->logkmin;
+    p.kf.gk_dlogk = gk->dlogk;
+    p.kf.gk_sign = gk->sign;
+  }
   p.g = ctx->g;
   p.tw = ctx->tw;
   TRY(peer_barrier(ctx));
@@ -672,13 +685,14 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
 
 // first derivatives of a K-layout k-vector -> three float fields (compute_first_derivatives,
 // src/fmax.c:193-222).  Uses A[0], A[1] as x-pass destinations and D[0..2] as y-pass outputs.
-static int first_derivs_to_vel(pinb200_ctx* ctx, const double2* kvec, double growth, float* const out[3], bool with_nyq) {
+static int first_derivs_to_vel(pinb200_ctx* ctx, const double2* kvec, double growth, float* const out[3], bool with_nyq,
+                               const GrowthK* gk = nullptr) {
   const Geom& g = ctx->g;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
   TRY(run_dc(ctx, kvec, norm, 1));
   double2* xdst[3] = {ctx->A[1], ctx->A[0], nullptr};  // p=0 -> A1, p=1 -> A0
   // Rsmooth = 0 (src/fmax.c:200 with R = 0): window = 1
-  TRY(run_xpass_inv(ctx, kvec, xdst, 0x3, false, 1, 1, norm * growth, with_nyq));
+  TRY(run_xpass_inv(ctx, kvec, xdst, 0x3, false, 1, 1, norm * growth, with_nyq, gk));
   const double2* ysrc[3] = {ctx->A[0], ctx->A[1], nullptr};
   double2* ydst[6] = {ctx->D[0], ctx->D[1], ctx->D[2], nullptr, nullptr, nullptr};
   static const YJob jobs[3] = {{0, 0, 0}, {1, 1, 1}, {1, 0, 2}};
@@ -699,8 +713,8 @@ static int first_derivs_to_vel(pinb200_ctx* ctx, const double2* kvec, double gro
   return 0;
 }
 
-extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, const double growth[4]) {
-  if (!ctx || !growth) return 1;
+// growth: scale-independent rates (gk == nullptr) or all ones with gk[0..3] the per-order tables
+static int displacements_impl(pinb200_ctx* ctx, int compute_sources, const double growth[4], const GrowthK* gk) {
   if (!ctx->kdens_valid) FAIL("kdensity not resident");
   NEED_PEERS();
   CK(cudaSetDevice(ctx->d.device));
@@ -770,12 +784,12 @@ extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, cons
   const int nvel = order == 1 ? 3 : (order == 2 ? 6 : 12);
   for (int i = 0; i < nvel; i++) TRY(dev_alloc(ctx, &ctx->vel[i], ctx->ncells));
   TRY(peer_barrier(ctx));  // all k-vectors complete everywhere before rank 0's k = 0 modes are read
-  if (order >= 2) TRY(first_derivs_to_vel(ctx, ctx->KV[0], growth[1], ctx->vel + 3, true));   // ScaleDep.order = 2
+  if (order >= 2) TRY(first_derivs_to_vel(ctx, ctx->KV[0], growth[1], ctx->vel + 3, true, gk ? gk + 1 : nullptr));   // ScaleDep.order = 2
   if (order >= 3) {
-    TRY(first_derivs_to_vel(ctx, ctx->KV[1], growth[2], ctx->vel + 6, true));                 // order 3
-    TRY(first_derivs_to_vel(ctx, ctx->KV[2], growth[3], ctx->vel + 9, true));                 // order 4
+    TRY(first_derivs_to_vel(ctx, ctx->KV[1], growth[2], ctx->vel + 6, true, gk ? gk + 2 : nullptr));                 // order 3
+    TRY(first_derivs_to_vel(ctx, ctx->KV[2], growth[3], ctx->vel + 9, true, gk ? gk + 3 : nullptr));                 // order 4
   }
-  TRY(first_derivs_to_vel(ctx, ctx->kdens, growth[0], ctx->vel + 0, false));                  // order 1, src/fmax.c:342-346
+  TRY(first_derivs_to_vel(ctx, ctx->kdens, growth[0], ctx->vel + 0, false, gk));                 // order 1, src/fmax.c:342-346
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   TRY(check_peer_error(ctx));
@@ -786,6 +800,33 @@ extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, cons
   ctx->tm.disp_sources += a * 1e-3;
   ctx->tm.disp_vel += b * 1e-3;
   return 0;
+}
+
+extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, const double growth[4]) {
+  if (!ctx || !growth) return 1;
+  return displacements_impl(ctx, compute_sources, growth, nullptr);
+}
+
+extern "C" int pinb200_displacements_scaledep(pinb200_ctx* ctx, int compute_sources, int nk, double logkmin, double dlogk,
+                                              const double* log10_growth) {
+  if (!ctx || !log10_growth) return 1;
+  if (nk < 1 || nk > 4096) FAIL("scale-dependent growth: nk out of range");
+  if (!(dlogk > 0.0)) FAIL("scale-dependent growth: dlogk must be positive");
+  CK(cudaSetDevice(ctx->d.device));
+  TRY(dev_free(ctx, &ctx->growthk));
+  TRY(dev_alloc(ctx, &ctx->growthk, (size_t)4 * nk));
+  // pageable source: the copy is staged before the call returns, so the caller's array may go away
+  CK(cudaMemcpyAsync(ctx->growthk, log10_growth, sizeof(double) * 4 * nk, cudaMemcpyHostToDevice, ctx->stream));
+  GrowthK gk[4];
+  for (int o = 0; o < 4; o++) {
+    gk[o].tab = ctx->growthk + (size_t)o * nk;
+    gk[o].n = nk;
+    gk[o].logkmin = logkmin;
+    gk[o].dlogk = dlogk;
+    gk[o].sign = (o == 2) ? -1.0 : 1.0;  // GrowingMode_3LPT_1 returns the negative, src/cosmo.c:1810
+  }
+  static const double ones[4] = {1.0, 1.0, 1.0, 1.0};
+  return displacements_impl(ctx, compute_sources, ones, gk);
 }
 
 extern "C" int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts) {
@@ -863,7 +904,7 @@ extern "C" int pinb200_get_timers(pinb200_ctx* ctx, pinb200_timers* t) {
 // ---- finer-grained entry points -------------------------------------------------------------
 extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* real_out) {
   if (!ctx || !cplx_in || !real_out) return 1;
-  if (ctx->P != 1) FAIL("pinb200_fft_c2r on host arrays is a single-rank entry point");
+  NEED_PEERS();  // collective on several ranks: every rank passes its own slab
   CK(cudaSetDevice(ctx->d.device));
   const Geom& g = ctx->g;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
@@ -894,7 +935,7 @@ extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* 
 
 extern "C" int pinb200_fft_r2c(pinb200_ctx* ctx, const double* real_in, double* cplx_out) {
   if (!ctx || !real_in || !cplx_out) return 1;
-  if (ctx->P != 1) FAIL("pinb200_fft_r2c on host arrays is a single-rank entry point");
+  NEED_PEERS();
   CK(cudaSetDevice(ctx->d.device));
   const Geom& g = ctx->g;
   const size_t rows = (size_t)g.lx * g.N;

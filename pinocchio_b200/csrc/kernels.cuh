@@ -34,7 +34,43 @@ struct KFactor {
   double scalar;        // 1/N^3 normalisation (src/fmax-pfft.c:224-225) times growth_rate
   int green;            // 1: divide by k^2, k=0 mode dropped here and re-added as a constant
   int times_i;          // 1: (re,im) -> (-im,re)  (first derivatives, src/fmax-pfft.c:389-394)
+  // Scale-dependent growth (ScaleDep.order 1..4, src/fmax-pfft.c:344-364): growth_rate(|k|) =
+  // gk_sign * 10^(interpolation, linear in log10 k, of gk[0..gk_n-1]) where gk[j] is
+  // InterpolateGrowth's j-th k-bin spline evaluated at the segment redshift (src/cosmo.c:1728-1757),
+  // |k| in grid units as the reference passes it.  nullptr: `scalar` already holds the growth rate.
+  const double* gk;
+  int gk_n;
+  double gk_logkmin, gk_dlogk;  // LOGKMIN, DELTALOGK (src/def_splines.h:41-42)
+  double gk_sign;               // -1 for GrowingMode_3LPT_1 (src/cosmo.c:1810)
 };
+
+// InterpolateGrowth (src/cosmo.c:1728-1757) at a fixed redshift, followed by the pow(10., .) of
+// GrowingMode* (src/cosmo.c:1786-1819).  kmin = 10^LOGKMIN, kmax = 10^(LOGKMIN + (n-1) DELTALOGK)
+// are recomputed with pow() exactly as src/cosmo.c:169-170 does.
+struct GrowthRange {
+  double kmin = 0.0, kmax = 0.0;
+  PINB_HD void set(const KFactor& kf) {
+    kmin = pow(10., kf.gk_logkmin);
+    kmax = pow(10., kf.gk_logkmin + (kf.gk_n - 1) * kf.gk_dlogk);
+  }
+};
+PINB_HD double growth_of_k(const KFactor& kf, const GrowthRange& gr, double k) {
+  const double kmin = gr.kmin, kmax = gr.kmax;
+  double v;
+  if (k < kmin) {
+    v = kf.gk[0];
+  } else if (k > kmax) {
+    v = kf.gk[kf.gk_n - 1];
+  } else {
+    double dk = (log10(k) - kf.gk_logkmin) / kf.gk_dlogk;
+    const int kk = (int)dk;
+    dk -= kk;
+    // k == kmax gives kk = n-1 and dk = 0: the reference reads SPLINE[pointer+kk+1] there too
+    // (the next table, times zero); here the weight-zero term is dropped instead
+    v = (kk + 1 < kf.gk_n) ? dk * kf.gk[kk + 1] + (1 - dk) * kf.gk[kk] : kf.gk[kk];
+  }
+  return kf.gk_sign * pow(10., v);
+}
 
 // Launch shapes shared by the CUDA instantiations and the host emulator.
 // kz-tile width of the strided passes: 8 complex (128 B contiguous per line element) while the
@@ -217,7 +253,9 @@ struct XPassParams {
 
 // MULTI = false: one rank; the owner look-up and the per-rank pointer table are compiled out
 // (they cost registers: the 1024-point kernel spilled 128 bytes with them).
-template <int L, int DIR, bool MULTI, class Ctx>
+// GK = true: the scale-dependent growth rate is evaluated per mode (separate instantiation so that
+// the Hessian pass keeps its register budget).
+template <int L, int DIR, bool MULTI, class Ctx, bool GK = false>
 PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   using C = XCfg<L, DIR>;
   constexpr int TK = C::TK, LT = C::LT;
@@ -248,6 +286,8 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   const double kyz2 = ky * ky + kz_t * kz_t;
   double fyz = p.kf.scalar;
   if (p.kf.gauss) fyz *= ld_ro(p.kf.gauss + (ny < 0 ? -ny : ny)) * ld_ro(p.kf.gauss + kz0 + tk0);
+  GrowthRange grange;
+  if constexpr (GK) grange.set(p.kf);
   auto mode = [&](int pw, int e, double2 c) {
     const int nx = fold(e, g.N, g.M);
     const double kx = g.knorm * nx;
@@ -255,6 +295,10 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
     if (p.kf.green) {
       const double k2 = kx * kx + kyz2;
       f = (k2 != 0.0) ? f / k2 : 0.0;  // (a MUFU seed + Newton reciprocal measured 30 % slower here)
+    }
+    if constexpr (GK) {
+      const double k2 = kx * kx + kyz2;
+      if (k2 != 0.0) f *= growth_of_k(p.kf, grange, sqrt(k2));  // k_module, src/fmax-pfft.c:340
     }
     if (p.kf.gauss) f *= ld_ro(p.kf.gauss + (nx < 0 ? -nx : nx));
     f *= ipow(kx, pw);

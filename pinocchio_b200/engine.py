@@ -52,6 +52,7 @@ ABI_SYMBOLS = [
     "pinb200_ipc_handle", "pinb200_connect",
     "pinb200_set_power_table", "pinb200_set_smoothing", "pinb200_set_invgrow_spline", "pinb200_genic",
     "pinb200_upload_kdensity", "pinb200_download_kdensity", "pinb200_fmax", "pinb200_displacements",
+    "pinb200_displacements_scaledep",
     "pinb200_fmax_pdf", "pinb200_download_products", "pinb200_download_field", "pinb200_get_timers",
     "pinb200_fft_r2c", "pinb200_fft_c2r", "pinb200_second_derivatives", "pinb200_collapse_cells",
     "pinb200_download_kvector",
@@ -87,6 +88,8 @@ def load_library() -> ctypes.CDLL:
     lib.pinb200_download_kdensity.argtypes = [ctypes.c_void_p, _PD]
     lib.pinb200_fmax.argtypes = [ctypes.c_void_p, _PD]
     lib.pinb200_displacements.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
+    lib.pinb200_displacements_scaledep.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                   ctypes.c_double, _PD]
     lib.pinb200_fmax_pdf.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]
     lib.pinb200_download_products.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ProductLayout),
                                               ctypes.c_size_t, ctypes.c_size_t]
@@ -211,10 +214,24 @@ class Pinocchio:
         return np.array([c.GrowingMode(redshift), c.GrowingMode_2LPT(redshift), c.GrowingMode_3LPT_1(redshift),
                          c.GrowingMode_3LPT_2(redshift)])
 
+    def set_scale_dependent_growth(self, log10_growth_of_z, logkmin: float = -3.0, dlogk: float = 0.5):
+        """-DSCALE_DEPENDENT (src/def_splines.h:40-42): ``log10_growth_of_z(z)`` returns the [4][NkBINS]
+        values my_spline_eval(SPLINE[SP_GROW1|2|31|32 + j], -log10(1+z)) that InterpolateGrowth
+        (src/cosmo.c:1728-1757) interpolates in log10 k; None switches back to scale-independent growth."""
+        self._scaledep = None if log10_growth_of_z is None else (log10_growth_of_z, float(logkmin), float(dlogk))
+
     def compute_displacements(self, compute_sources: int, recompute_sd: int, redshift: float) -> int:
         """src/fmax.c:292-367 (recompute_sd is the special-mode-3 path and is not supported)."""
         if recompute_sd:
             raise PinocchioError("recompute_sd=1 (special mode 3, src/pinocchio.c:186) is not supported")
+        sd = getattr(self, "_scaledep", None)
+        if sd is not None:
+            tab = np.ascontiguousarray(sd[0](redshift), dtype=np.float64)
+            if tab.ndim != 2 or tab.shape[0] != 4:
+                raise PinocchioError("scale-dependent growth tables must have shape [4][NkBINS]")
+            self._ck(self.lib.pinb200_displacements_scaledep(self.h, int(compute_sources), tab.shape[1], sd[1], sd[2],
+                                                             _dp(tab)))
+            return 0
         g = self.growth_rates(redshift)
         self._ck(self.lib.pinb200_displacements(self.h, int(compute_sources), _dp(g)))
         return 0
@@ -273,14 +290,17 @@ class Pinocchio:
 
     # -- finer-grained reference functions (parity tests) ----------------------------------
     def forward_transform(self, r: np.ndarray) -> np.ndarray:
+        """src/fmax-pfft.c:191-200 on this rank's slab: real [lx][N][N] -> half-complex [N][ly][N/2+1]."""
         r = np.ascontiguousarray(r, dtype=np.float64)
-        out = np.zeros((self.N, self.N, self.N // 2 + 1), dtype=np.complex128)
+        assert r.shape == (self.lx, self.N, self.N)
+        out = np.zeros((self.N, self.lx, self.N // 2 + 1), dtype=np.complex128)
         self._ck(self.lib.pinb200_fft_r2c(self.h, _dp(r), out.view(np.float64).ctypes.data_as(_PD)))
         return out
 
     def reverse_transform(self, c: np.ndarray) -> np.ndarray:
         c = np.ascontiguousarray(c, dtype=np.complex128)
-        out = np.zeros((self.N, self.N, self.N), dtype=np.float64)
+        assert c.shape == (self.N, self.lx, self.N // 2 + 1)
+        out = np.zeros((self.lx, self.N, self.N), dtype=np.float64)
         self._ck(self.lib.pinb200_fft_c2r(self.h, c.view(np.float64).ctypes.data_as(_PD), _dp(out)))
         return out
 

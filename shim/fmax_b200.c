@@ -14,6 +14,8 @@
 #include "pinb200.h"
 
 #include <stddef.h>
+#include <string.h>
+#include <sys/stat.h>
 
 static pinb200_ctx *pinb = NULL;
 
@@ -167,6 +169,21 @@ int compute_displacements(int compute_sources, int recompute_sd, double redshift
     printf("ERROR on task %d: recompute_sd (special mode 3) is not supported by the GPU path\n", ThisTask);
     return 1;
   }
+#ifdef SCALE_DEPENDENT
+  (void)growth;
+  {
+    /* growth_rate depends on |k| (src/fmax-pfft.c:340-364): hand InterpolateGrowth's k-bin splines,
+       evaluated at this redshift, to the device (src/cosmo.c:1728-1757; SP_GROW* src/def_splines.h:55-58) */
+    static const int first[4] = {SP_GROW1, SP_GROW2, SP_GROW31, SP_GROW32};
+    double tab[4 * NkBINS];
+    int o, j;
+    for (o = 0; o < 4; o++)
+      for (j = 0; j < NkBINS; j++)
+        tab[o * NkBINS + j] = my_spline_eval(SPLINE[first[o] + j], -log10(1. + redshift), ACCEL[first[o] + j]);
+    if (pinb200_displacements_scaledep(pinb, compute_sources, NkBINS, LOGKMIN, DELTALOGK, tab))
+      return pinb_fail("compute_displacements");
+  }
+#else
   /* growth_rate of src/fmax-pfft.c:344-364 for ScaleDep.order = 1..4 */
   growth[0] = GrowingMode(redshift, params.k_for_GM);
   growth[1] = GrowingMode_2LPT(redshift, params.k_for_GM);
@@ -174,6 +191,7 @@ int compute_displacements(int compute_sources, int recompute_sd, double redshift
   growth[3] = GrowingMode_3LPT_2(redshift, params.k_for_GM);
   if (pinb200_displacements(pinb, compute_sources, growth))
     return pinb_fail("compute_displacements");
+#endif
   cputime.lpt += MPI_Wtime() - t0;
 
   /* products[] is carved from the reference's arena; it is only filled here, never retained */
@@ -250,6 +268,151 @@ int compute_fmax(void)
     printf("[%s] Finishing fmax, total fmax cpu time = %14.6f\n", fdate(), cputime.fmax);
   return 0;
 }
+
+/* ---- replaces src/fmax-pfft.c:191-228, 459-560: the FFT work vectors of the host code ---------
+ * Used outside the replaced files only by the density special mode (src/pinocchio.c:146-150) and by
+ * -DWHITENOISE (src/ReadWhiteNoise.c:161,222).  rvector_fft / cvector_fft stay the host arrays that
+ * allocate_fft_vectors hands out (src/allocations.c:380-394); the transform itself runs on the device.
+ * Layouts: real [GSlocal_x][N][N], half-complex [N][GSlocal_k_y][N/2+1] (set_one_grid above). */
+void write_in_cvector(int ThisGrid, double *restrict vector)
+{
+  memcpy(cvector_fft[ThisGrid], vector, (size_t)MyGrids[ThisGrid].total_local_size_fft * sizeof(double));
+}
+
+void write_from_cvector(int ThisGrid, double *restrict vector)
+{
+  memcpy(vector, cvector_fft[ThisGrid], (size_t)MyGrids[ThisGrid].total_local_size_fft * sizeof(double));
+}
+
+void write_in_rvector(int ThisGrid, double *restrict vector)
+{
+  memcpy(rvector_fft[ThisGrid], vector, (size_t)MyGrids[ThisGrid].total_local_size * sizeof(double));
+}
+
+void write_from_rvector(int ThisGrid, double *restrict vector)
+{
+  memcpy(vector, rvector_fft[ThisGrid], (size_t)MyGrids[ThisGrid].total_local_size * sizeof(double));
+}
+
+double forward_transform(int ThisGrid)
+{
+  double t0 = MPI_Wtime();
+  if (pinb200_fft_r2c(pinb, rvector_fft[ThisGrid], (double *)cvector_fft[ThisGrid]))
+    pinb_fail("forward_transform");
+  return MPI_Wtime() - t0;
+}
+
+double reverse_transform(int ThisGrid)
+{
+  /* includes the 1/N^3 of src/fmax-pfft.c:220-225 */
+  double t0 = MPI_Wtime();
+  if (pinb200_fft_c2r(pinb, (double *)cvector_fft[ThisGrid], rvector_fft[ThisGrid]))
+    pinb_fail("reverse_transform");
+  return MPI_Wtime() - t0;
+}
+
+/* ---- replaces src/fmax.c:372-506: the DumpProducts file boundary ------------------------------
+ * DumpDir/summary (four "%d   # ..." lines: NTasks, RandomSeed, GridSize, sizeof(product_data)),
+ * DumpDir/TrueVariance (Nsmooth raw doubles), DumpDir/Task.<rank> (raw products[] of the rank). */
+static FILE *dump_open(const char *name, int task, const char *mode)
+{
+  char fname[LBLENGTH];
+  FILE *f;
+  if (task >= 0)
+    sprintf(fname, "%s%s.%d", params.DumpDir, name, task);
+  else
+    sprintf(fname, "%s%s", params.DumpDir, name);
+  f = fopen(fname, mode);
+  if (!f)
+    printf("ERROR on Task %d: could not open file %s\n", ThisTask, fname);
+  return f;
+}
+
+int dump_products(void)
+{
+  FILE *f;
+  int err = 0;
+  if (!ThisTask)
+  {
+    struct stat st;
+    if (stat(params.DumpDir, &st))
+    {
+      printf("Creating directory %s\n", params.DumpDir);
+      if (mkdir(params.DumpDir, 0755))
+      {
+        printf("ERROR IN CREATING DIRECTORY %s (task 0)\n", params.DumpDir);
+        err = 1;
+      }
+    }
+    if (!err && (f = dump_open("summary", -1, "w")))
+    {
+      fprintf(f, "%d   # NTasks\n%d   # random seed\n%d   # grid size\n%d   # length of product_data\n", NTasks,
+              params.RandomSeed, params.GridSize[0], (int)sizeof(product_data));
+      fclose(f);
+    }
+    else
+      err = 1;
+    if (!err && (f = dump_open("TrueVariance", -1, "wb")))
+    {
+      fwrite(Smoothing.TrueVariance, sizeof(double), Smoothing.Nsmooth, f);
+      fclose(f);
+    }
+    else
+      err = 1;
+  }
+  MPI_Barrier(MPI_COMM_WORLD); /* the directory exists before anybody writes into it */
+  if (err || !(f = dump_open("Task", ThisTask, "wb")))
+    return 1;
+  fwrite(products, sizeof(product_data), MyGrids[0].total_local_size, f);
+  fclose(f);
+  return 0;
+}
+
+int read_dumps(void)
+{
+  FILE *f;
+  if (!ThisTask)
+  {
+    int v[4], want[4], i, bad = 0;
+    static const char *what[4] = {"number of tasks", "random seed", "grid size", "length of product_data"};
+    char buf[SBLENGTH];
+    want[0] = NTasks; want[1] = params.RandomSeed; want[2] = params.GridSize[0]; want[3] = (int)sizeof(product_data);
+    if (!(f = dump_open("summary", -1, "r")))
+      return 1;
+    for (i = 0; i < 4; i++)
+      if (!fgets(buf, SBLENGTH, f) || sscanf(buf, "%d", &v[i]) != 1)
+        v[i] = -1;
+    fclose(f);
+    for (i = 0; i < 4; i++)
+      if (v[i] != want[i])
+      {
+        printf("ERROR: the %s in %ssummary does not match - %d vs %d\n", what[i], params.DumpDir, v[i], want[i]);
+        bad++;
+      }
+    if (bad)
+      return 1;
+    if (!(f = dump_open("TrueVariance", -1, "rb")))
+      return 1;
+    if (fread(Smoothing.TrueVariance, sizeof(double), Smoothing.Nsmooth, f) != (size_t)Smoothing.Nsmooth)
+      printf("WARNING: short read of %sTrueVariance\n", params.DumpDir);
+    fclose(f);
+  }
+  MPI_Bcast(Smoothing.TrueVariance, Smoothing.Nsmooth, MPI_DOUBLE, 0, MPI_COMM_WORLD);
+  if (!(f = dump_open("Task", ThisTask, "rb")))
+    return 1;
+  if (fread(products, sizeof(product_data), MyGrids[0].total_local_size, f) != MyGrids[0].total_local_size)
+  {
+    printf("ERROR on Task %d: short read of the products dump\n", ThisTask);
+    fclose(f);
+    return 1;
+  }
+  fclose(f);
+  return 0;
+}
+
+#ifdef TABULATED_CT
+#error "TABULATED_CT / ELL_SNG (src/collapse_times.c:239-400,780-1346) is not provided by the GPU path"
+#endif
 
 char *fdate(void)
 {

@@ -66,14 +66,22 @@ class EmuCluster:
             assert self.lib.emu_genic(self.N, r, self.P, ptr(np.ascontiguousarray(seeds), PU32), ptr(pk),
                                       ctypes.c_double(box), 0, 0, ptr(self.kdens[r])) == 0
 
-    def xpass_inv(self, src, dsts, pmask, with_nyq, gauss, scalar, green, times_i):
-        """src[rank]: K layout; dsts: {power: A-like [rank] list}."""
+    def xpass_inv(self, src, dsts, pmask, with_nyq, gauss, scalar, green, times_i, gk=None):
+        """src[rank]: K layout; dsts: {power: A-like [rank] list}; gk = (table, logkmin, dlogk, sign):
+        scale-dependent growth (KFactor::gk*)."""
         flat = []
         for pw in range(3):
             flat += dsts.get(pw, [None] * self.P)
         for r in range(self.P):
-            assert self.lib.emu_xpass(self.N, +1, r, self.P, ptr(src[r]), ptr_array(flat, 3 * self.P), 0, pmask,
-                                      with_nyq, ptr(gauss), ctypes.c_double(scalar), green, times_i, ptr(self.tw)) == 0
+            if gk is None:
+                assert self.lib.emu_xpass(self.N, +1, r, self.P, ptr(src[r]), ptr_array(flat, 3 * self.P), 0, pmask,
+                                          with_nyq, ptr(gauss), ctypes.c_double(scalar), green, times_i, ptr(self.tw)) == 0
+            else:
+                tab = np.ascontiguousarray(gk[0], dtype=np.float64)
+                assert self.lib.emu_xpass_gk(self.N, +1, r, self.P, ptr(src[r]), ptr_array(flat, 3 * self.P), 0, pmask,
+                                             with_nyq, ptr(gauss), ctypes.c_double(scalar), green, times_i, ptr(self.tw),
+                                             ptr(tab), tab.size, ctypes.c_double(gk[1]), ctypes.c_double(gk[2]),
+                                             ctypes.c_double(gk[3])) == 0
 
     def ypass_inv(self, srcs, dsts, jobs, with_nyq):
         ja = np.asarray(jobs, dtype=np.int32).ravel()
@@ -138,10 +146,10 @@ class EmuCluster:
                                               ptr(kz, PI32), 1, ptr(dc), 2, None, None, ptr_array(hs, 6), ptr(w),
                                               ptr(acc), ptr(self.tw)) == 0
 
-    def displacement(self, kvec, growth, with_nyq):
+    def displacement(self, kvec, growth, with_nyq, gk=None):
         """three float fields per rank from the K-layout k-vector kvec[rank]."""
         dc = np.array([-kvec[0][0, 0, 0].imag * self.norm])
-        self.xpass_inv(kvec, {0: self.A[1], 1: self.A[0]}, 3, with_nyq, None, self.norm * growth, 1, 1)
+        self.xpass_inv(kvec, {0: self.A[1], 1: self.A[0]}, 3, with_nyq, None, self.norm * growth, 1, 1, gk)
         self.ypass_inv([self.A[0], self.A[1]], self.D, [(0, 0, 0), (1, 1, 1), (1, 0, 2)], with_nyq)
         kz = np.array([0, 0, 1, 0, 0, 0], dtype=np.int32)
         out = []

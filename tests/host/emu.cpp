@@ -143,14 +143,35 @@ template <int N, int DIR> static void xpass_run(XPassParams& p, int with_nyq) {
   using C = XCfg<N, DIR>;
   p.ntiles_z = (N / 2) / C::TK + (with_nyq ? 1 : 0);
   std::vector<double2> smem((size_t)C::LT * C::TK);
-  run_blocks((long long)p.g.ly * p.ntiles_z, C::NT, [&](HostCtx& ctx) { xpass_body<N, DIR, true>(ctx, smem.data(), p); });
+  if (p.kf.gk)
+    run_blocks((long long)p.g.ly * p.ntiles_z, C::NT, [&](HostCtx& ctx) { xpass_body<N, DIR, true, HostCtx, true>(ctx, smem.data(), p); });
+  else
+    run_blocks((long long)p.g.ly * p.ntiles_z, C::NT, [&](HostCtx& ctx) { xpass_body<N, DIR, true>(ctx, smem.data(), p); });
 }
 
 // dsts: 3*nranks pointers, dsts[p*nranks + r] = destination field for power p on rank r
 extern "C" int emu_xpass(int N, int dir, int rank, int nranks, const double* src, double** dsts, int dst_klayout,
                          int pmask, int with_nyq, const double* gauss, double scalar, int green, int times_i,
+                         const double* tw);
+// the same with the scale-dependent growth table gk[gk_n] (see KFactor); gk == nullptr: plain emu_xpass
+extern "C" int emu_xpass_gk(int N, int dir, int rank, int nranks, const double* src, double** dsts, int dst_klayout,
+                            int pmask, int with_nyq, const double* gauss, double scalar, int green, int times_i,
+                            const double* tw, const double* gk, int gk_n, double gk_logkmin, double gk_dlogk, double gk_sign);
+extern "C" int emu_xpass(int N, int dir, int rank, int nranks, const double* src, double** dsts, int dst_klayout,
+                         int pmask, int with_nyq, const double* gauss, double scalar, int green, int times_i,
                          const double* tw) {
+  return emu_xpass_gk(N, dir, rank, nranks, src, dsts, dst_klayout, pmask, with_nyq, gauss, scalar, green, times_i, tw, nullptr, 0,
+                      0.0, 1.0, 1.0);
+}
+extern "C" int emu_xpass_gk(int N, int dir, int rank, int nranks, const double* src, double** dsts, int dst_klayout,
+                            int pmask, int with_nyq, const double* gauss, double scalar, int green, int times_i,
+                            const double* tw, const double* gk, int gk_n, double gk_logkmin, double gk_dlogk, double gk_sign) {
   XPassParams p{};
+  p.kf.gk = gk;
+  p.kf.gk_n = gk_n;
+  p.kf.gk_logkmin = gk_logkmin;
+  p.kf.gk_dlogk = gk_dlogk;
+  p.kf.gk_sign = gk_sign;
   p.src = (const double2*)src;
   for (int pw = 0; pw < 3; pw++)
     for (int r = 0; r < nranks; r++) p.dst[pw].r[r] = (double2*)dsts[pw * nranks + r];

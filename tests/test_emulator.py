@@ -137,6 +137,51 @@ def test_genic_hessian_collapse_lpt(cosmo, P, split):
             assert np.abs(V[a] - ref[a]).max() < 2e-7 * np.abs(ref[a]).max()   # float32 storage
 
 
+def scaledep_tables(nk=10, seed=11):
+    """[4][NkBINS] log10 growth tables with a pronounced k dependence (what InterpolateGrowth's
+    k-bin splines return at one redshift, src/cosmo.c:1728-1757)."""
+    rng = np.random.default_rng(seed)
+    base = np.log10(np.array([0.61, 0.16, 0.05, 0.11]))[:, None]
+    return base + 0.3 * np.cumsum(rng.uniform(-0.2, 0.2, (4, nk)), axis=1)
+
+
+def test_interpolate_growth_clamps_and_knots():
+    """Oracle restatement of InterpolateGrowth: knots are reproduced, clamped outside [kmin, kmax]."""
+    tab = scaledep_tables()[0]
+    kn = 10.0 ** (-3.0 + 0.5 * np.arange(10))
+    v = po.interpolate_growth(kn * (1 + 1e-13), tab)     # just inside each bin
+    assert np.abs(v[:-1] - tab[:-1]).max() < 1e-10
+    assert po.interpolate_growth(np.array([1e-5]), tab)[0] == tab[0]
+    assert po.interpolate_growth(np.array([1e3]), tab)[0] == tab[-1]
+    mid = po.interpolate_growth(np.array([10.0 ** -1.75]), tab)[0]      # halfway between bins 2 and 3
+    assert abs(mid - 0.5 * (tab[2] + tab[3])) < 1e-13
+
+
+@pytest.mark.parametrize("P,split", [(1, False), (2, False), (1, True)])
+def test_scale_dependent_displacements(P, split):
+    """-DSCALE_DEPENDENT: growth_rate(|k|) applied per mode in the x-pass loader
+    (src/fmax-pfft.c:340-364) for ScaleDep.order 1..4, k = 0 mode left unscaled."""
+    N = 32
+    cl = EmuCluster(N, P, split)
+    rng = np.random.default_rng(21)
+    tabs = scaledep_tables()
+    # tables whose bins straddle the grid's k range (2 pi/N .. pi sqrt 3): LOGKMIN -1.5, DELTALOGK 0.25,
+    # so that clamping below kmin, interpolation and clamping above kmax all occur
+    for logkmin, dlogk in ((-3.0, 0.5), (-0.6, 0.1)):
+        for order in (1, 2, 3, 4):
+            c = rng.standard_normal((N, N, N // 2 + 1)) + 1j * rng.standard_normal((N, N, N // 2 + 1))
+            if order == 1:
+                c[N // 2, :, :] = 0; c[:, N // 2, :] = 0; c[:, :, N // 2] = 0     # delta_k has no Nyquist planes
+            cl.scatter_k(c, cl.KV[0])
+            sign = -1.0 if order == 3 else 1.0
+            V = cl.displacement(cl.KV[0], 1.0, 0 if order == 1 else 1, gk=(tabs[order - 1], logkmin, dlogk, sign))
+            g = po.growth_rate_of_k(N, order, tabs, logkmin, dlogk)
+            assert g.std() > 1e-3 * abs(g.mean())          # the test tables really depend on k
+            ref = po.first_derivatives(c, g)
+            for a in range(3):
+                assert np.abs(V[a] - ref[a]).max() < 2e-7 * np.abs(ref[a]).max()
+
+
 def test_collapse_cells_branches(lib, cosmo):
     """inverse_collapse_time on synthetic Hessians covering the branches of ell_classic."""
     rng = np.random.default_rng(3)

@@ -158,3 +158,27 @@ def test_reference_compute_fmax_live_against_golden_and_oracle(gold, cosmo):
     # a second call on the same field: compute_fmax re-initialises products at ismooth == 0
     run.compute_fmax()
     assert np.array_equal(run.products(po.PRODUCT_DTYPE_3LPT)["Fmax"], gold["products"]["Fmax"])
+
+
+def test_oracle_scale_dependent_growth_against_reference_golden(gold):
+    """-DSCALE_DEPENDENT: the reference's own k loop (src/fmax-pfft.c:306-397) with a k-dependent
+    growth rate (fixture reference_scaledep_32.npz, made by make_reference_scaledep_golden.py)
+    against the oracle's growth_rate_of_k -- pins that |k| is passed in GRID units, that the
+    k = 0 mode stays unscaled and the sign of GrowingMode_3LPT_1."""
+    sd = dict(np.load(ROOT / "tests" / "golden" / "reference_scaledep_32.npz"))
+    N = int(sd["N"])
+    tab, lk, dk = sd["log10_growth"], float(sd["logkmin"]), float(sd["dlogk"])
+    g = [po.growth_rate_of_k(N, o, tab, lk, dk) for o in (1, 2, 3, 4)]
+    assert (g[2] < 0).all() and (g[0] > 0).all()
+    for gi in g:
+        assert gi.std() > 1e-2 * abs(gi.mean())
+    h = po.second_derivatives(gold["kdensity"], 0.0, float(gold["box"]) / N)
+    kv = po.lpt_kvectors(h)
+    fields = {"Vel": (gold["kdensity"], g[0]), "Vel_2LPT": (kv[0], g[1]), "Vel_3LPT_1": (kv[1], g[2]),
+              "Vel_3LPT_2": (kv[2], g[3])}
+    for name, (kvec, growth) in fields.items():
+        o = po.first_derivatives(kvec, growth)
+        for a in range(3):
+            v = sd[name][:, a].reshape(N, N, N)
+            assert np.abs(v.astype(np.float64) - o[a]).max() <= 2e-7 * np.abs(o[a]).max(), (name, a)
+            assert (v == o[a]).mean() > 0.999, (name, a)
