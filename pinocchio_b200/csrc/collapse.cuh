@@ -11,6 +11,9 @@
 //   * pow(x, 0.333333333333333) -> cbrt(x);   1/pow(10, y) -> exp10(-y);
 //   * divisions by literal constants -> multiplications; a/b/c -> a/(b*c);
 //   * the spline interval comes from a uniform look-up table instead of a 10-step search;
+//   * divisions and square roots on the common path use the MUFU seeds + Newton steps of
+//     fastmath.cuh without CUDA's range checks and called slow paths (fm_rcp, fm_div,
+//     fm_sqrt_pair); 2r/(q 2 sqrt q) becomes r (1/sqrt q)^3 from the same Newton chain;
 //   * the common path of ell_classic is branch free (both cubic cases are evaluated and
 //     selected) so that two cells can be interleaved per thread; the rare guarded cases
 //     (|l1| < SMALL, |den| < SMALL) fall back to the reference's nested branches.
@@ -168,7 +171,7 @@ PINB_HD double ell_classic_flat(double l1, double l2, double l3) {
   const double det = l1 * l2 * l3;
   const double den = det * mc(MC_1_126) + mc(MC_5_84) * l1 * del * (del - l1);
   if (fabs(l1) < PINB_SMALL || fabs(den) < PINB_SMALL) return ell_classic(l1, l2, l3);
-  const double rden = 1.0 / den;
+  const double rden = fm_rcp(den);  // |den| >= 1e-20 here
   const double a1 = 3. * l1 * (del - l1) * mc(MC_1_14) * rden;
   const double a1_2 = a1 * a1;
   const double a2 = l1 * rden;
@@ -183,14 +186,16 @@ PINB_HD double ell_classic_flat(double l1, double l2, double l3) {
   // cell in __cuda_sm20_div_rn_f64_full / dsqrt_rn_f64_mediumpath before this guard).
   const bool c1 = r_2_q_3 > 0;
   // case 1 (r^2 - q^3 > 0)
-  const double sqa = cbrt(sqrt(c1 ? r_2_q_3 : 1.0) + fabs(r));
+  const double sqa = cbrt(fm_sqrt_pair(c1 ? r_2_q_3 : 1.0).s + fabs(r));
   const double sg = (r > 0.) ? -1.0 : ((r < 0.) ? 1.0 : NAN);
-  double ella = sg * (sqa + q / sqa) - a1_3;
+  double ella = sg * (sqa + fm_div(q, sqa)) - a1_3;
   ella = (ella < 0.) ? -.1 : ella;
   // case 2 (r^2 <= q^3, hence q >= 0; a NaN discriminant lands here as in the reference)
+  // 2 r / (q * 2 sqrt q) = r * (1/sqrt q)^3: sqrt and its reciprocal come from one Newton chain
   const double q2 = c1 ? 1.0 : q;
-  const double sqb = 2 * sqrt(q2);
-  const double t = fm_acos(c1 ? 0.0 : 2 * r / (q2 * sqb));
+  const SqrtPair sp = fm_sqrt_pair(q2);
+  const double sqb = 2 * sp.s;
+  const double t = fm_acos(c1 ? 0.5 : r * (sp.rs * sp.rs * sp.rs));
   double c0, c1c, c2;
   cos_thirds(t, c0, c1c, c2);
   double s1 = -sqb * c0 - a1_3;
@@ -203,7 +208,7 @@ PINB_HD double ell_classic_flat(double l1, double l2, double l3) {
   ellb = (s3 < ellb ? s3 : ellb);
   ellb = (ellb == 1.e10) ? -.1 : ellb;
   double ell = c1 ? ella : ellb;
-  const double inv_del = 1.0 / del;
+  const double inv_del = fm_rcp(del);  // NaN for del = 0: corr is then unused
   const double corr = mc(MC_M0364) * inv_del * fm_exp_neg((mc(MC_M65) * (l1 - l2) + mc(MC_M28) * (l2 - l3)) * inv_del);
   if (del > 0. && ell > 0.) ell += corr;
   return ell;
@@ -225,8 +230,9 @@ PINB_HD double inverse_collapse_time(const double* d, const SplineView& sp) {
   // benign operands on the lanes whose trigonometric solution is not used (see ell_classic_flat)
   const bool unused = diag || bad;
   const double qs = unused ? 1.0 : q;
-  const double sq = 2 * sqrt(qs);
-  const double t = fm_acos(unused ? 0.0 : 2 * r / (qs * sq));
+  const SqrtPair rt = fm_sqrt_pair(qs);
+  const double sq = 2 * rt.s;
+  const double t = fm_acos(unused ? 0.5 : r * (rt.rs * rt.rs * rt.rs));  // 2 r / (q * 2 sqrt q)
   const double m3 = mu1 * mc(MC_1_3);
   double c0, c1, c2;
   cos_thirds(t, c0, c1, c2);
@@ -239,8 +245,11 @@ PINB_HD double inverse_collapse_time(const double* d, const SplineView& sp) {
   const double lo = (n12 < x3 ? n12 : x3);
   const double mid = x1 + x2 + x3 - lo - hi;
   const double bc = ell_classic_flat(hi, mid, lo);
-  double F = 0.0;
-  if (bc > 0.0) F = 1. + inverse_growing_mode(sp, bc);
+  // 92 % of the cells have b_c > 0: evaluated on every lane (benign operand 1 elsewhere) so that
+  // the code stays convergent
+  const bool pos = bc > 0.0;
+  const double igm = inverse_growing_mode(sp, pos ? bc : 1.0);
+  const double F = pos ? 1. + igm : 0.0;
   return bad ? -10.0 : F;
 }
 

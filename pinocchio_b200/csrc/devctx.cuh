@@ -9,6 +9,9 @@ struct DevCtx {
   __device__ __forceinline__ int bid() const { return blockIdx.x; }
   __device__ __forceinline__ int nthreads() const { return blockDim.x; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
+  // v has the same value in every lane of the warp (e.g. tid >> 5): routing it through a shuffle
+  // from lane 0 lets the compiler's divergence analysis see that
+  __device__ __forceinline__ int warp_uniform(int v) const { return __shfl_sync(0xffffffffu, v, 0); }
   // barrier among the n threads that own one z line: a warp-level sync when the line fits a warp
   // (several small lines may share a warp: every lane executes the same instruction stream),
   // else a named barrier (ids 1..15; n is a multiple of 32)

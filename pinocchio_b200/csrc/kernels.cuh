@@ -590,6 +590,41 @@ PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double*
   SplineView sp{spline_global ? p.spline : spl_s, p.nspl};
   const double dc = p.zs.dc_add ? ld_ro(p.zs.dc_add) : 0.0;
   double sd = 0.0, sd2 = 0.0;
+  // Warp-chunk form of the cell loop: warp w takes the 32-cell chunks w, w + NT/32, ...  The trip
+  // count then depends on a value the compiler knows to be warp-uniform (ctx.warp_uniform), so
+  // the loop is convergent control flow: the ~110 polynomial coefficients of the collapse
+  // arithmetic can be fetched through the uniform datapath (LDCU.128 + UR operands) instead of
+  // one LDC.64 into two vector registers each, in a kernel bound by issue slots and capped at 56
+  // registers.
+  constexpr bool CHUNKED = (CPT == 1) && (NT % 32 == 0) && ((TL * N) % 32 == 0);
+  if constexpr (CHUNKED) {
+    constexpr int NW = NT / 32, NCH = TL * N / 32;
+    const int warp = ctx.warp_uniform(tid >> 5), lane = tid & 31;
+    for (int ch = warp; ch < NCH; ch += NW) {
+      const int idx = ch * 32 + lane;
+      const int line = idx / N, z = idx % N, m = z >> 1;
+      double h[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        const double2 v = smem[((size_t)c * TL + line) * PITCH + zpad(m)];
+        h[c] = ((z & 1) ? v.y : v.x) + dc;
+      }
+      const size_t cell = (row0 + line) * N + z;
+      float fm = -10.0f;  // ismooth == 0: the -10 / -1 initialisation of src/collapse_times.c:468-469
+      if (p.ismooth > 0) fm = p.Fmax[cell];
+      const double delta = h[0] + h[1] + h[2];
+      sd += delta;
+      sd2 += delta * delta;
+      const double F = inverse_collapse_time(h, sp);
+      if ((double)fm < F) {  // running max, src/collapse_times.c:587-590
+        p.Fmax[cell] = (float)F;
+        p.Rmax[cell] = p.ismooth;
+      } else if (p.ismooth == 0) {
+        p.Fmax[cell] = fm;
+        p.Rmax[cell] = -1;
+      }
+    }
+  } else
   // CPT independent cells per thread and iteration (instruction-level parallelism for the long
   // FP64 dependency chains of the collapse arithmetic)
   for (int base = tid; base < TL * N; base += CPT * NT) {

@@ -30,6 +30,7 @@ struct HostCtx {
   int bid() const { return bid_; }
   int nthreads() const { return nt_; }
   void sync() const { pthread_barrier_wait(bar); }
+  int warp_uniform(int v) const { return v; }
   // every line group calls sync_line the same number of times, so a block-wide barrier is a
   // valid (stronger) stand-in on the host
   void sync_line(int, int) const { pthread_barrier_wait(bar); }
@@ -389,6 +390,10 @@ extern "C" int emu_fastmath(int which, const double* x, long long n, double* y) 
       case 1: y[i] = fm_log10(x[i]); break;
       case 2: y[i] = fm_exp_neg(x[i]); break;
       case 3: y[i] = fm_exp10(x[i]); break;
+      case 4: y[i] = fm_rcp(x[i]); break;
+      case 5: y[i] = fm_div(x[2 * i], x[2 * i + 1]); break;  // x holds n (a, b) pairs
+      case 6: y[i] = fm_sqrt(x[i]); break;
+      case 7: y[i] = fm_sqrt_pair(x[i]).rs; break;
       default: return 1;
     }
   }

@@ -231,3 +231,37 @@ def test_fastmath(lib):
     x = np.concatenate([rng.uniform(-20, 20, 200000), [0.0, 1.0, -1.0, 0.30102999566, 299.9, -299.9]])
     ref = 10.0 ** x
     assert (np.abs(run(3, x) - ref) <= 3e-15 * ref).all()
+
+
+def test_fastmath_div_sqrt_newton_schedules(lib):
+    """fm_rcp / fm_div / fm_sqrt / 1/sqrt (fastmath.cuh): MUFU-seed + Newton sequences without range
+    checks.  On the host the seed is the exact value cut to 20 mantissa bits (no better than the
+    hardware's), so this checks that the schedules converge to ~1 ulp from such a seed, over the
+    magnitudes the collapse epilogue produces (|den| >= 1e-20 => coefficients up to 1e60)."""
+    rng = np.random.default_rng(9)
+
+    def run(which, x, n=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = x.size if n is None else n
+        y = np.zeros(n)
+        assert lib.emu_fastmath(which, ptr(x), ctypes.c_longlong(n), ptr(y)) == 0
+        return y
+
+    mag = 10.0 ** rng.uniform(-150, 150, 300000)
+    x = np.concatenate([mag * rng.choice([-1.0, 1.0], mag.size), rng.uniform(0.5, 2.5, 100000), [1.0, -1.0, 3.0, 1e-20, 1e60]])
+    assert (np.abs(run(4, x) * x - 1.0) <= 3e-16).all()
+    a = np.concatenate([rng.standard_normal(x.size - 3) * 10.0 ** rng.uniform(-100, 100, x.size - 3), [0.0, 1.0, -7.0]])
+    q = run(5, np.stack([a, x], axis=1).ravel(), n=x.size)
+    ref = a / x
+    assert (np.abs(q - ref) <= 2.5e-16 * np.abs(ref)).all()
+    assert (q == ref).mean() > 0.95                    # the remainder correction makes most quotients exact
+    assert q[-3] == 0.0                                # zero numerator: exact zero, no special casing needed
+    xp = np.concatenate([10.0 ** rng.uniform(-250, 250, 300000), rng.uniform(0, 0.25, 100000), [0.25, 1.0, 2.0, 4.0, 1e-300]])
+    s = run(6, xp)
+    ref = np.sqrt(xp)
+    assert (np.abs(s - ref) <= 1.2e-16 * ref).all() and (s == ref).mean() > 0.95
+    assert run(6, np.array([0.0]))[0] == 0.0           # acos(+-1) needs sqrt(0) = 0
+    with np.errstate(invalid="ignore"):
+        assert np.isnan(run(6, np.array([-1.0, -1e-30, np.nan]))).all()      # acos(|x| > 1) must stay NaN
+    rs = run(7, xp)
+    assert (np.abs(rs * ref - 1.0) <= 4e-16).all()
