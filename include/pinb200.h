@@ -130,7 +130,10 @@ int pinb200_get_timers(pinb200_ctx* ctx, pinb200_timers* t);
 int pinb200_fft_r2c(pinb200_ctx* ctx, const double* real_in, double* cplx_out);
 int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* real_out);
 /* compute_second_derivatives(R) (src/fmax.c:225-258) of the resident kdensity: six real
- * [N][N][N] double fields in slot order xx,yy,zz,xy,xz,yz written to hessian_out (6*N^3). */
+ * [N/nranks][N][N] double fields in slot order xx,yy,zz,xy,xz,yz written to hessian_out
+ * (6 * local cells; may be NULL).  With R = 0 the fields also stay resident as the input of the
+ * LPT sources: this is recompute_sd = 1 of compute_displacements (src/fmax.c:301-319, special
+ * mode 3 of src/pinocchio.c:186), to be followed by pinb200_displacements(compute_sources = 1). */
 int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, double* hessian_out);
 /* inverse_collapse_time over ncells Hessians given as six arrays (SoA), ismooth selects the
  * spline; F_out[ncells] doubles (src/collapse_times.c:679-776). */

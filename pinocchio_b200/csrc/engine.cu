@@ -846,7 +846,8 @@ extern "C" int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts) {
 extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t cell_begin,
                                          size_t ncells) {
   if (!ctx || !products || !L) return 1;
-  if (!ctx->fmax) FAIL("products not computed");
+  // special mode 3 (displacements without an Fmax sweep, src/pinocchio.c:170-200) leaves Fmax/Rmax zero
+  if (!ctx->fmax && !ctx->vel[0]) FAIL("products not computed");
   if (cell_begin + ncells > ctx->ncells) FAIL("cell range outside the local slab");
   if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
   CK(cudaSetDevice(ctx->d.device));
@@ -951,7 +952,7 @@ extern "C" int pinb200_fft_r2c(pinb200_ctx* ctx, const double* real_in, double* 
 }
 
 extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, double* hessian_out) {
-  if (!ctx || !hessian_out) return 1;
+  if (!ctx) return 1;
   if (!ctx->kdens_valid) FAIL("kdensity not resident");
   NEED_PEERS();
   CK(cudaSetDevice(ctx->d.device));
@@ -972,8 +973,12 @@ extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, doubl
   z.tw = ctx->tw;
   z.mode = 0;
   LAUNCH(launch_zpass_out(g.N, z, (size_t)g.lx * g.N, ctx->stream));
-  for (int k = 0; k < 6; k++) TRY(download_real(ctx, ctx->B[k], hessian_out + (size_t)k * ctx->ncells));
-  ctx->hessian_valid = false;
+  if (hessian_out)
+    for (int k = 0; k < 6; k++) TRY(download_real(ctx, ctx->B[k], hessian_out + (size_t)k * ctx->ncells));
+  // the R = 0 Hessian is what the LPT sources need (recompute_sd of compute_displacements,
+  // src/fmax.c:301-319): it stays resident for pinb200_displacements(compute_sources = 1)
+  ctx->hessian_valid = (radius == 0.0);
+  CK(cudaStreamSynchronize(ctx->stream));
   return check_peer_error(ctx);
 }
 

@@ -110,14 +110,14 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackP
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.ncells; i += (size_t)gridDim.x * blockDim.x) {
     const size_t cell = p.cell_begin + i;
     unsigned char* rec = p.out + i * p.stride;
-    if (p.off_rmax >= 0) *reinterpret_cast<int*>(rec + p.off_rmax) = p.rmax[cell];
+    if (p.off_rmax >= 0 && p.rmax) *reinterpret_cast<int*>(rec + p.off_rmax) = p.rmax[cell];
     if (p.prodfloat_bytes == 4) {
-      if (p.off_fmax >= 0) *reinterpret_cast<float*>(rec + p.off_fmax) = p.fmax[cell];
+      if (p.off_fmax >= 0 && p.fmax) *reinterpret_cast<float*>(rec + p.off_fmax) = p.fmax[cell];
       for (int v = 0; v < 4; v++)
         if (p.off_vel[v] >= 0 && p.vel[3 * v])
           for (int a = 0; a < 3; a++) reinterpret_cast<float*>(rec + p.off_vel[v])[a] = p.vel[3 * v + a][cell];
     } else {
-      if (p.off_fmax >= 0) *reinterpret_cast<double*>(rec + p.off_fmax) = (double)p.fmax[cell];
+      if (p.off_fmax >= 0 && p.fmax) *reinterpret_cast<double*>(rec + p.off_fmax) = (double)p.fmax[cell];
       for (int v = 0; v < 4; v++)
         if (p.off_vel[v] >= 0 && p.vel[3 * v])
           for (int a = 0; a < 3; a++) reinterpret_cast<double*>(rec + p.off_vel[v])[a] = (double)p.vel[3 * v + a][cell];

@@ -221,9 +221,10 @@ class Pinocchio:
         self._scaledep = None if log10_growth_of_z is None else (log10_growth_of_z, float(logkmin), float(dlogk))
 
     def compute_displacements(self, compute_sources: int, recompute_sd: int, redshift: float) -> int:
-        """src/fmax.c:292-367 (recompute_sd is the special-mode-3 path and is not supported)."""
+        """src/fmax.c:292-367.  recompute_sd: the R = 0 second derivatives are computed first
+        (special mode 3, src/pinocchio.c:186: displacements without an Fmax sweep)."""
         if recompute_sd:
-            raise PinocchioError("recompute_sd=1 (special mode 3, src/pinocchio.c:186) is not supported")
+            self._ck(self.lib.pinb200_second_derivatives(self.h, 0.0, None))
         sd = getattr(self, "_scaledep", None)
         if sd is not None:
             tab = np.ascontiguousarray(sd[0](redshift), dtype=np.float64)

@@ -166,8 +166,13 @@ int compute_displacements(int compute_sources, int recompute_sd, double redshift
 
   if (recompute_sd)
   {
-    printf("ERROR on task %d: recompute_sd (special mode 3) is not supported by the GPU path\n", ThisTask);
-    return 1;
+    /* second derivatives at R = 0 are not in place (no Fmax sweep before): src/fmax.c:301-319 */
+    double t1 = MPI_Wtime();
+    ScaleDep.order = 0;
+    ScaleDep.redshift = 0.0;
+    if (pinb200_second_derivatives(pinb, 0.0, NULL))
+      return pinb_fail("compute_second_derivatives");
+    cputime.deriv += MPI_Wtime() - t1;
   }
 #ifdef SCALE_DEPENDENT
   (void)growth;

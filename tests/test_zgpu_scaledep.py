@@ -75,3 +75,25 @@ def test_scale_dependent_against_oracle(N, logkmin, dlogk, cosmo):
             for a in range(3):
                 assert np.abs(p.field(name, a).astype(np.float64) - ref[a]).max() <= 1e-6 * np.abs(ref[a]).max(), (z, name, a)
     p.close()
+
+
+def test_recompute_sd_special_mode_3(cosmo):
+    """compute_displacements(1, 1, z) (src/pinocchio.c:186, src/fmax.c:301-319): displacements without
+    an Fmax sweep -- the R = 0 second derivatives are recomputed first; Fmax/Rmax stay zero."""
+    N = 64
+    radii = [2.0, 0.0]
+    p = make(N, cosmo, radii, N / 0.7)
+    p.GenIC_large()
+    p.compute_fmax()
+    want = {n: [p.field(n, a) for a in range(3)] for n in ("Vel", "Vel_2LPT", "Vel_3LPT_1", "Vel_3LPT_2")}
+    p.close()
+    q = make(N, cosmo, radii, N / 0.7)
+    q.GenIC_large()
+    q.compute_displacements(1, 1, 0.0)
+    for n, fields in want.items():
+        for a in range(3):
+            assert np.array_equal(q.field(n, a), fields[a]), (n, a)
+    prod = q.products()
+    assert not prod["Fmax"].any() and not prod["Rmax"].any()
+    assert np.array_equal(prod["Vel_2LPT"][:, 2].reshape(N, N, N), want["Vel_2LPT"][2])
+    q.close()
