@@ -202,8 +202,8 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": round(abytes[dom]), "peak_source": peak_src,
-                "note": "the dominant kernel (z pass + collapse epilogue) is FP64-issue bound, not HBM bound (r01 ncu: FP64 pipe 54 %, "
-                        "issue slots 70 % busy, DRAM 13 %); frac is against the HBM peak as the contract defines it, "
+                "note": "the dominant kernel (z pass + collapse epilogue) is FP64-issue bound, not HBM bound (r01 ncu: FP64 pipe 70 %, "
+                        "issue slots 69 % busy, DRAM 20 %); frac is against the HBM peak as the contract defines it, "
                         "fp64_pipe.frac against the FP64 pipe",
                 "ms_per_launch": {k: round(v, 3) for k, v in per_launch_ms.items()},
                 "gbs_per_kernel": {k: round(abytes[k] / (v * 1e-3) / 1e9, 1) for k, v in per_launch_ms.items()},
@@ -212,17 +212,18 @@ def run_b200(args):
                 "lpt_stage_ms": round(lpt_ms, 3),
                 "lpt_frac_of_survey_roofline": round(survey_lpt / (lpt_ms * 1e-3) / 1e9 / peak, 4),
                 "whole_step_frac_of_survey_roofline": round(survey_total / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
-    # The collapse kernel's real ceiling is the FP64 pipe: FP64 instructions per
-    # cell (static SASS count of the epilogue's hot path, tools/sass_stats.py, + the r01 ncu dynamic
-    # count of its FFT part) against 148 SMs x 4 sub-partitions x one FP64 warp instruction per 2 clocks.
+    # The collapse kernel's real ceiling is the FP64 pipe: FP64-pipe instructions
+    # per cell (ncu sm__inst_executed_pipe_fp64.sum x 32 / cells = 538.6 at 1024^3,
+    # profiles/r01_ncu_zcollapse_1024_final.csv) against 148 SMs x 4 sub-partitions x one FP64 warp
+    # instruction per 2 clocks.
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    fp64_per_cell = 468 + 138
+    fp64_per_cell = 538.6
     pipe_peak = 148 * 4 * sm_mhz * 1e6 / 2.0                                   # warp instructions / s
     fp64_rate = fp64_per_cell * (cells / world / 32.0) / (per_launch_ms["zpass_collapse_kernel"] * 1e-3)
     roofline["fp64_pipe"] = {"kernel": "zpass_collapse_kernel", "fp64_inst_per_cell": fp64_per_cell,
                              "achieved_warp_inst_per_s": round(fp64_rate, -6), "peak_warp_inst_per_s": round(pipe_peak, -6),
                              "frac": round(fp64_rate / pipe_peak, 4), "sm_mhz": sm_mhz,
-                             "source": "static SASS count (epilogue hot path) + r01 ncu dynamic count (FFT part); not a live counter"}
+                             "source": "instruction count from the committed ncu capture (profiles/r01_ncu_zcollapse_1024_final.csv), time live"}
     launches = int(tm1.kernel_launches - tm0.kernel_launches)
 
     # ---- e2e: host buffers through the reference-facing calls (H2D kdensity, D2H products[])
