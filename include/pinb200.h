@@ -118,6 +118,17 @@ int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts);
  * src/pinocchio.h:84-85) into host AoS records. */
 int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* layout,
                               size_t cell_begin, size_t ncells);
+/* Hand-off to the fragmentation: the local cells with Fmax >= f_last -- the
+ * ones distribute() keeps (src/distribute.c:58-175,547-600) -- as cell indices
+ * (z + N*(y + N*x_local)) in order of descending Fmax, the order sort_and_organize gives frag[]
+ * (src/fragment.c:484-520); equal Fmax in ascending cell index.  *count = number of such cells;
+ * at most `capacity` indices are written (cell_index_out may be NULL to query the count). */
+int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned int* cell_index_out, size_t capacity, size_t* count);
+/* frag[first .. first+n) as sort_and_organize leaves it: the product_data records of the cells
+ * listed by the last pinb200_collapsed_cells call (which must have been given an output array), in
+ * that order, gathered on the device -- only collapsed cells cross PCIe and the host does not sort. */
+int pinb200_download_products_sorted(pinb200_ctx* ctx, void* products, const pinb200_product_layout* layout,
+                                     size_t first, size_t n);
 /* Structure-of-arrays access for tests: which = 0 Fmax(f32) 1 Rmax(i32) 2..4 Vel 5..7 Vel_2LPT
  * 8..10 Vel_3LPT_1 11..13 Vel_3LPT_2; dst holds N^3 (local) 4-byte values. */
 int pinb200_download_field(pinb200_ctx* ctx, int which, void* dst);

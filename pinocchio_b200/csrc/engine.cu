@@ -23,6 +23,7 @@
 
 #include "../../include/pinb200.h"
 #include "launch.h"
+#include "sort_cells.cuh"
 
 using namespace pinb;
 
@@ -72,6 +73,8 @@ struct pinb200_ctx {
   float* fmax = nullptr;
   int* rmax = nullptr;
   float* vel[12] = {nullptr};
+  unsigned int* sorted_idx = nullptr;  // pinb200_collapsed_cells: cell indices in order of descending Fmax
+  size_t sorted_n = 0;
 
   pinb200_timers tm{};
   unsigned long long launches = 0;
@@ -293,7 +296,7 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
   fr(ctx->d_error);
   for (auto p : ctx->B) fr(p);
   for (auto p : ctx->D) fr(p);
-  fr(ctx->fmax); fr(ctx->rmax);
+  fr(ctx->fmax); fr(ctx->rmax); fr(ctx->sorted_idx);
   for (auto p : ctx->vel) fr(p);
   fr(ctx->arena);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -625,6 +628,8 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   // a new Fmax sweep re-initialises the products (src/collapse_times.c:461-492 zeroes Vel*):
   // displacement fields of an earlier call are released here and read back as zeros
   for (auto& v : ctx->vel) TRY(dev_free(ctx, &v));
+  TRY(dev_free(ctx, &ctx->sorted_idx));
+  ctx->sorted_n = 0;
   ctx->kvec_valid = false;
   TRY(ensure_products(ctx));
   for (int i = 0; i < 6; i++) TRY(dev_alloc(ctx, &ctx->B[i], ctx->field_elems));
@@ -829,6 +834,80 @@ extern "C" int pinb200_displacements_scaledep(pinb200_ctx* ctx, int compute_sour
   return displacements_impl(ctx, compute_sources, ones, gk);
 }
 
+// Cells with Fmax >= f_last in order of descending Fmax (ties: ascending cell index): the selection
+// of src/distribute.c:58-175,547-600 and the ordering of sort_and_organize (src/fragment.c:484-520),
+// done on the device.  LSD radix sort, four 8-bit passes, filter folded into the first.
+extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned int* cell_index_out, size_t capacity,
+                                       size_t* count) {
+  if (!ctx || !count) return 1;
+  if (!ctx->fmax) FAIL("Fmax not computed");
+  if (!(f_last > 0.0f)) FAIL("f_last must be positive (F = 1 + z_collapse; the float keys are ordered by their bit patterns)");
+  if (ctx->ncells > 0xffffffffull) FAIL("more than 2^32 local cells");
+  CK(cudaSetDevice(ctx->d.device));
+  for (auto& w : ctx->D) TRY(dev_free(ctx, &w));  // y-pass scratch of the displacement stage: dead by now
+  const unsigned int ntiles_all = (unsigned int)((ctx->ncells + SORT_TILE - 1) / SORT_TILE);
+  unsigned int *counts = nullptr, *key[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr};
+  unsigned long long* d_total = nullptr;
+  TRY(dev_alloc(ctx, &counts, (size_t)256 * ntiles_all));
+  TRY(dev_alloc(ctx, &d_total, (size_t)1));
+  SortPassParams p{};
+  p.fmax = ctx->fmax;
+  p.f_last = f_last;
+  p.n = ctx->ncells;
+  p.shift = 0;
+  p.counts = counts;
+  p.ntiles = ntiles_all;
+  // the first pass needs its output size before the buffers exist: count + scan first
+  unsigned long long n = 0;
+  {
+    // a counting-only run of the first pass sizes the (key, index) buffers: worst case all cells
+    // collapse (16 bytes per cell for the two ping-pong pairs), typically 60 %
+    SortPassParams c = p;
+    c.key_out = nullptr;
+    c.idx_out = nullptr;
+    LAUNCH(launch_sort_count(c, d_total, ctx->stream));
+    CK(cudaMemcpyAsync(&n, d_total, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  *count = (size_t)n;
+  if (n > 0 && cell_index_out && capacity > 0) {
+    for (int b = 0; b < 2; b++) {
+      TRY(dev_alloc(ctx, &key[b], (size_t)n));
+      TRY(dev_alloc(ctx, &idx[b], (size_t)n));
+    }
+    int cur = 0;
+    for (int pass = 0; pass < 4; pass++) {
+      p.shift = 8 * pass;
+      p.key_out = key[cur];
+      p.idx_out = idx[cur];
+      LAUNCH(launch_sort_pass(p, d_total, ctx->stream));
+      ctx->launches += 2;  // a pass is three kernels
+      // the next pass reads what this one wrote
+      p.fmax = nullptr;
+      p.key_in = key[cur];
+      p.idx_in = idx[cur];
+      p.n = n;
+      p.ntiles = (unsigned int)((n + SORT_TILE - 1) / SORT_TILE);
+      cur ^= 1;
+    }
+    const size_t ncopy = capacity < (size_t)n ? capacity : (size_t)n;
+    CK(cudaMemcpyAsync(cell_index_out, idx[cur ^ 1], ncopy * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // the ordered indices stay resident for pinb200_download_products_sorted
+    TRY(dev_free(ctx, &ctx->sorted_idx));
+    ctx->sorted_idx = idx[cur ^ 1];
+    ctx->sorted_n = (size_t)n;
+    idx[cur ^ 1] = nullptr;
+  }
+  for (int b = 0; b < 2; b++) {
+    TRY(dev_free(ctx, &key[b]));
+    TRY(dev_free(ctx, &idx[b]));
+  }
+  TRY(dev_free(ctx, &counts));
+  TRY(dev_free(ctx, &d_total));
+  return 0;
+}
+
 extern "C" int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts) {
   if (!ctx || !counts) return 1;
   if (!ctx->fmax) FAIL("Fmax not computed");
@@ -878,6 +957,43 @@ extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
   ctx->tm.mem_transf += ms * 1e-3;
+  TRY(dev_free(ctx, &d));
+  return 0;
+}
+
+// frag[first .. first+n) as sort_and_organize leaves it (src/fragment.c:484-520): the records of the
+// collapsed cells in order of descending Fmax, gathered on the device through the index list of the
+// last pinb200_collapsed_cells call.
+extern "C" int pinb200_download_products_sorted(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t first,
+                                                size_t n) {
+  if (!ctx || !products || !L) return 1;
+  if (!ctx->sorted_idx) FAIL("no ordered cell list (call pinb200_collapsed_cells with an output array first)");
+  if (first + n > ctx->sorted_n) FAIL("record range outside the ordered cell list");
+  if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
+  CK(cudaSetDevice(ctx->d.device));
+  if (n == 0) return 0;
+  unsigned char* d = nullptr;
+  TRY(dev_alloc(ctx, &d, n * L->stride));
+  CK(cudaMemsetAsync(d, 0, n * L->stride, ctx->stream));
+  PackParams p{};
+  p.fmax = ctx->fmax;
+  p.rmax = ctx->rmax;
+  for (int i = 0; i < 12; i++) p.vel[i] = ctx->vel[i];
+  p.out = d;
+  p.stride = L->stride;
+  p.prodfloat_bytes = L->prodfloat_bytes;
+  p.off_rmax = L->off_Rmax;
+  p.off_fmax = L->off_Fmax;
+  p.off_vel[0] = L->off_Vel;
+  p.off_vel[1] = L->off_Vel_2LPT;
+  p.off_vel[2] = L->off_Vel_3LPT_1;
+  p.off_vel[3] = L->off_Vel_3LPT_2;
+  p.cell_begin = first;
+  p.ncells = n;
+  p.gather = ctx->sorted_idx;
+  LAUNCH(launch_pack_products(p, ctx->stream));
+  CK(cudaMemcpyAsync(products, d, n * L->stride, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   TRY(dev_free(ctx, &d));
   return 0;
 }

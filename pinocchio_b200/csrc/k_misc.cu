@@ -108,7 +108,7 @@ cudaError_t launch_collapse_cells(const double* h6, size_t n, const double* spli
 // SoA (device) -> AoS product_data records (K8, src/fmax-pfft.c:563-631)
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackParams p) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.ncells; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t cell = p.cell_begin + i;
+    const size_t cell = p.gather ? (size_t)p.gather[p.cell_begin + i] : p.cell_begin + i;
     unsigned char* rec = p.out + i * p.stride;
     if (p.off_rmax >= 0 && p.rmax) *reinterpret_cast<int*>(rec + p.off_rmax) = p.rmax[cell];
     if (p.prodfloat_bytes == 4) {

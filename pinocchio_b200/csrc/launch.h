@@ -32,8 +32,14 @@ struct PackParams {
   unsigned char* out; size_t stride; int prodfloat_bytes;
   int off_rmax, off_fmax, off_vel[4];
   size_t cell_begin, ncells;
+  const unsigned int* gather;  // nullptr: records of cells cell_begin .. ; else of cells gather[cell_begin + i]
 };
 cudaError_t launch_pack_products(const PackParams& p, cudaStream_t s);
+
+// collapsed-cell filter + radix sort (sort_cells.cuh): one 8-bit pass = count, scan, scatter (3 launches)
+struct SortPassParams;
+cudaError_t launch_sort_pass(const SortPassParams& p, unsigned long long* total, cudaStream_t s);
+cudaError_t launch_sort_count(const SortPassParams& p, unsigned long long* total, cudaStream_t s);
 
 // host <-> device layout converters (pitch P on the device, N/2+1 or N on the host)
 cudaError_t launch_repitch_c(const double2* src, double2* dst, size_t nrows, int ncols, int spitch, int dpitch, cudaStream_t s);

@@ -52,7 +52,7 @@ ABI_SYMBOLS = [
     "pinb200_ipc_handle", "pinb200_connect",
     "pinb200_set_power_table", "pinb200_set_smoothing", "pinb200_set_invgrow_spline", "pinb200_genic",
     "pinb200_upload_kdensity", "pinb200_download_kdensity", "pinb200_fmax", "pinb200_displacements",
-    "pinb200_displacements_scaledep",
+    "pinb200_displacements_scaledep", "pinb200_collapsed_cells", "pinb200_download_products_sorted",
     "pinb200_fmax_pdf", "pinb200_download_products", "pinb200_download_field", "pinb200_get_timers",
     "pinb200_fft_r2c", "pinb200_fft_c2r", "pinb200_second_derivatives", "pinb200_collapse_cells",
     "pinb200_download_kvector",
@@ -90,6 +90,10 @@ def load_library() -> ctypes.CDLL:
     lib.pinb200_displacements.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
     lib.pinb200_displacements_scaledep.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                                    ctypes.c_double, _PD]
+    lib.pinb200_collapsed_cells.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.POINTER(ctypes.c_uint), ctypes.c_size_t,
+                                            ctypes.POINTER(ctypes.c_size_t)]
+    lib.pinb200_download_products_sorted.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ProductLayout),
+                                                     ctypes.c_size_t, ctypes.c_size_t]
     lib.pinb200_fmax_pdf.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]
     lib.pinb200_download_products.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ProductLayout),
                                               ctypes.c_size_t, ctypes.c_size_t]
@@ -246,6 +250,34 @@ class Pinocchio:
             from .distributed import allreduce_sum
             pdf = allreduce_sum(pdf, self.group)
         return pdf.astype(np.uint64)
+
+    def collapsed_cells(self, Flast: float) -> np.ndarray:
+        """Local cells with Fmax >= Flast as indices z + N*(y + N*x_local), in order of descending Fmax
+        (ties: ascending index): the selection of src/distribute.c and the order of
+        sort_and_organize (src/fragment.c:484-520), computed on the device."""
+        n = ctypes.c_size_t(0)
+        self._ck(self.lib.pinb200_collapsed_cells(self.h, float(Flast), None, 0, ctypes.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        if n.value:
+            self._ck(self.lib.pinb200_collapsed_cells(self.h, float(Flast), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)),
+                                                      out.size, ctypes.byref(n)))
+        self._sorted_n = int(n.value)
+        return out
+
+    def sorted_products(self, first: int = 0, n: int | None = None, dtype=PRODUCT_DTYPE_3LPT) -> np.ndarray:
+        """frag[] of src/fragment.c:484-520: records of the cells of the last collapsed_cells() call, in
+        that order (descending Fmax), gathered on the device."""
+        if n is None:
+            n = self._sorted_n - first
+        out = np.zeros(n, dtype=dtype)
+        f = dtype.fields
+        off = lambda name: f[name][1] if name in f else -1
+        lay = ProductLayout(dtype.itemsize, 4, off("Rmax"), off("Fmax"), off("Vel"), off("Vel_2LPT"),
+                            off("Vel_3LPT_1"), off("Vel_3LPT_2"))
+        if n:
+            self._ck(self.lib.pinb200_download_products_sorted(self.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(lay),
+                                                               first, n))
+        return out
 
     # -- data movement ----------------------------------------------------------------------
     def write_kdensity(self, kdensity: np.ndarray):

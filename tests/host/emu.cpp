@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../pinocchio_b200/csrc/kernels.cuh"
+#include "../../pinocchio_b200/csrc/sort_cells.cuh"
 
 using namespace pinb;
 
@@ -398,4 +399,43 @@ extern "C" int emu_fastmath(int which, const double* x, long long n, double* y) 
     }
   }
   return 0;
+}
+
+// ---- collapsed-cell filter + radix sort (sort_cells.cuh): the engine's schedule of
+// pinb200_collapsed_cells on host arrays.  idx_out must hold n entries; returns the count.
+extern "C" long long emu_collapsed_cells(const float* fmax, long long n, float f_last, unsigned int* idx_out) {
+  const unsigned int ntiles_all = (unsigned int)((n + SORT_TILE - 1) / SORT_TILE);
+  std::vector<unsigned int> counts((size_t)256 * ntiles_all), key[2], idx[2];
+  std::vector<unsigned short> cnt(256 * SORT_ROW);
+  std::vector<unsigned int> base(256), scratch(64);
+  unsigned long long total = 0;
+  SortPassParams p{};
+  p.fmax = fmax;
+  p.f_last = f_last;
+  p.n = (unsigned long long)n;
+  p.counts = counts.data();
+  p.ntiles = ntiles_all;
+  auto count_scan = [&](const SortPassParams& q) {
+    run_blocks(q.ntiles, SORT_NT, [&](HostCtx& ctx) { sort_count_body(ctx, cnt.data(), q); });
+    run_blocks(1, 64, [&](HostCtx& ctx) { sort_scan_body(ctx, scratch.data(), q.counts, (unsigned long long)256 * q.ntiles, &total); });
+  };
+  count_scan(p);
+  const unsigned long long m = total;
+  for (int b = 0; b < 2; b++) { key[b].assign(m ? m : 1, 0xdeadbeefu); idx[b].assign(m ? m : 1, 0xdeadbeefu); }
+  int cur = 0;
+  for (int pass = 0; pass < 4 && m > 0; pass++) {
+    p.shift = 8 * pass;
+    p.key_out = key[cur].data();
+    p.idx_out = idx[cur].data();
+    count_scan(p);
+    run_blocks(p.ntiles, SORT_NT, [&](HostCtx& ctx) { sort_scatter_body(ctx, cnt.data(), base.data(), p); });
+    p.fmax = nullptr;
+    p.key_in = key[cur].data();
+    p.idx_in = idx[cur].data();
+    p.n = m;
+    p.ntiles = (unsigned int)((m + SORT_TILE - 1) / SORT_TILE);
+    cur ^= 1;
+  }
+  for (unsigned long long i = 0; i < m; i++) idx_out[i] = idx[cur ^ 1][i];
+  return (long long)m;
 }

@@ -265,3 +265,30 @@ def test_fastmath_div_sqrt_newton_schedules(lib):
         assert np.isnan(run(6, np.array([-1.0, -1e-30, np.nan]))).all()      # acos(|x| > 1) must stay NaN
     rs = run(7, xp)
     assert (np.abs(rs * ref - 1.0) <= 4e-16).all()
+
+
+@pytest.mark.parametrize("n,frac_ties", [(1, 0.0), (5000, 0.0), (16384, 0.5), (16385, 0.0), (100003, 0.3)])
+def test_collapsed_cells_filter_and_sort(lib, n, frac_ties):
+    """pinb200_collapsed_cells' kernels (sort_cells.cuh) under the block emulator: cells with
+    Fmax >= F_last in order of descending Fmax, ties in ascending cell index (the selection of
+    src/distribute.c and the order of sort_and_organize, src/fragment.c:484-520).  Sizes around
+    the 16384-element tile; values as the sweep leaves them (-10, 0, 1 + z)."""
+    rng = np.random.default_rng(n)
+    F = (1.0 + rng.exponential(1.5, n)).astype(np.float32)
+    kind = rng.uniform(size=n)
+    F[kind < 0.25] = 0.0            # never collapses
+    F[kind < 0.05] = -10.0          # the -10 of src/collapse_times.c:734-736
+    if frac_ties:
+        t = rng.uniform(size=n) < frac_ties
+        F[t] = np.round(F[t] * 4) / 4          # many exactly equal keys
+    F[rng.integers(0, n, 3)] = np.float32(np.nan)
+    for Flast in (1.0, 1.75):
+        out = np.full(n, 0xFFFFFFFF, dtype=np.uint32)
+        lib.emu_collapsed_cells.restype = ctypes.c_longlong
+        m = lib.emu_collapsed_cells(ptr(F, ctypes.POINTER(ctypes.c_float)), ctypes.c_longlong(n), ctypes.c_float(Flast),
+                                    ptr(out, ctypes.POINTER(ctypes.c_uint)))
+        with np.errstate(invalid="ignore"):
+            sel = np.flatnonzero(F >= np.float32(Flast))
+        want = sel[np.argsort(-F[sel].astype(np.float64), kind="stable")]
+        assert m == want.size
+        assert np.array_equal(out[:m], want.astype(np.uint32))
