@@ -280,6 +280,20 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_sample(args.cpu_grid, 1)
 
+    # ---- device-side fragmentation hand-off, in a fresh process after this one
+    #      has released the GPU: a failure there cannot touch the numbers above
+    handoff = None
+    if rank == 0 and world == 1 and not args.no_handoff:
+        pin.close()
+        torch.cuda.empty_cache()
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "scripts" / "gpu_handoff_probe.py"), str(N)], capture_output=True,
+                               text=True, timeout=240)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            handoff = json.loads(line[-1]) if line else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as ex:  # noqa: BLE001
+            handoff = {"error": str(ex)[:300]}
+
     if rank == 0:
         out = {"metric": METRIC, "value": round(value, 2), "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
@@ -290,7 +304,7 @@ def run_b200(args):
                           "seed": 486604, "parallelism": f"slab{world}" if world > 1 else "single GPU",
                           "l2_policy": "inputs larger than L2 (each field 8.7 GB at 1024^3)"},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-               "cpu_baseline": cpu_baseline, "checks": checks, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
+               "cpu_baseline": cpu_baseline, "fragment_handoff": handoff, "checks": checks, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
         print(json.dumps(out))
     pin.close()
     if world > 1:
@@ -370,6 +384,7 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=256, help="grid of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-handoff", action="store_true", help="skip the fragmentation hand-off probe (fresh process, N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

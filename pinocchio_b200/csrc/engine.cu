@@ -299,6 +299,10 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
   fr(ctx->fmax); fr(ctx->rmax); fr(ctx->sorted_idx);
   for (auto p : ctx->vel) fr(p);
   fr(ctx->arena);
+  {  // hand the stream-ordered pool's cached blocks back to the driver (another context may need them)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->d.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
