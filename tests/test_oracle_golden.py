@@ -74,3 +74,28 @@ def test_hmf_validation_sigma_and_fmaxpdf():
     d = np.abs(pdf - gold)
     assert d.max() <= 6 and d.sum() <= 100, (d.max(), d.sum())
     assert abs(int(pdf[10:].sum()) - 1230386) <= 3            # log_RUN.txt:407
+
+
+# BASELINE.json configs[0]: example/ as shipped.  The shipped example/log is an EH run (Omega0 = .25,
+# h = .7, sigma8 = .8; 128^3, BoxSize 500 Mpc/h, 4 MPI tasks, seed 486604): its seven "computed sigma"
+# values (log:161-311) and its collapsed-particle count (log:383,480-481) pin GenIC + the radius sweep
+# at a second cell size (3.9 Mpc/h).  (example/pinocchio.example.FmaxPDF.out belongs to another run --
+# it holds 741 412 collapsed particles against the log's 687 249 -- and is not used.)
+EXAMPLE_LOG_SIGMA = [0.2761, 0.3919, 0.5555, 0.7871, 1.1067, 1.4135, 1.5929]
+EXAMPLE_LOG_RADII = [20.635922, 13.996056, 9.026099, 5.465945, 3.058354, 1.548258, 0.0]      # log:55-61
+EXAMPLE_LOG_COLLAPSED = 687249
+
+
+def test_example_log_sigma_and_collapsed_count():
+    cosmo = Cosmology(pk_norm_override=2.03146e7)           # log:50
+    N, box = 128, 500.0 / 0.7                               # log:25-26
+    lad = set_smoothing(cosmo, box / N)
+    assert lad.Nsmooth == 7
+    assert np.abs(lad.Radius - EXAMPLE_LOG_RADII).max() < 5e-5
+    assert abs(lad.Variance[-1] - 3.913232) < 2e-5          # log:61
+    kd = po.genic(N, box, 486604, cosmo.PowerSpectrum)
+    res = po.compute_fmax(kd, EXAMPLE_LOG_RADII, box / N, cosmo.InverseGrowingMode, lpt_order=0)
+    assert np.abs(np.sqrt(res["TrueVariance"]) - EXAMPLE_LOG_SIGMA).max() < 6e-5
+    pdf = po.fmax_pdf(res["Fmax"]).astype(np.int64)
+    assert abs(int(pdf[10:].sum()) - EXAMPLE_LOG_COLLAPSED) <= 5
+    assert abs(int(pdf[:10].sum()) - 1409903) <= 5          # log:481
