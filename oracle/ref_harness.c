@@ -2,9 +2,9 @@
  * in this container, so that oracle/pinocchio_oracle.py and the CUDA path can be checked
  * against the reference's compiled arithmetic and not only against a restatement.
  *
- * Linked with /root/reference/src/collapse_times.c and /root/reference/src/variables.c, both
+ * Linked with /root/reference/src/{collapse_times,variables,fmax,fmax-pfft,LPT,GenIC}.c, all
  * compiled verbatim from where they lie (oracle/Makefile; never copied into this repo).  What
- * those two translation units need from the rest of PINOCCHIO and from MPI/GSL is provided
+ * those translation units need from the rest of PINOCCHIO and from MPI/GSL is provided
  * here, for one rank:
  *   - MPI_Wtime / MPI_Reduce / MPI_Bcast for a single task,
  *   - InverseGrowingMode (src/cosmo.c:1822-1832): 1/10^s(log10 D) - 1 with s the natural cubic
@@ -26,6 +26,7 @@
 
 #include "pinocchio.h"
 #include <gsl/gsl_odeiv2.h>
+#include <gsl/gsl_rng.h>
 
 /* ---- one-task MPI ---------------------------------------------------------------------- */
 double MPI_Wtime(void) {
@@ -303,6 +304,52 @@ int ref_setup(int N, double box, int nsmooth, const double* radius, const double
   cvector_fft[0] = pfft_alloc_complex(nfft / 2);
   ref_n = (long)nr;
   return 0;
+}
+
+/* ---- the reference's own GenIC_large (src/GenIC.c:73-460, seed plane :482-990) ---------------
+ * GSL's generators come from oracle/ref_gsl_rng.c; PowerSpectrum (src/cosmo.c, not compilable
+ * here) is answered from the caller's table on the integer lattice, pk[m] = P(2 pi sqrt(m) / Box),
+ * m = |n|^2 -- the same table the CUDA path is given (pinb200_set_power_table). */
+int GenIC_large(int);
+static const double* pk_tab = NULL;
+static long pk_n = 0;
+static double pk_box = 1.0;
+double PowerSpectrum(double k) {
+  const double x = k * pk_box / (2. * PI);
+  const long m = lround(x * x);
+  if (m < 0 || m >= pk_n) { fprintf(stderr, "oracle/_ref: PowerSpectrum(%g) outside the lattice table\n", k); abort(); }
+  return pk_tab[m];
+}
+/* after ref_setup: fills kdensity[0] for RandomSeed = seed; returns GenIC_large's status */
+int ref_genic(int seed, int fixed_ic, int paired_ic, const double* pk, long npk) {
+  pk_tab = pk;
+  pk_n = npk;
+  pk_box = MyGrids[0].BoxSize;
+  params.RandomSeed = seed;
+  params.FixedIC = fixed_ic;
+  params.PairedIC = paired_ic;
+  /* defaults of set_parameters, src/initialization.c:214-219 */
+  internal.verbose_level = VDIAG;
+  internal.dump_seedplane = 0;
+  internal.dump_kdensity = 0;
+  internal.large_plane = 1;
+  internal.mimic_original_seedtable = 0;
+  if (!random_generator) random_generator = gsl_rng_alloc(gsl_rng_ranlxd1); /* src/initialization.c:73 */
+  memset(kdensity[0], 0, (size_t)MyGrids[0].total_local_size_fft * sizeof(double));
+  return GenIC_large(0);
+}
+int ref_get_kdensity(double* kd) {
+  memcpy(kd, kdensity[0], (size_t)MyGrids[0].total_local_size_fft * sizeof(double));
+  return 0;
+}
+/* known answers of GSL's rng/test.c for the two restated generators */
+unsigned long ref_rng_nth(int kind, unsigned long seed, long n) {
+  gsl_rng* r = gsl_rng_alloc(kind == 1 ? gsl_rng_ranlxd1 : gsl_rng_mt19937);
+  unsigned long v = 0;
+  gsl_rng_set(r, seed);
+  for (long i = 0; i < n; i++) v = gsl_rng_get(r);
+  gsl_rng_free(r);
+  return v;
 }
 
 /* kd: [N][N][N/2+1] complex128 (the reference's non-transposed k layout) */

@@ -121,6 +121,19 @@ class ReferenceRun:
         assert t.ndim == 2 and t.shape[0] == 4
         self.lib.ref_set_growth_tables(t.shape[1], float(logkmin), float(dlogk), _p(t))
 
+    def genic(self, seed: int, pk_lattice: np.ndarray, fixed_ic: int = 0, paired_ic: int = 0) -> np.ndarray:
+        """The reference's own GenIC_large (src/GenIC.c) for RandomSeed = seed; ``pk_lattice[m]`` =
+        PowerSpectrum(2 pi sqrt(m)/Box), m = |n|^2 (pinocchio_b200.cosmology.pk_lattice_table).
+        Fills the reference's kdensity[0] and returns a copy [N][N][N/2+1]."""
+        self._pk = np.ascontiguousarray(pk_lattice, dtype=np.float64)      # must outlive the call
+        self.lib.ref_genic.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _PD, ctypes.c_long]
+        self._in_workdir(lambda: self._check(self.lib.ref_genic(int(seed), int(fixed_ic), int(paired_ic), _p(self._pk),
+                                                                self._pk.size)))
+        k = np.empty((self.N, self.N, self.N // 2 + 1), dtype=np.complex128)
+        self.lib.ref_get_kdensity.argtypes = [_PD]
+        self.lib.ref_get_kdensity(_p(k.view(np.float64)))
+        return k
+
     def compute_fmax(self):
         """The reference's compute_fmax(): returns (seconds by its own cputime.fmax, TrueVariance[])."""
         sec = ctypes.c_double()

@@ -182,3 +182,62 @@ def test_oracle_scale_dependent_growth_against_reference_golden(gold):
             v = sd[name][:, a].reshape(N, N, N)
             assert np.abs(v.astype(np.float64) - o[a]).max() <= 2e-7 * np.abs(o[a]).max(), (name, a)
             assert (v == o[a]).mean() > 0.999, (name, a)
+
+
+@needs_ref
+def test_restated_gsl_generators_known_answers():
+    """oracle/ref_gsl_rng.c against the known answers of GSL's own rng/test.c"""
+    lib = ctypes.CDLL(str(rr.LIB))
+    lib.ref_rng_nth.restype = ctypes.c_ulong
+    lib.ref_rng_nth.argtypes = [ctypes.c_int, ctypes.c_ulong, ctypes.c_long]
+    assert lib.ref_rng_nth(2, 4357, 1000) == 1186927261       # mt19937
+    assert lib.ref_rng_nth(1, 1, 10000) == 1998227290         # ranlxd1
+    # the same generators as restated in NumPy for the oracle
+    assert lib.ref_rng_nth(2, 486604, 77) == int(po.mt19937_outputs(486604, 77)[76])
+    r = po.RanLxd1([0xFFFFFFFE])
+    v = [int(r.get()[0]) for _ in range(500)][-1]
+    assert lib.ref_rng_nth(1, 0xFFFFFFFE, 500) == v           # seeds >= 2^31: the signed-int quirk
+
+
+GENIC_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from oracle.reference_runner import ReferenceRun
+from pinocchio_b200.cosmology import Cosmology, pk_lattice_table
+N, seed, fixed, paired, out = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6]
+cosmo = Cosmology(pk_norm_override=2.03146e7)
+box = N / 0.7
+x = np.linspace(-2, 0, 8)
+run = ReferenceRun(N, box, [0.0], np.ones(4), x, x, threads=2)
+np.save(out, run.genic(seed, pk_lattice_table(cosmo, N, box), fixed, paired))
+"""
+
+
+@needs_ref
+@pytest.mark.parametrize("N,seed,fixed,paired", [(32, 486604, 0, 0), (64, 486604, 0, 0), (32, 12345, 1, 1), (16, 7, 0, 1)])
+def test_reference_genic_against_oracle(N, seed, fixed, paired, cosmo, tmp_path):
+    """the reference's own GenIC_large + generate_seeds_plane (src/GenIC.c compiled verbatim) on the
+    restated GSL generators, mode by mode against the oracle's restatement: seed plane along the
+    square spiral, RANLUX chains per column, k = 0-plane mirror seeds, Nyquist planes, FixedIC/PairedIC"""
+    import subprocess
+    out = tmp_path / "kd.npy"
+    r = subprocess.run([sys.executable, "-c", GENIC_SCRIPT, str(ROOT), str(N), str(seed), str(fixed), str(paired), str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    kd_ref = np.load(out)
+    kd = po.genic(N, N / 0.7, seed, cosmo.PowerSpectrum, fixed_ic=bool(fixed), paired_ic=bool(paired))
+    assert np.array_equal(kd_ref != 0, kd != 0)
+    assert np.count_nonzero(kd_ref) > 0.4 * kd.size
+    assert np.abs(kd_ref - kd).max() <= 1e-13 * np.abs(kd).max()        # libm vs NumPy sin/cos/log/sqrt
+
+
+def test_oracle_genic_against_reference_genic_golden(cosmo):
+    """the committed fixture of the reference's own GenIC_large (runs without oracle/_ref)"""
+    g = dict(np.load(ROOT / "tests" / "golden" / "reference_genic_32.npz"))
+    N = int(g["N"])
+    for key, seed, fixed, paired in (("kd_486604", 486604, False, False), ("kd_12345_fixed_paired", 12345, True, True)):
+        kd = po.genic(N, float(g["box"]), seed, cosmo.PowerSpectrum, fixed_ic=fixed, paired_ic=paired)
+        assert np.array_equal(kd != 0, g[key] != 0)
+        assert np.abs(kd - g[key]).max() <= 1e-13 * np.abs(kd).max()
+    # the input field of reference_fmax_32.npz is this very field
+    assert np.abs(g["kd_486604"] - dict(np.load(GOLD))["kdensity"]).max() <= 1e-13 * np.abs(g["kd_486604"]).max()

@@ -28,3 +28,23 @@ def test_example_config_sigma_and_collapsed_count():
     ratio = cosmo.GrowingMode(2.0) / cosmo.GrowingMode(0.0)
     assert np.abs(p.field("Vel", 0).astype(np.float64) - ratio * v0).max() <= 2e-7 * np.abs(v0).max()
     p.close()
+
+
+def test_genic_against_reference_code_golden():
+    """CUDA GenIC against kdensity from the REFERENCE'S OWN GenIC_large (src/GenIC.c compiled verbatim
+    into oracle/_ref; fixture tests/golden/reference_genic_32.npz, make_reference_genic_golden.py)"""
+    from pathlib import Path
+    from pinocchio_b200.cosmology import Cosmology, SmoothingLadder
+    from pinocchio_b200.engine import Pinocchio, RunConfig
+    g = dict(np.load(Path(__file__).resolve().parent / "golden" / "reference_genic_32.npz"))
+    N = int(g["N"])
+    cosmo = Cosmology(pk_norm_override=float(g["pk_norm"]))
+    for key, seed, fixed, paired in (("kd_486604", 486604, 0, 0), ("kd_12345_fixed_paired", 12345, 1, 1)):
+        cfg = RunConfig(GridSize=N, BoxSize_htrue=float(g["box"]), RandomSeed=seed, FixedIC=fixed, PairedIC=paired)
+        p = Pinocchio(cfg, cosmo, smoothing=SmoothingLadder(np.array([0.0]), np.zeros(1)))
+        p.GenIC_large()
+        kd = p.read_kdensity()
+        ref = g[key]
+        assert np.array_equal(kd != 0, ref != 0)
+        assert np.abs(kd - ref).max() <= 1e-13 * np.abs(ref).max()
+        p.close()
