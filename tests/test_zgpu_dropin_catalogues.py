@@ -1,0 +1,96 @@
+"""THE DROP-IN, end to end: oracle/_ref/pinocchio_b200.x is the unchanged reference program with the
+five translation units of the hot path (fmax.c, fmax-pfft.c, collapse_times.c, LPT.c, GenIC.c)
+replaced by shim/fmax_b200.c + libpinb200.so, exactly as INTEGRATION.md section 2 describes;
+oracle/_ref/pinocchio_ref.x is the same program with the reference's own files (oracle/Makefile).
+Both run the HMF_Validation parameter file here, with the same host cosmology, parameter file,
+products[] layout and fragmentation: their halo catalogues and mass functions must match
+(BASELINE.json north_star).  Needs a B200: -m gpu.
+
+What may differ: products[] agree to 1e-6 with float-rounding flips in ~1e-3 of the cells and a
+handful of cells where the reference's own cubic solver is ill-conditioned, so
+a few particles may change group: the catalogues are compared halo by halo (same group ID, same
+number of particles) with a 99 % floor, the mass function bin by bin.
+"""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from test_reference_full import GOLDEN, REF_X, load_catalog, match_fraction, run_program
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (REF_X.exists() and (REF_X.parent / "pinocchio_b200.x").exists()),
+                                 reason="oracle/_ref/pinocchio_{ref,b200}.x not built (make -C oracle all)")]
+B200_X = REF_X.parent / "pinocchio_b200.x"
+
+
+@pytest.fixture(scope="module")
+def runs(tmp_path_factory):
+    da = tmp_path_factory.mktemp("pinocchio_b200")
+    log_b = run_program(B200_X, da)
+    db = tmp_path_factory.mktemp("pinocchio_ref")
+    log_r = run_program(REF_X, db, threads=16)
+    return da, log_b, db, log_r
+
+
+def test_dropin_log_values(runs):
+    da, log_b, db, log_r = runs
+    assert "B200 path" in log_b and "Pinocchio done!" in log_b
+    sig_b = [float(x) for x in re.findall(r"computed sigma:\s+([0-9.]+)", log_b)]
+    sig_r = [float(x) for x in re.findall(r"computed sigma:\s+([0-9.]+)", log_r)]
+    assert len(sig_b) == 9 and np.abs(np.array(sig_b) - np.array(sig_r)).max() <= 1e-4
+    nb = int(re.search(r"Number of collapsed particles to z=0: (\d+)", log_b).group(1))
+    nr = int(re.search(r"Number of collapsed particles to z=0: (\d+)", log_r).group(1))
+    assert abs(nb - nr) <= 5
+
+
+def test_dropin_fmaxpdf(runs):
+    da, _, db, _ = runs
+    a = np.loadtxt(da / "pinocchio.test.FmaxPDF.out")[:, 2].astype(np.int64)
+    b = np.loadtxt(db / "pinocchio.test.FmaxPDF.out")[:, 2].astype(np.int64)
+    assert a.sum() == b.sum() == 128 ** 3
+    assert np.abs(a - b).max() <= 6 and np.abs(a - b).sum() <= 250
+
+
+@pytest.mark.parametrize("z", ["0.0000", "0.5000", "1.0000", "2.0000"])
+def test_dropin_catalogues_match_reference(runs, z):
+    da, _, db, _ = runs
+    ia, na, ca = load_catalog(da / f"pinocchio.{z}.test.catalog.out")
+    ib, nb, cb = load_catalog(db / f"pinocchio.{z}.test.catalog.out")
+    assert abs(len(ia) - len(ib)) <= 0.005 * len(ib)
+    assert match_fraction(ia, na, ib, nb) > 0.99
+    assert abs(int(na.sum()) - int(nb.sum())) <= 0.002 * int(nb.sum())
+    # matched halos: final positions (columns 6-8, Mpc/h) and velocities (9-11, km/s) at print precision
+    pos = {int(i): row for i, row in zip(ib, cb)}
+    d_pos, d_vel = [], []
+    for i, row in zip(ia, ca):
+        r = pos.get(int(i))
+        if r is not None and r[11] == row[11]:
+            dx = np.abs(row[5:8] - r[5:8])
+            d_pos.append(np.minimum(dx, 128.0 - dx).max())       # periodic box
+            d_vel.append(np.abs(row[8:11] - r[8:11]).max())
+    assert np.percentile(d_pos, 99) <= 0.02 and np.percentile(d_vel, 99) <= 1.0
+
+
+@pytest.mark.parametrize("z", ["0.0000", "2.0000"])
+def test_dropin_mass_function_matches_reference(runs, z):
+    da, _, db, _ = runs
+    a = np.loadtxt(da / f"pinocchio.{z}.test.mf.out")
+    b = np.loadtxt(db / f"pinocchio.{z}.test.mf.out")
+    assert a.shape == b.shape
+    # column 5 = number of halos in the bin: a particle changing group can move a halo across a bin edge
+    na, nb = a[:, 4], b[:, 4]
+    assert abs(na.sum() - nb.sum()) <= 0.005 * nb.sum()
+    assert (np.abs(na - nb) <= np.maximum(3.0, 0.02 * nb)).all()
+    # column 7 (analytic n(m), a function of the host cosmology only) must be identical
+    assert np.allclose(a[:, 5], b[:, 5], rtol=1e-9, atol=0.0)
+
+
+def test_dropin_catalogue_against_shipped(runs):
+    """and against the catalogue the reference ships for this run (its full MPI + FFTW + GSL build)"""
+    da, _, _, _ = runs
+    ids, npart, _ = load_catalog(da / "pinocchio.0.0000.test.catalog.out")
+    g = np.load(GOLDEN / "catalog_0.0000_id_npart.npz")
+    assert abs(len(ids) - len(g["id"])) <= 0.005 * len(g["id"])
+    assert match_fraction(ids, npart, g["id"], g["npart"]) > 0.99
