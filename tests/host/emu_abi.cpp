@@ -1,0 +1,344 @@
+// TEST ONLY: the C ABI of include/pinb200.h implemented on HOST arrays with the kernel bodies of
+// kernels.cuh under the pthread block emulator (emu.cpp), single rank, grids 32 and 64.
+//
+// Purpose: run the linked drop-in -- the unchanged reference program + shim/fmax_b200.c -- end to
+// end on a machine WITHOUT a GPU (oracle/_ref/pinocchio_emu.x, tests/test_dropin_emulated.py), so
+// that the shim's run-time logic (order of calls, table marshalling, units, products[] download)
+// and the hand-over to the reference's fragmentation are checked here and not only on the B200.
+// The schedule below mirrors pinocchio_b200/csrc/engine.cu (pinb200_fmax, pinb200_displacements)
+// call by call; the kernels are the very templates the GPU runs.  This library is never part of
+// the product: libpinb200.so has no CPU path and pinocchio_b200/ does not know this file exists.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pinb200.h"
+#include "../../pinocchio_b200/csrc/seed_plane.h"
+
+// entry points of emu.cpp (same shared object)
+extern "C" {
+int emu_xpass(int N, int dir, int rank, int nranks, const double* src, double** dsts, int dst_klayout, int pmask, int with_nyq,
+              const double* gauss, double scalar, int green, int times_i, const double* tw);
+int emu_ypass(int N, int dir, int rank, int nranks, double** srcs, double** dsts, double** kdsts, int dst_klayout, const int* jobs,
+              int njobs, int with_nyq, const double* tw);
+int emu_zpass_collapse(int N, int nranks, double** srcs, const int* kzpow, int has_nyq, const double* dc, const double* spline,
+                       int nspl, int ismooth, float* fmax, int* rmax, double* sums, double** hdst, const double* tw);
+int emu_zpass_out(int N, int nranks, int ncomp, double** srcs, const int* kzpow, int has_nyq, const double* dc, int mode,
+                  double** rdst, float** fdst, double** hsrc, const double* weight, double* acc, const double* tw);
+int emu_zpass_r2c(int N, int nranks, const double* src, double* dst, const double* tw);
+int emu_sources(int N, int nranks, double** h, double* s2, double* s31, double* s32, int lpt_order);
+int emu_genic(int N, int rank, int nranks, const unsigned int* seeds, const double* pk, double box, int fixed_ic, int paired_ic,
+              double* kd);
+long long emu_spline_table_doubles(int n);
+int emu_pack_spline(const double* x, const double* y, int n, double* out);
+}
+
+typedef std::complex<double> cplx;
+
+struct pinb200_ctx {
+  pinb200_desc d{};
+  int N = 0, M = 0, P = 0;
+  std::string err;
+  std::vector<cplx> tw, kdens, A[3], B[6], D[3], KV[3];
+  std::vector<double> pk, radius, spline;
+  int nspl = 0;
+  std::vector<float> fmax, vel[12];
+  std::vector<int> rmax;
+  bool kdens_valid = false, hessian_valid = false, kvec_valid = false;
+  unsigned long long launches = 0;
+  size_t field() const { return (size_t)N * N * P; }
+  size_t ncells() const { return (size_t)N * N * N; }
+};
+
+static std::string g_err;
+#define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
+static double* dp(std::vector<cplx>& v) { return reinterpret_cast<double*>(v.data()); }
+
+extern "C" const char* pinb200_last_error(const pinb200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
+  if (!desc || !out) { g_err = "null argument"; return 1; }
+  if (desc->grid_size != 32 && desc->grid_size != 64) { g_err = "emulated ABI: grid_size must be 32 or 64"; return 1; }
+  if (desc->nranks != 1) { g_err = "emulated ABI: one rank only"; return 1; }
+  pinb200_ctx* c = new pinb200_ctx;
+  c->d = *desc;
+  c->N = desc->grid_size;
+  c->M = c->N / 2;
+  c->P = c->M + 8;
+  c->tw.resize(c->N);
+  for (int k = 0; k < c->N; k++) c->tw[k] = std::polar(1.0, 2.0 * M_PI * k / c->N);
+  // garbage on purpose wherever a kernel must write before anybody reads
+  const cplx junk(1e300, 0.0);
+  c->kdens.assign(c->field(), cplx(0.0, 0.0));
+  for (auto& f : c->A) f.assign(c->field(), junk);
+  for (auto& f : c->B) f.assign(c->field(), junk);
+  for (auto& f : c->D) f.assign(c->field(), junk);
+  for (auto& f : c->KV) f.assign(c->field(), junk);
+  *out = c;
+  return 0;
+}
+extern "C" int pinb200_destroy(pinb200_ctx* ctx) { delete ctx; return 0; }
+extern "C" int pinb200_ipc_handle(pinb200_ctx* ctx, void*) { FAIL("emulated ABI: one rank only"); }
+extern "C" int pinb200_connect(pinb200_ctx* ctx, const void*) { FAIL("emulated ABI: one rank only"); }
+extern "C" int pinb200_set_stream(pinb200_ctx*, void*) { return 0; }
+extern "C" int pinb200_synchronize(pinb200_ctx*) { return 0; }
+
+extern "C" int pinb200_set_power_table(pinb200_ctx* ctx, const double* pk, size_t n) {
+  if (!ctx || !pk) return 1;
+  if (n != (size_t)ctx->M * ctx->M + 1) FAIL("power table must have (N/2)^2 + 1 entries");
+  ctx->pk.assign(pk, pk + n);
+  return 0;
+}
+extern "C" int pinb200_set_smoothing(pinb200_ctx* ctx, int nsmooth, const double* radius) {
+  if (!ctx || !radius || nsmooth < 1 || nsmooth > 64) return 1;
+  ctx->radius.assign(radius, radius + nsmooth);
+  return 0;
+}
+extern "C" int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const double* x, const double* y, int n) {
+  if (!ctx || !x || !y) return 1;
+  if (ismooth >= 0) FAIL("emulated ABI: the global inverse-growth spline only");
+  ctx->nspl = n;
+  ctx->spline.assign((size_t)emu_spline_table_doubles(n), 0.0);
+  return emu_pack_spline(x, y, n, ctx->spline.data());
+}
+
+extern "C" int pinb200_genic(pinb200_ctx* ctx) {
+  if (!ctx) return 1;
+  if (ctx->pk.empty()) FAIL("power table not set");
+  std::vector<unsigned int> seeds;
+  pinb::build_seed_plane(ctx->N, ctx->d.random_seed, seeds);
+  std::fill(ctx->kdens.begin(), ctx->kdens.end(), cplx(0.0, 0.0));
+  if (emu_genic(ctx->N, 0, 1, seeds.data(), ctx->pk.data(), ctx->d.box_size, ctx->d.fixed_ic, ctx->d.paired_ic, dp(ctx->kdens)))
+    FAIL("genic");
+  ctx->kdens_valid = true;
+  ctx->launches++;
+  return 0;
+}
+extern "C" int pinb200_upload_kdensity(pinb200_ctx* ctx, const double* kd) {
+  if (!ctx || !kd) return 1;
+  const int N = ctx->N, M = ctx->M, P = ctx->P;
+  std::fill(ctx->kdens.begin(), ctx->kdens.end(), cplx(0.0, 0.0));
+  for (size_t r = 0; r < (size_t)N * N; r++) std::memcpy(&ctx->kdens[r * P], kd + 2 * r * (M + 1), sizeof(cplx) * (M + 1));
+  ctx->kdens_valid = true;
+  return 0;
+}
+static void download_c(pinb200_ctx* ctx, const std::vector<cplx>& f, double* out) {
+  const int N = ctx->N, M = ctx->M, P = ctx->P;
+  for (size_t r = 0; r < (size_t)N * N; r++) std::memcpy(out + 2 * r * (M + 1), &f[r * P], sizeof(cplx) * (M + 1));
+}
+extern "C" int pinb200_download_kdensity(pinb200_ctx* ctx, double* kd) {
+  if (!ctx || !kd) return 1;
+  if (!ctx->kdens_valid) FAIL("kdensity not resident");
+  download_c(ctx, ctx->kdens, kd);
+  return 0;
+}
+
+// ---- pass helpers: the engine's run_xpass_inv / run_ypass_inv / run_r2c on one rank ------------
+static int xpass_inv(pinb200_ctx* ctx, std::vector<cplx>& src, std::vector<cplx>* dst[3], int pmask, const double* gauss, int green,
+                     int times_i, double scalar, int with_nyq) {
+  double* d[3] = {dst[0] ? dp(*dst[0]) : nullptr, dst[1] ? dp(*dst[1]) : nullptr, dst[2] ? dp(*dst[2]) : nullptr};
+  ctx->launches++;
+  return emu_xpass(ctx->N, +1, 0, 1, dp(src), d, 0, pmask, with_nyq, gauss, scalar, green, times_i, dp(ctx->tw));
+}
+static int ypass_inv(pinb200_ctx* ctx, std::vector<cplx>* src[3], std::vector<cplx>* dst[6], const int* jobs, int njobs, int with_nyq) {
+  double *s[3], *d[6];
+  for (int i = 0; i < 3; i++) s[i] = src[i] ? dp(*src[i]) : nullptr;
+  for (int i = 0; i < 6; i++) d[i] = dst[i] ? dp(*dst[i]) : nullptr;
+  ctx->launches++;
+  return emu_ypass(ctx->N, +1, 0, 1, s, d, nullptr, 0, jobs, njobs, with_nyq, dp(ctx->tw));
+}
+static int r2c(pinb200_ctx* ctx, std::vector<cplx>& src, std::vector<cplx>& kdst) {
+  if (emu_zpass_r2c(ctx->N, 1, dp(src), dp(src), dp(ctx->tw))) return 1;
+  double* s[3] = {dp(src), nullptr, nullptr};
+  double* k[1] = {dp(kdst)};
+  const int job[3] = {0, 0, 0};
+  if (emu_ypass(ctx->N, -1, 0, 1, s, nullptr, k, 1, job, 1, 1, dp(ctx->tw))) return 1;
+  double* d[3] = {dp(kdst), nullptr, nullptr};
+  ctx->launches += 3;
+  return emu_xpass(ctx->N, -1, 0, 1, dp(kdst), d, 1, 1, 1, nullptr, 1.0, 0, 0, dp(ctx->tw));
+}
+
+static const int kHessJobs[18] = {2, 0, 0, 0, 2, 1, 0, 0, 2, 1, 1, 3, 1, 0, 4, 0, 1, 5};
+static const int kHessKzPow[6] = {0, 0, 2, 0, 1, 1};
+
+static int hessian_xy(pinb200_ctx* ctx, double rs, double& dc) {
+  const int M = ctx->M;
+  const double knorm = 2.0 * M_PI / ctx->N, norm = 1.0 / ((double)ctx->N * ctx->N * ctx->N);
+  std::vector<double> gauss(M + 1);
+  for (int n = 0; n <= M; n++) { const double k = knorm * n; gauss[n] = exp(-0.5 * (k * k) * rs * rs); }
+  dc = norm * ctx->kdens[0].real();
+  std::vector<cplx>* xd[3] = {&ctx->A[0], &ctx->A[1], &ctx->A[2]};
+  if (xpass_inv(ctx, ctx->kdens, xd, 7, gauss.data(), 1, 0, norm, 0)) return 1;
+  std::vector<cplx>* ys[3] = {&ctx->A[0], &ctx->A[1], &ctx->A[2]};
+  std::vector<cplx>* yd[6] = {&ctx->B[0], &ctx->B[1], &ctx->B[2], &ctx->B[3], &ctx->B[4], &ctx->B[5]};
+  return ypass_inv(ctx, ys, yd, kHessJobs, 6, 0);
+}
+
+extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
+  if (!ctx) return 1;
+  if (!ctx->kdens_valid) FAIL("kdensity not resident (call pinb200_genic or pinb200_upload_kdensity)");
+  if (ctx->radius.empty()) FAIL("smoothing ladder not set (pinb200_set_smoothing)");
+  if (ctx->spline.empty()) FAIL("inverse-growth spline not set (pinb200_set_invgrow_spline)");
+  const int ns = (int)ctx->radius.size();
+  const double cell = ctx->d.box_size / ctx->N;
+  ctx->fmax.assign(ctx->ncells(), 0.0f);
+  ctx->rmax.assign(ctx->ncells(), 0);
+  for (auto& v : ctx->vel) v.clear();
+  ctx->kvec_valid = false;
+  for (int is = 0; is < ns; is++) {
+    double dc = 0.0, sums[2] = {0.0, 0.0};
+    if (hessian_xy(ctx, ctx->radius[is] / cell, dc)) FAIL("hessian passes");
+    double* b[6];
+    for (int k = 0; k < 6; k++) b[k] = dp(ctx->B[k]);
+    if (emu_zpass_collapse(ctx->N, 1, b, kHessKzPow, 0, &dc, ctx->spline.data(), ctx->nspl, is, ctx->fmax.data(), ctx->rmax.data(),
+                           sums, is == ns - 1 ? b : nullptr, dp(ctx->tw)))
+      FAIL("collapse pass");
+    ctx->launches++;
+    if (true_variance) true_variance[is] = sums[1] / (double)ctx->ncells();
+  }
+  ctx->hessian_valid = true;
+  return 0;
+}
+
+static int first_derivs_to_vel(pinb200_ctx* ctx, std::vector<cplx>& kvec, double growth, int first, int with_nyq) {
+  const double norm = 1.0 / ((double)ctx->N * ctx->N * ctx->N);
+  double dc = -norm * kvec[0].imag();  // run_dc with times_i = 1
+  std::vector<cplx>* xd[3] = {&ctx->A[1], &ctx->A[0], nullptr};  // p = 0 -> A1, p = 1 -> A0
+  if (xpass_inv(ctx, kvec, xd, 3, nullptr, 1, 1, norm * growth, with_nyq)) return 1;
+  std::vector<cplx>* ys[3] = {&ctx->A[0], &ctx->A[1], nullptr};
+  std::vector<cplx>* yd[6] = {&ctx->D[0], &ctx->D[1], &ctx->D[2], nullptr, nullptr, nullptr};
+  static const int jobs[9] = {0, 0, 0, 1, 1, 1, 1, 0, 2};
+  if (ypass_inv(ctx, ys, yd, jobs, 3, with_nyq)) return 1;
+  double* s[6] = {dp(ctx->D[0]), dp(ctx->D[1]), dp(ctx->D[2]), nullptr, nullptr, nullptr};
+  float* f[6] = {nullptr};
+  for (int a = 0; a < 3; a++) {
+    ctx->vel[first + a].assign(ctx->ncells(), 0.0f);
+    f[a] = ctx->vel[first + a].data();
+  }
+  static const int kz[6] = {0, 0, 1, 0, 0, 0};
+  ctx->launches++;
+  return emu_zpass_out(ctx->N, 1, 3, s, kz, with_nyq, &dc, 1, nullptr, f, nullptr, nullptr, nullptr, dp(ctx->tw));
+}
+
+extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, const double growth[4]) {
+  if (!ctx || !growth) return 1;
+  if (!ctx->kdens_valid) FAIL("kdensity not resident");
+  const int N = ctx->N, order = ctx->d.lpt_order;
+  const double norm = 1.0 / ((double)N * N * N);
+  if (order >= 2 && compute_sources) {
+    if (!ctx->hessian_valid) FAIL("second derivatives of the R=0 radius are not in place (call pinb200_fmax first)");
+    double* h[6];
+    for (int k = 0; k < 6; k++) h[k] = dp(ctx->B[k]);
+    if (emu_sources(N, 1, h, dp(ctx->A[0]), dp(ctx->A[1]), dp(ctx->A[2]), order)) FAIL("sources");
+    ctx->launches++;
+    if (r2c(ctx, ctx->A[0], ctx->KV[0])) FAIL("r2c of source_2LPT");
+    if (order >= 3) {
+      double dc = norm * ctx->KV[0][0].real();
+      struct Grp { int pw, n; int jobs[9]; int kz[6]; int slot[3]; };
+      const Grp grp[3] = {{2, 1, {0, 0, 0}, {0, 0, 0, 0, 0, 0}, {0, 0, 0}},
+                          {1, 2, {0, 1, 0, 0, 0, 1}, {0, 1, 0, 0, 0, 0}, {3, 4, 0}},
+                          {0, 3, {0, 2, 0, 0, 1, 1, 0, 0, 2}, {0, 1, 2, 0, 0, 0}, {1, 5, 2}}};
+      for (const Grp& gr : grp) {
+        std::vector<cplx>* xd[3] = {nullptr, nullptr, nullptr};
+        xd[gr.pw] = &ctx->A[0];
+        if (xpass_inv(ctx, ctx->KV[0], xd, 1 << gr.pw, nullptr, 1, 0, norm, 1)) FAIL("contraction x pass");
+        std::vector<cplx>* ys[3] = {&ctx->A[0], nullptr, nullptr};
+        std::vector<cplx>* yd[6] = {&ctx->D[0], &ctx->D[1], &ctx->D[2], nullptr, nullptr, nullptr};
+        if (ypass_inv(ctx, ys, yd, gr.jobs, gr.n, 1)) FAIL("contraction y pass");
+        double* s[6] = {dp(ctx->D[0]), dp(ctx->D[1]), dp(ctx->D[2]), nullptr, nullptr, nullptr};
+        double* hs[6] = {nullptr};
+        double w[6] = {0};
+        for (int k = 0; k < gr.n; k++) {
+          hs[k] = dp(ctx->B[gr.slot[k]]);
+          w[k] = 2.0 * (gr.slot[k] <= 2 ? 1.0 : 2.0);
+        }
+        ctx->launches++;
+        if (emu_zpass_out(N, 1, gr.n, s, gr.kz, 1, &dc, 2, nullptr, nullptr, hs, w, dp(ctx->A[2]), dp(ctx->tw))) FAIL("contraction z pass");
+      }
+      if (r2c(ctx, ctx->A[1], ctx->KV[1])) FAIL("r2c of source_3LPT_1");
+      if (r2c(ctx, ctx->A[2], ctx->KV[2])) FAIL("r2c of source_3LPT_2");
+    }
+    ctx->hessian_valid = false;
+    ctx->kvec_valid = true;
+  }
+  if (order >= 2 && !ctx->kvec_valid) FAIL("LPT k-vectors are not resident");
+  if (order >= 2 && first_derivs_to_vel(ctx, ctx->KV[0], growth[1], 3, 1)) FAIL("Vel_2LPT");
+  if (order >= 3) {
+    if (first_derivs_to_vel(ctx, ctx->KV[1], growth[2], 6, 1)) FAIL("Vel_3LPT_1");
+    if (first_derivs_to_vel(ctx, ctx->KV[2], growth[3], 9, 1)) FAIL("Vel_3LPT_2");
+  }
+  if (first_derivs_to_vel(ctx, ctx->kdens, growth[0], 0, 0)) FAIL("Vel");
+  return 0;
+}
+extern "C" int pinb200_displacements_scaledep(pinb200_ctx* ctx, int, int, double, double, const double*) {
+  FAIL("emulated ABI: scale-dependent growth is not wired (tests/test_emulator.py covers the kernel)");
+}
+
+extern "C" int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts) {
+  if (!ctx || !counts) return 1;
+  if (ctx->fmax.empty()) FAIL("Fmax not computed");
+  std::memset(counts, 0, sizeof(unsigned long long) * PINB200_NBINS);
+  for (float f : ctx->fmax) {
+    int x = (int)(f * 10.);
+    if (x < 0) x = 0;
+    if (x >= PINB200_NBINS) x = PINB200_NBINS - 1;
+    counts[x]++;
+  }
+  return 0;
+}
+
+extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t cell_begin,
+                                         size_t ncells) {
+  if (!ctx || !products || !L) return 1;
+  if (ctx->fmax.empty() && ctx->vel[0].empty()) FAIL("products not computed");
+  if (cell_begin + ncells > ctx->ncells()) FAIL("cell range outside the local slab");
+  if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
+  unsigned char* out = static_cast<unsigned char*>(products);
+  std::memset(out, 0, ncells * L->stride);
+  const int off_vel[4] = {L->off_Vel, L->off_Vel_2LPT, L->off_Vel_3LPT_1, L->off_Vel_3LPT_2};
+  for (size_t i = 0; i < ncells; i++) {
+    const size_t cell = cell_begin + i;
+    unsigned char* rec = out + i * L->stride;
+    if (L->off_Rmax >= 0 && !ctx->rmax.empty()) *reinterpret_cast<int*>(rec + L->off_Rmax) = ctx->rmax[cell];
+    auto put = [&](int off, float v) {
+      if (L->prodfloat_bytes == 4) *reinterpret_cast<float*>(rec + off) = v;
+      else *reinterpret_cast<double*>(rec + off) = (double)v;
+    };
+    if (L->off_Fmax >= 0 && !ctx->fmax.empty()) put(L->off_Fmax, ctx->fmax[cell]);
+    for (int v = 0; v < 4; v++)
+      if (off_vel[v] >= 0 && !ctx->vel[3 * v].empty())
+        for (int a = 0; a < 3; a++) put(off_vel[v] + a * L->prodfloat_bytes, ctx->vel[3 * v + a][cell]);
+  }
+  return 0;
+}
+extern "C" int pinb200_download_field(pinb200_ctx* ctx, int which, void* dst) {
+  if (!ctx || !dst || which < 0 || which > 13) return 1;
+  if (which == 0) std::memcpy(dst, ctx->fmax.data(), ctx->fmax.size() * 4);
+  else if (which == 1) std::memcpy(dst, ctx->rmax.data(), ctx->rmax.size() * 4);
+  else std::memcpy(dst, ctx->vel[which - 2].data(), ctx->vel[which - 2].size() * 4);
+  return 0;
+}
+extern "C" int pinb200_get_timers(pinb200_ctx* ctx, pinb200_timers* t) {
+  if (!ctx || !t) return 1;
+  std::memset(t, 0, sizeof *t);
+  t->kernel_launches = ctx->launches;
+  return 0;
+}
+extern "C" int pinb200_download_kvector(pinb200_ctx* ctx, int which, double* kvec) {
+  if (!ctx || !kvec || which < 0 || which > 2) return 1;
+  if (!ctx->kvec_valid) FAIL("LPT k-vectors are not resident");
+  download_c(ctx, ctx->KV[which], kvec);
+  return 0;
+}
+// entry points the HMF-style run never reaches through the shim
+extern "C" int pinb200_fft_r2c(pinb200_ctx* ctx, const double*, double*) { FAIL("emulated ABI: not wired"); }
+extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double*, double*) { FAIL("emulated ABI: not wired"); }
+extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double, double*) { FAIL("emulated ABI: not wired"); }
+extern "C" int pinb200_collapse_cells(pinb200_ctx* ctx, int, const double*, size_t, double*) { FAIL("emulated ABI: not wired"); }
+extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float, unsigned int*, size_t, size_t*) { FAIL("emulated ABI: not wired"); }
+extern "C" int pinb200_download_products_sorted(pinb200_ctx* ctx, void*, const pinb200_product_layout*, size_t, size_t) {
+  FAIL("emulated ABI: not wired");
+}
