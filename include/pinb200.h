@@ -115,7 +115,10 @@ int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts);
 
 /* ---- results ----------------------------------------------------------------------------- */
 /* Pack cells [cell_begin, cell_begin+ncells) of the local slab (index = z + N*(y + N*x_local),
- * src/pinocchio.h:84-85) into host AoS records. */
+ * src/pinocchio.h:84-85) into host AoS records.  Only the members this path computes are written
+ * (Rmax, Fmax, Vel* -- as compute_collapse_times and write_from_rvector_to_products do,
+ * src/collapse_times.c:587-590, src/fmax-pfft.c:563-631): other bytes of the records (the *_prev
+ * members of -DRECOMPUTE_DISPLACEMENTS, zacc/group_ID of -DSNAPSHOT) keep the caller's values. */
 int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* layout,
                               size_t cell_begin, size_t ncells);
 /* Hand-off to the fragmentation: the local cells with Fmax >= f_last -- the

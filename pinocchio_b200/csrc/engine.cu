@@ -23,6 +23,7 @@
 
 #include "../../include/pinb200.h"
 #include "launch.h"
+#include "product_merge.h"
 #include "seed_plane.h"
 #include "sort_cells.cuh"
 
@@ -901,7 +902,23 @@ extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const
   p.ncells = ncells;
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   LAUNCH(launch_pack_products(p, ctx->stream));
-  CK(cudaMemcpyAsync(products, d, ncells * L->stride, cudaMemcpyDeviceToHost, ctx->stream));
+  // Records whose every byte is a member we deliver (the default 56-byte product_data) are copied
+  // straight over the caller's; records with foreign members (*_prev of RECOMPUTE_DISPLACEMENTS,
+  // zacc/group_ID of SNAPSHOT) are staged and merged member by member (product_merge.h).
+  const bool has_vel[4] = {ctx->vel[0] != nullptr, ctx->vel[3] != nullptr, ctx->vel[6] != nullptr, ctx->vel[9] != nullptr};
+  const std::vector<MemberRange> members = product_members(*L, ctx->fmax != nullptr, has_vel);
+  if (members_cover_record(members, L->stride)) {
+    CK(cudaMemcpyAsync(products, d, ncells * L->stride, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    const size_t chunk = (size_t)1 << 22;  // records per staging round
+    std::vector<unsigned char> stage((ncells < chunk ? ncells : chunk) * L->stride);
+    for (size_t b = 0; b < ncells; b += chunk) {
+      const size_t n = ncells - b < chunk ? ncells - b : chunk;
+      CK(cudaMemcpyAsync(stage.data(), d + b * L->stride, n * L->stride, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      merge_product_members(static_cast<unsigned char*>(products) + b * L->stride, stage.data(), L->stride, n, members);
+    }
+  }
   CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0;

@@ -16,12 +16,16 @@
 #include <vector>
 
 #include "../../include/pinb200.h"
+#include "../../pinocchio_b200/csrc/product_merge.h"
 #include "../../pinocchio_b200/csrc/seed_plane.h"
 
 // entry points of emu.cpp (same shared object)
 extern "C" {
 int emu_xpass(int N, int dir, int rank, int nranks, const double* src, double** dsts, int dst_klayout, int pmask, int with_nyq,
               const double* gauss, double scalar, int green, int times_i, const double* tw);
+int emu_xpass_gk(int N, int dir, int rank, int nranks, const double* src, double** dsts, int dst_klayout, int pmask, int with_nyq,
+                 const double* gauss, double scalar, int green, int times_i, const double* tw, const double* gk, int gk_n,
+                 double gk_logkmin, double gk_dlogk, double gk_sign);
 int emu_ypass(int N, int dir, int rank, int nranks, double** srcs, double** dsts, double** kdsts, int dst_klayout, const int* jobs,
               int njobs, int with_nyq, const double* tw);
 int emu_zpass_collapse(int N, int nranks, double** srcs, const int* kzpow, int has_nyq, const double* dc, const double* spline,
@@ -44,6 +48,7 @@ struct pinb200_ctx {
   std::string err;
   std::vector<cplx> tw, kdens, A[3], B[6], D[3], KV[3];
   std::vector<double> pk, radius, spline;
+  std::vector<std::vector<double>> spline_r;  // SPLINE_INVGROW[ismooth] of -DSCALE_DEPENDENT builds
   int nspl = 0;
   std::vector<float> fmax, vel[12];
   std::vector<int> rmax;
@@ -99,10 +104,16 @@ extern "C" int pinb200_set_smoothing(pinb200_ctx* ctx, int nsmooth, const double
 }
 extern "C" int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const double* x, const double* y, int n) {
   if (!ctx || !x || !y) return 1;
-  if (ismooth >= 0) FAIL("emulated ABI: the global inverse-growth spline only");
+  if (ctx->nspl && ctx->nspl != n) FAIL("all inverse-growth splines must have the same number of knots");
   ctx->nspl = n;
-  ctx->spline.assign((size_t)emu_spline_table_doubles(n), 0.0);
-  return emu_pack_spline(x, y, n, ctx->spline.data());
+  std::vector<double>* t = &ctx->spline;
+  if (ismooth >= 0) {
+    if (ismooth >= 64) FAIL("ismooth out of range");
+    if ((int)ctx->spline_r.size() <= ismooth) ctx->spline_r.resize(ismooth + 1);
+    t = &ctx->spline_r[ismooth];
+  }
+  t->assign((size_t)emu_spline_table_doubles(n), 0.0);
+  return emu_pack_spline(x, y, n, t->data());
 }
 
 extern "C" int pinb200_genic(pinb200_ctx* ctx) {
@@ -193,7 +204,9 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     if (hessian_xy(ctx, ctx->radius[is] / cell, dc)) FAIL("hessian passes");
     double* b[6];
     for (int k = 0; k < 6; k++) b[k] = dp(ctx->B[k]);
-    if (emu_zpass_collapse(ctx->N, 1, b, kHessKzPow, 0, &dc, ctx->spline.data(), ctx->nspl, is, ctx->fmax.data(), ctx->rmax.data(),
+    // spline_for() of the engine: the per-radius table when one was given, else the global one
+    const std::vector<double>& spl = (is < (int)ctx->spline_r.size() && !ctx->spline_r[is].empty()) ? ctx->spline_r[is] : ctx->spline;
+    if (emu_zpass_collapse(ctx->N, 1, b, kHessKzPow, 0, &dc, spl.data(), ctx->nspl, is, ctx->fmax.data(), ctx->rmax.data(),
                            sums, is == ns - 1 ? b : nullptr, dp(ctx->tw)))
       FAIL("collapse pass");
     ctx->launches++;
@@ -203,11 +216,19 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   return 0;
 }
 
-static int first_derivs_to_vel(pinb200_ctx* ctx, std::vector<cplx>& kvec, double growth, int first, int with_nyq) {
+struct GrowthK { const double* tab = nullptr; int n = 0; double logkmin = 0, dlogk = 1, sign = 1; };
+static int first_derivs_to_vel(pinb200_ctx* ctx, std::vector<cplx>& kvec, double growth, int first, int with_nyq,
+                               const GrowthK* gk = nullptr) {
   const double norm = 1.0 / ((double)ctx->N * ctx->N * ctx->N);
   double dc = -norm * kvec[0].imag();  // run_dc with times_i = 1
   std::vector<cplx>* xd[3] = {&ctx->A[1], &ctx->A[0], nullptr};  // p = 0 -> A1, p = 1 -> A0
-  if (xpass_inv(ctx, kvec, xd, 3, nullptr, 1, 1, norm * growth, with_nyq)) return 1;
+  if (gk) {
+    double* d[3] = {dp(ctx->A[1]), dp(ctx->A[0]), nullptr};
+    ctx->launches++;
+    if (emu_xpass_gk(ctx->N, +1, 0, 1, dp(kvec), d, 0, 3, with_nyq, nullptr, norm * growth, 1, 1, dp(ctx->tw), gk->tab, gk->n,
+                     gk->logkmin, gk->dlogk, gk->sign))
+      return 1;
+  } else if (xpass_inv(ctx, kvec, xd, 3, nullptr, 1, 1, norm * growth, with_nyq)) return 1;
   std::vector<cplx>* ys[3] = {&ctx->A[0], &ctx->A[1], nullptr};
   std::vector<cplx>* yd[6] = {&ctx->D[0], &ctx->D[1], &ctx->D[2], nullptr, nullptr, nullptr};
   static const int jobs[9] = {0, 0, 0, 1, 1, 1, 1, 0, 2};
@@ -223,8 +244,7 @@ static int first_derivs_to_vel(pinb200_ctx* ctx, std::vector<cplx>& kvec, double
   return emu_zpass_out(ctx->N, 1, 3, s, kz, with_nyq, &dc, 1, nullptr, f, nullptr, nullptr, nullptr, dp(ctx->tw));
 }
 
-extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, const double growth[4]) {
-  if (!ctx || !growth) return 1;
+static int displacements_impl(pinb200_ctx* ctx, int compute_sources, const double growth[4], const GrowthK* gk) {
   if (!ctx->kdens_valid) FAIL("kdensity not resident");
   const int N = ctx->N, order = ctx->d.lpt_order;
   const double norm = 1.0 / ((double)N * N * N);
@@ -265,16 +285,31 @@ extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, cons
     ctx->kvec_valid = true;
   }
   if (order >= 2 && !ctx->kvec_valid) FAIL("LPT k-vectors are not resident");
-  if (order >= 2 && first_derivs_to_vel(ctx, ctx->KV[0], growth[1], 3, 1)) FAIL("Vel_2LPT");
+  if (order >= 2 && first_derivs_to_vel(ctx, ctx->KV[0], growth[1], 3, 1, gk ? gk + 1 : nullptr)) FAIL("Vel_2LPT");
   if (order >= 3) {
-    if (first_derivs_to_vel(ctx, ctx->KV[1], growth[2], 6, 1)) FAIL("Vel_3LPT_1");
-    if (first_derivs_to_vel(ctx, ctx->KV[2], growth[3], 9, 1)) FAIL("Vel_3LPT_2");
+    if (first_derivs_to_vel(ctx, ctx->KV[1], growth[2], 6, 1, gk ? gk + 2 : nullptr)) FAIL("Vel_3LPT_1");
+    if (first_derivs_to_vel(ctx, ctx->KV[2], growth[3], 9, 1, gk ? gk + 3 : nullptr)) FAIL("Vel_3LPT_2");
   }
-  if (first_derivs_to_vel(ctx, ctx->kdens, growth[0], 0, 0)) FAIL("Vel");
+  if (first_derivs_to_vel(ctx, ctx->kdens, growth[0], 0, 0, gk)) FAIL("Vel");
   return 0;
 }
-extern "C" int pinb200_displacements_scaledep(pinb200_ctx* ctx, int, int, double, double, const double*) {
-  FAIL("emulated ABI: scale-dependent growth is not wired (tests/test_emulator.py covers the kernel)");
+extern "C" int pinb200_displacements(pinb200_ctx* ctx, int compute_sources, const double growth[4]) {
+  if (!ctx || !growth) return 1;
+  return displacements_impl(ctx, compute_sources, growth, nullptr);
+}
+extern "C" int pinb200_displacements_scaledep(pinb200_ctx* ctx, int compute_sources, int nk, double logkmin, double dlogk,
+                                              const double* log10_growth) {
+  if (!ctx || !log10_growth || nk < 1 || !(dlogk > 0.0)) return 1;
+  GrowthK gk[4];
+  for (int o = 0; o < 4; o++) {
+    gk[o].tab = log10_growth + (size_t)o * nk;
+    gk[o].n = nk;
+    gk[o].logkmin = logkmin;
+    gk[o].dlogk = dlogk;
+    gk[o].sign = (o == 2) ? -1.0 : 1.0;
+  }
+  static const double ones[4] = {1.0, 1.0, 1.0, 1.0};
+  return displacements_impl(ctx, compute_sources, ones, gk);
 }
 
 extern "C" int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts) {
@@ -296,8 +331,9 @@ extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const
   if (ctx->fmax.empty() && ctx->vel[0].empty()) FAIL("products not computed");
   if (cell_begin + ncells > ctx->ncells()) FAIL("cell range outside the local slab");
   if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
-  unsigned char* out = static_cast<unsigned char*>(products);
-  std::memset(out, 0, ncells * L->stride);
+  // packed records first (as the device packer writes them), then the engine's copy-or-merge rule
+  std::vector<unsigned char> packed(ncells * L->stride, 0);
+  unsigned char* out = packed.data();
   const int off_vel[4] = {L->off_Vel, L->off_Vel_2LPT, L->off_Vel_3LPT_1, L->off_Vel_3LPT_2};
   for (size_t i = 0; i < ncells; i++) {
     const size_t cell = cell_begin + i;
@@ -312,6 +348,10 @@ extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const
       if (off_vel[v] >= 0 && !ctx->vel[3 * v].empty())
         for (int a = 0; a < 3; a++) put(off_vel[v] + a * L->prodfloat_bytes, ctx->vel[3 * v + a][cell]);
   }
+  const bool has_vel[4] = {!ctx->vel[0].empty(), !ctx->vel[3].empty(), !ctx->vel[6].empty(), !ctx->vel[9].empty()};
+  const std::vector<pinb::MemberRange> members = pinb::product_members(*L, !ctx->fmax.empty(), has_vel);
+  if (pinb::members_cover_record(members, L->stride)) std::memcpy(products, packed.data(), packed.size());
+  else pinb::merge_product_members(static_cast<unsigned char*>(products), packed.data(), L->stride, ncells, members);
   return 0;
 }
 extern "C" int pinb200_download_field(pinb200_ctx* ctx, int which, void* dst) {

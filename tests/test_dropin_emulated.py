@@ -23,15 +23,24 @@ EMU_X = REF_X.parent / "pinocchio_emu.x"
 pytestmark = pytest.mark.skipif(not (REF_X.exists() and EMU_X.exists()),
                                 reason="oracle/_ref/pinocchio_{ref,emu}.x not built (make -C oracle all)")
 N = 32
+# "": the default build (-DTWO_LPT -DTHREE_LPT -DELL_CLASSIC -DNORADIATION).
+# "_sd": the same + -DSCALE_DEPENDENT -DRECOMPUTE_DISPLACEMENTS -- growth rates per k bin handed to
+# pinb200_displacements_scaledep, one inverse-growth spline per smoothing radius, displacements
+# recomputed for each of the four redshift segments (compute_displacements(0,0,z), src/fragment.c:409)
+# and the *_prev members of the 104-byte product_data, which belong to the fragmentation, preserved
+# by the member-wise download (product_merge.h).
+VARIANTS = ["", "_sd"]
 
 
-def run32(exe, workdir):
+def run32(exe, workdir, variant=""):
     import os
     import subprocess
     workdir.mkdir(parents=True, exist_ok=True)
     text = (GOLDEN / "parameter_file").read_text()
     text = re.sub(r"(?m)^BoxSize\s+\S+", f"BoxSize                {N}", text)
     text = re.sub(r"(?m)^GridSize\s+\S+", f"GridSize               {N}", text)
+    if variant == "_sd":                                # 104-byte records + fields kept for the re-entry
+        text = re.sub(r"(?m)^MaxMemPerParticle\s+\S+", "MaxMemPerParticle      400", text)
     (workdir / "parameter_file").write_text(text)
     (workdir / "outputs").write_bytes((GOLDEN / "outputs").read_bytes())
     r = subprocess.run([str(exe), "parameter_file"], cwd=workdir, capture_output=True, text=True, timeout=1500,
@@ -40,11 +49,15 @@ def run32(exe, workdir):
     return r.stdout
 
 
-@pytest.fixture(scope="module")
-def runs(tmp_path_factory):
-    a = tmp_path_factory.mktemp("emu")
-    b = tmp_path_factory.mktemp("ref")
-    return a, run32(EMU_X, a), b, run32(REF_X, b)
+@pytest.fixture(scope="module", params=VARIANTS)
+def runs(request, tmp_path_factory):
+    v = request.param
+    emu, ref = REF_X.parent / f"pinocchio_emu{v}.x", REF_X.parent / f"pinocchio_ref{v}.x"
+    if not (emu.exists() and ref.exists()):
+        pytest.skip(f"{emu.name} / {ref.name} not built")
+    a = tmp_path_factory.mktemp("emu" + v)
+    b = tmp_path_factory.mktemp("ref" + v)
+    return a, run32(emu, a, v), b, run32(ref, b, v)
 
 
 def test_emulated_dropin_log(runs):
@@ -54,6 +67,9 @@ def test_emulated_dropin_log(runs):
     assert len(sig(log_a)) == 9 and sig(log_a) == sig(log_b)
     ncoll = lambda log: int(re.search(r"Number of collapsed particles to z=0: (\d+)", log).group(1))
     assert ncoll(log_a) == ncoll(log_b) > 0.4 * N ** 3
+    # -DRECOMPUTE_DISPLACEMENTS: both programs recompute the displacements for segments 2..4
+    nre = lambda log: len(re.findall(r"Computing displacements for redshift", log))
+    assert nre(log_a) == nre(log_b)
 
 
 def test_emulated_dropin_fmaxpdf_identical(runs):

@@ -94,3 +94,37 @@ def test_dropin_catalogue_against_shipped(runs):
     g = np.load(GOLDEN / "catalog_0.0000_id_npart.npz")
     assert abs(len(ids) - len(g["id"])) <= 0.005 * len(g["id"])
     assert match_fraction(ids, npart, g["id"], g["npart"]) > 0.99
+
+
+def test_dropin_scale_dependent_recompute_variant(tmp_path_factory):
+    """-DSCALE_DEPENDENT -DRECOMPUTE_DISPLACEMENTS builds of both programs (oracle/Makefile FLAGS_SD): G(k)
+    tables through pinb200_displacements_scaledep, per-radius inverse-growth splines, displacements
+    recomputed per redshift segment, *_prev members preserved by the member-wise download."""
+    import re as _re
+    bx, rx = REF_X.parent / "pinocchio_b200_sd.x", REF_X.parent / "pinocchio_ref_sd.x"
+    if not (bx.exists() and rx.exists()):
+        pytest.skip("SD variants not built")
+
+    def run(exe, d, threads):
+        import os
+        import subprocess
+        d.mkdir(parents=True, exist_ok=True)
+        text = (GOLDEN / "parameter_file").read_text()
+        text = _re.sub(r"(?m)^BoxSize\s+\S+", "BoxSize                64", text)
+        text = _re.sub(r"(?m)^GridSize\s+\S+", "GridSize               64", text)
+        text = _re.sub(r"(?m)^MaxMemPerParticle\s+\S+", "MaxMemPerParticle      400", text)
+        (d / "parameter_file").write_text(text)
+        (d / "outputs").write_bytes((GOLDEN / "outputs").read_bytes())
+        r = subprocess.run([str(exe), "parameter_file"], cwd=d, capture_output=True, text=True, timeout=900,
+                           env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        return r.stdout
+
+    da, db = tmp_path_factory.mktemp("b200_sd"), tmp_path_factory.mktemp("ref_sd")
+    log_b, log_r = run(bx, da, 8), run(rx, db, 16)
+    assert len(_re.findall(r"Computing displacements for redshift", log_b)) == len(_re.findall(r"Computing displacements for redshift", log_r)) == 3
+    for z in ("0.0000", "0.5000", "1.0000", "2.0000"):
+        ia, na, _ = load_catalog(da / f"pinocchio.{z}.test.catalog.out")
+        ib, nb, _ = load_catalog(db / f"pinocchio.{z}.test.catalog.out")
+        assert abs(len(ia) - len(ib)) <= max(2, 0.005 * len(ib))
+        assert match_fraction(ia, na, ib, nb) > 0.99
