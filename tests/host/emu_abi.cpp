@@ -376,7 +376,25 @@ extern "C" int pinb200_download_kvector(pinb200_ctx* ctx, int which, double* kve
 // entry points the HMF-style run never reaches through the shim
 extern "C" int pinb200_fft_r2c(pinb200_ctx* ctx, const double*, double*) { FAIL("emulated ABI: not wired"); }
 extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double*, double*) { FAIL("emulated ABI: not wired"); }
-extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double, double*) { FAIL("emulated ABI: not wired"); }
+// compute_second_derivatives(R): x/y passes, then the plain c2r z pass in place (engine: zpass_out mode 0)
+extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, double* hessian_out) {
+  if (!ctx) return 1;
+  if (!ctx->kdens_valid) FAIL("kdensity not resident");
+  double dc = 0.0;
+  if (hessian_xy(ctx, radius / (ctx->d.box_size / ctx->N), dc)) FAIL("hessian passes");
+  double* b[6];
+  for (int k = 0; k < 6; k++) b[k] = dp(ctx->B[k]);
+  ctx->launches++;
+  if (emu_zpass_out(ctx->N, 1, 6, b, kHessKzPow, 0, &dc, 0, b, nullptr, nullptr, nullptr, nullptr, dp(ctx->tw))) FAIL("z pass");
+  if (hessian_out) {
+    const int N = ctx->N, P2 = 2 * ctx->P;
+    for (int k = 0; k < 6; k++)
+      for (size_t r = 0; r < (size_t)N * N; r++)
+        std::memcpy(hessian_out + ((size_t)k * N * N + r) * N, reinterpret_cast<double*>(ctx->B[k].data()) + r * P2, sizeof(double) * N);
+  }
+  ctx->hessian_valid = (radius == 0.0);
+  return 0;
+}
 extern "C" int pinb200_collapse_cells(pinb200_ctx* ctx, int, const double*, size_t, double*) { FAIL("emulated ABI: not wired"); }
 extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float, unsigned int*, size_t, size_t*) { FAIL("emulated ABI: not wired"); }
 extern "C" int pinb200_download_products_sorted(pinb200_ctx* ctx, void*, const pinb200_product_layout*, size_t, size_t) {

@@ -99,3 +99,60 @@ def test_emulated_dropin_mass_function_matches(runs):
     ma = np.loadtxt(a / "pinocchio.0.0000.test.mf.out")
     mb = np.loadtxt(b / "pinocchio.0.0000.test.mf.out")
     assert np.array_equal(ma[:, 4], mb[:, 4])          # halos per mass bin
+
+
+# ---- -DSNAPSHOT builds: product_data with zacc / group_ID; special mode 3 ---------------------------
+SNAP_REF, SNAP_EMU = REF_X.parent / "pinocchio_ref_snap.x", REF_X.parent / "pinocchio_emu_snap.x"
+needs_snap = pytest.mark.skipif(not (SNAP_REF.exists() and SNAP_EMU.exists()), reason="SNAPSHOT variants not built")
+
+
+def run32_args(exe, workdir, extra_param_lines=(), args=()):
+    import os
+    import subprocess
+    workdir.mkdir(parents=True, exist_ok=True)
+    text = (GOLDEN / "parameter_file").read_text()
+    text = re.sub(r"(?m)^BoxSize\s+\S+", f"BoxSize                {N}", text)
+    text = re.sub(r"(?m)^GridSize\s+\S+", f"GridSize               {N}", text)
+    (workdir / "parameter_file").write_text(text + "".join(l + "\n" for l in extra_param_lines))
+    (workdir / "outputs").write_bytes((GOLDEN / "outputs").read_bytes())
+    r = subprocess.run([str(exe), "parameter_file", *args], cwd=workdir, capture_output=True, text=True, timeout=1500,
+                       env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    return r.stdout
+
+
+def differing_bytes(a, b):
+    x, y = np.frombuffer(a.read_bytes(), dtype=np.uint8), np.frombuffer(b.read_bytes(), dtype=np.uint8)
+    assert x.size == y.size
+    return int((x != y).sum())
+
+
+@needs_snap
+def test_emulated_dropin_special_mode_3_lpt_snapshot(tmp_path):
+    """`pinocchio.x parameter_file 3` (src/pinocchio.c:170-200): compute_displacements(1, 1, z) -- the shim's
+    recompute_sd path, pinb200_second_derivatives(pinb, 0, NULL) -- then write_LPT_snapshot: positions and
+    velocities of every particle from the 3LPT displacements, compared as bytes"""
+    a, b = tmp_path / "emu", tmp_path / "ref"
+    log = run32_args(SNAP_EMU, a, args=("3",))
+    run32_args(SNAP_REF, b, args=("3",))
+    assert "only produce a GADGET snapshot" in log
+    fa = next(a.glob("*.LPT_snapshot.out"))
+    fb = b / fa.name
+    assert fa.stat().st_size > 12 * 4 * N ** 3 // 2
+    # float products differ by last-bit rounding flips in ~1e-4 of the values at most
+    assert differing_bytes(fa, fb) <= 2e-4 * fa.stat().st_size
+
+
+@needs_snap
+def test_emulated_dropin_snapshot_build_and_timeless_snapshot(tmp_path):
+    """-DSNAPSHOT run with WriteTimelessSnapshot: the 64-byte records carry zacc / group_ID, which belong to
+    the fragmentation (member-wise download); FMAX, ZEL, 2LPT, 31PT, 32PT, ZACC, GRUP blocks of the timeless
+    snapshot (src/write_snapshot.c:207-345) and all catalogues against the reference's"""
+    a, b = tmp_path / "emu", tmp_path / "ref"
+    run32_args(SNAP_EMU, a, extra_param_lines=("WriteTimelessSnapshot",))
+    run32_args(SNAP_REF, b, extra_param_lines=("WriteTimelessSnapshot",))
+    for z in ("0.0000", "2.0000"):
+        assert (a / f"pinocchio.{z}.test.catalog.out").read_bytes() == (b / f"pinocchio.{z}.test.catalog.out").read_bytes()
+    ts = a / "pinocchio.test.t_snapshot.out"
+    assert ts.stat().st_size > 14 * 4 * N ** 3
+    assert differing_bytes(ts, b / ts.name) <= 2e-4 * ts.stat().st_size
