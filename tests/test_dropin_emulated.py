@@ -156,3 +156,22 @@ def test_emulated_dropin_snapshot_build_and_timeless_snapshot(tmp_path):
     ts = a / "pinocchio.test.t_snapshot.out"
     assert ts.stat().st_size > 14 * 4 * N ** 3
     assert differing_bytes(ts, b / ts.name) <= 2e-4 * ts.stat().st_size
+
+
+def test_emulated_dropin_dump_products_file_boundary(tmp_path):
+    """DumpProducts / ReadProductsFromDumps (src/fmax.c:372-506, src/pinocchio.c:220-234) across the two
+    programs: the drop-in dumps products[], the unchanged reference resumes from the dump and fragments;
+    and the other way round.  Catalogues must equal those of the straight runs."""
+    straight = tmp_path / "straight"
+    run32_args(REF_X, straight)
+    want = (straight / "pinocchio.0.0000.test.catalog.out").read_bytes()
+    for writer, reader in ((EMU_X, REF_X), (REF_X, EMU_X)):
+        d = tmp_path / f"{writer.stem}_to_{reader.stem}"
+        run32_args(writer, d, extra_param_lines=("DumpProducts",))
+        dumps = d / "DumpProducts"
+        assert (dumps / "Task.0").stat().st_size == 56 * N ** 3 and (dumps / "summary").exists()
+        for f in d.glob("pinocchio.*"):
+            f.unlink()
+        log = run32_args(reader, d, extra_param_lines=("ReadProductsFromDumps",))
+        assert "B200 path" not in log or reader == EMU_X
+        assert (d / "pinocchio.0.0000.test.catalog.out").read_bytes() == want
