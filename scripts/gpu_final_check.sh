@@ -4,7 +4,7 @@
 # the engine's own CUDA-event timers; then (if time is left) instruction counters of the collapse kernel.
 # No torch import (ctypes + numpy only) to keep start-up short.
 mkdir -p gpurun_out
-timeout 45 python -m pytest tests/test_gpu_parity.py tests/test_zgpu_scaledep.py -x -q \
+timeout 45 python -m pytest tests/test_gpu_parity.py tests/test_zgpu_1_scaledep.py -x -q \
   -k "collapse_cells or reference_code_golden or (fmax_and_displacements and 64) or against_reference_golden or (against_oracle and 64) or recompute_sd" \
   > gpurun_out/final_parity.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/final_parity.log

@@ -9,7 +9,7 @@ What this pins on a CPU-only box: the shim's run-time logic (order of calls, P(k
 smoothing ladder, inverse-growth spline knots taken from the reference's gsl_spline, growth factors,
 units, the products[] download into the reference's arena) and the hand-over to the unchanged
 fragmentation -- BASELINE.json's "halo catalogue and mass function produced by the unchanged
-fragmentation stage must match the reference".  tests/test_zgpu_dropin_catalogues.py repeats it at
+fragmentation stage must match the reference".  tests/test_zgpu_4_dropin_catalogues.py repeats it at
 128^3 with the real libpinb200.so on the B200.
 """
 import re

@@ -2,7 +2,7 @@
 PINOCCHIO V5.1 compiled verbatim over one-task MPI/PFFT stand-ins and the restated GSL subset of
 oracle/ref_full/) against the outputs the reference ships for the same run (HMF_Validation/:
 128^3, 128 Mpc/h, seed 486604, EH spectrum).  This is what pins the stand-ins -- and with them
-"Oracle B", the authority for catalogues: the GPU drop-in (tests/test_zgpu_dropin_catalogues.py) is
+"Oracle B", the authority for catalogues: the GPU drop-in (tests/test_zgpu_4_dropin_catalogues.py) is
 compared with this program's catalogues.
 
 Expected agreement: the quadrature stand-in is not GSL's QAGS, so PkNorm and the radius ladder
