@@ -24,7 +24,7 @@ pytestmark = pytest.mark.skipif(not (REF_X.exists() and EMU_X.exists()),
                                 reason="oracle/_ref/pinocchio_{ref,emu}.x not built (make -C oracle all)")
 N = 32
 # "": the default build (-DTWO_LPT -DTHREE_LPT -DELL_CLASSIC -DNORADIATION).
-# "_sd": the same + -DSCALE_DEPENDENT -DRECOMPUTE_DISPLACEMENTS -- growth rates per k bin handed to
+# "_sd": the same + -DSCALE_DEPENDENT -DRECOMPUTE_DISPLACEMENTS -DPLC -- growth rates per k bin handed to
 # pinb200_displacements_scaledep, one inverse-growth spline per smoothing radius, displacements
 # recomputed for each of the four redshift segments (compute_displacements(0,0,z), src/fragment.c:409)
 # and the *_prev members of the 104-byte product_data, which belong to the fragmentation, preserved
@@ -78,6 +78,18 @@ def test_emulated_dropin_fmaxpdf_identical(runs):
     pb = np.loadtxt(b / "pinocchio.test.FmaxPDF.out")[:, 2]
     assert pa.sum() == N ** 3
     assert np.abs(pa - pb).max() <= 1          # float-rounding flips of Fmax at a bin edge at most
+
+
+def test_emulated_dropin_past_light_cone(runs):
+    """the _sd variant is also built with -DPLC (BASELINE.json configs[4]: scale-dependent growth with
+    past light-cone output): the light-cone catalogue and n(z) of the two programs are the same bytes"""
+    a, _, b, _ = runs
+    plc = list(b.glob("*.plc.out"))
+    if not plc:
+        pytest.skip("variant built without -DPLC")
+    for f in plc + list(b.glob("*.nz.out")):
+        assert (a / f.name).read_bytes() == f.read_bytes(), f.name
+    assert plc[0].stat().st_size > 1000
 
 
 @pytest.mark.parametrize("z", ["0.0000", "0.5000", "1.0000", "2.0000"])
