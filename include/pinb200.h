@@ -84,6 +84,40 @@ int pinb200_set_smoothing(pinb200_ctx* ctx, int nsmooth, const double* radius);
  * The natural-cubic-spline coefficients are recomputed here as gsl_interp_cspline does. */
 int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const double* x, const double* y, int n);
 
+/* ---- tabulated collapse times: -DTABULATED_CT, with ELL_CLASSIC or ELL_SNG ---- */
+/* The reference fills, for every smoothing radius, a table F(delta, x, y) of nbins_d * nbins_xy^2
+ * points with ell() -- ell_classic, or the numerical ellipsoidal collapse ell_sng: one 9-variable
+ * rkf45 integration per point (initialize_collapse_times, src/collapse_times.c:824-1046; ell_sng
+ * :315-400; sng_system :239-290) -- and evaluates per cell four cubic splines in delta blended
+ * bilinearly in (x, y) (interpolate_collapse_time, BILINEAR_SPLINE, :1132-1222).  model is the type
+ * code of the CTtable file header (write_CTtable_header, :1307-1326): 1 = ELL_CLASSIC tabulated,
+ * 3 = ELL_SNG standard gravity (4 = f(R) gravity: not built). */
+#define PINB200_CT_CLASSIC 1
+#define PINB200_CT_SNG 3
+typedef struct {
+  int model;
+  int nbins_d, nbins_xy;      /* CT_NBINS_D (100, at most 128), CT_NBINS_XY (50) */
+  double range_x;             /* CT_RANGE_X (3.5): bin_x = range_x / nbins_xy */
+  const double* delta_vector; /* nbins_d increasing knots; NULL = pinb200_ct_delta_vector() */
+  /* ELL_SNG only: OmegaMatter(z), OmegaLambda(z) of src/cosmo.c:1675-1718 for a cosmological constant:
+   * E^2(z) = omega_rad (1+z)^4 + omega0 (1+z)^3 + omega_k (1+z)^2 + omega_lambda */
+  double omega0, omega_lambda, omega_rad, omega_k;
+} pinb200_ct_desc;
+/* delta_vector of the reference's compiled sampling (CT_EXPO 1.75, CT_SQUEEZE 1.2, CT_RANGE_D 7,
+ * CT_DELTA0 -1; src/collapse_times.c:781-787, 836-877); host code, no device needed */
+int pinb200_ct_delta_vector(double* delta_vector, int nbins_d);
+/* Switch pinb200_fmax / pinb200_collapse_cells to tabulated collapse times (desc = NULL: back to the
+ * direct ell_classic evaluation).  variance[ismooth] = Smoothing.Variance (the table is sampled in
+ * units of its square root); d_in[ismooth] = GrowingMode(1/1e-5 - 1, k(R_ismooth)), ELL_SNG only
+ * (src/collapse_times.c:345-353).  tables = nsmooth * nbins_d * nbins_xy^2 doubles in the reference's
+ * CT_table order (delta fastest, then x, then y) as read from a CTtableFile, or NULL: the tables are
+ * computed on the device -- with ELL_CLASSIC from the inverse-growth splines set before this call.
+ * Needs pinb200_set_smoothing first. */
+int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_desc* desc, const double* variance, const double* d_in,
+                                const double* tables);
+/* CT_table of one radius (what the reference writes to pinocchio.<run>.CTtable.out) */
+int pinb200_download_collapse_table(pinb200_ctx* ctx, int ismooth, double* table);
+
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* GenIC_large (src/GenIC.c:73-460): fills kdensity on the device. */
 int pinb200_genic(pinb200_ctx* ctx);

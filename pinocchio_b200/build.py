@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
-SOURCES = ["engine.cu", "k_strided.cu", "k_zpass.cu", "k_misc.cu", "k_sort.cu"]
+SOURCES = ["engine.cu", "k_strided.cu", "k_zpass.cu", "k_misc.cu", "k_sort.cu", "k_ctable.cu"]
 
 
 # Test-only variant: the code paths the product only takes at N = 2048 (8 GPUs) -- the

@@ -64,6 +64,14 @@ struct pinb200_ctx {
   double* spl_dev = nullptr;                  // (1+nsmooth) packed tables (spline_pack.h)
   int nspl = 0;
   bool spl_dirty = true;
+  // TABULATED_CT (collapse_table.cuh): per radius the table, its spline records; shared knots
+  bool ct_on = false;
+  int ct_nd = 0, ct_nxy = 0, ct_ns = 0;
+  double ct_bin_x = 0.0;
+  std::vector<double> ct_ampl;
+  double* ct_tables = nullptr;  // [ns][nxy*nxy][nd]
+  CTRec* ct_coef = nullptr;     // [ns][nxy*nxy][nd + 2]
+  double* ct_knots = nullptr;   // packed knots + look-up (ct_pack_knots), then the plain nd knots
 
   // fields
   double2* kdens = nullptr;                       // arena
@@ -240,7 +248,7 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
     if (r != ctx->d.rank && ctx->peer_arena[r]) cudaIpcCloseMemHandle(ctx->peer_arena[r]);
   auto fr = [&](void* p) { if (p) cudaFree(p); };
   fr(ctx->tw); fr(ctx->gauss); fr(ctx->dc); fr(ctx->growthk); fr(ctx->sums); fr(ctx->seeds); fr(ctx->pk); fr(ctx->spl_dev);
-  fr(ctx->d_error);
+  fr(ctx->d_error); fr(ctx->ct_tables); fr(ctx->ct_coef); fr(ctx->ct_knots);
   for (auto p : ctx->B) fr(p);
   for (auto p : ctx->D) fr(p);
   fr(ctx->fmax); fr(ctx->rmax); fr(ctx->sorted_idx);
@@ -326,6 +334,124 @@ static int upload_splines(pinb200_ctx* ctx) {
   CK(cudaMalloc(&ctx->spl_dev, all.size() * sizeof(double)));
   CK(cudaMemcpy(ctx->spl_dev, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice));
   ctx->spl_dirty = false;
+  return 0;
+}
+
+static int ct_release(pinb200_ctx* ctx) {
+  ctx->ct_on = false;
+  if (ctx->ct_tables || ctx->ct_coef || ctx->ct_knots) CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->ct_tables) { CK(cudaFree(ctx->ct_tables)); ctx->ct_tables = nullptr; }
+  if (ctx->ct_coef) { CK(cudaFree(ctx->ct_coef)); ctx->ct_coef = nullptr; }
+  if (ctx->ct_knots) { CK(cudaFree(ctx->ct_knots)); ctx->ct_knots = nullptr; }
+  return 0;
+}
+
+static CTView ct_view(const pinb200_ctx* ctx, int ismooth) {
+  CTView v{};
+  const size_t ncols = (size_t)ctx->ct_nxy * ctx->ct_nxy;
+  v.knots = ctx->ct_knots;
+  v.coef = ctx->ct_coef + (size_t)ismooth * ncols * (ctx->ct_nd + 2);
+  v.nd = ctx->ct_nd;
+  v.nxy = ctx->ct_nxy;
+  v.inv_ampl = 1.0 / ctx->ct_ampl[ismooth];
+  v.inv_bin_x = 1.0 / ctx->ct_bin_x;
+  return v;
+}
+
+extern "C" int pinb200_ct_delta_vector(double* delta_vector, int nbins_d) {
+  if (!delta_vector || nbins_d < 4 || nbins_d > PINB_CT_MAXD) return 1;
+  ct_default_delta_vector(delta_vector, nbins_d);
+  return 0;
+}
+
+static const double* spline_for(pinb200_ctx* ctx, int ismooth);
+extern "C" int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_desc* desc, const double* variance, const double* d_in,
+                                           const double* tables) {
+  if (!ctx) return 1;
+  CK(cudaSetDevice(ctx->d.device));
+  TRY(ct_release(ctx));
+  if (!desc) return 0;
+  if (ctx->radius.empty()) FAIL("smoothing ladder not set (pinb200_set_smoothing)");
+  if (!variance) FAIL("variance[] missing");
+  if (desc->model != PINB200_CT_CLASSIC && desc->model != PINB200_CT_SNG) FAIL("model must be PINB200_CT_CLASSIC or PINB200_CT_SNG");
+  if (desc->nbins_d < 4 || desc->nbins_d > PINB_CT_MAXD) FAIL("nbins_d out of range [4, 128]");
+  if (desc->nbins_xy < 2 || desc->nbins_xy > 1024) FAIL("nbins_xy out of range [2, 1024]");
+  if (!(desc->range_x > 0.0)) FAIL("range_x must be positive");
+  const int ns = (int)ctx->radius.size(), nd = desc->nbins_d, nxy = desc->nbins_xy;
+  const size_t ncols = (size_t)nxy * nxy, npoints = ncols * nd;
+  if (npoints > 0x7fffffffull) FAIL("table too large");
+  std::vector<double> dv(nd);
+  if (desc->delta_vector) dv.assign(desc->delta_vector, desc->delta_vector + nd);
+  else ct_default_delta_vector(dv.data(), nd);
+  for (int i = 1; i < nd; i++)
+    if (!(dv[i] > dv[i - 1])) FAIL("delta_vector must be strictly increasing");
+  // the interval look-up holds one knot boundary per bin at most (one forward step in ct_interpolate
+  // is then enough; more are still handled by its loop)
+  for (int is = 0; is < ns; is++)
+    if (!(variance[is] > 0.0)) FAIL("variance[] must be positive");
+  if (desc->model == PINB200_CT_SNG && !tables) {
+    if (!d_in) FAIL("d_in[] missing (ELL_SNG)");
+    if (!(desc->omega0 > 0.0)) FAIL("omega0 must be positive (ELL_SNG)");
+  }
+  if (desc->model == PINB200_CT_CLASSIC && !tables) TRY(upload_splines(ctx));
+  ctx->ct_nd = nd;
+  ctx->ct_nxy = nxy;
+  ctx->ct_ns = ns;
+  ctx->ct_bin_x = desc->range_x / (double)nxy;
+  ctx->ct_ampl.resize(ns);
+  for (int is = 0; is < ns; is++) ctx->ct_ampl[is] = sqrt(variance[is]);
+  const size_t nk = ct_knots_doubles(nd);
+  std::vector<double> knots(nk + nd);
+  ct_pack_knots(dv.data(), nd, knots.data());
+  memcpy(knots.data() + nk, dv.data(), nd * sizeof(double));
+  CK(cudaMalloc(&ctx->ct_knots, knots.size() * sizeof(double)));
+  CK(cudaMalloc(&ctx->ct_tables, (size_t)ns * npoints * sizeof(double)));
+  CK(cudaMalloc(&ctx->ct_coef, (size_t)ns * ncols * (nd + 2) * sizeof(CTRec)));
+  CK(cudaMemcpyAsync(ctx->ct_knots, knots.data(), knots.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const double* dv_dev = ctx->ct_knots + nk;
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  if (tables) CK(cudaMemcpyAsync(ctx->ct_tables, tables, (size_t)ns * npoints * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  for (int is = 0; is < ns; is++) {
+    double* tab = ctx->ct_tables + (size_t)is * npoints;
+    if (!tables) {
+      CTBuildParams b{};
+      b.model = desc->model;
+      b.dv = dv_dev;
+      b.nd = nd;
+      b.nxy = nxy;
+      b.bin_x = ctx->ct_bin_x;
+      b.ampl = ctx->ct_ampl[is];
+      if (desc->model == PINB200_CT_CLASSIC) {
+        b.spline = spline_for(ctx, is);
+        b.nspl = ctx->nspl;
+      } else {
+        b.D_in = d_in[is];
+        b.cosmo = SngCosmo{desc->omega0, desc->omega_lambda, desc->omega_rad, desc->omega_k};
+      }
+      b.table = tab;
+      b.npoints = (int)npoints;
+      LAUNCH(launch_ct_build(b, ctx->stream));
+    }
+    CTSplineParams sp{dv_dev, nd, (int)ncols, tab, ctx->ct_coef + (size_t)is * ncols * (nd + 2)};
+    LAUNCH(launch_ct_spline(sp, ctx->stream));
+  }
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // `knots`, `tables` may go out of scope
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+  ctx->tm.coll += ms * 1e-3;  // the reference books the table build under cputime.coll (src/fmax.c:102-118)
+  ctx->ct_on = true;
+  return 0;
+}
+
+extern "C" int pinb200_download_collapse_table(pinb200_ctx* ctx, int ismooth, double* table) {
+  if (!ctx || !table) return 1;
+  if (!ctx->ct_on) FAIL("collapse tables not set (pinb200_set_collapse_tables)");
+  if (ismooth < 0 || ismooth >= ctx->ct_ns) FAIL("ismooth out of range");
+  CK(cudaSetDevice(ctx->d.device));
+  const size_t npoints = (size_t)ctx->ct_nxy * ctx->ct_nxy * ctx->ct_nd;
+  CK(cudaMemcpyAsync(table, ctx->ct_tables + (size_t)ismooth * npoints, npoints * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
@@ -571,7 +697,8 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   if (ctx->radius.empty()) FAIL("smoothing ladder not set (pinb200_set_smoothing)");
   NEED_PEERS();
   CK(cudaSetDevice(ctx->d.device));
-  TRY(upload_splines(ctx));
+  if (ctx->ct_on && ctx->ct_ns != (int)ctx->radius.size()) FAIL("collapse tables were set for another smoothing ladder");
+  if (!ctx->ct_on) TRY(upload_splines(ctx));
   const Geom& g = ctx->g;
   const int ns = (int)ctx->radius.size();
   const double cell = ctx->d.box_size / g.N;  // GRID.CellSize, src/fmax-pfft.c:88
@@ -601,9 +728,13 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     c.zs.dc_add = ctx->dc;
     c.g = g;
     c.tw = ctx->tw;
-    c.spline = spline_for(ctx, is);
-    c.nspl = ctx->nspl;
-    c.spl_doubles = (int)spline_table_doubles(ctx->nspl);
+    if (ctx->ct_on) {
+      c.ct = ct_view(ctx, is);  // TABULATED_CT: F from the table of this radius
+    } else {
+      c.spline = spline_for(ctx, is);
+      c.nspl = ctx->nspl;
+      c.spl_doubles = (int)spline_table_doubles(ctx->nspl);
+    }
     c.ismooth = is;
     c.Fmax = ctx->fmax;
     c.Rmax = ctx->rmax;
@@ -1068,13 +1199,15 @@ extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, doubl
 extern "C" int pinb200_collapse_cells(pinb200_ctx* ctx, int ismooth, const double* hessian6, size_t ncells, double* F_out) {
   if (!ctx || !hessian6 || !F_out) return 1;
   CK(cudaSetDevice(ctx->d.device));
-  TRY(upload_splines(ctx));
+  if (ctx->ct_on && (ismooth < 0 || ismooth >= ctx->ct_ns)) FAIL("ismooth out of range of the collapse tables");
+  if (!ctx->ct_on) TRY(upload_splines(ctx));
   if (ncells == 0) return 0;
   double *dh = nullptr, *dF = nullptr;
   TRY(dev_alloc(ctx, &dh, 6 * ncells));
   TRY(dev_alloc(ctx, &dF, ncells));
   CK(cudaMemcpyAsync(dh, hessian6, 6 * ncells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(launch_collapse_cells(dh, ncells, spline_for(ctx, ismooth), ctx->nspl, dF, ctx->stream));
+  if (ctx->ct_on) LAUNCH(launch_collapse_cells_tab(dh, ncells, ct_view(ctx, ismooth), dF, ctx->stream));
+  else LAUNCH(launch_collapse_cells(dh, ncells, spline_for(ctx, ismooth), ctx->nspl, dF, ctx->stream));
   CK(cudaMemcpyAsync(F_out, dF, ncells * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   TRY(dev_free(ctx, &dh));

@@ -32,6 +32,17 @@ __global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, CollapseCfg<M>::MINB) z
   zpass_collapse_body<M, TL, CG>(ctx, smem, spl, scratch, p, SG);
 }
 
+// TABULATED_CT variant: the epilogue reads F from the collapse-time table of this radius (four 32-byte
+// gathers from L2 per cell, ~60 FP64 instructions instead of ~400), no spline in shared memory.
+template <int M, int TL, int CG>
+__global__ void __launch_bounds__(ZShape<M, TL, CG>::NT, CollapseCfg<M>::MINB) zpass_collapse_tab_kernel(const __grid_constant__ CollapseParams p) {
+  extern __shared__ double2 smem[];
+  using ZS = ZShape<M, TL, CG>;
+  double* scratch = reinterpret_cast<double*>(smem + ZS::fft_elems(6));
+  DevCtx ctx;
+  zpass_collapse_body<M, TL, CG, DevCtx, 1, true>(ctx, smem, nullptr, scratch, p, true);
+}
+
 // all components of a row are transformed concurrently (CG = ncomp): a 64-thread block per row
 // left the z epilogues latency bound (20.7 ms for the 39 GB float store at 1024^3)
 // register budget: keep >= 768 resident threads per SM (the compiler otherwise takes 168 registers)
@@ -65,6 +76,13 @@ template <int N> static cudaError_t collapse_launch(const CollapseParams& p_in, 
   fill_pretw<N / 2>(p.zs);
   constexpr int M = N / 2, TL = ZCfg<M>::TL, CG = 6;
   using ZS = ZShape<M, TL, CG>;
+  if (p.ct.coef) {
+    const size_t smem_tab = ZS::fft_elems(6) * sizeof(double2) + sum_scratch_bytes<ZS::NT>();
+    cudaError_t e = allow_smem(zpass_collapse_tab_kernel<M, TL, CG>, smem_tab);
+    if (e != cudaSuccess) return e;
+    zpass_collapse_tab_kernel<M, TL, CG><<<(unsigned)(nrows / TL), ZS::NT, smem_tab, s>>>(p);
+    return cudaGetLastError();
+  }
   const size_t smem = ZS::fft_elems(6) * sizeof(double2) + (CollapseCfg<M>::SPLINE_GLOBAL ? 0 : (size_t)p.spl_doubles * sizeof(double)) +
                       sum_scratch_bytes<ZS::NT>();
   cudaError_t e = allow_smem(zpass_collapse_kernel<M, TL, CG>, smem);

@@ -15,6 +15,7 @@
 // LPT sources/contraction (src/LPT.c:64-141), GenIC column loop (src/GenIC.c:188-411).
 #pragma once
 #include "collapse.cuh"
+#include "collapse_table.cuh"
 #include "fft_core.cuh"
 
 #define PINB_NBINS_PDF 210 /* NBINS, src/pinocchio.h:65 */
@@ -574,9 +575,12 @@ struct CollapseParams {
   int* Rmax;
   double* sums;          // [2]: sum(delta), sum(delta^2)   (atomicAdd)
   double2* hdst[6];      // if hdst[0] != nullptr: store the six real fields (in place allowed)
+  CTView ct;             // TABULATED_CT: the table of this radius (collapse_table.cuh); unused otherwise
 };
 
-template <int M, int TL, int CG, class Ctx, int CPT = 1>
+// TAB = true: F comes from the collapse-time table (TABULATED_CT, src/collapse_times.c:751) instead of
+// ell_classic + InverseGrowingMode; the spline is then neither staged nor read.
+template <int M, int TL, int CG, class Ctx, int CPT = 1, bool TAB = false>
 PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double* scratch, const CollapseParams& p,
                                  const bool spline_global = false) {
   using ZS = ZShape<M, TL, CG>;
@@ -584,7 +588,7 @@ PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double*
   const int tid = ctx.tid();
   const size_t row0 = (size_t)ctx.bid() * TL;
   // spline_global (a compile-time constant at the call site): evaluate the table where it lies
-  if (!spline_global)
+  if (!spline_global && !TAB)
     for (int i = 2 * tid; i < p.spl_doubles; i += 2 * NT) ctx.async_copy16(spl_s + i, p.spline + i);  // even count
   zpass_c2r_tile<M, TL, CG>(ctx, smem, p.zs, p.g, row0, p.tw);  // waits for the copies, ends with a barrier
   SplineView sp{spline_global ? p.spline : spl_s, p.nspl};
@@ -615,7 +619,9 @@ PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double*
       const double delta = h[0] + h[1] + h[2];
       sd += delta;
       sd2 += delta * delta;
-      const double F = inverse_collapse_time(h, sp);
+      double F;
+      if constexpr (TAB) F = inverse_collapse_time_tab(h, p.ct);
+      else F = inverse_collapse_time(h, sp);
       if ((double)fm < F) {  // running max, src/collapse_times.c:587-590
         p.Fmax[cell] = (float)F;
         p.Rmax[cell] = p.ismooth;
@@ -653,7 +659,8 @@ PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double*
         sd += delta;
         sd2 += delta * delta;
       }
-      F[u] = inverse_collapse_time(h, sp);
+      if constexpr (TAB) F[u] = inverse_collapse_time_tab(h, p.ct);
+      else F[u] = inverse_collapse_time(h, sp);
     }
 #pragma unroll
     for (int u = 0; u < CPT; u++) {

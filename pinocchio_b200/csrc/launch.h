@@ -27,6 +27,12 @@ cudaError_t launch_dc_scalar(const double2* src, double* out, double scale, int 
 cudaError_t launch_fmax_pdf(const float* fmax, size_t n, unsigned long long* counts, cudaStream_t s);
 cudaError_t launch_collapse_cells(const double* h6, size_t n, const double* spline, int nspl, double* F, cudaStream_t s);
 
+// collapse-time tables (collapse_table.cuh, k_ctable.cu).  launch_zpass_collapse takes the tabulated
+// variant of the kernel when CollapseParams::ct.coef is set.
+cudaError_t launch_ct_build(const CTBuildParams& p, cudaStream_t s);
+cudaError_t launch_ct_spline(const CTSplineParams& p, cudaStream_t s);
+cudaError_t launch_collapse_cells_tab(const double* h6, size_t n, const CTView& v, double* F, cudaStream_t s);
+
 struct PackParams {
   const float* fmax; const int* rmax; const float* vel[12];
   unsigned char* out; size_t stride; int prodfloat_bytes;

@@ -37,6 +37,18 @@ class ProductLayout(ctypes.Structure):
                 ("off_Vel_3LPT_1", ctypes.c_int), ("off_Vel_3LPT_2", ctypes.c_int)]
 
 
+class CTDesc(ctypes.Structure):
+    """pinb200_ct_desc: tabulated collapse times (-DTABULATED_CT, src/collapse_times.c:780-1346)"""
+    _fields_ = [("model", ctypes.c_int), ("nbins_d", ctypes.c_int), ("nbins_xy", ctypes.c_int),
+                ("range_x", ctypes.c_double), ("delta_vector", ctypes.POINTER(ctypes.c_double)),
+                ("omega0", ctypes.c_double), ("omega_lambda", ctypes.c_double), ("omega_rad", ctypes.c_double),
+                ("omega_k", ctypes.c_double)]
+
+
+CT_CLASSIC, CT_SNG = 1, 3            # type codes of the CTtable file header (src/collapse_times.c:1307-1326)
+CT_NBINS_D, CT_NBINS_XY, CT_RANGE_X = 100, 50, 3.5   # src/collapse_times.c:781-787
+
+
 class Timers(ctypes.Structure):
     _fields_ = [("dens", ctypes.c_double), ("fmax", ctypes.c_double), ("deriv", ctypes.c_double),
                 ("fft", ctypes.c_double), ("coll", ctypes.c_double), ("lpt", ctypes.c_double),
@@ -56,6 +68,7 @@ ABI_SYMBOLS = [
     "pinb200_fmax_pdf", "pinb200_download_products", "pinb200_download_field", "pinb200_get_timers",
     "pinb200_fft_r2c", "pinb200_fft_c2r", "pinb200_second_derivatives", "pinb200_collapse_cells",
     "pinb200_download_kvector",
+    "pinb200_ct_delta_vector", "pinb200_set_collapse_tables", "pinb200_download_collapse_table",
 ]
 
 _lib = None
@@ -104,6 +117,9 @@ def load_library() -> ctypes.CDLL:
     lib.pinb200_second_derivatives.argtypes = [ctypes.c_void_p, ctypes.c_double, _PD]
     lib.pinb200_collapse_cells.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD, ctypes.c_size_t, _PD]
     lib.pinb200_download_kvector.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
+    lib.pinb200_ct_delta_vector.argtypes = [_PD, ctypes.c_int]
+    lib.pinb200_set_collapse_tables.argtypes = [ctypes.c_void_p, ctypes.POINTER(CTDesc), _PD, _PD, _PD]
+    lib.pinb200_download_collapse_table.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
     _lib = lib
     return lib
 
@@ -240,6 +256,49 @@ class Pinocchio:
         g = self.growth_rates(redshift)
         self._ck(self.lib.pinb200_displacements(self.h, int(compute_sources), _dp(g)))
         return 0
+
+    # -- -DTABULATED_CT -------------------------------------------------------------------------
+    def initialize_collapse_times(self, model: int = CT_CLASSIC, tables: np.ndarray | None = None, nbins_d: int = CT_NBINS_D,
+                                  nbins_xy: int = CT_NBINS_XY, delta_vector: np.ndarray | None = None) -> int:
+        """initialize_collapse_times for every smoothing radius (src/collapse_times.c:824-1046): from now on
+        compute_fmax / inverse_collapse_time interpolate F in per-radius tables -- computed on the device
+        with ell_classic (model CT_CLASSIC) or with the ELL_SNG ellipsoid integration (CT_SNG), or taken
+        from ``tables`` [Nsmooth][nbins_xy][nbins_xy][nbins_d] (a CTtableFile).  model None: back to the
+        direct evaluation."""
+        if model is None:
+            self._ck(self.lib.pinb200_set_collapse_tables(self.h, None, None, None, None))
+            return 0
+        c = self.cosmo
+        d = CTDesc(int(model), int(nbins_d), int(nbins_xy), CT_RANGE_X, None, c.p.Omega0, c.p.OmegaLambda, c.OmegaRad, c.OmegaK)
+        dv = None
+        if delta_vector is not None:
+            dv = np.ascontiguousarray(delta_vector, dtype=np.float64)
+            assert dv.size == nbins_d
+            d.delta_vector = _dp(dv)
+        var = np.ascontiguousarray(self.Smoothing.Variance, dtype=np.float64)
+        # GrowingMode(1/amin - 1, .) of ell_sng (src/collapse_times.c:345-353); scale-independent growth
+        d_in = np.full(var.size, c.GrowingMode(1.0 / 1.0e-5 - 1.0))
+        tab = None
+        if tables is not None:
+            tab = np.ascontiguousarray(tables, dtype=np.float64)
+            assert tab.size == var.size * nbins_d * nbins_xy * nbins_xy
+        self._ck(self.lib.pinb200_set_collapse_tables(self.h, ctypes.byref(d), _dp(var), _dp(d_in),
+                                                      _dp(tab) if tab is not None else None))
+        self._ct_shape = (nbins_xy, nbins_xy, nbins_d)
+        return 0
+
+    def collapse_table(self, ismooth: int) -> np.ndarray:
+        """CT_table of one radius, [iy][ix][id] (index id + nd*(ix + nxy*iy), src/collapse_times.c:966-977)."""
+        out = np.zeros(self._ct_shape)
+        self._ck(self.lib.pinb200_download_collapse_table(self.h, int(ismooth), _dp(out)))
+        return out
+
+    @staticmethod
+    def ct_delta_vector(nbins_d: int = CT_NBINS_D) -> np.ndarray:
+        dv = np.zeros(nbins_d)
+        if load_library().pinb200_ct_delta_vector(_dp(dv), nbins_d):
+            raise PinocchioError("pinb200_ct_delta_vector failed")
+        return dv
 
     def Fmax_PDF(self) -> np.ndarray:
         """src/fmax.c:509-550; returns the 210 counts."""

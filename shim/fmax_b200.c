@@ -18,6 +18,9 @@
 #include <sys/stat.h>
 
 static pinb200_ctx *pinb = NULL;
+#ifdef TABULATED_CT
+static int shim_collapse_tables(int onlycompute);
+#endif
 
 static int pinb_fail(const char *where)
 {
@@ -246,6 +249,22 @@ int compute_fmax(void)
 
   ScaleDep.order = 0;
   ScaleDep.redshift = 0.0;
+#ifdef TABULATED_CT
+  {
+    /* initialize_collapse_times for every radius, src/fmax.c:102-118 */
+    double cputmp = MPI_Wtime();
+    if (shim_collapse_tables(0))
+      return 1;
+    cputmp = MPI_Wtime() - cputmp;
+    if (!ThisTask)
+    {
+      if (strcmp(params.CTtableFile, "none"))
+        printf("[%s] Collapse times read from file %s\n", fdate(), params.CTtableFile);
+      else
+        printf("[%s] Collapse times computed for interpolation, cpu time =%f s\n", fdate(), cputmp);
+    }
+  }
+#endif
   if (pinb200_fmax(pinb, tv))
     return pinb_fail("compute_fmax");
   /* the library returns this rank's share of Sum(delta^2)/Ntotal (src/collapse_times.c:656-670) */
@@ -415,9 +434,226 @@ int read_dumps(void)
   return 0;
 }
 
-#ifdef TABULATED_CT
-#error "TABULATED_CT / ELL_SNG (src/collapse_times.c:239-400,780-1346) is not provided by the GPU path"
+/* ---- replaces src/collapse_times.c:780-1346 (-DTABULATED_CT) -----------------------------------------
+ * The tables of all smoothing radii are filled in one go on the device (ell_classic or the ELL_SNG
+ * ellipsoid integration per table point), or read from params.CTtableFile; the file the reference
+ * writes (header + per radius {int ismooth, CT_table}) is written from the downloaded tables. */
+#if defined(ELL_SNG) && !defined(TABULATED_CT)
+#error "ELL_SNG without TABULATED_CT (one ODE integration per cell and radius) is not provided by the GPU path"
 #endif
+#ifdef MOD_GRAV_FR
+#error "MOD_GRAV_FR (f(R) force modification in sng_system, src/collapse_times.c:270-311) is not provided by the GPU path"
+#endif
+#ifdef TABULATED_CT
+#define SHIM_CT_NBINS_XY 50 /* CT_NBINS_XY, CT_NBINS_D, CT_RANGE_X of src/collapse_times.c:781-787 */
+#define SHIM_CT_NBINS_D 100
+#define SHIM_CT_RANGE_X 3.5
+static int shim_ct_ready = 0;
+
+static int shim_ct_model(void)
+{
+#ifdef ELL_SNG
+  return PINB200_CT_SNG;
+#else
+  return PINB200_CT_CLASSIC;
+#endif
+}
+
+static void shim_ct_write_header(FILE *f, int npoints)
+{
+  /* write_CTtable_header, src/collapse_times.c:1307-1346 */
+  int dummy = shim_ct_model();
+  fwrite(&dummy, sizeof(int), 1, f);
+  fwrite(&params.Omega0, sizeof(double), 1, f);
+  fwrite(&params.OmegaLambda, sizeof(double), 1, f);
+  fwrite(&params.Hubble100, sizeof(double), 1, f);
+  fwrite(&npoints, sizeof(int), 1, f);
+  dummy = SHIM_CT_NBINS_D;
+  fwrite(&dummy, sizeof(int), 1, f);
+  dummy = SHIM_CT_NBINS_XY;
+  fwrite(&dummy, sizeof(int), 1, f);
+}
+
+static int shim_ct_check_header(FILE *f, int npoints)
+{
+  /* check_CTtable_header, src/collapse_times.c:1226-1303 */
+  int fail = 0, dummy = 0;
+  double fdummy = 0.0;
+  if (fread(&dummy, sizeof(int), 1, f) != 1 || dummy != shim_ct_model())
+  {
+    printf("ERROR: CT table not constructed for this collapse model, %d\n", dummy);
+    fail = 1;
+  }
+  if (fread(&fdummy, sizeof(double), 1, f) != 1 || fabs(fdummy - params.Omega0) > 1.e-10)
+  {
+    printf("ERROR: CT table constructed for the wrong Omega0, %f in place of %f\n", fdummy, params.Omega0);
+    fail = 1;
+  }
+  if (fread(&fdummy, sizeof(double), 1, f) != 1 || fabs(fdummy - params.OmegaLambda) > 1.e-10)
+  {
+    printf("ERROR: CT table constructed for the wrong OmegaLambda, %f in place of %f\n", fdummy, params.OmegaLambda);
+    fail = 1;
+  }
+  if (fread(&fdummy, sizeof(double), 1, f) != 1 || fabs(fdummy - params.Hubble100) > 1.e-10)
+  {
+    printf("ERROR: CT table constructed for the wrong Hubble100, %f in place of %f\n", fdummy, params.Hubble100);
+    fail = 1;
+  }
+  if (fread(&dummy, sizeof(int), 1, f) != 1 || dummy != npoints)
+  {
+    printf("ERROR: CT table has the wrong size, %d in place of %d\n", dummy, npoints);
+    fail = 1;
+  }
+  if (fread(&dummy, sizeof(int), 1, f) != 1 || dummy != SHIM_CT_NBINS_D)
+  {
+    printf("ERROR: CT table has the wrong density sampling, %d in place of %d\n", dummy, SHIM_CT_NBINS_D);
+    fail = 1;
+  }
+  if (fread(&dummy, sizeof(int), 1, f) != 1 || dummy != SHIM_CT_NBINS_XY)
+  {
+    printf("ERROR: CT table has the wrong x and y sampling, %d in place of %d\n", dummy, SHIM_CT_NBINS_XY);
+    fail = 1;
+  }
+  return fail;
+}
+
+/* all radii at once; onlycompute as in initialize_collapse_times(ismooth, onlycompute) */
+static int shim_collapse_tables(int onlycompute)
+{
+  const int ns = Smoothing.Nsmooth, npoints = SHIM_CT_NBINS_D * SHIM_CT_NBINS_XY * SHIM_CT_NBINS_XY;
+  int ismooth, fail = 0;
+  pinb200_ct_desc d;
+  double *d_in = (double *)malloc(ns * sizeof(double));
+  double *tables = NULL;
+  const int from_file = strcmp(params.CTtableFile, "none") && !onlycompute;
+
+  memset(&d, 0, sizeof d);
+  d.model = shim_ct_model();
+  d.nbins_d = SHIM_CT_NBINS_D;
+  d.nbins_xy = SHIM_CT_NBINS_XY;
+  d.range_x = SHIM_CT_RANGE_X;
+  d.delta_vector = NULL; /* the reference's compiled sampling */
+#ifdef ELL_SNG
+  /* OmegaMatter(z), OmegaLambda(z) of src/cosmo.c:1675-1718 as closed forms of a cosmological constant */
+  if (!params.simpleLambda)
+  {
+    printf("ERROR on task %d: the GPU path integrates ELL_SNG for a cosmological constant only\n", ThisTask);
+    return 1;
+  }
+  d.omega0 = params.Omega0;
+  d.omega_lambda = params.OmegaLambda;
+#ifdef NORADIATION
+  d.omega_rad = 0.0; /* OMEGARAD_H2, src/cosmo.c:36-40 */
+#else
+  d.omega_rad = 4.2e-5 / params.Hubble100 / params.Hubble100;
+#endif
+  d.omega_k = 1.0 - params.Omega0 - params.OmegaLambda - d.omega_rad;
+  {
+    /* the closed form must be the host cosmology's own E(z) (no READ_HUBBLE_TABLE, no tabulated EoS) */
+    const double z = 1.0, e2 = d.omega_rad * pow(1. + z, 4.) + d.omega0 * pow(1. + z, 3.) + d.omega_k * pow(1. + z, 2.) + d.omega_lambda;
+    const double om = d.omega0 * pow(1. + z, 3.) / e2;
+    if (fabs(om - OmegaMatter(z)) > 1.e-12)
+    {
+      printf("ERROR on task %d: OmegaMatter(z) of the host cosmology is not that of a cosmological constant\n", ThisTask);
+      return 1;
+    }
+  }
+#endif
+  for (ismooth = 0; ismooth < ns; ismooth++)
+  {
+    /* D_in of ell_sng, src/collapse_times.c:345-353 */
+#ifdef SCALE_DEPENDENT
+    d_in[ismooth] = GrowingMode(1. / 1.e-5 - 1., params.k_for_GM / Smoothing.Radius[ismooth] * params.InterPartDist);
+#else
+    d_in[ismooth] = GrowingMode(1. / 1.e-5 - 1., 1. / Smoothing.Radius[ismooth]);
+#endif
+  }
+
+  if (from_file)
+  {
+    /* Task 0 reads, everybody gets the tables (src/collapse_times.c:937-963) */
+    tables = (double *)malloc((size_t)ns * npoints * sizeof(double));
+    if (!ThisTask)
+    {
+      FILE *f = fopen(params.CTtableFile, "r");
+      if (!f)
+      {
+        printf("ERROR: cannot open CTtableFile %s\n", params.CTtableFile);
+        fail = 1;
+      }
+      else
+      {
+        fail = shim_ct_check_header(f, npoints);
+        for (ismooth = 0; ismooth < ns && !fail; ismooth++)
+        {
+          int dummy;
+          if (fread(&dummy, sizeof(int), 1, f) != 1 || fread(tables + (size_t)ismooth * npoints, sizeof(double), npoints, f) != (size_t)npoints)
+          {
+            printf("ERROR: short read of CTtableFile %s at smoothing radius %d\n", params.CTtableFile, ismooth);
+            fail = 1;
+          }
+        }
+        fclose(f);
+      }
+    }
+    MPI_Bcast(&fail, sizeof(int), MPI_BYTE, 0, MPI_COMM_WORLD);
+    if (fail)
+      return 1;
+    MPI_Bcast(tables, ns * npoints, MPI_DOUBLE, 0, MPI_COMM_WORLD);
+  }
+
+  if (pinb200_set_collapse_tables(pinb, &d, Smoothing.Variance, d_in, tables))
+    return pinb_fail("pinb200_set_collapse_tables");
+  free(d_in);
+  if (tables)
+    free(tables);
+
+  if (!from_file && !ThisTask)
+  {
+    /* the table file of src/collapse_times.c:991-1033 (binary form) */
+    char fname[LBLENGTH];
+    FILE *f;
+    double *t = (double *)malloc((size_t)npoints * sizeof(double));
+    if (onlycompute)
+      strcpy(fname, params.CTtableFile);
+    else
+      sprintf(fname, "pinocchio.%s.CTtable.out", params.RunFlag);
+    f = fopen(fname, "w");
+    if (!f)
+    {
+      printf("ERROR: cannot write %s\n", fname);
+      return 1;
+    }
+    shim_ct_write_header(f, npoints);
+    for (ismooth = 0; ismooth < ns; ismooth++)
+    {
+      if (pinb200_download_collapse_table(pinb, ismooth, t))
+        return pinb_fail("pinb200_download_collapse_table");
+      fwrite(&ismooth, sizeof(int), 1, f);
+      fwrite(t, sizeof(double), npoints, f);
+    }
+    fclose(f);
+    free(t);
+  }
+  shim_ct_ready = 1;
+  return 0;
+}
+
+/* external symbols of src/pinocchio.h:546-549: the special mode `pinocchio.x parameter_file 1`
+ * (src/pinocchio.c:97-125) calls this once per radius; all tables are made at the first call */
+int initialize_collapse_times(int ismooth, int onlycompute)
+{
+  if (ismooth == 0 || !shim_ct_ready)
+    return shim_collapse_tables(onlycompute);
+  return 0;
+}
+
+int reset_collapse_times(int ismooth)
+{
+  (void)ismooth;
+  return 0;
+}
+#endif /* TABULATED_CT */
 
 char *fdate(void)
 {

@@ -9,6 +9,7 @@
 // This library is never loaded by the product (pinocchio_b200/), which has no CPU path.
 #include <pthread.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -237,14 +238,14 @@ template <int M> static void fill_pretw(ZSrc& zs) {
   }
 }
 
-template <int N> static void collapse_run(CollapseParams p) {
+template <int N, bool TAB = false> static void collapse_run(CollapseParams p) {
   fill_pretw<N / 2>(p.zs);
   constexpr int M = N / 2, TL = ZCfg<M>::TL, CG = 6;
   using ZS = ZShape<M, TL, CG>;
   std::vector<double2> smem(ZS::fft_elems(6));
-  std::vector<double> spl((size_t)p.spl_doubles), scratch(2 * ZS::NT);
+  std::vector<double> spl((size_t)p.spl_doubles + 2), scratch(2 * ZS::NT);
   run_blocks((long long)p.g.lx * N / TL, ZS::NT,
-             [&](HostCtx& ctx) { zpass_collapse_body<M, TL, CG>(ctx, smem.data(), spl.data(), scratch.data(), p); });
+             [&](HostCtx& ctx) { zpass_collapse_body<M, TL, CG, HostCtx, 1, TAB>(ctx, smem.data(), spl.data(), scratch.data(), p); });
 }
 
 extern "C" int emu_zpass_collapse(int N, int nranks, double** srcs, const int* kzpow, int has_nyq, const double* dc,
@@ -362,6 +363,113 @@ extern "C" int emu_genic(int N, int rank, int nranks, const unsigned int* seeds,
   std::vector<double> smem(2 * 12 * NT);
   run_blocks(((long long)N * p.g.ly + NT - 1) / NT, NT, [&](HostCtx& ctx) { genic_body<NT>(ctx, smem.data(), p); });
   return 0;
+}
+
+// ---- TABULATED_CT / ELL_SNG (collapse_table.cuh) ---------------------------------------------------
+extern "C" int emu_ct_delta_vector(double* dv, int nd) {
+  ct_default_delta_vector(dv, nd);
+  return 0;
+}
+// the table of one smoothing radius: ct_build_body over all points (blocks of 8 host threads)
+extern "C" int emu_ct_build(int model, const double* dv, int nd, int nxy, double bin_x, double ampl, const double* spline, int nspl,
+                            double D_in, const double* cosmo4, int first, int npoints, double* table) {
+  CTBuildParams p{};
+  p.model = model;
+  p.dv = dv;
+  p.nd = nd;
+  p.nxy = nxy;
+  p.bin_x = bin_x;
+  p.ampl = ampl;
+  p.spline = spline;
+  p.nspl = nspl;
+  p.D_in = D_in;
+  if (cosmo4) p.cosmo = SngCosmo{cosmo4[0], cosmo4[1], cosmo4[2], cosmo4[3]};
+  p.table = table;
+  p.npoints = first + npoints;
+  // these bodies have no barrier: every (block, thread) pair is run as an independent call, spread over
+  // the host cores
+  constexpr int NT = 128;
+  const int nw = (int)std::max(1u, std::thread::hardware_concurrency());
+  std::vector<std::thread> th;
+  for (int w = 0; w < nw; w++)
+    th.emplace_back([&, w]() {
+      for (int i = first + w; i < first + npoints; i += nw) {
+        HostCtx ctx{i % NT, i / NT, NT, nullptr};
+        ct_build_body(ctx, p);
+      }
+    });
+  for (auto& x : th) x.join();
+  return 0;
+}
+extern "C" long long emu_ct_knots_doubles(int nd) { return (long long)ct_knots_doubles(nd); }
+extern "C" int emu_ct_pack_knots(const double* dv, int nd, double* out) {
+  ct_pack_knots(dv, nd, out);
+  return 0;
+}
+// spline records of all columns: coef holds ncols * (nd + 2) * 4 doubles, 32-byte aligned
+extern "C" int emu_ct_spline(const double* dv, int nd, int ncols, const double* table, double* coef) {
+  CTSplineParams p{dv, nd, ncols, table, reinterpret_cast<CTRec*>(coef)};
+  constexpr int NT = 64;
+  for (int col = 0; col < ncols; col++) {
+    HostCtx ctx{col % NT, col / NT, NT, nullptr};
+    ct_spline_body(ctx, p);
+  }
+  return 0;
+}
+static CTView make_ct_view(const double* knots, const double* coef, int nd, int nxy, double ampl, double bin_x) {
+  CTView v{};
+  v.knots = knots;
+  v.coef = reinterpret_cast<const CTRec*>(coef);
+  v.nd = nd;
+  v.nxy = nxy;
+  v.inv_ampl = 1.0 / ampl;
+  v.inv_bin_x = 1.0 / bin_x;
+  return v;
+}
+// per-cell evaluation on eigenvalues (which = 0) or on Hessians h6[6][n] (which = 1)
+extern "C" int emu_ct_cells(int which, const double* in, long long n, const double* knots, const double* coef, int nd, int nxy,
+                            double ampl, double bin_x, double* F) {
+  const CTView v = make_ct_view(knots, coef, nd, nxy, ampl, bin_x);
+  for (long long i = 0; i < n; i++) {
+    if (which == 0) {
+      F[i] = ct_interpolate(v, in[3 * i], in[3 * i + 1], in[3 * i + 2]);
+    } else {
+      double h[6];
+      for (int c = 0; c < 6; c++) h[c] = in[c * n + i];
+      F[i] = inverse_collapse_time_tab(h, v);
+    }
+  }
+  return 0;
+}
+extern "C" double emu_ell_sng(double l1, double l2, double l3, double D_in, const double* cosmo4) {
+  return ell_sng(l1, l2, l3, D_in, SngCosmo{cosmo4[0], cosmo4[1], cosmo4[2], cosmo4[3]});
+}
+// the collapse z pass with the table in place of ell_classic
+extern "C" int emu_zpass_collapse_tab(int N, int nranks, double** srcs, const int* kzpow, int has_nyq, const double* dc,
+                                      const double* knots, const double* coef, int nd, int nxy, double ampl, double bin_x, int ismooth,
+                                      float* fmax, int* rmax, double* sums, double** hdst, const double* tw) {
+  CollapseParams p{};
+  for (int k = 0; k < 6; k++) {
+    p.zs.src[k] = (const double2*)srcs[k];
+    p.zs.kzpow[k] = kzpow[k];
+    p.hdst[k] = hdst ? (double2*)hdst[k] : nullptr;
+  }
+  p.zs.ncomp = 6;
+  p.zs.has_nyq = has_nyq;
+  p.zs.dc_add = dc;
+  p.g = make_geom(N, 0, nranks);
+  p.tw = (const double2*)tw;
+  p.ismooth = ismooth;
+  p.Fmax = fmax;
+  p.Rmax = rmax;
+  p.sums = sums;
+  p.ct = make_ct_view(knots, coef, nd, nxy, ampl, bin_x);
+  switch (N) {
+#define X(LL) case LL: collapse_run<LL, true>(p); return 0;
+    EMU_GRIDS(X)
+#undef X
+  }
+  return 1;
 }
 
 // the packed spline table, built by the same host code the engine uses (spline_pack.h)

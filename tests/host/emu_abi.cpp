@@ -11,6 +11,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -36,6 +37,15 @@ int emu_zpass_r2c(int N, int nranks, const double* src, double* dst, const doubl
 int emu_sources(int N, int nranks, double** h, double* s2, double* s31, double* s32, int lpt_order);
 int emu_genic(int N, int rank, int nranks, const unsigned int* seeds, const double* pk, double box, int fixed_ic, int paired_ic,
               double* kd);
+int emu_zpass_collapse_tab(int N, int nranks, double** srcs, const int* kzpow, int has_nyq, const double* dc, const double* knots,
+                           const double* coef, int nd, int nxy, double ampl, double bin_x, int ismooth, float* fmax, int* rmax,
+                           double* sums, double** hdst, const double* tw);
+int emu_ct_delta_vector(double* dv, int nd);
+int emu_ct_build(int model, const double* dv, int nd, int nxy, double bin_x, double ampl, const double* spline, int nspl, double D_in,
+                 const double* cosmo4, int first, int npoints, double* table);
+long long emu_ct_knots_doubles(int nd);
+int emu_ct_pack_knots(const double* dv, int nd, double* out);
+int emu_ct_spline(const double* dv, int nd, int ncols, const double* table, double* coef);
 long long emu_spline_table_doubles(int n);
 int emu_pack_spline(const double* x, const double* y, int n, double* out);
 }
@@ -53,6 +63,13 @@ struct pinb200_ctx {
   std::vector<float> fmax, vel[12];
   std::vector<int> rmax;
   bool kdens_valid = false, hessian_valid = false, kvec_valid = false;
+  // TABULATED_CT: per radius the table and its spline records (32-byte aligned storage), shared knots
+  bool ct_on = false;
+  int ct_nd = 0, ct_nxy = 0;
+  double ct_bin_x = 0.0;
+  std::vector<double> ct_ampl, ct_knots;
+  std::vector<std::vector<double>> ct_tables;
+  std::vector<void*> ct_coef;
   unsigned long long launches = 0;
   size_t field() const { return (size_t)N * N * P; }
   size_t ncells() const { return (size_t)N * N * N; }
@@ -188,11 +205,67 @@ static int hessian_xy(pinb200_ctx* ctx, double rs, double& dc) {
   return ypass_inv(ctx, ys, yd, kHessJobs, 6, 0);
 }
 
+// ---- TABULATED_CT: the engine's pinb200_set_collapse_tables on host arrays -------------------------
+extern "C" int pinb200_ct_delta_vector(double* dv, int nd) { return (dv && nd >= 4 && nd <= 128) ? emu_ct_delta_vector(dv, nd) : 1; }
+extern "C" int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_desc* desc, const double* variance, const double* d_in,
+                                           const double* tables) {
+  if (!ctx) return 1;
+  for (void* p : ctx->ct_coef) free(p);
+  ctx->ct_coef.clear();
+  ctx->ct_tables.clear();
+  ctx->ct_on = false;
+  if (!desc) return 0;
+  if (ctx->radius.empty()) FAIL("smoothing ladder not set (pinb200_set_smoothing)");
+  if (!variance) FAIL("variance[] missing");
+  if (desc->model != PINB200_CT_CLASSIC && desc->model != PINB200_CT_SNG) FAIL("model must be PINB200_CT_CLASSIC or PINB200_CT_SNG");
+  if (desc->model == PINB200_CT_CLASSIC && !tables && ctx->spline.empty()) FAIL("inverse-growth spline not set (pinb200_set_invgrow_spline)");
+  if (desc->model == PINB200_CT_SNG && !tables && !d_in) FAIL("d_in[] missing (ELL_SNG)");
+  const int ns = (int)ctx->radius.size(), nd = desc->nbins_d, nxy = desc->nbins_xy;
+  const size_t ncols = (size_t)nxy * nxy, npoints = ncols * nd;
+  std::vector<double> dv(nd);
+  if (desc->delta_vector) dv.assign(desc->delta_vector, desc->delta_vector + nd);
+  else emu_ct_delta_vector(dv.data(), nd);
+  ctx->ct_nd = nd;
+  ctx->ct_nxy = nxy;
+  ctx->ct_bin_x = desc->range_x / (double)nxy;
+  ctx->ct_ampl.resize(ns);
+  ctx->ct_knots.assign((size_t)emu_ct_knots_doubles(nd), 0.0);
+  emu_ct_pack_knots(dv.data(), nd, ctx->ct_knots.data());
+  ctx->ct_tables.resize(ns);
+  const double cosmo4[4] = {desc->omega0, desc->omega_lambda, desc->omega_rad, desc->omega_k};
+  for (int is = 0; is < ns; is++) {
+    ctx->ct_ampl[is] = sqrt(variance[is]);
+    ctx->ct_tables[is].assign(npoints, 0.0);
+    if (tables) {
+      memcpy(ctx->ct_tables[is].data(), tables + (size_t)is * npoints, npoints * sizeof(double));
+    } else {
+      const std::vector<double>& spl = (is < (int)ctx->spline_r.size() && !ctx->spline_r[is].empty()) ? ctx->spline_r[is] : ctx->spline;
+      emu_ct_build(desc->model, dv.data(), nd, nxy, ctx->ct_bin_x, ctx->ct_ampl[is], spl.empty() ? nullptr : spl.data(), ctx->nspl,
+                   d_in ? d_in[is] : 0.0, cosmo4, 0, (int)npoints, ctx->ct_tables[is].data());
+      ctx->launches++;
+    }
+    void* coef = aligned_alloc(32, ncols * (size_t)(nd + 2) * 32);
+    ctx->ct_coef.push_back(coef);
+    emu_ct_spline(dv.data(), nd, (int)ncols, ctx->ct_tables[is].data(), static_cast<double*>(coef));
+    ctx->launches++;
+  }
+  ctx->ct_on = true;
+  return 0;
+}
+extern "C" int pinb200_download_collapse_table(pinb200_ctx* ctx, int ismooth, double* table) {
+  if (!ctx || !table) return 1;
+  if (!ctx->ct_on) FAIL("collapse tables not set (pinb200_set_collapse_tables)");
+  if (ismooth < 0 || ismooth >= (int)ctx->ct_tables.size()) FAIL("ismooth out of range");
+  memcpy(table, ctx->ct_tables[ismooth].data(), ctx->ct_tables[ismooth].size() * sizeof(double));
+  return 0;
+}
+
 extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   if (!ctx) return 1;
   if (!ctx->kdens_valid) FAIL("kdensity not resident (call pinb200_genic or pinb200_upload_kdensity)");
   if (ctx->radius.empty()) FAIL("smoothing ladder not set (pinb200_set_smoothing)");
-  if (ctx->spline.empty()) FAIL("inverse-growth spline not set (pinb200_set_invgrow_spline)");
+  if (!ctx->ct_on && ctx->spline.empty()) FAIL("inverse-growth spline not set (pinb200_set_invgrow_spline)");
+  if (ctx->ct_on && ctx->ct_tables.size() != ctx->radius.size()) FAIL("collapse tables were set for another smoothing ladder");
   const int ns = (int)ctx->radius.size();
   const double cell = ctx->d.box_size / ctx->N;
   ctx->fmax.assign(ctx->ncells(), 0.0f);
@@ -206,7 +279,12 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     for (int k = 0; k < 6; k++) b[k] = dp(ctx->B[k]);
     // spline_for() of the engine: the per-radius table when one was given, else the global one
     const std::vector<double>& spl = (is < (int)ctx->spline_r.size() && !ctx->spline_r[is].empty()) ? ctx->spline_r[is] : ctx->spline;
-    if (emu_zpass_collapse(ctx->N, 1, b, kHessKzPow, 0, &dc, spl.data(), ctx->nspl, is, ctx->fmax.data(), ctx->rmax.data(),
+    if (ctx->ct_on) {
+      if (emu_zpass_collapse_tab(ctx->N, 1, b, kHessKzPow, 0, &dc, ctx->ct_knots.data(), static_cast<const double*>(ctx->ct_coef[is]),
+                                 ctx->ct_nd, ctx->ct_nxy, ctx->ct_ampl[is], ctx->ct_bin_x, is, ctx->fmax.data(), ctx->rmax.data(), sums,
+                                 is == ns - 1 ? b : nullptr, dp(ctx->tw)))
+        FAIL("collapse pass (tabulated)");
+    } else if (emu_zpass_collapse(ctx->N, 1, b, kHessKzPow, 0, &dc, spl.data(), ctx->nspl, is, ctx->fmax.data(), ctx->rmax.data(),
                            sums, is == ns - 1 ? b : nullptr, dp(ctx->tw)))
       FAIL("collapse pass");
     ctx->launches++;
