@@ -404,6 +404,186 @@ def inverse_collapse_time(h, inverse_growing_mode):
     return F
 
 
+# ======================================================================================
+# TABULATED_CT and ELL_SNG (src/collapse_times.c:239-400, 780-1346)
+# ======================================================================================
+CT_NBINS_XY, CT_NBINS_D = 50, 100                      # src/collapse_times.c:781-782
+CT_SQUEEZE, CT_EXPO, CT_RANGE_D, CT_RANGE_X, CT_DELTA0 = 1.2, 1.75, 7.0, 3.5, -1.0   # :783-787
+
+
+def ct_delta_vector(nd: int = CT_NBINS_D) -> np.ndarray:
+    """delta_vector of initialize_collapse_times (src/collapse_times.c:836-877): bins growing like
+    |delta - CT_DELTA0|^(CT_EXPO-1) away from CT_DELTA0, never smaller than CT_SQUEEZE * ref_interval."""
+    deltaf = (CT_SQUEEZE / CT_EXPO) ** (1.0 / (CT_EXPO - 1.0))
+    ref = (((CT_RANGE_D - CT_DELTA0) ** (2.0 - CT_EXPO) + (CT_RANGE_D + CT_DELTA0) ** (2.0 - CT_EXPO)
+            - 2.0 * deltaf ** (2.0 - CT_EXPO)) / CT_EXPO / (2.0 - CT_EXPO) + 2.0 * deltaf / CT_SQUEEZE) / (nd - 2.0)
+    dv = np.zeros(nd)
+    d = -CT_RANGE_D
+    for i in range(nd):
+        dv[i] = d
+        interval = CT_EXPO * ref * abs(d - CT_DELTA0) ** (CT_EXPO - 1.0)
+        if interval / ref < CT_SQUEEZE:
+            interval = ref * CT_SQUEEZE
+        d += interval
+    return dv
+
+
+def ct_table_lambdas(ampl: float, dv=None, nxy: int = CT_NBINS_XY):
+    """(l1, l2, l3) of every table point, arrays [iy][ix][id] (src/collapse_times.c:966-976)."""
+    dv = ct_delta_vector() if dv is None else np.asarray(dv)
+    bin_x = CT_RANGE_X / nxy
+    y, x, d = np.meshgrid(np.arange(nxy) * bin_x, np.arange(nxy) * bin_x, dv, indexing="ij")
+    return (d + 2.0 * x + y) / 3.0 * ampl, (d - x + y) / 3.0 * ampl, (d - x - 2.0 * y) / 3.0 * ampl
+
+
+def ct_table_classic(ampl: float, inverse_growing_mode, dv=None, nxy: int = CT_NBINS_XY) -> np.ndarray:
+    """CT_table of one radius with ELL_CLASSIC: ell() = 1 + InverseGrowingMode(b_c) or 0 (:404-415, 977)."""
+    l1, l2, l3 = ct_table_lambdas(ampl, dv, nxy)
+    bc = ell_classic(l1, l2, l3)
+    with np.errstate(all="ignore"):
+        pos = bc > 0.0
+        return np.where(pos, 1.0 + inverse_growing_mode(np.where(pos, bc, 1.0)), 0.0)
+
+
+def sng_system(t, y, omega0, omega_lambda, omega_rad=0.0, omega_k=None):
+    """r.h.s. of the nine eigenvalue equations of Nadkarni-Ghosh & Singhal (src/collapse_times.c:239-290);
+    OmegaMatter / OmegaLambda of src/cosmo.c:1675-1718 for a cosmological constant."""
+    if omega_k is None:
+        omega_k = 1.0 - omega0 - omega_lambda - omega_rad
+    z = 1.0 / t - 1.0
+    e2 = omega_rad * (1 + z) ** 4 + omega0 * (1 + z) ** 3 + omega_k * (1 + z) ** 2 + omega_lambda
+    e2 /= omega_rad + omega0 + omega_k + omega_lambda
+    om, ol = omega0 * (1 + z) ** 3 / e2, omega_lambda / e2
+    delta = y[6] + y[7] + y[8]
+    f = [0.0] * 9
+    for i in range(3):
+        s = 0.0
+        for j in range(3):
+            if i == j or y[i] == y[j]:
+                continue
+            s += (y[j + 6] - y[i + 6]) * ((1 - y[i]) ** 2 * (1 + y[i + 3]) - (1 - y[j]) ** 2 * (1 + y[j + 3])) / \
+                 ((1 - y[i]) ** 2 - (1 - y[j]) ** 2)
+        f[i] = y[i + 3] * (y[i] - 1.0) / t
+        f[i + 3] = 0.5 * (y[i + 3] * (om - 2.0 * ol - 2.0) - 3.0 * om * y[i + 6] - 2.0 * y[i + 3] ** 2) / t
+        f[i + 6] = ((5.0 / 6.0 + y[i + 6]) * ((3.0 + y[3] + y[4] + y[5]) - (1.0 + delta) / (2.5 + delta) * (y[3] + y[4] + y[5]))
+                    - (2.5 + delta) * (1.0 + y[i + 3]) + s) / t
+    return np.array(f)
+
+
+_RKF45_A = (0.25, 0.375, 12.0 / 13.0, 1.0, 0.5)
+_RKF45_B = ((0.25,), (3 / 32, 9 / 32), (1932 / 2197, -7200 / 2197, 7296 / 2197), (8341 / 4104, -32832 / 4104, 29440 / 4104, -845 / 4104),
+            (-6080 / 20520, 41040 / 20520, -28352 / 20520, 9295 / 20520, -5643 / 20520))
+_RKF45_C = (902880 / 7618050, 0.0, 3953664 / 7618050, 3855735 / 7618050, -1371249 / 7618050, 277020 / 7618050)
+_RKF45_E = (1 / 360, 0.0, -128 / 4275, -2197 / 75240, 1 / 50, 2 / 55)
+
+
+def ell_sng(l1, l2, l3, D_in, omega0, omega_lambda, omega_rad=0.0):
+    """ell_sng (src/collapse_times.c:315-400) for one point: gsl_odeiv2 rkf45 (GSL 2.7 rkf45.c) driven by
+    evolve_apply with control_standard_new(1e-6, 1e-6, 1, 1) (cstd.c: shrink by 0.9 r^-1/5 >= 0.2 above 1.1,
+    grow by 0.9 r^-1/6 <= 5 below 0.5) from a = 1e-5 to 5; collapse when lambda_a1 >= 0.99999, the epoch
+    interpolated linearly from the INITIAL point as the reference does (olda / oldlam are never advanced)."""
+    amin, amax = 1.0e-5, 5.0
+    rhs = lambda t, y: sng_system(t, y, omega0, omega_lambda, omega_rad)
+    y = np.array([l1 * D_in, l2 * D_in, l3 * D_in, l1 * D_in / (l1 * D_in - 1.0), l2 * D_in / (l2 * D_in - 1.0),
+                  l3 * D_in / (l3 * D_in - 1.0), l1 * D_in, l2 * D_in, l3 * D_in])
+    t, hh, olda, oldlam = amin, 1.0e-6, amin, l1 * D_in
+    with np.errstate(all="ignore"):
+        k1 = rhs(t, y)
+        while t < amax:
+            h0, final = hh, False
+            if h0 > amax - t:
+                h0, final = amax - t, True
+            while True:
+                k = [k1]
+                for st in range(5):
+                    k.append(rhs(t + _RKF45_A[st] * h0, y + h0 * sum(b * kk for b, kk in zip(_RKF45_B[st], k))))
+                ynew = y + h0 * sum(c * kk for c, kk in zip(_RKF45_C, k))
+                yerr = h0 * sum(e * kk for e, kk in zip(_RKF45_E, k))
+                dnew = rhs(t + h0, ynew)
+                d0 = 1.0e-6 * (np.abs(ynew) + np.abs(h0 * dnew)) + 1.0e-6
+                r = np.abs(yerr) / np.abs(d0)
+                rmax = max(2.2250738585072014e-308, np.nanmax(r) if np.any(~np.isnan(r)) else 0.0)
+                if rmax > 1.1:
+                    hnew = h0 * max(0.2, 0.9 / rmax ** 0.2)
+                    if not abs(hnew) < abs(h0) or t + hnew == t:
+                        return -1.0
+                    h0, final = hnew, False
+                    continue
+                break
+            hn = h0 * min(5.0, max(1.0, 0.9 / rmax ** (1.0 / 6.0))) if rmax < 0.5 else h0
+            y, k1 = ynew, dnew
+            t = amax if final else t + h0
+            if not final:
+                hh = hn
+            if y[0] >= 0.99999:
+                return olda + (1.0 - oldlam) * (t - olda) / (y[0] - oldlam)
+    return 0.0
+
+
+def _natural_spline_c(x, y):
+    """second-derivative coefficients c of gsl_interp_cspline for many columns at once: y [..., n]"""
+    n = x.size
+    h = np.diff(x)
+    dy = np.diff(y, axis=-1)
+    diag = 2.0 * (h[:-1] + h[1:])
+    off = h[1:-1]
+    rhs = 3.0 * (dy[..., 1:] / h[1:] - dy[..., :-1] / h[:-1])
+    m = n - 2
+    cp = np.zeros(m)
+    dp = np.zeros(rhs.shape)
+    cp[0] = off[0] / diag[0]
+    dp[..., 0] = rhs[..., 0] / diag[0]
+    for i in range(1, m):
+        den = diag[i] - off[i - 1] * cp[i - 1]
+        if i < m - 1:
+            cp[i] = off[i] / den
+        dp[..., i] = (rhs[..., i] - off[i - 1] * dp[..., i - 1]) / den
+    c = np.zeros(y.shape)
+    c[..., m] = dp[..., m - 1]
+    for i in range(m - 2, -1, -1):
+        c[..., i + 1] = dp[..., i] - cp[i] * c[..., i + 2]
+    return c
+
+
+def interpolate_collapse_time(table, dv, ampl, l1, l2, l3):
+    """interpolate_collapse_time, BILINEAR_SPLINE (src/collapse_times.c:1132-1147, 1211-1221): four natural
+    cubic splines in delta = (l1+l2+l3)/ampl (my_spline_eval: linear extrapolation outside the knots,
+    src/cosmo.c:2016-2027) blended bilinearly in x = (l1-l2)/ampl, y = (l2-l3)/ampl.  table [iy][ix][id]."""
+    table, dv = np.asarray(table), np.asarray(dv)
+    nxy, nd = table.shape[0], dv.size
+    bin_x = CT_RANGE_X / nxy
+    c = _natural_spline_c(dv, table)
+    d = (l1 + l2 + l3) / ampl
+    x = (l1 - l2) / ampl
+    y = (l2 - l3) / ampl
+    ix = np.clip((x / bin_x).astype(np.int64), 0, nxy - 2)
+    iy = np.clip((y / bin_x).astype(np.int64), 0, nxy - 2)
+    dx, dy = x / bin_x - ix, y / bin_x - iy
+    i = np.clip(np.searchsorted(dv, d, side="right") - 1, 0, nd - 2)
+    hh = dv[i + 1] - dv[i]
+    t = d - dv[i]
+
+    def column(jx, jy):
+        y0, y1, c0, c1 = table[jy, jx, i], table[jy, jx, i + 1], c[jy, jx, i], c[jy, jx, i + 1]
+        b = (y1 - y0) / hh - hh * (c1 + 2.0 * c0) / 3.0
+        val = y0 + t * (b + t * (c0 + t * (c1 - c0) / (3.0 * hh)))
+        lo = table[jy, jx, 0] + (d - dv[0]) * (table[jy, jx, 1] - table[jy, jx, 0]) / (dv[1] - dv[0])
+        hi = table[jy, jx, -1] + (d - dv[-1]) * (table[jy, jx, -1] - table[jy, jx, -2]) / (dv[-1] - dv[-2])
+        return np.where(d < dv[0], lo, np.where(d > dv[-1], hi, val))
+
+    return ((1.0 - dx) * (1.0 - dy) * column(ix, iy) + dx * (1.0 - dy) * column(ix + 1, iy)
+            + (1.0 - dx) * dy * column(ix, iy + 1) + dx * dy * column(ix + 1, iy + 1))
+
+
+def inverse_collapse_time_tab(h, table, dv, ampl):
+    """inverse_collapse_time with -DTABULATED_CT (src/collapse_times.c:679-776): eigenvalues as before, F from
+    the table of this smoothing radius."""
+    x1, x2, x3, bad = eigenvalues(h)
+    with np.errstate(all="ignore"):
+        F = interpolate_collapse_time(table, dv, ampl, np.where(bad, 0.0, x1), np.where(bad, 0.0, x2), np.where(bad, 0.0, x3))
+    return np.where(bad, -10.0, F)
+
+
 def ill_conditioned_mask(h, inverse_growing_mode, eps=1e-13, ntrial=2, tol=1e-7, seed=0):
     """Cells whose F is numerically ill-conditioned in the REFERENCE algorithm itself.
 

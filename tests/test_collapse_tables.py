@@ -1,0 +1,274 @@
+"""-DTABULATED_CT and -DELL_SNG (src/collapse_times.c:239-400, 780-1346) on a
+CPU-only box.
+
+Three layers, each against the one below it:
+  * tests/golden/reference_ct_32.npz -- outputs of the WHOLE reference program compiled with
+    -DTABULATED_CT (ELL_CLASSIC) and with -DELL_SNG -DTABULATED_CT (oracle/_ref/pinocchio_ref_{tab,sng}.x,
+    made by tests/golden/make_reference_ct_golden.py): the collapse-time tables it writes, FmaxPDF,
+    catalogues, mass function;
+  * the NumPy oracle (ct_delta_vector, ct_table_classic, ell_sng, interpolate_collapse_time);
+  * the device code of collapse_table.cuh under the CPU emulator, and the drop-in program linked over
+    the emulated ABI (oracle/_ref/pinocchio_emu_{tab,sng}.x: reference host code + shim + kernels),
+    whose output files must equal the reference program's byte for byte.
+The host cosmology of pinocchio_b200.cosmology is not bit-identical with the program's (PkNorm to 5e-6),
+so table values computed from it agree with the golden to ~1e-6 only; the exact comparison is the
+program-level one.
+"""
+import ctypes
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from emu_util import PD, load_emulator, packed_spline, ptr
+from oracle import pinocchio_oracle as po
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden" / "reference_ct_32.npz"
+REF = ROOT / "oracle" / "_ref"
+ND, NXY, BIN_X = po.CT_NBINS_D, po.CT_NBINS_XY, po.CT_RANGE_X / po.CT_NBINS_XY
+NPOINTS = ND * NXY * NXY
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def cosmo():
+    from pinocchio_b200.cosmology import Cosmology, set_smoothing
+    c = Cosmology()
+    return c, set_smoothing(c, 1.0 / 0.7)        # 1 Mpc/h cells: the nine-radius ladder of the golden run
+
+
+@pytest.fixture(scope="module")
+def lib():
+    lib = load_emulator()
+    lib.emu_ct_build.argtypes = [ctypes.c_int, PD, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, PD, ctypes.c_int,
+                                 ctypes.c_double, PD, ctypes.c_int, ctypes.c_int, PD]
+    lib.emu_ct_cells.argtypes = [ctypes.c_int, PD, ctypes.c_longlong, PD, PD, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                 ctypes.c_double, PD]
+    lib.emu_ell_sng.argtypes = [ctypes.c_double] * 4 + [PD]
+    lib.emu_ell_sng.restype = ctypes.c_double
+    lib.emu_ct_knots_doubles.restype = ctypes.c_longlong
+    return lib
+
+
+def relerr(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
+
+
+def cosmo4(c):
+    return np.array([c.p.Omega0, c.p.OmegaLambda, c.OmegaRad, c.OmegaK])
+
+
+# ---- oracle against the reference program's tables ----------------------------------------------------
+def test_golden_header_and_delta_vector(gold, lib):
+    for tag, model in (("tab", 1), ("sng", 3)):
+        h = gold[f"{tag}_header"].tobytes()
+        assert np.frombuffer(h[:4], np.int32)[0] == model                       # write_CTtable_header, :1307-1346
+        assert np.allclose(np.frombuffer(h[4:28], np.float64), [0.25, 0.75, 0.70])
+        assert list(np.frombuffer(h[28:40], np.int32)) == [NPOINTS, ND, NXY]
+    dv = po.ct_delta_vector()
+    assert dv[0] == -7.0 and np.all(np.diff(dv) > 0) and 7.0 < dv[-1] < 7.6
+    assert np.isclose(np.diff(dv).min() * 1.0, np.diff(dv)[np.argmin(np.abs(dv[:-1] + 1.0))])   # finest bins around CT_DELTA0
+    dv_dev = np.zeros(ND)
+    assert lib.emu_ct_delta_vector(ptr(dv_dev), ND) == 0
+    assert np.array_equal(dv_dev, dv)
+
+
+def test_oracle_classic_table_against_reference(gold, cosmo):
+    c, lad = cosmo
+    idx = gold["tab_table_idx"]
+    for ism in (0, 4, 8):
+        t = po.ct_table_classic(np.sqrt(lad.Variance[ism]), c.InverseGrowingMode).ravel()[idx]
+        e = relerr(t, gold["tab_table"][ism])
+        assert np.array_equal(t == 0, gold["tab_table"][ism] == 0)
+        assert np.quantile(e, 0.999) < 2e-5 and e.max() < 1e-3       # inputs agree to ~5e-6; den ~ 0 points amplify
+
+
+def test_oracle_ell_sng_against_reference(gold, cosmo):
+    c, lad = cosmo
+    idx = gold["sng_table_idx"]
+    D_in = c.GrowingMode(1.0 / 1.0e-5 - 1.0)
+    for ism in (1, 6):
+        l1, l2, l3 = [a.ravel() for a in po.ct_table_lambdas(np.sqrt(lad.Variance[ism]))]
+        for k in range(3, idx.size, 211):
+            i = idx[k]
+            a = po.ell_sng(l1[i], l2[i], l3[i], D_in, c.p.Omega0, c.p.OmegaLambda, c.OmegaRad)
+            F = 1.0 / a if a > 0 else 0.0
+            assert abs(F - gold["sng_table"][ism][k]) <= 2e-6 * max(1e-3, gold["sng_table"][ism][k]), (ism, i)
+
+
+# ---- device code under the emulator against the oracle -----------------------------------------------
+def test_emulator_classic_table_against_oracle(lib, cosmo):
+    c, lad = cosmo
+    dv = po.ct_delta_vector()
+    spl = packed_spline(lib, c.sp_invgrow)
+    ampl = float(np.sqrt(lad.Variance[5]))
+    tab = np.zeros(NPOINTS)
+    assert lib.emu_ct_build(1, ptr(dv), ND, NXY, BIN_X, ampl, ptr(spl), c.sp_invgrow.size, 0.0, None, 0, NPOINTS, ptr(tab)) == 0
+    ref = po.ct_table_classic(ampl, c.InverseGrowingMode).ravel()
+    e = relerr(tab, ref)
+    assert np.array_equal(tab == 0, ref == 0)
+    # ell_classic is ill-conditioned where its leading coefficient vanishes
+    assert (e > 1e-9).sum() < 100 and (e > 1e-6).sum() < 10
+
+
+def test_emulator_ell_sng_against_reference_and_oracle(lib, gold, cosmo):
+    c, lad = cosmo
+    idx = gold["sng_table_idx"]
+    D_in = c.GrowingMode(1.0 / 1.0e-5 - 1.0)
+    c4 = cosmo4(c)
+    ism = 3
+    l1, l2, l3 = [a.ravel() for a in po.ct_table_lambdas(np.sqrt(lad.Variance[ism]))]
+    got = np.array([lib.emu_ell_sng(l1[i], l2[i], l3[i], D_in, ptr(c4)) for i in idx])
+    F = np.where(got > 0, 1.0 / np.where(got > 0, got, 1.0), 0.0)
+    ref = gold["sng_table"][ism]
+    assert np.array_equal(F == 0, ref == 0)
+    assert relerr(F, ref).max() < 2e-6                     # host-cosmology inputs, see the module docstring
+    # same inputs: the NumPy restatement of GSL's rkf45 + step control takes the same steps
+    for k in range(5, idx.size, 97):
+        a = po.ell_sng(l1[idx[k]], l2[idx[k]], l3[idx[k]], D_in, c.p.Omega0, c.p.OmegaLambda, c.OmegaRad)
+        assert abs(a - got[k]) <= 1e-9 * max(abs(a), 1e-3)
+    # a contiguous range through the kernel body (one thread per table point)
+    dv = po.ct_delta_vector()
+    first, n = 101 * ND, 3 * ND
+    tab = np.zeros(NPOINTS)
+    assert lib.emu_ct_build(3, ptr(dv), ND, NXY, BIN_X, float(np.sqrt(lad.Variance[ism])), None, 0, D_in, ptr(c4), first, n, ptr(tab)) == 0
+    assert not tab[:first].any() and not tab[first + n:].any() and tab[first:first + n].any()
+    for i in range(first + 40, first + n, 37):
+        a = lib.emu_ell_sng(l1[i], l2[i], l3[i], D_in, ptr(c4))
+        assert tab[i] == (1.0 / a if a > 0 else 0.0)
+
+
+def device_table(lib, table, dv):
+    knots = np.zeros(lib.emu_ct_knots_doubles(ND))
+    lib.emu_ct_pack_knots(ptr(dv), ND, ptr(knots))
+    raw = np.zeros(NXY * NXY * (ND + 2) * 4 + 4)
+    off = (-raw.ctypes.data // 8) % 4                        # 32-byte alignment of the records
+    coef = raw[off:off + NXY * NXY * (ND + 2) * 4]
+    assert coef.ctypes.data % 32 == 0
+    assert lib.emu_ct_spline(ptr(dv), ND, NXY * NXY, ptr(np.ascontiguousarray(table.ravel())), ptr(coef)) == 0
+    return knots, coef
+
+
+def test_emulator_lookup_against_oracle(lib, cosmo):
+    """interpolate_collapse_time per cell: interval search, the two extrapolation records, clamped (x, y) bins"""
+    c, lad = cosmo
+    dv = po.ct_delta_vector()
+    ampl = float(np.sqrt(lad.Variance[6]))
+    table = po.ct_table_classic(ampl, c.InverseGrowingMode)
+    knots, coef = device_table(lib, table, dv)
+    rng = np.random.default_rng(5)
+    n = 20000
+    d = rng.uniform(-9.0, 9.5, n)                            # beyond both ends of the knots
+    x = np.abs(rng.normal(0, 1.5, n))                        # beyond CT_RANGE_X = 3.5 for some
+    y = np.abs(rng.normal(0, 1.5, n))
+    d[:ND] = dv                                              # exactly on the knots
+    x[:50], y[:50] = np.arange(50) * BIN_X, 0.0              # exactly on bin edges
+    l1, l2, l3 = (d + 2 * x + y) / 3 * ampl, (d - x + y) / 3 * ampl, (d - x - 2 * y) / 3 * ampl
+    lam = np.ascontiguousarray(np.stack([l1, l2, l3], axis=1))
+    F = np.zeros(n)
+    assert lib.emu_ct_cells(0, ptr(lam), n, ptr(knots), ptr(coef), ND, NXY, ampl, BIN_X, ptr(F)) == 0
+    ref = po.interpolate_collapse_time(table, dv, ampl, l1, l2, l3)
+    assert np.abs(F - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())
+    # from Hessians: eigenvalues + table, the -10 flag for complex eigenvalues
+    h = rng.normal(0, 1.0, (6, 5000))
+    F2 = np.zeros(5000)
+    assert lib.emu_ct_cells(1, ptr(np.ascontiguousarray(h)), 5000, ptr(knots), ptr(coef), ND, NXY, ampl, BIN_X, ptr(F2)) == 0
+    ref2 = po.inverse_collapse_time_tab(h, table, dv, ampl)
+    assert np.abs(F2 - ref2).max() <= 1e-9 * max(1.0, np.abs(ref2).max())
+
+
+# ---- the drop-in program over the emulated ABI against the reference program ---------------------------
+def run32(exe: Path, workdir: Path):
+    workdir.mkdir(parents=True, exist_ok=True)
+    text = (ROOT / "tests" / "golden" / "hmf_validation" / "parameter_file").read_text()
+    text = re.sub(r"(?m)^BoxSize\s+\S+", "BoxSize                32", text)
+    text = re.sub(r"(?m)^GridSize\s+\S+", "GridSize               32", text)
+    text = re.sub(r"(?m)^MaxMemPerParticle\s+\S+", "MaxMemPerParticle      400", text)
+    (workdir / "parameter_file").write_text(text + "\nCTtableFile none\n")
+    (workdir / "outputs").write_bytes((ROOT / "tests" / "golden" / "hmf_validation" / "outputs").read_bytes())
+    r = subprocess.run([str(exe), "parameter_file"], cwd=workdir, capture_output=True, text=True, timeout=1500,
+                       env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    return r.stdout
+
+
+def read_cttable(path: Path):
+    raw = path.read_bytes()
+    off, tabs = 40, []
+    while off < len(raw):
+        off += 4
+        tabs.append(np.frombuffer(raw[off:off + 8 * NPOINTS], dtype=np.float64))
+        off += 8 * NPOINTS
+    return raw[:40], np.array(tabs)
+
+
+@pytest.fixture(scope="module")
+def emu_run(tmp_path_factory):
+    """one run of pinocchio_emu_{tab,sng}.x per module: (workdir, log)"""
+    cache = {}
+
+    def get(tag):
+        if tag not in cache:
+            exe = REF / f"pinocchio_emu_{tag}.x"
+            if not exe.exists():
+                pytest.skip(f"{exe.name} not built (make -C oracle all)")
+            d = tmp_path_factory.mktemp(f"emu_{tag}")
+            cache[tag] = (d, run32(exe, d))
+        return cache[tag]
+    return get
+
+
+@pytest.mark.parametrize("tag", ["tab", "sng"])
+def test_emulated_dropin_tabulated_collapse_times(tag, gold, emu_run):
+    tmp_path, log = emu_run(tag)
+    assert "B200 path" in log and "Collapse times computed for interpolation" in log and "Pinocchio done!" in log
+    sig = np.array([float(x) for x in re.findall(r"computed sigma:\s+([0-9.]+)", log)])
+    assert np.array_equal(sig, gold[f"{tag}_sigma"])
+    # FmaxPDF, the four catalogues and the mass function: byte for byte the reference program's
+    for key in gold.files:
+        if key.startswith(f"{tag}_file_"):
+            name = key[len(f"{tag}_file_"):]
+            assert (tmp_path / name).read_bytes() == gold[key].tobytes(), name
+    # the table file: same header, same zero pattern, values to the accuracy of the arithmetic
+    header, tabs = read_cttable(tmp_path / "pinocchio.test.CTtable.out")
+    assert header == gold[f"{tag}_header"].tobytes() and tabs.shape == (9, NPOINTS)
+    assert np.array_equal((tabs != 0).sum(axis=1), gold[f"{tag}_nonzero_per_radius"])
+    e = relerr(tabs[:, gold[f"{tag}_table_idx"]], gold[f"{tag}_table"])
+    if tag == "sng":
+        assert e.max() < 1e-8                        # same rkf45 step sequence; 1.3e-9 over all 2.25 M points
+    else:
+        assert (e > 1e-9).sum() <= 20 and e.max() < 1e-3    # ell_classic near den = 0
+
+
+def test_emulated_dropin_reads_collapse_table_file(gold, emu_run, tmp_path):
+    """CTtableFile: a table file written by one run is read back by the next (header check, Bcast, upload)"""
+    exe = REF / "pinocchio_emu_tab.x"
+    a, _ = emu_run("tab")
+    b = tmp_path / "read"
+    b.mkdir()
+    (b / "table.bin").write_bytes((a / "pinocchio.test.CTtable.out").read_bytes())
+    text = (a / "parameter_file").read_text().replace("CTtableFile none", "CTtableFile table.bin")
+    (b / "parameter_file").write_text(text)
+    (b / "outputs").write_bytes((a / "outputs").read_bytes())
+    r = subprocess.run([str(exe), "parameter_file"], cwd=b, capture_output=True, text=True, timeout=1500,
+                       env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "Collapse times read from file table.bin" in r.stdout
+    assert not (b / "pinocchio.test.CTtable.out").exists()
+    for name in ("pinocchio.test.FmaxPDF.out", "pinocchio.0.0000.test.catalog.out"):
+        assert (b / name).read_bytes() == gold[f"tab_file_{name}"].tobytes()
+    # a table made for another collapse model is refused (check_CTtable_header, :1226-1303)
+    bad = bytearray((a / "pinocchio.test.CTtable.out").read_bytes())
+    bad[0] = 3
+    (b / "table.bin").write_bytes(bytes(bad))
+    r = subprocess.run([str(exe), "parameter_file"], cwd=b, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 or "ERROR" in r.stdout
+    assert "CT table not constructed for this collapse model" in r.stdout
