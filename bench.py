@@ -304,6 +304,17 @@ def run_b200(args):
         except Exception as ex:  # noqa: BLE001
             dropin = {"error": str(ex)[:300]}
 
+    # ---- collapse-time tables (-DTABULATED_CT / -DELL_SNG): table build + tabulated sweep, isolated
+    ctable = None
+    if rank == 0 and world == 1 and not args.no_handoff:
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "scripts" / "gpu_ctable_probe.py"), str(N)], capture_output=True,
+                               text=True, timeout=300)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            ctable = json.loads(line[-1]) if line else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as ex:  # noqa: BLE001
+            ctable = {"error": str(ex)[:300]}
+
     if rank == 0:
         out = {"metric": METRIC, "value": round(value, 2), "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
@@ -314,7 +325,7 @@ def run_b200(args):
                           "seed": 486604, "parallelism": f"slab{world}" if world > 1 else "single GPU",
                           "l2_policy": "inputs larger than L2 (each field 8.7 GB at 1024^3)"},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-               "cpu_baseline": cpu_baseline, "fragment_handoff": handoff, "dropin_program": dropin, "checks": checks, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
+               "cpu_baseline": cpu_baseline, "fragment_handoff": handoff, "dropin_program": dropin, "collapse_tables": ctable, "checks": checks, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
         print(json.dumps(out))
     pin.close()
     if world > 1:

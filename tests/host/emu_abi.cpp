@@ -46,6 +46,9 @@ int emu_ct_build(int model, const double* dv, int nd, int nxy, double bin_x, dou
 long long emu_ct_knots_doubles(int nd);
 int emu_ct_pack_knots(const double* dv, int nd, double* out);
 int emu_ct_spline(const double* dv, int nd, int ncols, const double* table, double* coef);
+int emu_ct_cells(int which, const double* in, long long n, const double* knots, const double* coef, int nd, int nxy, double ampl,
+                 double bin_x, double* F);
+int emu_collapse_cells(const double* h6, long long n, const double* spline, int nspl, double* F);
 long long emu_spline_table_doubles(int n);
 int emu_pack_spline(const double* x, const double* y, int n, double* out);
 }
@@ -225,6 +228,8 @@ extern "C" int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_de
   std::vector<double> dv(nd);
   if (desc->delta_vector) dv.assign(desc->delta_vector, desc->delta_vector + nd);
   else emu_ct_delta_vector(dv.data(), nd);
+  for (int i = 1; i < nd; i++)
+    if (!(dv[i] > dv[i - 1])) FAIL("delta_vector must be strictly increasing");
   ctx->ct_nd = nd;
   ctx->ct_nxy = nxy;
   ctx->ct_bin_x = desc->range_x / (double)nxy;
@@ -473,7 +478,17 @@ extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, doubl
   ctx->hessian_valid = (radius == 0.0);
   return 0;
 }
-extern "C" int pinb200_collapse_cells(pinb200_ctx* ctx, int, const double*, size_t, double*) { FAIL("emulated ABI: not wired"); }
+extern "C" int pinb200_collapse_cells(pinb200_ctx* ctx, int ismooth, const double* h6, size_t n, double* F) {
+  if (!ctx || !h6 || !F) return 1;
+  if (ctx->ct_on) {
+    if (ismooth < 0 || ismooth >= (int)ctx->ct_tables.size()) FAIL("ismooth out of range of the collapse tables");
+    return emu_ct_cells(1, h6, (long long)n, ctx->ct_knots.data(), static_cast<const double*>(ctx->ct_coef[ismooth]), ctx->ct_nd, ctx->ct_nxy,
+                        ctx->ct_ampl[ismooth], ctx->ct_bin_x, F);
+  }
+  if (ctx->spline.empty()) FAIL("inverse-growth spline not set (pinb200_set_invgrow_spline)");
+  const std::vector<double>& spl = (ismooth >= 0 && ismooth < (int)ctx->spline_r.size() && !ctx->spline_r[ismooth].empty()) ? ctx->spline_r[ismooth] : ctx->spline;
+  return emu_collapse_cells(h6, (long long)n, spl.data(), ctx->nspl, F);
+}
 extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float, unsigned int*, size_t, size_t*) { FAIL("emulated ABI: not wired"); }
 extern "C" int pinb200_download_products_sorted(pinb200_ctx* ctx, void*, const pinb200_product_layout*, size_t, size_t) {
   FAIL("emulated ABI: not wired");
