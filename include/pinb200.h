@@ -91,9 +91,11 @@ int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const double* x, c
  * :315-400; sng_system :239-290) -- and evaluates per cell four cubic splines in delta blended
  * bilinearly in (x, y) (interpolate_collapse_time, BILINEAR_SPLINE, :1132-1222).  model is the type
  * code of the CTtable file header (write_CTtable_header, :1307-1326): 1 = ELL_CLASSIC tabulated,
- * 3 = ELL_SNG standard gravity (4 = f(R) gravity: not built). */
+ * 3 = ELL_SNG standard gravity, 4 = ELL_SNG with the Hu-Sawicki f(R) force modification (MOD_GRAV_FR,
+ * ForceModification, :294-311). */
 #define PINB200_CT_CLASSIC 1
 #define PINB200_CT_SNG 3
+#define PINB200_CT_SNG_FR 4
 typedef struct {
   int model;
   int nbins_d, nbins_xy;      /* CT_NBINS_D (100, at most 128), CT_NBINS_XY (50) */
@@ -102,6 +104,10 @@ typedef struct {
   /* ELL_SNG only: OmegaMatter(z), OmegaLambda(z) of src/cosmo.c:1675-1718 for a cosmological constant:
    * E^2(z) = omega_rad (1+z)^4 + omega0 (1+z)^3 + omega_k (1+z)^2 + omega_lambda */
   double omega0, omega_lambda, omega_rad, omega_k;
+  /* model 4 only: FR0, H_over_c = 100 / SPEEDOFLIGHT (src/cosmo.c:109) and, per smoothing radius, the size handed
+   * to sng_system: Smoothing.Radius[ismooth], the previous radius for the last one (src/collapse_times.c:362-372) */
+  double fr0, h_over_c;
+  const double* fr_size;
 } pinb200_ct_desc;
 /* delta_vector of the reference's compiled sampling (CT_EXPO 1.75, CT_SQUEEZE 1.2, CT_RANGE_D 7,
  * CT_DELTA0 -1; src/collapse_times.c:781-787, 836-877); host code, no device needed */

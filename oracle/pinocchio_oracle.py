@@ -445,9 +445,25 @@ def ct_table_classic(ampl: float, inverse_growing_mode, dv=None, nxy: int = CT_N
         return np.where(pos, 1.0 + inverse_growing_mode(np.where(pos, bc, 1.0)), 0.0)
 
 
-def sng_system(t, y, omega0, omega_lambda, omega_rad=0.0, omega_k=None):
+H_OVER_C = 100.0 / 299792.458       # H_over_c = 100 / SPEEDOFLIGHT (src/cosmo.c:109, src/pinocchio.h:63)
+
+
+def force_modification(size, a, delta, omega0, omega_lambda, fr0):
+    """ForceModification of Hu-Sawicki f(R) gravity (-DMOD_GRAV_FR, src/collapse_times.c:294-311)."""
+    ff = 4.0 * omega_lambda / omega0
+    with np.errstate(all="ignore"):
+        thickness = fr0 / omega0 / (H_OVER_C * size) ** 2 * a ** 7 * np.float64(1.0 + delta) ** (-1.0 / 3.0) * \
+            (((1.0 + ff) / (1.0 + ff * a ** 3)) ** 2 - ((1.0 + ff) / (1.0 + delta + ff * a ** 3)) ** 2)
+    f3 = thickness * (3.0 + thickness * (-3.0 + thickness))
+    if f3 < 0.0:
+        f3 = 0.0
+    return f3 / 3.0 if f3 < 1.0 else 1.0 / 3.0
+
+
+def sng_system(t, y, omega0, omega_lambda, omega_rad=0.0, omega_k=None, fr0=0.0, fr_size=1.0):
     """r.h.s. of the nine eigenvalue equations of Nadkarni-Ghosh & Singhal (src/collapse_times.c:239-290);
-    OmegaMatter / OmegaLambda of src/cosmo.c:1675-1718 for a cosmological constant."""
+    OmegaMatter / OmegaLambda of src/cosmo.c:1675-1718 for a cosmological constant; fr0 > 0: the gravity term
+    of the velocity equations times 1 + ForceModification(fr_size, a, delta) (-DMOD_GRAV_FR, :276-277)."""
     if omega_k is None:
         omega_k = 1.0 - omega0 - omega_lambda - omega_rad
     z = 1.0 / t - 1.0
@@ -455,6 +471,7 @@ def sng_system(t, y, omega0, omega_lambda, omega_rad=0.0, omega_k=None):
     e2 /= omega_rad + omega0 + omega_k + omega_lambda
     om, ol = omega0 * (1 + z) ** 3 / e2, omega_lambda / e2
     delta = y[6] + y[7] + y[8]
+    grav = 1.0 + force_modification(fr_size, t, delta, omega0, omega_lambda, fr0) if fr0 else 1.0
     f = [0.0] * 9
     for i in range(3):
         s = 0.0
@@ -464,7 +481,7 @@ def sng_system(t, y, omega0, omega_lambda, omega_rad=0.0, omega_k=None):
             s += (y[j + 6] - y[i + 6]) * ((1 - y[i]) ** 2 * (1 + y[i + 3]) - (1 - y[j]) ** 2 * (1 + y[j + 3])) / \
                  ((1 - y[i]) ** 2 - (1 - y[j]) ** 2)
         f[i] = y[i + 3] * (y[i] - 1.0) / t
-        f[i + 3] = 0.5 * (y[i + 3] * (om - 2.0 * ol - 2.0) - 3.0 * om * y[i + 6] - 2.0 * y[i + 3] ** 2) / t
+        f[i + 3] = 0.5 * (y[i + 3] * (om - 2.0 * ol - 2.0) - 3.0 * om * y[i + 6] * grav - 2.0 * y[i + 3] ** 2) / t
         f[i + 6] = ((5.0 / 6.0 + y[i + 6]) * ((3.0 + y[3] + y[4] + y[5]) - (1.0 + delta) / (2.5 + delta) * (y[3] + y[4] + y[5]))
                     - (2.5 + delta) * (1.0 + y[i + 3]) + s) / t
     return np.array(f)
@@ -477,13 +494,13 @@ _RKF45_C = (902880 / 7618050, 0.0, 3953664 / 7618050, 3855735 / 7618050, -137124
 _RKF45_E = (1 / 360, 0.0, -128 / 4275, -2197 / 75240, 1 / 50, 2 / 55)
 
 
-def ell_sng(l1, l2, l3, D_in, omega0, omega_lambda, omega_rad=0.0):
+def ell_sng(l1, l2, l3, D_in, omega0, omega_lambda, omega_rad=0.0, fr0=0.0, fr_size=1.0):
     """ell_sng (src/collapse_times.c:315-400) for one point: gsl_odeiv2 rkf45 (GSL 2.7 rkf45.c) driven by
     evolve_apply with control_standard_new(1e-6, 1e-6, 1, 1) (cstd.c: shrink by 0.9 r^-1/5 >= 0.2 above 1.1,
     grow by 0.9 r^-1/6 <= 5 below 0.5) from a = 1e-5 to 5; collapse when lambda_a1 >= 0.99999, the epoch
     interpolated linearly from the INITIAL point as the reference does (olda / oldlam are never advanced)."""
     amin, amax = 1.0e-5, 5.0
-    rhs = lambda t, y: sng_system(t, y, omega0, omega_lambda, omega_rad)
+    rhs = lambda t, y: sng_system(t, y, omega0, omega_lambda, omega_rad, None, fr0, fr_size)
     y = np.array([l1 * D_in, l2 * D_in, l3 * D_in, l1 * D_in / (l1 * D_in - 1.0), l2 * D_in / (l2 * D_in - 1.0),
                   l3 * D_in / (l3 * D_in - 1.0), l1 * D_in, l2 * D_in, l3 * D_in])
     t, hh, olda, oldlam = amin, 1.0e-6, amin, l1 * D_in

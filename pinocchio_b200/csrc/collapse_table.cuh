@@ -115,9 +115,25 @@ PINB_HD void ct_point_lambdas(int i, const double* dv, int nd, int nxy, double b
 // (params.simpleLambda): E^2(z) = [OmegaRad (1+z)^4 + Omega0 (1+z)^3 + OmegaK (1+z)^2 + OmegaLambda] / E^2(0)
 struct SngCosmo {
   double omega0, omega_lambda, omega_rad, omega_k;
+  // MOD_GRAV_FR (Hu-Sawicki f(R), src/collapse_times.c:292-311): fr0 = FR0 (0: standard gravity),
+  // h_over_c = 100 / SPEEDOFLIGHT (src/cosmo.c:109), fr_size = the smoothing radius handed to sng_system
+  double fr0, h_over_c, fr_size;
 };
 
-// r.h.s. of the nine eigenvalue equations, src/collapse_times.c:239-290 (standard gravity)
+// ForceModification(size, a, delta), src/collapse_times.c:294-311
+PINB_HD double sng_force_modification(const SngCosmo& c, double a, double delta) {
+  const double ff = 4. * c.omega_lambda / c.omega0;
+  const double a3 = a * a * a;
+  const double hs = c.h_over_c * c.fr_size;
+  const double u = (1.0 + ff) / (1.0 + ff * a3), w = (1.0 + ff) / (1.0 + delta + ff * a3);
+  const double thickness = c.fr0 / c.omega0 / (hs * hs) * (a3 * a3 * a) * pow(1. + delta, -1. / 3.) * (u * u - w * w);
+  double F3 = thickness * (3. + thickness * (-3. + thickness));
+  if (F3 < 0.) F3 = 0.;
+  return (F3 < 1. ? F3 / 3. : 1. / 3);
+}
+
+// r.h.s. of the nine eigenvalue equations, src/collapse_times.c:239-290; with MOD_GRAV_FR the gravity
+// term of the velocity equations is multiplied by 1 + ForceModification
 PINB_HD void sng_rhs(double t, const double* y, double* f, const SngCosmo& c) {
   const double z = 1. / t - 1.;
   const double zp = 1. + z, zp2 = zp * zp;
@@ -129,6 +145,7 @@ PINB_HD void sng_rhs(double t, const double* y, double* f, const SngCosmo& c) {
   const double delta = y[6] + y[7] + y[8];
   const double sv = y[3] + y[4] + y[5];
   const double rt = 1.0 / t;
+  const double grav = (c.fr0 != 0.0) ? 1. + sng_force_modification(c, t, delta) : 1.0;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     double sum = 0.;
@@ -139,7 +156,7 @@ PINB_HD void sng_rhs(double t, const double* y, double* f, const SngCosmo& c) {
       sum += (y[j + 6] - y[i + 6]) * (ai * (1. + y[i + 3]) - aj * (1. + y[j + 3])) / (ai - aj);
     }
     f[i] = (y[i + 3] * (y[i] - 1.0)) * rt;
-    f[i + 3] = (0.5 * (y[i + 3] * (omegam - 2.0 * omegal - 2.0) - 3.0 * omegam * y[i + 6] - 2.0 * y[i + 3] * y[i + 3])) * rt;
+    f[i + 3] = (0.5 * (y[i + 3] * (omegam - 2.0 * omegal - 2.0) - 3.0 * omegam * y[i + 6] * grav - 2.0 * y[i + 3] * y[i + 3])) * rt;
     f[i + 6] = ((5. / 6. + y[i + 6]) * ((3. + sv) - (1. + delta) / (2.5 + delta) * sv) - (2.5 + delta) * (1. + y[i + 3]) + sum) * rt;
   }
 }
@@ -247,6 +264,7 @@ PINB_HD double ell_sng(double l1, double l2, double l3, double D_in, const SngCo
 // model 1: ELL_CLASSIC (1 + InverseGrowingMode(b_c));  model 3: ELL_SNG (1 / a_c)
 #define PINB_CT_MODEL_CLASSIC 1
 #define PINB_CT_MODEL_SNG 3
+#define PINB_CT_MODEL_SNG_FR 4 /* same integration, SngCosmo::fr0 != 0 */
 PINB_HD double ct_build_point(int model, int i, const double* dv, int nd, int nxy, double bin_x, double ampl, const SplineView& invgrow,
                               double D_in, const SngCosmo& cosmo) {
   double l1, l2, l3;

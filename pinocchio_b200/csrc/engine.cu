@@ -373,7 +373,8 @@ extern "C" int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_de
   if (!desc) return 0;
   if (ctx->radius.empty()) FAIL("smoothing ladder not set (pinb200_set_smoothing)");
   if (!variance) FAIL("variance[] missing");
-  if (desc->model != PINB200_CT_CLASSIC && desc->model != PINB200_CT_SNG) FAIL("model must be PINB200_CT_CLASSIC or PINB200_CT_SNG");
+  if (desc->model != PINB200_CT_CLASSIC && desc->model != PINB200_CT_SNG && desc->model != PINB200_CT_SNG_FR)
+    FAIL("model must be PINB200_CT_CLASSIC, PINB200_CT_SNG or PINB200_CT_SNG_FR");
   if (desc->nbins_d < 4 || desc->nbins_d > PINB_CT_MAXD) FAIL("nbins_d out of range [4, 128]");
   if (desc->nbins_xy < 2 || desc->nbins_xy > 1024) FAIL("nbins_xy out of range [2, 1024]");
   if (!(desc->range_x > 0.0)) FAIL("range_x must be positive");
@@ -389,9 +390,12 @@ extern "C" int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_de
   // is then enough; more are still handled by its loop)
   for (int is = 0; is < ns; is++)
     if (!(variance[is] > 0.0)) FAIL("variance[] must be positive");
-  if (desc->model == PINB200_CT_SNG && !tables) {
+  const bool sng = desc->model == PINB200_CT_SNG || desc->model == PINB200_CT_SNG_FR;
+  if (sng && !tables) {
     if (!d_in) FAIL("d_in[] missing (ELL_SNG)");
     if (!(desc->omega0 > 0.0)) FAIL("omega0 must be positive (ELL_SNG)");
+    if (desc->model == PINB200_CT_SNG_FR && (!(desc->fr0 > 0.0) || !(desc->h_over_c > 0.0) || !desc->fr_size))
+      FAIL("fr0, h_over_c and fr_size[] must be set (MOD_GRAV_FR)");
   }
   if (desc->model == PINB200_CT_CLASSIC && !tables) TRY(upload_splines(ctx));
   ctx->ct_nd = nd;
@@ -426,7 +430,12 @@ extern "C" int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_de
         b.nspl = ctx->nspl;
       } else {
         b.D_in = d_in[is];
-        b.cosmo = SngCosmo{desc->omega0, desc->omega_lambda, desc->omega_rad, desc->omega_k};
+        b.cosmo = SngCosmo{desc->omega0, desc->omega_lambda, desc->omega_rad, desc->omega_k, 0.0, 0.0, 0.0};
+        if (desc->model == PINB200_CT_SNG_FR) {
+          b.cosmo.fr0 = desc->fr0;
+          b.cosmo.h_over_c = desc->h_over_c;
+          b.cosmo.fr_size = desc->fr_size[is];
+        }
       }
       b.table = tab;
       b.npoints = (int)npoints;

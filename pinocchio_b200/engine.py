@@ -42,10 +42,12 @@ class CTDesc(ctypes.Structure):
     _fields_ = [("model", ctypes.c_int), ("nbins_d", ctypes.c_int), ("nbins_xy", ctypes.c_int),
                 ("range_x", ctypes.c_double), ("delta_vector", ctypes.POINTER(ctypes.c_double)),
                 ("omega0", ctypes.c_double), ("omega_lambda", ctypes.c_double), ("omega_rad", ctypes.c_double),
-                ("omega_k", ctypes.c_double)]
+                ("omega_k", ctypes.c_double), ("fr0", ctypes.c_double), ("h_over_c", ctypes.c_double),
+                ("fr_size", ctypes.POINTER(ctypes.c_double))]
 
 
-CT_CLASSIC, CT_SNG = 1, 3            # type codes of the CTtable file header (src/collapse_times.c:1307-1326)
+CT_CLASSIC, CT_SNG, CT_SNG_FR = 1, 3, 4   # type codes of the CTtable file header (src/collapse_times.c:1307-1326)
+H_OVER_C = 100.0 / 299792.458             # H_over_c = 100 / SPEEDOFLIGHT (src/cosmo.c:109)
 CT_NBINS_D, CT_NBINS_XY, CT_RANGE_X = 100, 50, 3.5   # src/collapse_times.c:781-787
 
 
@@ -259,17 +261,25 @@ class Pinocchio:
 
     # -- -DTABULATED_CT -------------------------------------------------------------------------
     def initialize_collapse_times(self, model: int = CT_CLASSIC, tables: np.ndarray | None = None, nbins_d: int = CT_NBINS_D,
-                                  nbins_xy: int = CT_NBINS_XY, delta_vector: np.ndarray | None = None) -> int:
+                                  nbins_xy: int = CT_NBINS_XY, delta_vector: np.ndarray | None = None, fr0: float = 0.0,
+                                  d_in: np.ndarray | None = None) -> int:
         """initialize_collapse_times for every smoothing radius (src/collapse_times.c:824-1046): from now on
         compute_fmax / inverse_collapse_time interpolate F in per-radius tables -- computed on the device
         with ell_classic (model CT_CLASSIC) or with the ELL_SNG ellipsoid integration (CT_SNG), or taken
         from ``tables`` [Nsmooth][nbins_xy][nbins_xy][nbins_d] (a CTtableFile).  model None: back to the
-        direct evaluation."""
+        direct evaluation.  CT_SNG_FR: Hu-Sawicki f(R) force modification with ``fr0`` = FR0 (-DMOD_GRAV_FR); ``d_in``
+        then carries the scale-dependent GrowingMode(1/1e-5 - 1, k(R)) of the host cosmology per radius."""
         if model is None:
             self._ck(self.lib.pinb200_set_collapse_tables(self.h, None, None, None, None))
             return 0
         c = self.cosmo
-        d = CTDesc(int(model), int(nbins_d), int(nbins_xy), CT_RANGE_X, None, c.p.Omega0, c.p.OmegaLambda, c.OmegaRad, c.OmegaK)
+        d = CTDesc(int(model), int(nbins_d), int(nbins_xy), CT_RANGE_X, None, c.p.Omega0, c.p.OmegaLambda, c.OmegaRad, c.OmegaK,
+                   float(fr0), H_OVER_C, None)
+        # the size handed to sng_system: the radius, the previous one for the last (R = 0) (src/collapse_times.c:362-372)
+        size = np.ascontiguousarray(self.Smoothing.Radius, dtype=np.float64).copy()
+        if size.size > 1:
+            size[-1] = size[-2]
+        d.fr_size = _dp(size)
         dv = None
         if delta_vector is not None:
             dv = np.ascontiguousarray(delta_vector, dtype=np.float64)
@@ -277,7 +287,8 @@ class Pinocchio:
             d.delta_vector = _dp(dv)
         var = np.ascontiguousarray(self.Smoothing.Variance, dtype=np.float64)
         # GrowingMode(1/amin - 1, .) of ell_sng (src/collapse_times.c:345-353); scale-independent growth
-        d_in = np.full(var.size, c.GrowingMode(1.0 / 1.0e-5 - 1.0))
+        d_in = np.full(var.size, c.GrowingMode(1.0 / 1.0e-5 - 1.0)) if d_in is None else np.ascontiguousarray(d_in, dtype=np.float64)
+        assert d_in.size == var.size
         tab = None
         if tables is not None:
             tab = np.ascontiguousarray(tables, dtype=np.float64)

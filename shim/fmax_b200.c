@@ -441,8 +441,8 @@ int read_dumps(void)
 #if defined(ELL_SNG) && !defined(TABULATED_CT)
 #error "ELL_SNG without TABULATED_CT (one ODE integration per cell and radius) is not provided by the GPU path"
 #endif
-#ifdef MOD_GRAV_FR
-#error "MOD_GRAV_FR (f(R) force modification in sng_system, src/collapse_times.c:270-311) is not provided by the GPU path"
+#if defined(MOD_GRAV_FR) && !defined(ELL_SNG)
+#error "MOD_GRAV_FR needs ELL_SNG (the force modification lives in sng_system, src/collapse_times.c:270-311)"
 #endif
 #ifdef TABULATED_CT
 #define SHIM_CT_NBINS_XY 50 /* CT_NBINS_XY, CT_NBINS_D, CT_RANGE_X of src/collapse_times.c:781-787 */
@@ -452,7 +452,9 @@ static int shim_ct_ready = 0;
 
 static int shim_ct_model(void)
 {
-#ifdef ELL_SNG
+#ifdef MOD_GRAV_FR
+  return PINB200_CT_SNG_FR;
+#elif defined(ELL_SNG)
   return PINB200_CT_SNG;
 #else
   return PINB200_CT_CLASSIC;
@@ -524,6 +526,7 @@ static int shim_collapse_tables(int onlycompute)
   int ismooth, fail = 0;
   pinb200_ct_desc d;
   double *d_in = (double *)malloc(ns * sizeof(double));
+  double *fr_size = (double *)malloc(ns * sizeof(double));
   double *tables = NULL;
   const int from_file = strcmp(params.CTtableFile, "none") && !onlycompute;
 
@@ -567,7 +570,14 @@ static int shim_collapse_tables(int onlycompute)
 #else
     d_in[ismooth] = GrowingMode(1. / 1.e-5 - 1., 1. / Smoothing.Radius[ismooth]);
 #endif
+    /* ode_param of ell_sng, src/collapse_times.c:362-372 */
+    fr_size[ismooth] = (ismooth < ns - 1 || ns == 1) ? Smoothing.Radius[ismooth] : Smoothing.Radius[ismooth - 1];
   }
+#ifdef MOD_GRAV_FR
+  d.fr0 = FR0;
+  d.h_over_c = H_over_c;
+  d.fr_size = fr_size;
+#endif
 
   if (from_file)
   {
@@ -605,6 +615,7 @@ static int shim_collapse_tables(int onlycompute)
   if (pinb200_set_collapse_tables(pinb, &d, Smoothing.Variance, d_in, tables))
     return pinb_fail("pinb200_set_collapse_tables");
   free(d_in);
+  free(fr_size);
   if (tables)
     free(tables);
 

@@ -1,9 +1,10 @@
 """Generates tests/golden/reference_ct_32.npz: outputs of the WHOLE reference program compiled with
 -DTABULATED_CT (ELL_CLASSIC: oracle/_ref/pinocchio_ref_tab.x) and with -DELL_SNG -DTABULATED_CT
-(oracle/_ref/pinocchio_ref_sng.x; oracle/Makefile) on the HMF_Validation parameter file scaled to a
-32^3 box of 32 Mpc/h (nine smoothing radii, 1 Mpc/h cells as in the 128^3 run).
+(oracle/_ref/pinocchio_ref_sng.x; oracle/Makefile), and with -DMOD_GRAV_FR -DFR0=1.e-5 on top of that
+(pinocchio_ref_fr.x: Hu-Sawicki f(R), scale-dependent growth, ten radii), on the HMF_Validation parameter
+file scaled to a 32^3 box of 32 Mpc/h (nine smoothing radii, 1 Mpc/h cells as in the 128^3 run).
 
-Stored per variant (`tab_*`, `sng_*`): every 97th point of the nine collapse-time tables the program
+Stored per variant (`tab_*`, `sng_*`, `fr_*`): every 97th point of the nine collapse-time tables the program
 writes to pinocchio.test.CTtable.out (+ the 40-byte header), the FmaxPDF file, the four halo
 catalogues and the z = 0 mass function as text.  The ELL_SNG run integrates 2.25 million ODE systems
 on one core: about seven minutes.
@@ -68,15 +69,19 @@ def collect(tag: str, d: Path, out: dict):
         out[f"{tag}_file_{name}"] = np.frombuffer((d / name).read_bytes(), dtype=np.uint8)
     log = (d / "log.txt").read_text()
     out[f"{tag}_sigma"] = np.array([float(x) for x in re.findall(r"computed sigma:\s+([0-9.]+)", log)])
+    rv = re.findall(r"\d+\)\s+Radius=\s*([0-9.]+), Variance=\s*([0-9.]+)", log)
+    out[f"{tag}_radius"] = np.array([float(r) for r, _ in rv])
+    out[f"{tag}_variance"] = np.array([float(v) for _, v in rv])
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reuse-tab")
     ap.add_argument("--reuse-sng")
+    ap.add_argument("--reuse-fr")
     a = ap.parse_args()
     out = {}
-    for tag, reuse in (("tab", a.reuse_tab), ("sng", a.reuse_sng)):
+    for tag, reuse in (("tab", a.reuse_tab), ("sng", a.reuse_sng), ("fr", a.reuse_fr)):
         d = Path(reuse) if reuse else Path(tempfile.mkdtemp(prefix=f"pinref_{tag}_"))
         if not reuse:
             run(REF / f"pinocchio_ref_{tag}.x", d)

@@ -383,7 +383,7 @@ extern "C" int emu_ct_build(int model, const double* dv, int nd, int nxy, double
   p.spline = spline;
   p.nspl = nspl;
   p.D_in = D_in;
-  if (cosmo4) p.cosmo = SngCosmo{cosmo4[0], cosmo4[1], cosmo4[2], cosmo4[3]};
+  if (cosmo4) p.cosmo = SngCosmo{cosmo4[0], cosmo4[1], cosmo4[2], cosmo4[3], cosmo4[4], cosmo4[5], cosmo4[6]};  // 7 values
   p.table = table;
   p.npoints = first + npoints;
   // these bodies have no barrier: every (block, thread) pair is run as an independent call, spread over
@@ -442,7 +442,7 @@ extern "C" int emu_ct_cells(int which, const double* in, long long n, const doub
   return 0;
 }
 extern "C" double emu_ell_sng(double l1, double l2, double l3, double D_in, const double* cosmo4) {
-  return ell_sng(l1, l2, l3, D_in, SngCosmo{cosmo4[0], cosmo4[1], cosmo4[2], cosmo4[3]});
+  return ell_sng(l1, l2, l3, D_in, SngCosmo{cosmo4[0], cosmo4[1], cosmo4[2], cosmo4[3], cosmo4[4], cosmo4[5], cosmo4[6]});
 }
 // the collapse z pass with the table in place of ell_classic
 extern "C" int emu_zpass_collapse_tab(int N, int nranks, double** srcs, const int* kzpow, int has_nyq, const double* dc,

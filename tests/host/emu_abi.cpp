@@ -220,9 +220,12 @@ extern "C" int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_de
   if (!desc) return 0;
   if (ctx->radius.empty()) FAIL("smoothing ladder not set (pinb200_set_smoothing)");
   if (!variance) FAIL("variance[] missing");
-  if (desc->model != PINB200_CT_CLASSIC && desc->model != PINB200_CT_SNG) FAIL("model must be PINB200_CT_CLASSIC or PINB200_CT_SNG");
+  if (desc->model != PINB200_CT_CLASSIC && desc->model != PINB200_CT_SNG && desc->model != PINB200_CT_SNG_FR)
+    FAIL("model must be PINB200_CT_CLASSIC, PINB200_CT_SNG or PINB200_CT_SNG_FR");
   if (desc->model == PINB200_CT_CLASSIC && !tables && ctx->spline.empty()) FAIL("inverse-growth spline not set (pinb200_set_invgrow_spline)");
-  if (desc->model == PINB200_CT_SNG && !tables && !d_in) FAIL("d_in[] missing (ELL_SNG)");
+  if (desc->model != PINB200_CT_CLASSIC && !tables && !d_in) FAIL("d_in[] missing (ELL_SNG)");
+  if (desc->model == PINB200_CT_SNG_FR && !tables && (!(desc->fr0 > 0.0) || !(desc->h_over_c > 0.0) || !desc->fr_size))
+    FAIL("fr0, h_over_c and fr_size[] must be set (MOD_GRAV_FR)");
   const int ns = (int)ctx->radius.size(), nd = desc->nbins_d, nxy = desc->nbins_xy;
   const size_t ncols = (size_t)nxy * nxy, npoints = ncols * nd;
   std::vector<double> dv(nd);
@@ -237,8 +240,13 @@ extern "C" int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_de
   ctx->ct_knots.assign((size_t)emu_ct_knots_doubles(nd), 0.0);
   emu_ct_pack_knots(dv.data(), nd, ctx->ct_knots.data());
   ctx->ct_tables.resize(ns);
-  const double cosmo4[4] = {desc->omega0, desc->omega_lambda, desc->omega_rad, desc->omega_k};
+  double cosmo4[7] = {desc->omega0, desc->omega_lambda, desc->omega_rad, desc->omega_k, 0.0, 0.0, 0.0};
   for (int is = 0; is < ns; is++) {
+    if (desc->model == PINB200_CT_SNG_FR && !tables) {
+      cosmo4[4] = desc->fr0;
+      cosmo4[5] = desc->h_over_c;
+      cosmo4[6] = desc->fr_size[is];
+    }
     ctx->ct_ampl[is] = sqrt(variance[is]);
     ctx->ct_tables[is].assign(npoints, 0.0);
     if (tables) {

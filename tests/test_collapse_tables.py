@@ -62,8 +62,8 @@ def relerr(a, b):
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
 
 
-def cosmo4(c):
-    return np.array([c.p.Omega0, c.p.OmegaLambda, c.OmegaRad, c.OmegaK])
+def cosmo4(c, fr0=0.0, fr_size=1.0):
+    return np.array([c.p.Omega0, c.p.OmegaLambda, c.OmegaRad, c.OmegaK, fr0, po.H_OVER_C, fr_size])     # SngCosmo of collapse_table.cuh
 
 
 # ---- oracle against the reference program's tables ----------------------------------------------------
@@ -146,6 +146,26 @@ def test_emulator_ell_sng_against_reference_and_oracle(lib, gold, cosmo):
         assert tab[i] == (1.0 / a if a > 0 else 0.0)
 
 
+def test_emulator_fr_force_modification_against_oracle(lib, cosmo):
+    """-DMOD_GRAV_FR: the f(R) force modification inside the ellipsoid equations (src/collapse_times.c:276-311)"""
+    c, lad = cosmo
+    D_in = c.GrowingMode(1.0 / 1.0e-5 - 1.0)
+    ism, fr0 = 4, 1.0e-5
+    size = float(lad.Radius[ism])
+    l1, l2, l3 = [a.ravel() for a in po.ct_table_lambdas(np.sqrt(lad.Variance[ism]))]
+    c_gr, c_fr = cosmo4(c), cosmo4(c, fr0, size)
+    changed = 0
+    for i in range(60, NPOINTS, 9973):
+        a_fr = lib.emu_ell_sng(l1[i], l2[i], l3[i], D_in, ptr(c_fr))
+        a_gr = lib.emu_ell_sng(l1[i], l2[i], l3[i], D_in, ptr(c_gr))
+        ref = po.ell_sng(l1[i], l2[i], l3[i], D_in, c.p.Omega0, c.p.OmegaLambda, c.OmegaRad, fr0, size)
+        assert abs(a_fr - ref) <= 1e-8 * max(abs(ref), 1e-3), i
+        if a_gr > 0:
+            assert 0 < a_fr <= a_gr * (1 + 1e-12)          # enhanced gravity collapses earlier
+            changed += a_fr < a_gr * (1 - 1e-6)
+    assert changed >= 3
+
+
 def device_table(lib, table, dv):
     knots = np.zeros(lib.emu_ct_knots_doubles(ND))
     lib.emu_ct_pack_knots(ptr(dv), ND, ptr(knots))
@@ -226,12 +246,15 @@ def emu_run(tmp_path_factory):
     return get
 
 
-@pytest.mark.parametrize("tag", ["tab", "sng"])
+@pytest.mark.parametrize("tag", ["tab", "sng", "fr"])
 def test_emulated_dropin_tabulated_collapse_times(tag, gold, emu_run):
+    if f"{tag}_header" not in gold.files:
+        pytest.skip(f"no golden outputs for the {tag} variant")
     tmp_path, log = emu_run(tag)
     assert "B200 path" in log and "Collapse times computed for interpolation" in log and "Pinocchio done!" in log
     sig = np.array([float(x) for x in re.findall(r"computed sigma:\s+([0-9.]+)", log)])
     assert np.array_equal(sig, gold[f"{tag}_sigma"])
+    ns = sig.size                                    # 9 radii; 10 with the f(R) growth
     # FmaxPDF, the four catalogues and the mass function: byte for byte the reference program's
     for key in gold.files:
         if key.startswith(f"{tag}_file_"):
@@ -239,11 +262,13 @@ def test_emulated_dropin_tabulated_collapse_times(tag, gold, emu_run):
             assert (tmp_path / name).read_bytes() == gold[key].tobytes(), name
     # the table file: same header, same zero pattern, values to the accuracy of the arithmetic
     header, tabs = read_cttable(tmp_path / "pinocchio.test.CTtable.out")
-    assert header == gold[f"{tag}_header"].tobytes() and tabs.shape == (9, NPOINTS)
+    assert header == gold[f"{tag}_header"].tobytes() and tabs.shape == (ns, NPOINTS)
     assert np.array_equal((tabs != 0).sum(axis=1), gold[f"{tag}_nonzero_per_radius"])
     e = relerr(tabs[:, gold[f"{tag}_table_idx"]], gold[f"{tag}_table"])
     if tag == "sng":
         assert e.max() < 1e-8                        # same rkf45 step sequence; 1.3e-9 over all 2.25 M points
+    elif tag == "fr":
+        assert e.max() < 1e-6                        # pow() in the force modification: 5.6e-8 over all points
     else:
         assert (e > 1e-9).sum() <= 20 and e.max() < 1e-3    # ell_classic near den = 0
 
@@ -272,3 +297,16 @@ def test_emulated_dropin_reads_collapse_table_file(gold, emu_run, tmp_path):
     r = subprocess.run([str(exe), "parameter_file"], cwd=b, capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 or "ERROR" in r.stdout
     assert "CT table not constructed for this collapse model" in r.stdout
+
+
+def test_emulated_dropin_only_compute_mode(emu_run, tmp_path):
+    """`pinocchio.x parameter_file 1` (src/pinocchio.c:97-125): only the collapse-time tables are computed and
+    written to CTtableFile -- initialize_collapse_times(ismooth, 1) of the shim, once per radius"""
+    exe = REF / "pinocchio_emu_tab.x"
+    a, _ = emu_run("tab")
+    (tmp_path / "parameter_file").write_text((a / "parameter_file").read_text().replace("CTtableFile none", "CTtableFile only.bin"))
+    (tmp_path / "outputs").write_bytes((a / "outputs").read_bytes())
+    r = subprocess.run([str(exe), "parameter_file", "1"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "only compute a table of collapse times" in r.stdout, (r.stdout + r.stderr)[-2000:]
+    assert (tmp_path / "only.bin").read_bytes() == (a / "pinocchio.test.CTtable.out").read_bytes()
+    assert not (tmp_path / "pinocchio.test.FmaxPDF.out").exists()
