@@ -185,7 +185,8 @@ def test_linked_dropin_program(tag, gold, tmp_path):
     if tag == "sng":
         assert e.max() < 1e-7
     elif tag == "fr":
-        assert e.max() < 1e-5                          # pow() of the force modification (5.6e-8 on the CPU)
+        # kinks of the force modification: see tests/test_collapse_tables.py
+        assert (e > 1e-6).mean() < 2e-3 and e.max() < 5e-2
     else:
         assert (e > 1e-9).sum() <= 30 and e.max() < 1e-3
     pdf = np.loadtxt(tmp_path / "pinocchio.test.FmaxPDF.out")[:, 2].astype(np.int64)
