@@ -1,6 +1,6 @@
 """Emulated multi-rank run of the engine's schedule (pinocchio_b200/csrc/engine.cu) on the CPU.
 
-Every rank's buffers are host arrays; the kernel bodies run under the pthread block emulator
+Every rank's buffers are host arrays; the kernel bodies run under the fiber block emulator
 (tests/host/emu.cpp), rank after rank, so the peer-memory scatter addressing of the x and y
 passes (the fused all-to-all) is exercised without a GPU.  The barriers of the real schedule
 become trivial because the emulated ranks execute each phase in turn.

@@ -1,18 +1,19 @@
 // CPU block emulator for the kernel bodies of pinocchio_b200/csrc/kernels.cuh.  TEST ONLY.
 //
-// Each "block" is executed by NT host threads that share a heap buffer as shared memory and a
-// pthread barrier as __syncthreads(); blocks run one after another.  The bodies are the very
+// Each "block" is executed by NT fibers of one host thread that share a heap buffer as shared memory;
+// __syncthreads() is a switch to the next fiber (see FiberLaunch); blocks run one after another.  The bodies are the very
 // same templates that k_*.cu instantiate for sm_100a, so index math, plans, twiddles, the
 // multi-rank scatter addressing and the collapse arithmetic are checked on a CPU-only box
 // against the oracle (tests/test_emulator.py).  Several ranks are emulated one after the other
 // in one process: "peer memory" is simply another host array.
 // This library is never loaded by the product (pinocchio_b200/), which has no CPU path.
-#include <pthread.h>
+#include <ucontext.h>
 
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -25,17 +26,33 @@ using namespace pinb;
 namespace {
 std::mutex g_atomic_mutex;
 
+// A block's "threads" are fibers of ONE host thread (ucontext), scheduled round-robin: a fiber runs until its
+// next barrier (or its end), then the next one runs; when the sweep is over every fiber stands at the same
+// barrier, which is thereby complete.  (A first version used one OS thread per emulated thread and a pthread
+// barrier: with a few hundred threads on a handful of cores two thirds of the run time of a 32^3 sweep went
+// into futex system calls.)  Blocks run one after another because the callers share one "shared memory" buffer.
+struct FiberLaunch {
+  ucontext_t main_ctx;
+  std::vector<ucontext_t> fibers;
+  std::vector<char*> stacks;
+  std::vector<char> done;
+  int cur = 0;
+  void yield_to_scheduler() { swapcontext(&fibers[cur], &main_ctx); }
+};
+thread_local FiberLaunch* g_launch = nullptr;
+thread_local std::function<void(int)>* g_fiber_body = nullptr;
+
 struct HostCtx {
   int tid_, bid_, nt_;
-  pthread_barrier_t* bar;
+  FiberLaunch* launch;
   int tid() const { return tid_; }
   int bid() const { return bid_; }
   int nthreads() const { return nt_; }
-  void sync() const { pthread_barrier_wait(bar); }
+  void sync() const { if (launch) launch->yield_to_scheduler(); }
   int warp_uniform(int v) const { return v; }
   // every line group calls sync_line the same number of times, so a block-wide barrier is a
   // valid (stronger) stand-in on the host
-  void sync_line(int, int) const { pthread_barrier_wait(bar); }
+  void sync_line(int, int) const { sync(); }
   void async_copy16(void* dst, const void* src) const { std::memcpy(dst, src, 16); }
   void async_wait() const {}
   void prefetch_l2(const void*) const {}
@@ -48,22 +65,51 @@ struct HostCtx {
   }
 };
 
+extern "C" void emu_fiber_trampoline(int t) {
+  (*g_fiber_body)(t);
+  g_launch->done[t] = 1;
+  // returning switches to uc_link (the scheduler)
+}
+
 template <class F> void run_blocks(long long nblocks, int nt, F body) {
-  pthread_barrier_t bar;
-  pthread_barrier_init(&bar, nullptr, nt);
-  std::vector<std::thread> th;
-  th.reserve(nt);
-  for (int t = 0; t < nt; t++)
-    th.emplace_back([&, t]() {
-      HostCtx ctx{t, 0, nt, &bar};
-      for (long long b = 0; b < nblocks; b++) {
-        ctx.bid_ = (int)b;
-        body(ctx);
-        pthread_barrier_wait(&bar);  // block boundary: shared memory is reused
+  constexpr size_t STACK = 256 * 1024;
+  FiberLaunch L;
+  L.fibers.resize(nt);
+  L.stacks.resize(nt);
+  L.done.assign(nt, 0);
+  for (int t = 0; t < nt; t++) L.stacks[t] = static_cast<char*>(std::malloc(STACK));
+  FiberLaunch* prev_launch = g_launch;
+  std::function<void(int)>* prev_body = g_fiber_body;
+  long long block = 0;
+  std::function<void(int)> fiber_body = [&](int t) {
+    HostCtx ctx{t, (int)block, nt, &L};
+    body(ctx);
+  };
+  g_launch = &L;
+  g_fiber_body = &fiber_body;
+  for (block = 0; block < nblocks; block++) {
+    for (int t = 0; t < nt; t++) {
+      getcontext(&L.fibers[t]);
+      L.fibers[t].uc_stack.ss_sp = L.stacks[t];
+      L.fibers[t].uc_stack.ss_size = STACK;
+      L.fibers[t].uc_link = &L.main_ctx;
+      makecontext(&L.fibers[t], (void (*)())emu_fiber_trampoline, 1, t);
+      L.done[t] = 0;
+    }
+    int remaining = nt;
+    while (remaining > 0) {
+      remaining = 0;
+      for (int t = 0; t < nt; t++) {
+        if (L.done[t]) continue;
+        L.cur = t;
+        swapcontext(&L.main_ctx, &L.fibers[t]);
+        if (!L.done[t]) remaining++;
       }
-    });
-  for (auto& x : th) x.join();
-  pthread_barrier_destroy(&bar);
+    }
+  }
+  g_launch = prev_launch;
+  g_fiber_body = prev_body;
+  for (int t = 0; t < nt; t++) std::free(L.stacks[t]);
 }
 
 Geom make_geom(int N, int rank, int nranks) {

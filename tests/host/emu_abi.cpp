@@ -1,5 +1,5 @@
 // TEST ONLY: the C ABI of include/pinb200.h implemented on HOST arrays with the kernel bodies of
-// kernels.cuh under the pthread block emulator (emu.cpp), single rank, grids 32 and 64.
+// kernels.cuh under the fiber block emulator (emu.cpp), single rank, grids 32 and 64.
 //
 // Purpose: run the linked drop-in -- the unchanged reference program + shim/fmax_b200.c -- end to
 // end on a machine WITHOUT a GPU (oracle/_ref/pinocchio_emu.x, tests/test_dropin_emulated.py), so

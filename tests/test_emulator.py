@@ -1,4 +1,4 @@
-"""CPU-only checks of the CUDA kernel bodies through the pthread block emulator.
+"""CPU-only checks of the CUDA kernel bodies through the fiber block emulator.
 
 The templates of pinocchio_b200/csrc/kernels.cuh are compiled for the host with g++ and run
 block by block (tests/host/emu.cpp); results are compared with the oracle.  This verifies the
