@@ -224,6 +224,28 @@ def run_b200(args):
                              "achieved_warp_inst_per_s": round(fp64_rate, -6), "peak_warp_inst_per_s": round(pipe_peak, -6),
                              "frac": round(fp64_rate / pipe_peak, 4), "sm_mhz": sm_mhz,
                              "source": "instruction count from the committed ncu capture (profiles/r01_ncu_zcollapse_1024_final.csv), time live"}
+    if world > 1:
+        # NVLink side of the metric: the only exchange is the transpose fused into the x pass as
+        # peer stores.  Per GPU and radius this design moves 3 x-transformed fields (the y pass makes the 6
+        # Hessian components from them), i.e. 3*16*Nc*(P-1)/P^2 bytes out and as many in;
+        # SURVEY's unfused model counts one transpose per FFT = 6 fields.  `achieved` divides the bytes a GPU
+        # sends by the whole x-pass kernel time (line FFTs and local stores included), so it is a lower bound
+        # on the link rate.  Combined roofline of a radius = max(HBM time, NVLink time), perfect overlap.
+        nvl_peak = 900.0
+        Ncs = float(N) * N * (N // 2 + 1)
+        sent = 3 * 16 * Ncs * (world - 1) / world ** 2
+        sent_survey = 6 * 16 * Ncs * (world - 1) / world ** 2
+        t_hbm = survey_rad / (peak * 1e9)
+        t_nvl, t_nvl_survey = sent / (nvl_peak * 1e9), sent_survey / (nvl_peak * 1e9)
+        roofline["nvlink"] = {"kernel": "xpass_kernel (transpose fused as peer stores)", "unit": "GB/s", "peak": nvl_peak,
+                              "peak_source": "nominal NVLink 5, per direction per GPU",
+                              "bytes_sent_per_gpu_per_radius": round(sent),
+                              "bytes_sent_per_gpu_per_radius_survey_model": round(sent_survey),
+                              "achieved": round(sent / (per_launch_ms["xpass_kernel"] * 1e-3) / 1e9, 1),
+                              "frac": round(sent / (per_launch_ms["xpass_kernel"] * 1e-3) / 1e9 / nvl_peak, 4),
+                              "per_radius_frac_of_combined_roofline": round(max(t_hbm, t_nvl) / (rad_ms * 1e-3), 4),
+                              "per_radius_frac_of_combined_roofline_survey_model": round(max(t_hbm, t_nvl_survey) / (rad_ms * 1e-3), 4),
+                              "per_radius_frac_of_summed_roofline": round((t_hbm + t_nvl) / (rad_ms * 1e-3), 4)}
     launches = int(tm1.kernel_launches - tm0.kernel_launches)
 
     # ---- e2e: host buffers through the reference-facing calls (H2D kdensity, D2H products[])
