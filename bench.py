@@ -297,6 +297,27 @@ def run_b200(args):
             e2e = {"value": round(cells / float(tw.item()) / 1e6, 2), "unit": "Mcells/s",
                    "h2d_bytes_per_step": int(N * N * (N // 2 + 1) * 16), "d2h_bytes_per_step": int(N ** 3 * 56),
                    "steps": ne, "ms_per_step": round(float(tw.item()) * 1e3, 2)}
+            # the e2e step is PCIe-bound: report the bare pinned-copy rates of this box beside it, so that
+            # (h2d_bytes / h2d_gbs + d2h_bytes / d2h_gbs + device step) can be compared with ms_per_step
+            try:
+                nb = int(min(stage.numel(), 1 << 30))
+                dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+                rates = {}
+                for name, (dst, src) in {"d2h_gbs": (stage[:nb], dbuf), "h2d_gbs": (dbuf, stage[:nb])}.items():
+                    dst.copy_(src, non_blocking=True)
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                    for _ in range(3):
+                        dst.copy_(src, non_blocking=True)
+                    ev1.record()
+                    ev1.synchronize()
+                    rates[name] = round(3 * nb / (ev0.elapsed_time(ev1) * 1e-3) / 1e9, 1)
+                del dbuf
+                e2e["pcie_pinned_copy"] = dict(rates, bytes=nb)
+                pcie_ms = (e2e["h2d_bytes_per_step"] / rates["h2d_gbs"] + e2e["d2h_bytes_per_step"] / rates["d2h_gbs"]) / world / 1e6
+                e2e["pcie_floor_ms_per_step"] = round(pcie_ms, 1)
+            except Exception as ex:  # noqa: BLE001
+                e2e["pcie_pinned_copy"] = {"error": str(ex)[:200]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
