@@ -95,6 +95,16 @@ def default_grid(ngpus: int) -> int:
     return 2048 if ngpus >= 8 else 1024
 
 
+def workload_config(N: int, world: int, S: int) -> dict:
+    """`config` of the JSON line, shared by both arms (the reference arm times a bounded sample of it)."""
+    lx = N // world
+    return {"workload": f"synthetic {N}^3 grid, full smoothing-radius sweep (S={S}) + 3LPT on {world} B200"
+                        + (f", x-slabs of {lx} planes, FFT transposes as peer stores over NVLink" if world > 1 else ""),
+            "grid": N, "nsmooth": S, "lpt_order": 3, "cosmology": "HMF_Validation (EH, Omega0=.25, h=.7, sigma8=.8)",
+            "seed": 486604, "parallelism": f"slab{world}" if world > 1 else "single GPU",
+            "l2_policy": f"inputs larger than L2 (each field {8 * N ** 3 / world / 1e9:.1f} GB per GPU)"}
+
+
 def algorithmic_bytes(N: int, S: int):
     """Per-kernel algorithmic HBM bytes of the radius loop and SURVEY 8d totals."""
     Nr = float(N) ** 3
@@ -374,11 +384,7 @@ def run_b200(args):
         out = {"metric": METRIC, "value": round(value, 2), "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
                "scaling": "weak" if world in (1, 8) else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": f"synthetic {N}^3 grid, full smoothing-radius sweep (S={S}) + 3LPT on {world} B200"
-                          + (f", x-slabs of {lx} planes, FFT transposes as peer stores over NVLink" if world > 1 else ""),
-                          "grid": N, "nsmooth": S, "lpt_order": 3, "cosmology": "HMF_Validation (EH, Omega0=.25, h=.7, sigma8=.8)",
-                          "seed": 486604, "parallelism": f"slab{world}" if world > 1 else "single GPU",
-                          "l2_policy": "inputs larger than L2 (each field 8.7 GB at 1024^3)"},
+               "config": workload_config(N, world, S),
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                "cpu_baseline": cpu_baseline, "fragment_handoff": handoff, "dropin_program": dropin, "collapse_tables": ctable, "checks": checks, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
         print(json.dumps(out))
@@ -442,9 +448,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Mcells/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"synthetic {args.grid or default_grid(world)}^3 grid, full smoothing-radius sweep (S={S}) + 3LPT"
-                      f" -- CPU arm timed on a bounded {N}^3 sample of it",
-                      "grid": N, "nsmooth": S, "lpt_order": 3},
+           # the B200 arm's config verbatim; the bounded sample this arm times is described in cpu_baseline.sample
+           "config": workload_config(args.grid or default_grid(world), world, S),
            "cpu_baseline": cb, "gpu_launches": 0,
            "e2e": {"value": cb["value"], "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
