@@ -49,6 +49,7 @@ int emu_ct_spline(const double* dv, int nd, int ncols, const double* table, doub
 int emu_ct_cells(int which, const double* in, long long n, const double* knots, const double* coef, int nd, int nxy, double ampl,
                  double bin_x, double* F);
 int emu_collapse_cells(const double* h6, long long n, const double* spline, int nspl, double* F);
+long long emu_collapsed_cells(const float* fmax, long long n, float f_last, unsigned int* idx_out);
 long long emu_spline_table_doubles(int n);
 int emu_pack_spline(const double* x, const double* y, int n, double* out);
 }
@@ -65,6 +66,8 @@ struct pinb200_ctx {
   int nspl = 0;
   std::vector<float> fmax, vel[12];
   std::vector<int> rmax;
+  std::vector<unsigned int> sorted_idx;  // pinb200_collapsed_cells keeps the ordered list for the sorted download
+  bool sorted_valid = false;
   bool kdens_valid = false, hessian_valid = false, kvec_valid = false;
   // TABULATED_CT: per radius the table and its spline records (32-byte aligned storage), shared knots
   bool ct_on = false;
@@ -416,18 +419,12 @@ extern "C" int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts) {
   return 0;
 }
 
-extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t cell_begin,
-                                         size_t ncells) {
-  if (!ctx || !products || !L) return 1;
-  if (ctx->fmax.empty() && ctx->vel[0].empty()) FAIL("products not computed");
-  if (cell_begin + ncells > ctx->ncells()) FAIL("cell range outside the local slab");
-  if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
-  // packed records first (as the device packer writes them), then the engine's copy-or-merge rule
-  std::vector<unsigned char> packed(ncells * L->stride, 0);
-  unsigned char* out = packed.data();
+// the device packer (pack_kernel): record i = cell cell_begin + i, or cell gather[cell_begin + i]
+static void pack_records(pinb200_ctx* ctx, const pinb200_product_layout* L, size_t cell_begin, size_t ncells, const unsigned int* gather,
+                         unsigned char* out) {
   const int off_vel[4] = {L->off_Vel, L->off_Vel_2LPT, L->off_Vel_3LPT_1, L->off_Vel_3LPT_2};
   for (size_t i = 0; i < ncells; i++) {
-    const size_t cell = cell_begin + i;
+    const size_t cell = gather ? (size_t)gather[cell_begin + i] : cell_begin + i;
     unsigned char* rec = out + i * L->stride;
     if (L->off_Rmax >= 0 && !ctx->rmax.empty()) *reinterpret_cast<int*>(rec + L->off_Rmax) = ctx->rmax[cell];
     auto put = [&](int off, float v) {
@@ -439,6 +436,16 @@ extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const
       if (off_vel[v] >= 0 && !ctx->vel[3 * v].empty())
         for (int a = 0; a < 3; a++) put(off_vel[v] + a * L->prodfloat_bytes, ctx->vel[3 * v + a][cell]);
   }
+}
+extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t cell_begin,
+                                         size_t ncells) {
+  if (!ctx || !products || !L) return 1;
+  if (ctx->fmax.empty() && ctx->vel[0].empty()) FAIL("products not computed");
+  if (cell_begin + ncells > ctx->ncells()) FAIL("cell range outside the local slab");
+  if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
+  // packed records first (as the device packer writes them), then the engine's copy-or-merge rule
+  std::vector<unsigned char> packed(ncells * L->stride, 0);
+  pack_records(ctx, L, cell_begin, ncells, nullptr, packed.data());
   const bool has_vel[4] = {!ctx->vel[0].empty(), !ctx->vel[3].empty(), !ctx->vel[6].empty(), !ctx->vel[9].empty()};
   const std::vector<pinb::MemberRange> members = pinb::product_members(*L, !ctx->fmax.empty(), has_vel);
   if (pinb::members_cover_record(members, L->stride)) std::memcpy(products, packed.data(), packed.size());
@@ -497,7 +504,33 @@ extern "C" int pinb200_collapse_cells(pinb200_ctx* ctx, int ismooth, const doubl
   const std::vector<double>& spl = (ismooth >= 0 && ismooth < (int)ctx->spline_r.size() && !ctx->spline_r[ismooth].empty()) ? ctx->spline_r[ismooth] : ctx->spline;
   return emu_collapse_cells(h6, (long long)n, spl.data(), ctx->nspl, F);
 }
-extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float, unsigned int*, size_t, size_t*) { FAIL("emulated ABI: not wired"); }
-extern "C" int pinb200_download_products_sorted(pinb200_ctx* ctx, void*, const pinb200_product_layout*, size_t, size_t) {
-  FAIL("emulated ABI: not wired");
+// engine.cu's argument checks and hand-over rules; the passes themselves are the kernel bodies of
+// sort_cells.cuh under the block emulator (emu_collapsed_cells in emu.cpp)
+extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned int* cell_index_out, size_t capacity, size_t* count) {
+  if (!ctx || !count) return 1;
+  if (ctx->fmax.empty()) FAIL("Fmax not computed");
+  if (!(f_last > 0.0f)) FAIL("f_last must be positive (F = 1 + z_collapse; the float keys are ordered by their bit patterns)");
+  std::vector<unsigned int> idx(ctx->ncells());
+  const long long n = emu_collapsed_cells(ctx->fmax.data(), (long long)ctx->ncells(), f_last, idx.data());
+  ctx->launches += 2;
+  *count = (size_t)n;
+  if (n > 0 && cell_index_out && capacity > 0) {
+    idx.resize((size_t)n);
+    std::memcpy(cell_index_out, idx.data(), sizeof(unsigned int) * (capacity < (size_t)n ? capacity : (size_t)n));
+    ctx->sorted_idx.swap(idx);
+    ctx->sorted_valid = true;
+    ctx->launches += 12;
+  }
+  return 0;
+}
+extern "C" int pinb200_download_products_sorted(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t first, size_t n) {
+  if (!ctx || !products || !L) return 1;
+  if (!ctx->sorted_valid) FAIL("no ordered cell list (call pinb200_collapsed_cells with an output array first)");
+  if (first + n > ctx->sorted_idx.size()) FAIL("record range outside the ordered cell list");
+  if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
+  if (n == 0) return 0;
+  std::memset(products, 0, n * L->stride);
+  pack_records(ctx, L, first, n, ctx->sorted_idx.data(), static_cast<unsigned char*>(products));
+  ctx->launches++;
+  return 0;
 }
