@@ -341,8 +341,8 @@ def run_b200(args):
             (ROOT / "gpurun_out").mkdir(exist_ok=True)
             (ROOT / "gpurun_out" / "bench_before_probes.json").write_text(json.dumps(
                 {"value": round(value, 2), "ms_per_step": round(ms_per_step, 3), "n_gpus": world, "grid": N, "e2e": e2e,
-                 "roofline": roofline, "clocks": clocks, "cpu_baseline": cpu_baseline, "checks": checks}))
-        except OSError:
+                 "roofline": roofline, "clocks": clocks, "cpu_baseline": cpu_baseline, "checks": checks}, default=float))
+        except (OSError, TypeError, ValueError):
             pass
 
     # ---- device-side fragmentation hand-off, in a fresh process after this one
