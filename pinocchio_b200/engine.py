@@ -134,6 +134,10 @@ def _dp(a: np.ndarray):
 # product_data for -DTWO_LPT -DTHREE_LPT, float products (src/pinocchio.h:233-259): 56 bytes
 PRODUCT_DTYPE_3LPT = np.dtype([("Rmax", "<i4"), ("Fmax", "<f4"), ("Vel", "<f4", 3), ("Vel_2LPT", "<f4", 3),
                                ("Vel_3LPT_1", "<f4", 3), ("Vel_3LPT_2", "<f4", 3)])
+# the same with -DDOUBLE_PRECISION_PRODUCTS (PRODFLOAT = double, src/pinocchio.h:225-231): Fmax at offset 8, 112 bytes
+PRODUCT_DTYPE_3LPT_DOUBLE = np.dtype({"names": ["Rmax", "Fmax", "Vel", "Vel_2LPT", "Vel_3LPT_1", "Vel_3LPT_2"],
+                                      "formats": ["<i4", "<f8", ("<f8", 3), ("<f8", 3), ("<f8", 3), ("<f8", 3)],
+                                      "offsets": [0, 8, 16, 40, 64, 88], "itemsize": 112})
 FIELD_INDEX = {"Fmax": 0, "Rmax": 1, "Vel": 2, "Vel_2LPT": 5, "Vel_3LPT_1": 8, "Vel_3LPT_2": 11}
 
 
@@ -342,7 +346,7 @@ class Pinocchio:
         out = np.zeros(n, dtype=dtype)
         f = dtype.fields
         off = lambda name: f[name][1] if name in f else -1
-        lay = ProductLayout(dtype.itemsize, 4, off("Rmax"), off("Fmax"), off("Vel"), off("Vel_2LPT"),
+        lay = ProductLayout(dtype.itemsize, dtype["Fmax"].itemsize, off("Rmax"), off("Fmax"), off("Vel"), off("Vel_2LPT"),
                             off("Vel_3LPT_1"), off("Vel_3LPT_2"))
         if n:
             self._ck(self.lib.pinb200_download_products_sorted(self.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(lay),
@@ -380,7 +384,7 @@ class Pinocchio:
         out = np.zeros(ncells, dtype=dtype)
         f = dtype.fields
         off = lambda n: f[n][1] if n in f else -1
-        lay = ProductLayout(dtype.itemsize, 4, off("Rmax"), off("Fmax"), off("Vel"), off("Vel_2LPT"),
+        lay = ProductLayout(dtype.itemsize, dtype["Fmax"].itemsize, off("Rmax"), off("Fmax"), off("Vel"), off("Vel_2LPT"),
                             off("Vel_3LPT_1"), off("Vel_3LPT_2"))
         self._ck(self.lib.pinb200_download_products(self.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(lay),
                                                     cell_begin, ncells))

@@ -39,7 +39,7 @@ def run32(exe, workdir, variant=""):
     text = (GOLDEN / "parameter_file").read_text()
     text = re.sub(r"(?m)^BoxSize\s+\S+", f"BoxSize                {N}", text)
     text = re.sub(r"(?m)^GridSize\s+\S+", f"GridSize               {N}", text)
-    if variant == "_sd":                                # 104-byte records + fields kept for the re-entry
+    if variant in ("_sd", "_dp"):                       # 104- / 112-byte records (+ fields kept for the re-entry)
         text = re.sub(r"(?m)^MaxMemPerParticle\s+\S+", "MaxMemPerParticle      400", text)
     (workdir / "parameter_file").write_text(text)
     (workdir / "outputs").write_bytes((GOLDEN / "outputs").read_bytes())
@@ -187,3 +187,34 @@ def test_emulated_dropin_dump_products_file_boundary(tmp_path):
         log = run32_args(reader, d, extra_param_lines=("ReadProductsFromDumps",))
         assert "B200 path" not in log or reader == EMU_X
         assert (d / "pinocchio.0.0000.test.catalog.out").read_bytes() == want
+
+
+# ---- -DDOUBLE_PRECISION_PRODUCTS: PRODFLOAT = double (src/pinocchio.h:225-231) ---------------------
+DP_REF, DP_EMU = REF_X.parent / "pinocchio_ref_dp.x", REF_X.parent / "pinocchio_emu_dp.x"
+
+
+@pytest.mark.skipif(not (DP_REF.exists() and DP_EMU.exists()), reason="DOUBLE_PRECISION_PRODUCTS variants not built")
+def test_emulated_dropin_double_precision_products(tmp_path):
+    """112-byte records of doubles (prodfloat_bytes = 8 in the packer).  The library keeps its products as
+    float SoA, so the doubles it delivers carry float precision (6e-8 relative, inside the 1e-6 contract)
+    while the reference's carry the full double: catalogues, mass functions and the FmaxPDF still come out
+    byte for byte, the merger histories to the printed digits but for rounding flips of the last one."""
+    a, b = tmp_path / "emu", tmp_path / "ref"
+    log = run32(DP_EMU, a, "_dp")
+    run32(DP_REF, b, "_dp")
+    assert "B200 path" in log
+    for z in ("0.0000", "0.5000", "1.0000", "2.0000"):
+        for kind in ("catalog", "mf"):
+            name = f"pinocchio.{z}.test.{kind}.out"
+            assert (a / name).read_bytes() == (b / name).read_bytes(), name
+    assert (a / "pinocchio.test.FmaxPDF.out").read_bytes() == (b / "pinocchio.test.FmaxPDF.out").read_bytes()
+    def branches(path):       # the nine-column branch lines (tree headers and counts have fewer)
+        rows = [l.split() for l in path.read_text().splitlines() if not l.startswith("#")]
+        return np.array([r for r in rows if len(r) == 9], dtype=np.float64)
+
+    ha, hb = branches(a / "pinocchio.test.histories.out"), branches(b / "pinocchio.test.histories.out")
+    assert ha.shape[0] > 100
+    assert ha.shape == hb.shape
+    assert np.array_equal(ha[:, :6], hb[:, :6])                 # tree structure: identical
+    assert np.abs(ha[:, 6:] - hb[:, 6:]).max() <= 1.5e-4        # redshifts printed with four decimals
+    assert (ha != hb).sum() <= 5

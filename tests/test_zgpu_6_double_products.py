@@ -1,0 +1,76 @@
+"""-DDOUBLE_PRECISION_PRODUCTS (PRODFLOAT = double, src/pinocchio.h:225-231): the packer's 8-byte path
+(112-byte product_data records, members merged one by one because the 4 bytes after Rmax are padding)
+and the linked drop-in built with that option against the reference built with it.  The library
+keeps its products as float SoA: the doubles it delivers are the floats widened.
+Needs a B200: -m gpu.  Written after round 1's GPU budget was spent; dry-run on the emulated ABI by
+tests/test_gpu_tests_dry_run.py.  (File name sorts after the other parity tests.)
+"""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_reference_full import GOLDEN, REF_X, load_catalog, match_fraction
+
+pytestmark = pytest.mark.gpu
+
+
+def test_double_records_are_the_float_records_widened():
+    from pinocchio_b200.cosmology import Cosmology, SmoothingLadder
+    from pinocchio_b200.engine import PRODUCT_DTYPE_3LPT, PRODUCT_DTYPE_3LPT_DOUBLE, Pinocchio, RunConfig
+    N = 64
+    p = Pinocchio(RunConfig(GridSize=N, BoxSize_htrue=N / 0.7, lpt_order=3), Cosmology(pk_norm_override=2.03146e7),
+                  smoothing=SmoothingLadder(np.array([6.0, 2.5, 0.0]), np.zeros(3)))
+    p.GenIC_large()
+    p.compute_fmax()
+    a = p.products(dtype=PRODUCT_DTYPE_3LPT)
+    b = p.products(dtype=PRODUCT_DTYPE_3LPT_DOUBLE)
+    assert a.dtype.itemsize == 56 and b.dtype.itemsize == 112
+    assert np.array_equal(a["Rmax"], b["Rmax"])
+    for name in ("Fmax", "Vel", "Vel_2LPT", "Vel_3LPT_1", "Vel_3LPT_2"):
+        assert np.array_equal(a[name].astype(np.float64), b[name]), name
+    # the padding after Rmax is not a member: the caller's bytes there survive the download
+    raw = np.full(1000 * 112, 0xAB, dtype=np.uint8)
+    out = raw.view(PRODUCT_DTYPE_3LPT_DOUBLE)
+    f = PRODUCT_DTYPE_3LPT_DOUBLE.fields
+    from pinocchio_b200.engine import ProductLayout
+    import ctypes
+    lay = ProductLayout(112, 8, f["Rmax"][1], f["Fmax"][1], f["Vel"][1], f["Vel_2LPT"][1], f["Vel_3LPT_1"][1], f["Vel_3LPT_2"][1])
+    p._ck(p.lib.pinb200_download_products(p.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(lay), 4321, 1000))
+    assert np.array_equal(out, b[4321:5321])
+    assert (raw.reshape(1000, 112)[:, 4:8] == 0xAB).all()
+    p.close()
+
+
+def test_linked_dropin_with_double_products(tmp_path):
+    bx, rx = REF_X.parent / "pinocchio_b200_dp.x", REF_X.parent / "pinocchio_ref_dp.x"
+    if not (bx.exists() and rx.exists()):
+        pytest.skip("DOUBLE_PRECISION_PRODUCTS variants not built (make -C oracle all)")
+
+    def run(exe, d, threads):
+        d.mkdir(parents=True, exist_ok=True)
+        text = (GOLDEN / "parameter_file").read_text()
+        text = re.sub(r"(?m)^BoxSize\s+\S+", "BoxSize                64", text)
+        text = re.sub(r"(?m)^GridSize\s+\S+", "GridSize               64", text)
+        text = re.sub(r"(?m)^MaxMemPerParticle\s+\S+", "MaxMemPerParticle      400", text)
+        (d / "parameter_file").write_text(text)
+        (d / "outputs").write_bytes((GOLDEN / "outputs").read_bytes())
+        r = subprocess.run([str(exe), "parameter_file"], cwd=d, capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        return r.stdout
+
+    da, db = tmp_path / "b200_dp", tmp_path / "ref_dp"
+    log_b = run(bx, da, 8)
+    run(rx, db, 16)
+    assert "B200 path" in log_b and "Products in double precision" in log_b
+    pa = np.loadtxt(da / "pinocchio.test.FmaxPDF.out")[:, 2].astype(np.int64)
+    pb = np.loadtxt(db / "pinocchio.test.FmaxPDF.out")[:, 2].astype(np.int64)
+    assert pa.sum() == pb.sum() == 64 ** 3 and np.abs(pa - pb).sum() <= 60
+    for z in ("0.0000", "2.0000"):
+        ia, na, _ = load_catalog(da / f"pinocchio.{z}.test.catalog.out")
+        ib, nb, _ = load_catalog(db / f"pinocchio.{z}.test.catalog.out")
+        assert abs(len(ia) - len(ib)) <= max(2, 0.005 * len(ib))
+        assert match_fraction(ia, na, ib, nb) > 0.99
