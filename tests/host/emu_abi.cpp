@@ -454,6 +454,8 @@ extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const
 }
 extern "C" int pinb200_download_field(pinb200_ctx* ctx, int which, void* dst) {
   if (!ctx || !dst || which < 0 || which > 13) return 1;
+  if (which == 0 ? ctx->fmax.empty() : which == 1 ? ctx->rmax.empty() : ctx->vel[which - 2].empty())
+    FAIL("requested field is not resident");  // as engine.cu: fields beyond lpt_order are never allocated
   if (which == 0) std::memcpy(dst, ctx->fmax.data(), ctx->fmax.size() * 4);
   else if (which == 1) std::memcpy(dst, ctx->rmax.data(), ctx->rmax.size() * 4);
   else std::memcpy(dst, ctx->vel[which - 2].data(), ctx->vel[which - 2].size() * 4);

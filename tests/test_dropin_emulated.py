@@ -218,3 +218,24 @@ def test_emulated_dropin_double_precision_products(tmp_path):
     assert np.array_equal(ha[:, :6], hb[:, :6])                 # tree structure: identical
     assert np.abs(ha[:, 6:] - hb[:, 6:]).max() <= 1.5e-4        # redshifts printed with four decimals
     assert (ha != hb).sum() <= 5
+
+
+# ---- builds without -DTHREE_LPT / -DTWO_LPT (src/Makefile:46-47): lpt_order 2 and 1 --------------
+@pytest.mark.parametrize("tag,record_bytes", [("lpt2", 32), ("zel", 20)])
+def test_emulated_dropin_lower_lpt_orders(tag, record_bytes, tmp_path):
+    """product_data shrinks to {Rmax, Fmax, Vel[, Vel_2LPT]}; the shim passes lpt_order 2 / 1 and the
+    layout of the smaller record.  Every output file byte for byte, DumpProducts records of the right size and equal but for float rounding flips."""
+    ref, emu = REF_X.parent / f"pinocchio_ref_{tag}.x", REF_X.parent / f"pinocchio_emu_{tag}.x"
+    if not (ref.exists() and emu.exists()):
+        pytest.skip(f"{ref.name} / {emu.name} not built")
+    a, b = tmp_path / "emu", tmp_path / "ref"
+    log = run32_args(emu, a, extra_param_lines=("DumpProducts",))
+    run32_args(ref, b, extra_param_lines=("DumpProducts",))
+    assert "B200 path" in log
+    names = sorted(f.name for f in b.glob("pinocchio.*"))
+    assert len(names) >= 11
+    for name in names:
+        assert (a / name).read_bytes() == (b / name).read_bytes(), name
+    assert (a / "DumpProducts" / "Task.0").stat().st_size == record_bytes * N ** 3
+    # raw float products: last-bit rounding flips in ~1e-4 of the values at most
+    assert differing_bytes(a / "DumpProducts" / "Task.0", b / "DumpProducts" / "Task.0") <= 2e-4 * record_bytes * N ** 3

@@ -1,9 +1,11 @@
-"""-DDOUBLE_PRECISION_PRODUCTS (PRODFLOAT = double, src/pinocchio.h:225-231): the packer's 8-byte path
-(112-byte product_data records, members merged one by one because the 4 bytes after Rmax are padding)
-and the linked drop-in built with that option against the reference built with it.  The library
-keeps its products as float SoA: the doubles it delivers are the floats widened.
+"""Compile-time variants of the reference that change what the path delivers (src/Makefile:46-68):
+builds without -DTHREE_LPT / -DTWO_LPT (lpt_order 2 and 1: 32- and 20-byte product_data) and
+-DDOUBLE_PRECISION_PRODUCTS (PRODFLOAT = double, src/pinocchio.h:225-231: the packer's 8-byte path,
+112-byte records, members merged one by one because the 4 bytes after Rmax are padding; the library
+keeps its products as float SoA, so the doubles it delivers are the floats widened).
 Needs a B200: -m gpu.  Written after round 1's GPU budget was spent; dry-run on the emulated ABI by
-tests/test_gpu_tests_dry_run.py.  (File name sorts after the other parity tests.)
+tests/test_gpu_tests_dry_run.py, the linked programs by tests/test_dropin_emulated.py.
+(File name sorts after the other parity tests.)
 """
 import os
 import re
@@ -44,10 +46,11 @@ def test_double_records_are_the_float_records_widened():
     p.close()
 
 
-def test_linked_dropin_with_double_products(tmp_path):
-    bx, rx = REF_X.parent / "pinocchio_b200_dp.x", REF_X.parent / "pinocchio_ref_dp.x"
+@pytest.mark.parametrize("tag", ["dp", "lpt2", "zel"])
+def test_linked_dropin_build_variants(tag, tmp_path):
+    bx, rx = REF_X.parent / f"pinocchio_b200_{tag}.x", REF_X.parent / f"pinocchio_ref_{tag}.x"
     if not (bx.exists() and rx.exists()):
-        pytest.skip("DOUBLE_PRECISION_PRODUCTS variants not built (make -C oracle all)")
+        pytest.skip(f"{tag} variants not built (make -C oracle all)")
 
     def run(exe, d, threads):
         d.mkdir(parents=True, exist_ok=True)
@@ -62,10 +65,10 @@ def test_linked_dropin_with_double_products(tmp_path):
         assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
         return r.stdout
 
-    da, db = tmp_path / "b200_dp", tmp_path / "ref_dp"
+    da, db = tmp_path / f"b200_{tag}", tmp_path / f"ref_{tag}"
     log_b = run(bx, da, 8)
     run(rx, db, 16)
-    assert "B200 path" in log_b and "Products in double precision" in log_b
+    assert "B200 path" in log_b and (tag != "dp" or "Products in double precision" in log_b)
     pa = np.loadtxt(da / "pinocchio.test.FmaxPDF.out")[:, 2].astype(np.int64)
     pb = np.loadtxt(db / "pinocchio.test.FmaxPDF.out")[:, 2].astype(np.int64)
     assert pa.sum() == pb.sum() == 64 ** 3 and np.abs(pa - pb).sum() <= 60
@@ -74,3 +77,41 @@ def test_linked_dropin_with_double_products(tmp_path):
         ib, nb, _ = load_catalog(db / f"pinocchio.{z}.test.catalog.out")
         assert abs(len(ia) - len(ib)) <= max(2, 0.005 * len(ib))
         assert match_fraction(ia, na, ib, nb) > 0.99
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_lower_lpt_orders(order):
+    """builds without -DTHREE_LPT (order 2) or without -DTWO_LPT (order 1): same Fmax / Rmax as the full
+    build, displacement fields up to that order against the oracle, the higher ones not delivered"""
+    from oracle import pinocchio_oracle as po
+    from pinocchio_b200.cosmology import Cosmology, SmoothingLadder
+    from pinocchio_b200.engine import Pinocchio, PinocchioError, RunConfig
+    N, radii = 64, [6.0, 2.5, 0.0]
+    cosmo = Cosmology(pk_norm_override=2.03146e7)
+    lad = SmoothingLadder(np.array(radii), np.zeros(3))
+    full = Pinocchio(RunConfig(GridSize=N, BoxSize_htrue=N / 0.7, lpt_order=3), cosmo, smoothing=lad)
+    full.GenIC_large()
+    full.compute_fmax()
+    kd = full.read_kdensity()
+    F3, R3, V3 = full.field("Fmax"), full.field("Rmax"), [full.field("Vel", a) for a in range(3)]
+    full.close()
+    p = Pinocchio(RunConfig(GridSize=N, BoxSize_htrue=N / 0.7, lpt_order=order), cosmo, smoothing=lad)
+    p.GenIC_large()
+    p.compute_fmax()
+    assert np.array_equal(p.field("Fmax"), F3) and np.array_equal(p.field("Rmax"), R3)
+    for a in range(3):
+        assert np.array_equal(p.field("Vel", a), V3[a])
+    ref = po.compute_fmax(kd, radii, 1.0 / 0.7, cosmo.InverseGrowingMode, growth=tuple(p.growth_rates(0.0)), lpt_order=order)
+    names = ["Vel"] + (["Vel_2LPT"] if order >= 2 else [])
+    for name in names:
+        for a in range(3):
+            scale = np.abs(ref[name][a]).max()
+            assert np.abs(p.field(name, a).astype(np.float64) - ref[name][a]).max() <= 1e-6 * scale, (name, a)
+    for name in (["Vel_2LPT"] if order < 2 else []) + ["Vel_3LPT_1", "Vel_3LPT_2"]:
+        with pytest.raises(PinocchioError):
+            p.field(name, 0)
+    prod = p.products()                      # 56-byte layout asked for: the absent members stay zero
+    assert np.array_equal(prod["Fmax"].reshape(N, N, N), F3)
+    assert not prod["Vel_3LPT_1"].any() and not prod["Vel_3LPT_2"].any()
+    assert prod["Vel_2LPT"].any() == (order >= 2)
+    p.close()
