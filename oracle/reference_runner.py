@@ -44,7 +44,7 @@ def build(force: bool = False) -> Path | None:
         # `all` also links oracle/_ref/libshim_host.so (the drop-in shim's host side) against the
         # in-tree libpinb200.so when that has been built
         target = "all" if (HERE.parent / "pinocchio_b200" / "libpinb200.so").exists() else "_ref/libpinocchio_ref.so"
-        r = subprocess.run(["make", "-C", str(HERE), target], capture_output=True, text=True)
+        r = subprocess.run(["make", "-j", "4", "-C", str(HERE), target], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"oracle/_ref build failed:\n{r.stdout}\n{r.stderr}")
     return LIB if LIB.exists() else None
