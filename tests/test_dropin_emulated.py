@@ -220,11 +220,12 @@ def test_emulated_dropin_double_precision_products(tmp_path):
     assert (ha != hb).sum() <= 5
 
 
-# ---- builds without -DTHREE_LPT / -DTWO_LPT (src/Makefile:46-47): lpt_order 2 and 1 --------------
-@pytest.mark.parametrize("tag,record_bytes", [("lpt2", 32), ("zel", 20)])
-def test_emulated_dropin_lower_lpt_orders(tag, record_bytes, tmp_path):
-    """product_data shrinks to {Rmax, Fmax, Vel[, Vel_2LPT]}; the shim passes lpt_order 2 / 1 and the
-    layout of the smaller record.  Every output file byte for byte, DumpProducts records of the right size and equal but for float rounding flips."""
+# ---- builds without -DTHREE_LPT / -DTWO_LPT (src/Makefile:46-47): lpt_order 2 and 1; and the shipped
+#      default without -DNORADIATION (src/Makefile:85: radiation in the host cosmology) -------------
+@pytest.mark.parametrize("tag,record_bytes", [("lpt2", 32), ("zel", 20), ("rad", 56)])
+def test_emulated_dropin_lower_lpt_orders_and_radiation(tag, record_bytes, tmp_path):
+    """lpt2 / zel: product_data shrinks to {Rmax, Fmax, Vel[, Vel_2LPT]}; the shim passes lpt_order 2 / 1 and the
+    layout of the smaller record.  rad: growth tables and inverse-growth spline of a cosmology with radiation.  Every output file byte for byte, DumpProducts records of the right size and equal but for float rounding flips."""
     ref, emu = REF_X.parent / f"pinocchio_ref_{tag}.x", REF_X.parent / f"pinocchio_emu_{tag}.x"
     if not (ref.exists() and emu.exists()):
         pytest.skip(f"{ref.name} / {emu.name} not built")

@@ -46,7 +46,7 @@ def test_double_records_are_the_float_records_widened():
     p.close()
 
 
-@pytest.mark.parametrize("tag", ["dp", "lpt2", "zel"])
+@pytest.mark.parametrize("tag", ["dp", "lpt2", "zel", "rad"])
 def test_linked_dropin_build_variants(tag, tmp_path):
     bx, rx = REF_X.parent / f"pinocchio_b200_{tag}.x", REF_X.parent / f"pinocchio_ref_{tag}.x"
     if not (bx.exists() and rx.exists()):
