@@ -125,6 +125,13 @@ int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_desc* desc, c
 int pinb200_download_collapse_table(pinb200_ctx* ctx, int ismooth, double* table);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
+/* Seed plane given by the caller instead of the spiral of gsl_rng_mt19937(RandomSeed) outputs
+ * (src/GenIC.c:840-855,953-973): seeds[j * GridSize + i] = seed of the (kx = i, ky = j) column, the
+ * whole plane on every rank, as SEEDTABLE of src/GenIC.c:229-235.  The shim uses it for the
+ * `MimicOldSeed` parameter-file option (internal.mimic_original_seedtable: the N-GenIC table of
+ * src/GenIC.c:493-537, copied column for column by copy_seeds_subregion, :990-1012).  Call before
+ * pinb200_genic; n must be GridSize^2. */
+int pinb200_set_seed_plane(pinb200_ctx* ctx, const unsigned int* seeds, size_t n);
 /* GenIC_large (src/GenIC.c:73-460): fills kdensity on the device. */
 int pinb200_genic(pinb200_ctx* ctx);
 /* Alternative to genic: supply / fetch kdensity as [x (N)][y_local (N/nranks)][N/2+1] complex128.

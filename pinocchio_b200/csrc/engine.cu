@@ -493,6 +493,15 @@ static PeerPtrs peers_of(pinb200_ctx* ctx, size_t arena_off) {
 static size_t arena_off_of(pinb200_ctx* ctx, const void* p) { return (size_t)((const unsigned char*)p - ctx->arena); }
 
 // ------------------------------------------------------------------------------------------
+extern "C" int pinb200_set_seed_plane(pinb200_ctx* ctx, const unsigned int* seeds, size_t n) {
+  if (!ctx || !seeds) return 1;
+  if (n != (size_t)ctx->g.N * ctx->g.N) FAIL("seed plane must hold GridSize^2 entries");
+  CK(cudaSetDevice(ctx->d.device));
+  if (!ctx->seeds) CK(cudaMalloc(&ctx->seeds, n * sizeof(unsigned int)));
+  CK(cudaMemcpy(ctx->seeds, seeds, n * sizeof(unsigned int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 extern "C" int pinb200_genic(pinb200_ctx* ctx) {
   if (!ctx) return 1;
   if (!ctx->pk) FAIL("power table not set (pinb200_set_power_table)");

@@ -64,7 +64,7 @@ class Timers(ctypes.Structure):
 ABI_SYMBOLS = [
     "pinb200_create", "pinb200_destroy", "pinb200_last_error", "pinb200_set_stream", "pinb200_synchronize",
     "pinb200_ipc_handle", "pinb200_connect",
-    "pinb200_set_power_table", "pinb200_set_smoothing", "pinb200_set_invgrow_spline", "pinb200_genic",
+    "pinb200_set_power_table", "pinb200_set_smoothing", "pinb200_set_invgrow_spline", "pinb200_set_seed_plane", "pinb200_genic",
     "pinb200_upload_kdensity", "pinb200_download_kdensity", "pinb200_fmax", "pinb200_displacements",
     "pinb200_displacements_scaledep", "pinb200_collapsed_cells", "pinb200_download_products_sorted",
     "pinb200_fmax_pdf", "pinb200_download_products", "pinb200_download_field", "pinb200_get_timers",
@@ -98,6 +98,7 @@ def load_library() -> ctypes.CDLL:
     lib.pinb200_set_power_table.argtypes = [ctypes.c_void_p, _PD, ctypes.c_size_t]
     lib.pinb200_set_smoothing.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
     lib.pinb200_set_invgrow_spline.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD, _PD, ctypes.c_int]
+    lib.pinb200_set_seed_plane.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint), ctypes.c_size_t]
     lib.pinb200_genic.argtypes = [ctypes.c_void_p]
     lib.pinb200_upload_kdensity.argtypes = [ctypes.c_void_p, _PD]
     lib.pinb200_download_kdensity.argtypes = [ctypes.c_void_p, _PD]
@@ -218,6 +219,12 @@ class Pinocchio:
         self._ck(self.lib.pinb200_synchronize(self.h))
 
     # -- reference entry points ---------------------------------------------------------------
+    def set_seed_plane(self, seeds: np.ndarray) -> None:
+        """SEEDTABLE[j * N + i] of src/GenIC.c:229-235 given by the caller (the `MimicOldSeed` table of
+        src/GenIC.c:493-537 in the shim); the default is the spiral table of generate_seeds_plane."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32).ravel()
+        self._ck(self.lib.pinb200_set_seed_plane(self.h, seeds.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), seeds.size))
+
     def GenIC_large(self, ThisGrid: int = 0) -> int:
         """src/GenIC.c:73-460."""
         self._ck(self.lib.pinb200_genic(self.h))

@@ -153,9 +153,40 @@ int finalize_fft(void)
 }
 
 /* ---- replaces src/GenIC.c:73-460 ------------------------------------------------------------ */
+/* `MimicOldSeed` (internal.mimic_original_seedtable, src/ReadParamfile.c:253-255): the seed of column
+ * (i, j) comes from the N-GenIC table of src/GenIC.c:493-537 instead of the spiral -- N/2 square rings
+ * grown inwards from the four corners of the plane, ring r of a corner being r cells of a column and
+ * then r + 1 cells of a row, each cell 0x7fffffff * gsl_rng_uniform(random_generator) with the host's
+ * own generator (ranlxd1, src/initialization.c:73) seeded with RandomSeed.  copy_seeds_subregion
+ * (src/GenIC.c:990-1012) hands the table over column for column, so it IS the seed plane. */
+static int mimic_old_seed_plane(void)
+{
+  const size_t n = (size_t)params.GridSize[0];
+  unsigned int *t = (unsigned int *)calloc(n * n, sizeof(unsigned int));
+  int rc;
+  if (t == NULL)
+    return 1;
+  gsl_rng_set(random_generator, params.RandomSeed);
+  for (size_t r = 0; r < n / 2; r++)
+    for (int corner = 0; corner < 4; corner++)
+    {
+      const int flip_col = corner & 1, flip_row = corner >> 1; /* (0,0), (N,0), (0,N), (N,N) */
+      const size_t ring_c = flip_col ? n - 1 - r : r, ring_r = flip_row ? n - 1 - r : r;
+      for (size_t m = 0; m < r; m++) /* the column piece of the ring */
+        t[(flip_row ? n - 1 - m : m) * n + ring_c] = 0x7fffffff * gsl_rng_uniform(random_generator);
+      for (size_t m = 0; m < r + 1; m++) /* the row piece, corner cell included */
+        t[ring_r * n + (flip_col ? n - 1 - m : m)] = 0x7fffffff * gsl_rng_uniform(random_generator);
+    }
+  rc = pinb200_set_seed_plane(pinb, t, n * n);
+  free(t);
+  return rc;
+}
+
 int GenIC_large(int ThisGrid)
 {
   (void)ThisGrid;
+  if (internal.mimic_original_seedtable && mimic_old_seed_plane())
+    return pinb_fail("GenIC_large (MimicOldSeed seed plane)");
   if (pinb200_genic(pinb))
     return pinb_fail("GenIC_large");
   return 0;

@@ -66,6 +66,7 @@ struct pinb200_ctx {
   int nspl = 0;
   std::vector<float> fmax, vel[12];
   std::vector<int> rmax;
+  std::vector<unsigned int> seed_plane;  // pinb200_set_seed_plane (empty: the spiral table)
   std::vector<unsigned int> sorted_idx;  // pinb200_collapsed_cells keeps the ordered list for the sorted download
   bool sorted_valid = false;
   bool kdens_valid = false, hessian_valid = false, kvec_valid = false;
@@ -139,11 +140,17 @@ extern "C" int pinb200_set_invgrow_spline(pinb200_ctx* ctx, int ismooth, const d
   return emu_pack_spline(x, y, n, t->data());
 }
 
+extern "C" int pinb200_set_seed_plane(pinb200_ctx* ctx, const unsigned int* seeds, size_t n) {
+  if (!ctx || !seeds) return 1;
+  if (n != (size_t)ctx->N * ctx->N) FAIL("seed plane must hold GridSize^2 entries");
+  ctx->seed_plane.assign(seeds, seeds + n);
+  return 0;
+}
 extern "C" int pinb200_genic(pinb200_ctx* ctx) {
   if (!ctx) return 1;
   if (ctx->pk.empty()) FAIL("power table not set");
-  std::vector<unsigned int> seeds;
-  pinb::build_seed_plane(ctx->N, ctx->d.random_seed, seeds);
+  std::vector<unsigned int> seeds = ctx->seed_plane;
+  if (seeds.empty()) pinb::build_seed_plane(ctx->N, ctx->d.random_seed, seeds);
   std::fill(ctx->kdens.begin(), ctx->kdens.end(), cplx(0.0, 0.0));
   if (emu_genic(ctx->N, 0, 1, seeds.data(), ctx->pk.data(), ctx->d.box_size, ctx->d.fixed_ic, ctx->d.paired_ic, dp(ctx->kdens)))
     FAIL("genic");

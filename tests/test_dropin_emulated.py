@@ -240,3 +240,33 @@ def test_emulated_dropin_lower_lpt_orders_and_radiation(tag, record_bytes, tmp_p
     assert (a / "DumpProducts" / "Task.0").stat().st_size == record_bytes * N ** 3
     # raw float products: last-bit rounding flips in ~1e-4 of the values at most
     assert differing_bytes(a / "DumpProducts" / "Task.0", b / "DumpProducts" / "Task.0") <= 2e-4 * record_bytes * N ** 3
+
+
+# ---- parameter-file options that reach the path (src/ReadParamfile.c:207-255) ---------------------
+@pytest.mark.parametrize("lines", [("FixedIC", "PairedIC"), ("MimicOldSeed",)], ids=["fixed_paired", "mimic_old_seed"])
+def test_emulated_dropin_parameter_file_options(lines, tmp_path):
+    """FixedIC / PairedIC (amplitudes fixed to the spectrum, phases shifted by pi, src/GenIC.c:370-376) travel
+    in pinb200_desc; MimicOldSeed (internal.mimic_original_seedtable) replaces the spiral seed plane by the
+    N-GenIC table of src/GenIC.c:493-537, which the shim builds with the host's own generator and hands
+    over through pinb200_set_seed_plane.  Each option is a different realisation, reproduced byte for byte."""
+    a, b, c = tmp_path / "emu", tmp_path / "ref", tmp_path / "ref_plain"
+    run32_args(EMU_X, a, extra_param_lines=lines)
+    run32_args(REF_X, b, extra_param_lines=lines)
+    run32_args(REF_X, c)
+    names = sorted(f.name for f in b.glob("pinocchio.*"))
+    assert len(names) >= 11
+    for name in names:
+        assert (a / name).read_bytes() == (b / name).read_bytes(), name
+    assert (b / "pinocchio.0.0000.test.catalog.out").read_bytes() != (c / "pinocchio.0.0000.test.catalog.out").read_bytes()
+
+
+def test_emulated_dropin_ignores_use_transposed_fft(tmp_path):
+    """UseTransposedFFT only chooses PFFT's internal k-space layout (src/fmax-pfft.c:92,159-181,271); the
+    real-space results are the same, so the drop-in accepts the option and delivers the same run.  (The
+    one-task PFFT stand-in under the reference program does not provide transposed layouts, hence the
+    comparison with the drop-in's own run without the option.)"""
+    a, b = tmp_path / "transposed", tmp_path / "plain"
+    run32_args(EMU_X, a, extra_param_lines=("UseTransposedFFT",))
+    run32_args(EMU_X, b)
+    for name in sorted(f.name for f in b.glob("pinocchio.*")):
+        assert (a / name).read_bytes() == (b / name).read_bytes(), name

@@ -24,7 +24,7 @@ pytestmark = pytest.mark.skipif(not EMU_ABI.exists(), reason="oracle/_ref/libpin
     # collapse-time tables without the linked programs (those run in test_collapse_tables.py)
     ("tests/test_zgpu_5_collapse_tables.py", "not linked", 4),
     # -DDOUBLE_PRECISION_PRODUCTS records and lpt_order 1 / 2 through the ABI (the linked programs run in test_dropin_emulated.py)
-    ("tests/test_zgpu_6_build_variants.py", "widened or lower_lpt", 3),
+    ("tests/test_zgpu_6_build_variants.py", "widened or lower_lpt or seed_plane", 4),
 ])
 def test_late_gpu_tests_pass_on_the_emulated_abi(target, select, npass):
     env = dict(os.environ, PINB200_LIB=str(EMU_ABI))

@@ -115,3 +115,32 @@ def test_lower_lpt_orders(order):
     assert not prod["Vel_3LPT_1"].any() and not prod["Vel_3LPT_2"].any()
     assert prod["Vel_2LPT"].any() == (order >= 2)
     p.close()
+
+
+def test_seed_plane_given_by_the_caller():
+    """pinb200_set_seed_plane (the MimicOldSeed hand-over of the shim): the spiral table given explicitly
+    reproduces the default delta_k bit for bit; another table gives another realisation; wrong sizes are refused"""
+    from oracle import pinocchio_oracle as po
+    from pinocchio_b200.cosmology import Cosmology, SmoothingLadder
+    from pinocchio_b200.engine import Pinocchio, PinocchioError, RunConfig
+    N = 64
+    cosmo = Cosmology(pk_norm_override=2.03146e7)
+
+    def make():
+        return Pinocchio(RunConfig(GridSize=N, BoxSize_htrue=N / 0.7, lpt_order=3), cosmo,
+                         smoothing=SmoothingLadder(np.array([2.5, 0.0]), np.zeros(2)))
+    p = make()
+    p.GenIC_large()
+    kd0 = p.read_kdensity()
+    p.close()
+    table = np.asarray(po.seed_table(N, 486604), dtype=np.uint32).reshape(N, N)
+    p = make()
+    with pytest.raises(PinocchioError):
+        p.set_seed_plane(table[:-1])
+    p.set_seed_plane(table)
+    p.GenIC_large()
+    assert np.array_equal(p.read_kdensity(), kd0)
+    p.set_seed_plane(table[::-1].copy())
+    p.GenIC_large()
+    assert not np.array_equal(p.read_kdensity(), kd0)
+    p.close()
