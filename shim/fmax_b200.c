@@ -185,6 +185,9 @@ static int mimic_old_seed_plane(void)
 int GenIC_large(int ThisGrid)
 {
   (void)ThisGrid;
+  if ((internal.dump_seedplane || internal.dump_kdensity) && !ThisTask)
+    printf("[B200 path] DumpSeedPlane / DumpKDensity are debugging dumps of the replaced src/GenIC.c:152,451 "
+           "and src/fmax-pfft.c:669-707: not written\n");
   if (internal.mimic_original_seedtable && mimic_old_seed_plane())
     return pinb_fail("GenIC_large (MimicOldSeed seed plane)");
   if (pinb200_genic(pinb))
