@@ -141,6 +141,32 @@ def seed_table(nmesh: int, random_seed: int) -> np.ndarray:
     return out[m - 1].astype(np.uint32)
 
 
+def seed_table_old(nmesh: int, random_seed: int) -> np.ndarray:
+    """The `MimicOldSeed` seed plane (internal.mimic_original_seedtable): OLDSEEDTABLE of
+    src/GenIC.c:493-537, which copy_seeds_subregion (:990-1012) hands over column for column.
+
+    N/2 square rings grown inwards from the four corners (0,0), (N,0), (0,N), (N,N) in that order;
+    ring r of a corner = r cells of the column at distance r, then r + 1 cells of the row at distance
+    r (corner cell last); each cell (unsigned)(0x7fffffff * gsl_rng_uniform) of ONE ranlxd1 stream
+    seeded with RandomSeed.  Returned with shape [j, i] like seed_table()."""
+    n = nmesh
+    rng = RanLxd1([random_seed])
+    t = np.zeros((n, n), dtype=np.uint32)
+
+    def draw():
+        return np.uint32(int(float(0x7FFFFFFF) * float(rng.get_double()[0])))
+
+    for r in range(n // 2):
+        for flip_row, flip_col in ((0, 0), (0, 1), (1, 0), (1, 1)):
+            col = n - 1 - r if flip_col else r
+            row = n - 1 - r if flip_row else r
+            for m in range(r):
+                t[n - 1 - m if flip_row else m, col] = draw()
+            for m in range(r + 1):
+                t[row, n - 1 - m if flip_col else m] = draw()
+    return t
+
+
 # ======================================================================================
 # GenIC (src/GenIC.c:73-460)
 # ======================================================================================

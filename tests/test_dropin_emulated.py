@@ -270,3 +270,18 @@ def test_emulated_dropin_ignores_use_transposed_fft(tmp_path):
     run32_args(EMU_X, b)
     for name in sorted(f.name for f in b.glob("pinocchio.*")):
         assert (a / name).read_bytes() == (b / name).read_bytes(), name
+
+
+@pytest.mark.parametrize("mimic", [False, True], ids=["spiral", "mimic_old_seed"])
+def test_oracle_seed_planes_against_the_reference_dump(mimic, tmp_path):
+    """`DumpSeedPlane 1` makes the reference program write SEEDTABLE (src/GenIC.c:152,1144-1200): pins the
+    oracle's spiral table (seed_table) and its N-GenIC table (seed_table_old) entry by entry"""
+    from oracle import pinocchio_oracle as po
+    lines = ("DumpSeedPlane 1",) + (("MimicOldSeed",) if mimic else ())
+    run32_args(REF_X, tmp_path, extra_param_lines=lines)
+    a = np.loadtxt(tmp_path / f"seed_plane.Ng_{N}_Nt_1.dat", dtype=np.int64)
+    assert a.shape == (N * N, 4) and np.array_equal(a[:, 2], a[:, 1] * N + a[:, 0])
+    table = np.zeros((N, N), dtype=np.uint32)
+    table[a[:, 1], a[:, 0]] = a[:, 3]
+    want = po.seed_table_old(N, 486604) if mimic else po.seed_table(N, 486604)
+    assert np.array_equal(table, want)

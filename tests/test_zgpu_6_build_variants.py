@@ -140,7 +140,7 @@ def test_seed_plane_given_by_the_caller():
     p.set_seed_plane(table)
     p.GenIC_large()
     assert np.array_equal(p.read_kdensity(), kd0)
-    p.set_seed_plane(table[::-1].copy())
+    p.set_seed_plane(po.seed_table_old(N, 486604))                 # the MimicOldSeed plane: another realisation
     p.GenIC_large()
     assert not np.array_equal(p.read_kdensity(), kd0)
     p.close()
