@@ -334,6 +334,12 @@ int compute_fmax(void)
  * Layouts: real [GSlocal_x][N][N], half-complex [N][GSlocal_k_y][N/2+1] (set_one_grid above). */
 void write_in_cvector(int ThisGrid, double *restrict vector)
 {
+  /* GenIC_large leaves delta_k on the device; the reference's leaves it in the host array kdensity[]
+   * (src/GenIC.c:384).  The only reader of that array outside the replaced files is special mode 2
+   * (src/pinocchio.c:136-168: write_in_cvector(kdensity) -> reverse_transform -> write_density), so it
+   * is fetched here, when somebody asks for it, instead of after every GenIC. */
+  if (vector == (double *)kdensity[ThisGrid] && pinb200_download_kdensity(pinb, vector))
+    pinb_fail("write_in_cvector (kdensity download)");
   memcpy(cvector_fft[ThisGrid], vector, (size_t)MyGrids[ThisGrid].total_local_size_fft * sizeof(double));
 }
 

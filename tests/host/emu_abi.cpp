@@ -480,9 +480,37 @@ extern "C" int pinb200_download_kvector(pinb200_ctx* ctx, int which, double* kve
   download_c(ctx, ctx->KV[which], kvec);
   return 0;
 }
-// entry points the HMF-style run never reaches through the shim
-extern "C" int pinb200_fft_r2c(pinb200_ctx* ctx, const double*, double*) { FAIL("emulated ABI: not wired"); }
-extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double*, double*) { FAIL("emulated ABI: not wired"); }
+// one 3-D transform of a host work vector, engine.cu's schedule (forward_transform / reverse_transform of the shim:
+// special mode 2 of src/pinocchio.c:136-168 writes the linear density field through them)
+extern "C" int pinb200_fft_c2r(pinb200_ctx* ctx, const double* cplx_in, double* real_out) {
+  if (!ctx || !cplx_in || !real_out) return 1;
+  const int N = ctx->N, M = ctx->M, P = ctx->P;
+  const double norm = 1.0 / ((double)N * N * N);
+  ctx->hessian_valid = false;
+  std::fill(ctx->A[0].begin(), ctx->A[0].end(), cplx(0.0, 0.0));
+  for (size_t r = 0; r < (size_t)N * N; r++) std::memcpy(&ctx->A[0][r * P], cplx_in + 2 * r * (M + 1), sizeof(cplx) * (M + 1));
+  std::vector<cplx>* xdst[3] = {&ctx->A[1], nullptr, nullptr};
+  if (xpass_inv(ctx, ctx->A[0], xdst, 1, nullptr, 0, 0, norm, 1)) FAIL("x pass");
+  std::vector<cplx>* ysrc[3] = {&ctx->A[1], nullptr, nullptr};
+  std::vector<cplx>* ydst[6] = {&ctx->A[2], nullptr, nullptr, nullptr, nullptr, nullptr};
+  const int job[3] = {0, 0, 0};
+  if (ypass_inv(ctx, ysrc, ydst, job, 1, 1)) FAIL("y pass");
+  double* zsrc[1] = {dp(ctx->A[2])};
+  const int kz[1] = {0};
+  ctx->launches++;
+  if (emu_zpass_out(N, 1, 1, zsrc, kz, 1, nullptr, 0, zsrc, nullptr, nullptr, nullptr, nullptr, dp(ctx->tw))) FAIL("z pass");
+  for (size_t r = 0; r < (size_t)N * N; r++) std::memcpy(real_out + r * N, dp(ctx->A[2]) + r * 2 * P, sizeof(double) * N);
+  return 0;
+}
+extern "C" int pinb200_fft_r2c(pinb200_ctx* ctx, const double* real_in, double* cplx_out) {
+  if (!ctx || !real_in || !cplx_out) return 1;
+  const int N = ctx->N, P = ctx->P;
+  std::fill(ctx->A[0].begin(), ctx->A[0].end(), cplx(0.0, 0.0));
+  for (size_t r = 0; r < (size_t)N * N; r++) std::memcpy(dp(ctx->A[0]) + r * 2 * P, real_in + r * N, sizeof(double) * N);
+  if (r2c(ctx, ctx->A[0], ctx->A[1])) FAIL("r2c");
+  download_c(ctx, ctx->A[1], cplx_out);
+  return 0;
+}
 // compute_second_derivatives(R): x/y passes, then the plain c2r z pass in place (engine: zpass_out mode 0)
 extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, double* hessian_out) {
   if (!ctx) return 1;

@@ -285,3 +285,20 @@ def test_oracle_seed_planes_against_the_reference_dump(mimic, tmp_path):
     table[a[:, 1], a[:, 0]] = a[:, 3]
     want = po.seed_table_old(N, 486604) if mimic else po.seed_table(N, 486604)
     assert np.array_equal(table, want)
+
+
+@needs_snap
+def test_emulated_dropin_special_mode_2_density_snapshot(tmp_path):
+    """`pinocchio.x parameter_file 2` (src/pinocchio.c:136-168): write_in_cvector(kdensity) -> reverse_transform ->
+    write_from_rvector -> write_density.  delta_k lives on the device: the shim fetches it into the host
+    kdensity[] when write_in_cvector is handed that array, and reverse_transform is pinb200_fft_c2r."""
+    a, b = tmp_path / "emu", tmp_path / "ref"
+    log = run32_args(SNAP_EMU, a, args=("2",))
+    run32_args(SNAP_REF, b, args=("2",))
+    assert "only writes the linear density field" in log
+    fa, fb = a / "pinocchio.test.density0.out", b / "pinocchio.test.density0.out"
+    assert fa.stat().st_size == fb.stat().st_size > 4 * N ** 3
+    da = np.frombuffer(fa.read_bytes()[-(4 * N ** 3 + 4):-4], dtype=np.float32)
+    db = np.frombuffer(fb.read_bytes()[-(4 * N ** 3 + 4):-4], dtype=np.float32)
+    assert np.abs(db).max() > 0 and np.abs(da.astype(np.float64) - db).max() <= 1e-6 * np.abs(db).max()
+    assert differing_bytes(fa, fb) <= 2e-4 * fa.stat().st_size
