@@ -302,3 +302,21 @@ def test_emulated_dropin_special_mode_2_density_snapshot(tmp_path):
     db = np.frombuffer(fb.read_bytes()[-(4 * N ** 3 + 4):-4], dtype=np.float32)
     assert np.abs(db).max() > 0 and np.abs(da.astype(np.float64) - db).max() <= 1e-6 * np.abs(db).max()
     assert differing_bytes(fa, fb) <= 2e-4 * fa.stat().st_size
+
+
+def test_emulated_dropin_refuses_an_unsupported_grid_loudly(tmp_path):
+    """error convention of the boundary: a non-zero return of the C ABI reaches the caller, which
+    prints and aborts (src/pinocchio.c:229-230,259-263); the library accepts powers of two only (the
+    emulated ABI 32 and 64), the reference any FFTW size"""
+    import os
+    import subprocess
+    text = (GOLDEN / "parameter_file").read_text()
+    text = re.sub(r"(?m)^BoxSize\s+\S+", "BoxSize                48", text)
+    text = re.sub(r"(?m)^GridSize\s+\S+", "GridSize               48", text)
+    (tmp_path / "parameter_file").write_text(text)
+    (tmp_path / "outputs").write_bytes((GOLDEN / "outputs").read_bytes())
+    r = subprocess.run([str(EMU_X), "parameter_file"], cwd=tmp_path, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode != 0
+    assert "pinb200_create" in r.stdout + r.stderr and "aborting" in r.stdout + r.stderr
+    assert not list(tmp_path.glob("pinocchio.*.catalog.out"))
