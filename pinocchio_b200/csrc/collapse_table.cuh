@@ -360,14 +360,16 @@ PINB_HD double ct_interpolate(const CTView& v, double l1, double l2, double l3) 
 // (the eigenvalue block is repeated here rather than shared so that the tuned ELL_CLASSIC kernel's
 // code generation is untouched)
 PINB_HD void hessian_eigenvalues(const double* d, double& hi, double& mid, double& lo, bool& bad) {
-  const double mu1 = d[0] + d[1] + d[2];
-  const double mu1_2 = mu1 * mu1;
+  // mu1, mu2 and q rounded operation by operation (mul_rn / add_rn): `q == 0.` must hold for an
+  // isotropic tensor exactly as in the reference's unfused arithmetic (:694-724)
+  const double mu1 = add_rn(add_rn(d[0], d[1]), d[2]);
+  const double mu1_2 = mul_rn(mu1, mu1);
   double mu2 = 0.5 * mu1_2;
-  mu2 -= 0.5 * (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-  const double add0 = d[3] * d[3], add1 = d[4] * d[4], add2 = d[5] * d[5];
-  mu2 -= add0 + add1 + add2;
+  mu2 = add_rn(mu2, -0.5 * add_rn(add_rn(mul_rn(d[0], d[0]), mul_rn(d[1], d[1])), mul_rn(d[2], d[2])));
+  const double add0 = mul_rn(d[3], d[3]), add1 = mul_rn(d[4], d[4]), add2 = mul_rn(d[5], d[5]);
+  mu2 = add_rn(mu2, -add_rn(add_rn(add0, add1), add2));
   const double mu3 = d[0] * d[1] * d[2] + 2. * d[3] * d[4] * d[5] - d[0] * add2 - d[1] * add1 - d[2] * add0;
-  const double q = (mu1_2 - 3.0 * mu2) * mc(MC_1_9);
+  const double q = add_rn(mu1_2, -mul_rn(3.0, mu2)) * mc(MC_1_9);
   const double r = -(2. * mu1_2 * mu1 - 9.0 * mu1 * mu2 + 27.0 * mu3) * mc(MC_1_54);
   const bool diag = (q == 0.);
   bad = !diag && (q * q * q < r * r || q < 0.0);

@@ -17,6 +17,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,6 +50,7 @@ struct pinb200_ctx {
   bool connected = false;
   size_t off_flags = 0, off_kdens = 0, off_A[3] = {0, 0, 0}, off_KV[3] = {0, 0, 0};
   unsigned long long epoch = 0;
+  double barrier_timeout_s = 600.0;
   int* d_error = nullptr;
 
   // tables
@@ -80,6 +82,7 @@ struct pinb200_ctx {
   double2* B[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // y-pass outputs; Hessian of the last radius
   double2* D[3] = {nullptr, nullptr, nullptr};    // y-pass outputs of the displacement stage
   bool kdens_valid = false, hessian_valid = false, kvec_valid = false;
+  bool kdens_has_nyq = false;  // uploaded fields may carry power on the kz = N/2 plane; GenIC never fills it (src/GenIC.c:280)
   float* fmax = nullptr;
   int* rmax = nullptr;
   float* vel[12] = {nullptr};
@@ -208,6 +211,10 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
   for (int i = 0; i < nkv; i++) ctx->KV[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_KV[i]);
   ctx->peer_arena[desc->rank] = ctx->arena;
   ctx->connected = (P == 1);
+  if (const char* t = getenv("PINB200_BARRIER_TIMEOUT_S")) {
+    const double v = atof(t);
+    if (v > 0.0) ctx->barrier_timeout_s = v;
+  }
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
   *out = ctx;
@@ -481,6 +488,7 @@ static int peer_barrier(pinb200_ctx* ctx) {
   b.nranks = ctx->P;
   b.epoch = ++ctx->epoch;
   b.error = ctx->d_error;
+  b.timeout_ns = (unsigned long long)(ctx->barrier_timeout_s * 1e9);
   LAUNCH(launch_barrier(b, ctx->stream));
   return 0;
 }
@@ -530,6 +538,7 @@ extern "C" int pinb200_genic(pinb200_ctx* ctx) {
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   ctx->tm.dens += ms * 1e-3;
   ctx->kdens_valid = true;
+  ctx->kdens_has_nyq = false;
   return 0;
 }
 
@@ -572,8 +581,24 @@ extern "C" int pinb200_upload_kdensity(pinb200_ctx* ctx, const double* kd) {
   if (!ctx || !kd) return 1;
   CK(cudaSetDevice(ctx->d.device));
   TRY(upload_cplx(ctx, kd, ctx->kdens));
+  // a field that did not come from pinb200_genic (forward_transform output, white noise) may have power at
+  // kz = N/2: the Hessian and Zel'dovich passes then process the Nyquist tile as compute_derivative does
+  // for idz = N/2 (src/fmax-pfft.c:306-397).  On one rank the plane is probed (a re-uploaded GenIC field
+  // keeps the cheaper schedule); on several ranks the decision must be the same everywhere, so an uploaded
+  // field is always treated as carrying it.
+  int nyq = 1;
+  if (ctx->P == 1) {
+    int* flag = nullptr;
+    TRY(dev_alloc(ctx, &flag, (size_t)1));
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    LAUNCH(launch_nyq_probe(ctx->kdens, (size_t)ctx->g.N * ctx->g.ly, ctx->g.P, ctx->g.M, flag, ctx->stream));
+    CK(cudaMemcpyAsync(&nyq, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    TRY(dev_free(ctx, &flag));
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->kdens_valid = true;
+  ctx->kdens_has_nyq = (nyq != 0);
   return 0;
 }
 
@@ -696,15 +721,24 @@ static int ensure_products(pinb200_ctx* ctx) {
 
 // Hessian passes for one radius: fills B[0..5] (half-complex, after x and y passes).
 // slot order xx,yy,zz,xy,xz,yz (src/fmax.c:239)
+// The k = 0 constant of delta_k (the same for every radius: the window is 1 at k = 0) is read from rank 0
+// through the peer mapping.  The barrier orders the read after rank 0's GenIC / upload on ITS stream:
+// those calls end with a local synchronisation only, so without it a rank > 0 could read a stale value.
+static int hessian_dc(pinb200_ctx* ctx) {
+  const Geom& g = ctx->g;
+  TRY(peer_barrier(ctx));
+  TRY(run_dc(ctx, ctx->kdens, 1.0 / ((double)g.N * g.N * g.N), 0));
+  return 0;
+}
 static int hessian_xy(pinb200_ctx* ctx, double rsmooth, cudaEvent_t mid_event = nullptr) {
   const Geom& g = ctx->g;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
+  const bool nyq = ctx->kdens_has_nyq;
   LAUNCH(launch_gauss_table(ctx->gauss, g.M, g.knorm, rsmooth, ctx->stream));
-  TRY(run_dc(ctx, ctx->kdens, norm, 0));
-  TRY(run_xpass_inv(ctx, ctx->kdens, ctx->A, 0x7, true, 1, 0, norm, false));
+  TRY(run_xpass_inv(ctx, ctx->kdens, ctx->A, 0x7, true, 1, 0, norm, nyq));
   if (mid_event) CK(cudaEventRecord(mid_event, ctx->stream));
   static const YJob jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
-  TRY(run_ypass_inv(ctx, ctx->A, ctx->B, jobs, 6, false));
+  TRY(run_ypass_inv(ctx, ctx->A, ctx->B, jobs, 6, nyq));
   return 0;
 }
 static const int kHessKzPow[6] = {0, 0, 2, 0, 1, 1};
@@ -731,6 +765,7 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   for (int i = 0; i < 6; i++) TRY(dev_alloc(ctx, &ctx->B[i], ctx->field_elems));
   CK(cudaMemsetAsync(ctx->sums, 0, sizeof(double) * 2 * 64, ctx->stream));
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  TRY(hessian_dc(ctx));
   for (int is = 0; is < ns; is++) {
     const double rs = ctx->radius[is] / cell;  // Rsmooth in grid units, src/fmax.c:233
     TRY(hessian_xy(ctx, rs, ctx->ev[8 + 3 * is]));
@@ -742,7 +777,7 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
       c.hdst[k] = (is == ns - 1) ? ctx->B[k] : nullptr;  // keep the R=0 Hessian for the LPT sources
     }
     c.zs.ncomp = 6;
-    c.zs.has_nyq = 0;
+    c.zs.has_nyq = ctx->kdens_has_nyq ? 1 : 0;
     c.zs.dc_add = ctx->dc;
     c.g = g;
     c.tw = ctx->tw;
@@ -761,7 +796,10 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     CK(cudaEventRecord(ctx->ev[8 + 3 * is + 2], ctx->stream));
   }
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  ctx->hessian_valid = true;
+  // the Hessian kept for the LPT sources is that of the LAST radius: it is the unsmoothed one only when the
+  // ladder ends with R = 0 as set_smoothing guarantees (src/initialization.c:386-435); any other ladder
+  // must go through pinb200_second_derivatives(ctx, 0, NULL) before pinb200_displacements(compute_sources = 1)
+  ctx->hessian_valid = (ctx->radius.back() == 0.0);
   std::vector<double> sums(2 * 64);
   CK(cudaMemcpyAsync(sums.data(), ctx->sums, sizeof(double) * 2 * 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -830,7 +868,8 @@ static int displacements_impl(pinb200_ctx* ctx, int compute_sources, const doubl
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   for (int i = 0; i < 3; i++) TRY(dev_alloc(ctx, &ctx->D[i], ctx->field_elems));
   if (order >= 2 && compute_sources) {
-    if (!ctx->hessian_valid) FAIL("second derivatives of the R=0 radius are not in place (call pinb200_fmax first)");
+    if (!ctx->hessian_valid)
+      FAIL("second derivatives of the R=0 radius are not in place (call pinb200_fmax with a ladder ending in R = 0, or pinb200_second_derivatives(ctx, 0, NULL), first)");
     // ---- sources (src/LPT.c:64-93): A0 = S2, A1 = S31, A2 = S32 (real, R layout)
     SourcesParams sp{};
     for (int k = 0; k < 6; k++) sp.h[k] = reinterpret_cast<const double*>(ctx->B[k]);
@@ -894,7 +933,7 @@ static int displacements_impl(pinb200_ctx* ctx, int compute_sources, const doubl
     TRY(first_derivs_to_vel(ctx, ctx->KV[1], growth[2], ctx->vel + 6, true, gk ? gk + 2 : nullptr));                 // order 3
     TRY(first_derivs_to_vel(ctx, ctx->KV[2], growth[3], ctx->vel + 9, true, gk ? gk + 3 : nullptr));                 // order 4
   }
-  TRY(first_derivs_to_vel(ctx, ctx->kdens, growth[0], ctx->vel + 0, false, gk));                 // order 1, src/fmax.c:342-346
+  TRY(first_derivs_to_vel(ctx, ctx->kdens, growth[0], ctx->vel + 0, ctx->kdens_has_nyq, gk));    // order 1, src/fmax.c:342-346
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   TRY(check_peer_error(ctx));
@@ -1191,6 +1230,7 @@ extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, doubl
   const Geom& g = ctx->g;
   for (int i = 0; i < 6; i++) TRY(dev_alloc(ctx, &ctx->B[i], ctx->field_elems));
   const double cell = ctx->d.box_size / g.N;
+  TRY(hessian_dc(ctx));
   TRY(hessian_xy(ctx, radius / cell));
   ZOutParams z{};
   for (int k = 0; k < 6; k++) {
@@ -1199,7 +1239,7 @@ extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, doubl
     z.rdst[k] = ctx->B[k];
   }
   z.zs.ncomp = 6;
-  z.zs.has_nyq = 0;
+  z.zs.has_nyq = ctx->kdens_has_nyq ? 1 : 0;
   z.zs.dc_add = ctx->dc;
   z.g = g;
   z.tw = ctx->tw;

@@ -58,6 +58,23 @@ cudaError_t launch_dc_scalar(const double2* src, double* out, double scale, int 
   return cudaGetLastError();
 }
 
+// does a half-complex field carry anything on its kz = N/2 plane?  (flag |= 1)
+__global__ void __launch_bounds__(256) nyq_probe_kernel(const double2* __restrict__ f, size_t nrows, int pitch, int M, int* flag) {
+  bool any = false;
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (size_t)gridDim.x * blockDim.x) {
+    const double2 v = f[r * pitch + M];
+    any |= (v.x != 0.0) || (v.y != 0.0);
+  }
+  if (any) *flag = 1;
+}
+
+cudaError_t launch_nyq_probe(const double2* f, size_t nrows, int pitch, int M, int* flag, cudaStream_t s) {
+  size_t nb = (nrows + 255) / 256;
+  if (nb > 148 * 8) nb = 148 * 8;
+  nyq_probe_kernel<<<(unsigned)nb, 256, 0, s>>>(f, nrows, pitch, M, flag);
+  return cudaGetLastError();
+}
+
 // Fmax_PDF, src/fmax.c:509-550
 __global__ void __launch_bounds__(256) pdf_kernel(const float* __restrict__ fmax, size_t n, unsigned long long* counts) {
   __shared__ unsigned int h[PINB_NBINS_PDF];

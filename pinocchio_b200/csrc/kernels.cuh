@@ -410,9 +410,20 @@ struct BarrierParams {
   int rank, nranks;
   unsigned long long epoch;
   int* error;  // set to 1 on timeout
+  unsigned long long timeout_ns;  // how long a rank waits for its peers before it reports instead of hanging
 };
 
 #if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Ranks reach a collective call with the skew of whatever the host did before it (the reference's
+// fragmentation is load-imbalanced by seconds), so the wait is long (default 10 minutes, pinb200_desc /
+// PINB200_BARRIER_TIMEOUT_S); it exists only so that a dead peer turns into an error instead of a hung GPU.
+// Once the sticky error flag is set every later barrier returns at once: the call fails at its next
+// host-side check instead of waiting again.
 __device__ __forceinline__ void barrier_body(const BarrierParams& p) {
   const int t = threadIdx.x;
   __threadfence_system();
@@ -421,12 +432,16 @@ __device__ __forceinline__ void barrier_body(const BarrierParams& p) {
     *remote = p.epoch;
     __threadfence_system();
     volatile unsigned long long* mine = p.flags[p.rank] + t;
-    long long spins = 0;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
     while (*mine < p.epoch) {
       __nanosleep(200);
-      if (++spins > 20000000LL) {  // ~4+ s: a peer died; fail loudly instead of hanging the GPU
-        *p.error = 1;
-        break;
+      if ((++spins & 1023u) == 0) {
+        if (*reinterpret_cast<volatile int*>(p.error)) break;
+        if (global_timer_ns() - t0 > p.timeout_ns) {  // a peer died; fail loudly instead of hanging the GPU
+          *p.error = 1;
+          break;
+        }
       }
     }
   }

@@ -24,6 +24,7 @@ cudaError_t launch_barrier(const BarrierParams& p, cudaStream_t s);
 // small helpers
 cudaError_t launch_gauss_table(double* gauss, int M, double knorm, double rsmooth, cudaStream_t s);
 cudaError_t launch_dc_scalar(const double2* src, double* out, double scale, int times_i, cudaStream_t s);
+cudaError_t launch_nyq_probe(const double2* f, size_t nrows, int pitch, int M, int* flag, cudaStream_t s);
 cudaError_t launch_fmax_pdf(const float* fmax, size_t n, unsigned long long* counts, cudaStream_t s);
 cudaError_t launch_collapse_cells(const double* h6, size_t n, const double* spline, int nspl, double* F, cudaStream_t s);
 

@@ -225,6 +225,13 @@ class Pinocchio:
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32).ravel()
         self._ck(self.lib.pinb200_set_seed_plane(self.h, seeds.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), seeds.size))
 
+    def _host_barrier(self) -> None:
+        """Every rank enters a collective device call together (MPI_Barrier in the shim): the cross-GPU
+        barrier inside the library orders memory, it is not meant to absorb seconds of host-side skew."""
+        if self.nranks > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+
     def GenIC_large(self, ThisGrid: int = 0) -> int:
         """src/GenIC.c:73-460."""
         self._ck(self.lib.pinb200_genic(self.h))
@@ -233,6 +240,7 @@ class Pinocchio:
     def compute_fmax(self, displacements: bool = True) -> int:
         """src/fmax.c:36-190: radii loop, then compute_displacements(1, 0, ScaleDep.z[0])."""
         tv = np.zeros(self.Smoothing.Nsmooth)
+        self._host_barrier()
         self._ck(self.lib.pinb200_fmax(self.h, _dp(tv)))
         if self.nranks > 1:
             from .distributed import allreduce_sum
@@ -256,6 +264,7 @@ class Pinocchio:
     def compute_displacements(self, compute_sources: int, recompute_sd: int, redshift: float) -> int:
         """src/fmax.c:292-367.  recompute_sd: the R = 0 second derivatives are computed first
         (special mode 3, src/pinocchio.c:186: displacements without an Fmax sweep)."""
+        self._host_barrier()
         if recompute_sd:
             self._ck(self.lib.pinb200_second_derivatives(self.h, 0.0, None))
         sd = getattr(self, "_scaledep", None)
@@ -420,6 +429,7 @@ class Pinocchio:
 
     def compute_second_derivatives(self, R: float) -> np.ndarray:
         out = np.zeros((6, self.lx, self.N, self.N), dtype=np.float64)
+        self._host_barrier()
         self._ck(self.lib.pinb200_second_derivatives(self.h, float(R), _dp(out)))
         return out
 

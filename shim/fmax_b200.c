@@ -207,10 +207,15 @@ int compute_displacements(int compute_sources, int recompute_sd, double redshift
     double t1 = MPI_Wtime();
     ScaleDep.order = 0;
     ScaleDep.redshift = 0.0;
+    MPI_Barrier(MPI_COMM_WORLD); /* collective on the device: absorb the ranks' host-side skew here */
     if (pinb200_second_derivatives(pinb, 0.0, NULL))
       return pinb_fail("compute_second_derivatives");
     cputime.deriv += MPI_Wtime() - t1;
   }
+  /* Every rank enters the device collective together: with RECOMPUTE_DISPLACEMENTS this function is
+     re-entered from fragment.c right after the load-imbalanced build_groups/distribute, where a skew of
+     seconds is normal; the cross-GPU barrier inside the library is not meant to wait that long */
+  MPI_Barrier(MPI_COMM_WORLD);
 #ifdef SCALE_DEPENDENT
   (void)growth;
   {
@@ -299,6 +304,7 @@ int compute_fmax(void)
     }
   }
 #endif
+  MPI_Barrier(MPI_COMM_WORLD); /* (rank 0 alone may just have written the CTtable file) */
   if (pinb200_fmax(pinb, tv))
     return pinb_fail("compute_fmax");
   /* the library returns this rank's share of Sum(delta^2)/Ntotal (src/collapse_times.c:656-670) */
