@@ -331,7 +331,7 @@ def run_b200(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_reference_sample(args.cpu_grid, 1)
+        cpu_baseline = cpu_reference_sample(args.cpu_grid or 256, 1)
 
     # The probes below run code that round 1 could not time on hardware; their budget is bounded (120 + 180
     # + 150 s at worst) and the measurements above are parked on disk first, so a probe that misbehaves
@@ -437,20 +437,42 @@ def cpu_reference_sample(grid: int, steps: int, warmup: int = 0):
             "host_cores_available": os.cpu_count()}
 
 
+def reference_sample_grid(steps: int, warmup: int, budget_s: float = 240.0) -> tuple[int, float]:
+    """Grid of the bounded sample the reference arm times: the largest of 256^3 / 128^3 whose `steps + warmup`
+    passes fit `budget_s` on this box's cores, estimated from one calibration pass at 128^3 (N^3 log N scaling)."""
+    cal = cpu_reference_sample(128, 1)
+    t128 = cal["ms_per_step"] * 1e-3
+    t256 = t128 * 8.0 * 8.0 / 7.0
+    return (256 if (steps + warmup) * t256 <= budget_s else 128), t128
+
+
 def run_reference(args):
+    """CPU arm: the reference's own C sources (oracle/_ref) on the host cores.  It runs EXACTLY `--steps` timed and
+    `--warmup` untimed passes, each pass one bounded sample (a 256^3 or 128^3 box, chosen so that the whole run ends
+    within a few minutes) of the B200 arm's workload, and says so in `config`: Mcells/s is size-normalised, but this
+    is a sample, not the 1024^3 box."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    N = args.cpu_grid
-    cb = cpu_reference_sample(N, max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if args.cpu_grid > 0:
+        N, t128 = args.cpu_grid, None
+    else:
+        N, t128 = reference_sample_grid(steps, warmup)
+    cb = cpu_reference_sample(N, steps, warmup=warmup)
     S = len(HMF_RADII)
+    cfg = workload_config(args.grid or default_grid(world), world, S)
+    cfg["sample_of"] = cfg["workload"]
+    cfg["workload"] = (f"bounded CPU sample of the B200 arm's workload: synthetic {N}^3 grid per step, the same smoothing-radius "
+                       f"sweep (S={S}) + 3LPT, same cosmology and seed, one task on {cb['cores']} host threads")
+    cfg["sample_grid"] = N
+    if t128 is not None:
+        cfg["sample_choice"] = f"calibration pass at 128^3: {t128:.2f} s; largest of 256^3/128^3 whose {steps}+{warmup} passes fit 240 s"
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Mcells/s", "n_gpus": world,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+           "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           # the B200 arm's config verbatim; the bounded sample this arm times is described in cpu_baseline.sample
-           "config": workload_config(args.grid or default_grid(world), world, S),
-           "cpu_baseline": cb, "gpu_launches": 0,
+           "config": cfg, "cpu_baseline": cb, "gpu_launches": 0,
            "e2e": {"value": cb["value"], "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -462,7 +484,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=0, help="override the grid side (default 1024)")
-    ap.add_argument("--cpu-grid", type=int, default=256, help="grid of the bounded CPU sample")
+    ap.add_argument("--cpu-grid", type=int, default=0,
+                    help="grid of the bounded CPU sample (0: 256 for the cpu_baseline leg; the reference arm picks 256 or 128 so that "
+                         "steps + warmup passes fit a few minutes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-handoff", action="store_true", help="skip the fragmentation hand-off probe (fresh process, N=1 only)")

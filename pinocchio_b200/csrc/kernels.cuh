@@ -100,10 +100,13 @@ template <int L, int DIR> struct XCfg {
 #ifndef PINB_SPLIT_ABOVE_Y
 #define PINB_SPLIT_ABOVE_Y 4096
 #endif
+#ifndef PINB_YTK
+#define PINB_YTK 8  // kz-tile width of the y pass for lines up to 1024 (tools/passbench explores 4)
+#endif
 template <int L> struct YCfg {
   static constexpr bool SPLIT = (L > PINB_SPLIT_ABOVE_Y);
   static constexpr int LT = SPLIT ? L / 2 : L;
-  static constexpr int TK = LT <= 1024 ? 8 : 4;
+  static constexpr int TK = LT <= 1024 ? PINB_YTK : 4;
   static constexpr int CHUNK = SPLIT ? 4 : 0;
   using PL = Plan<LT, false>;
   static constexpr int NT = PL::TPL * TK;
@@ -635,8 +638,12 @@ PINB_HD void zpass_collapse_body(Ctx& ctx, double2* smem, double* spl_s, double*
       sd += delta;
       sd2 += delta * delta;
       double F;
+#ifdef PINB_BENCH_NOEPI  // tools/passbench only: the z pass without the collapse arithmetic
+      F = h[0] * h[1] + h[2] * h[3] + h[4] * h[5];
+#else
       if constexpr (TAB) F = inverse_collapse_time_tab(h, p.ct);
       else F = inverse_collapse_time(h, sp);
+#endif
       if ((double)fm < F) {  // running max, src/collapse_times.c:587-590
         p.Fmax[cell] = (float)F;
         p.Rmax[cell] = p.ismooth;

@@ -241,3 +241,51 @@ def test_oracle_genic_against_reference_genic_golden(cosmo):
         assert np.abs(kd - g[key]).max() <= 1e-13 * np.abs(kd).max()
     # the input field of reference_fmax_32.npz is this very field
     assert np.abs(g["kd_486604"] - dict(np.load(GOLD))["kdensity"]).max() <= 1e-13 * np.abs(g["kd_486604"]).max()
+
+
+@needs_ref
+def test_reference_disagrees_with_itself_only_on_flagged_cells(cosmo):
+    """Why parity tests may set the `ill_conditioned_mask` cells aside: the reference's OWN
+    inverse_collapse_time, compiled from the same sources under three code generations (oracle/Makefile: -O3,
+    -O0 -ffp-contract=off, -O3 -mfma -ffp-contract=fast), differs from itself by more than the 1e-6 contract on
+    some cells -- and every such cell is one the perturbation test flags.  Outside the mask the three builds agree
+    to 1e-7, so a comparison there is meaningful; inside it "the reference's value" depends on the compiler."""
+    libs = {}
+    for tag in ("", "_O0", "_fma"):
+        path = ROOT / "oracle" / "_ref" / f"libpinocchio_ref{tag}.so"
+        if not path.exists():
+            pytest.skip(f"{path.name} not built (make -C oracle all)")
+        libs[tag] = ctypes.CDLL(str(path))
+    PD = ctypes.POINTER(ctypes.c_double)
+    x = np.ascontiguousarray(cosmo.sp_invgrow.x)
+    y = np.ascontiguousarray(cosmo.sp_invgrow.y)
+    # Hessians of a real 64^3 field at three smoothing radii, plus the synthetic set of the per-cell test
+    N = 64
+    kd = po.genic(N, N / 0.7, 486604, cosmo.PowerSpectrum)
+    hs = [np.stack([a.ravel() for a in po.second_derivatives(kd, R, 1.0 / 0.7)]) for R in (3.058354, 0.689079, 0.0)]
+    rng = np.random.default_rng(11)
+    syn = rng.standard_normal((6, 200000)) * np.array([1.5, 1.5, 1.5, 0.8, 0.8, 0.8])[:, None]
+    syn[:3] += 0.6
+    h = np.ascontiguousarray(np.concatenate(hs + [syn], axis=1))
+    n = h.shape[1]
+    F = {}
+    for tag, lib in libs.items():
+        lib.ref_set_invgrow.argtypes = [ctypes.c_int, PD, PD]
+        lib.ref_set_invgrow(len(x), x.ctypes.data_as(PD), y.ctypes.data_as(PD))
+        lib.ref_inverse_collapse_time.argtypes = [ctypes.c_long, PD, PD, PD]
+        F[tag] = np.empty(n)
+        lib.ref_inverse_collapse_time(n, h.ctypes.data_as(PD), F[tag].ctypes.data_as(PD), None)
+    mask = po.ill_conditioned_mask([h[i] for i in range(6)], cosmo.InverseGrowingMode)
+
+    def differ(a, b, tol):
+        with np.errstate(invalid="ignore"):
+            return ~(np.abs(a - b) <= tol * np.maximum(1.0, np.abs(a))) & ~(np.isnan(a) & np.isnan(b))
+
+    self_dis = differ(F[""], F["_O0"], 1e-6) | differ(F[""], F["_fma"], 1e-6) | differ(F["_O0"], F["_fma"], 1e-6)
+    print(f"{n} cells: flagged {int(mask.sum())}, reference disagrees with itself on {int(self_dis.sum())}, "
+          f"of which flagged {int((self_dis & mask).sum())}")
+    assert self_dis.sum() >= 1                       # the effect exists in the reference's own code ...
+    assert not (self_dis & ~mask).any()              # ... and only on flagged cells
+    assert mask.mean() < 2e-4
+    loose = differ(F[""], F["_O0"], 1e-7) | differ(F[""], F["_fma"], 1e-7)
+    assert not (loose & ~mask).any()                 # elsewhere the three builds agree to 1e-7, ten times inside the contract

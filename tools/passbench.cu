@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <string>
 #include <cmath>
 #include "../pinocchio_b200/csrc/devctx.cuh"
 #include "../pinocchio_b200/csrc/kernels.cuh"
@@ -132,7 +133,7 @@ template <int N, int TK, int MINB> void bench_y(const Geom& g, double2** A, doub
 template <int N, int TL, int CG, int MINB, int CPT> void bench_zc(const Geom& g, double2** B, const double2* tw, const double* spline, int nspl, float* fmax, int* rmax, double* sums, const char* tag) {
   constexpr int M = N / 2;
   using ZS = ZShape<M, TL, CG>;
-  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + spline_table_doubles(nspl) * sizeof(double) + 2 * ZS::NT * sizeof(double);
+  const size_t smem = ZS::fft_elems(6) * sizeof(double2) + spline_table_doubles(nspl) * sizeof(double) + 64 * sizeof(double);  // as the product kernel (k_zpass.cu): three blocks per SM
   CKE(cudaFuncSetAttribute(zck<M, TL, CG, MINB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CollapseParams p{};
   static const int kz[6] = {0, 0, 2, 0, 1, 1};
@@ -196,9 +197,36 @@ int main(int argc, char** argv) {
   CKE(cudaMalloc(&fmax, (size_t)N * N * N * 4)); CKE(cudaMalloc(&rmax, (size_t)N * N * N * 4)); CKE(cudaMalloc(&sums, 16));
   CKE(cudaMemset(fmax, 0, (size_t)N * N * N * 4));
 
-  bench_x<N, 8, 1>(g, src, A, tw, gauss, 7, "base", 0);
-  bench_x<N, 8, 1>(g, src, A, tw, gauss, 1, "base", 0);
-  bench_y<N, 8, 1>(g, A, B, tw, 6, "base", 0);
-  bench_y<N, 8, 1>(g, A, B, tw, 1, "base", 0);
+  // tests selected by name on the command line (default: the strided passes)
+  auto want = [&](const char* name) {
+    if (argc < 2) return std::string(name) == "x" || std::string(name) == "y";
+    for (int i = 1; i < argc; i++) if (std::string(argv[i]) == name) return true;
+    return false;
+  };
+  constexpr int YTK = PINB_YTK;
+#ifndef PB_MINB
+#define PB_MINB 1
+#endif
+  if (want("x")) {
+    bench_x<N, 8, 1>(g, src, A, tw, gauss, 7, "base", 0);
+    bench_x<N, 8, 1>(g, src, A, tw, gauss, 1, "base", 0);
+  } else {  // the later passes need their inputs
+    bench_x<N, 8, 1>(g, src, A, tw, gauss, 7, "fill", 0);
+  }
+  if (want("y")) {
+    bench_y<N, YTK, PB_MINB>(g, A, B, tw, 6, "ytk", 0);
+    bench_y<N, YTK, PB_MINB>(g, A, B, tw, 1, "ytk", 0);
+  } else {
+    bench_y<N, YTK, PB_MINB>(g, A, B, tw, 6, "fill", 0);
+  }
+  if (want("z")) {
+#ifdef PINB_BENCH_NOEPI
+    const char* tag = "NOEPI";
+#else
+    const char* tag = "classic";
+#endif
+    bench_zc<N, 1, 6, 3, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, tag);
+    bench_zc<N, 1, 6, 2, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, tag);
+  }
   return 0;
 }
