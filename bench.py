@@ -120,6 +120,23 @@ def algorithmic_bytes(N: int, S: int):
     return per, survey_rad, survey_lpt, S * survey_rad + survey_lpt
 
 
+PARITY_FIXTURE = ROOT / "tests" / "golden" / "b200_1gpu_fmax_1024.json"
+
+
+def parity_vs_fixture(N: int, world: int, tvar, pdf) -> dict:
+    """TrueVariance and FmaxPDF of this run against the committed single-GPU run of the same box."""
+    if not PARITY_FIXTURE.exists():
+        return {"parity_vs_1gpu": None, "parity_note": "no fixture (tests/golden/b200_1gpu_fmax_1024.json)"}
+    fx = json.loads(PARITY_FIXTURE.read_text())
+    if fx["grid"] != N:
+        return {"parity_vs_1gpu": None, "parity_note": f"fixture is a {fx['grid']}^3 run, this one {N}^3"}
+    tv0, pdf0 = np.array(fx["true_variance"]), np.array(fx["fmax_pdf"], dtype=np.int64)
+    dv = float(np.abs(np.asarray(tvar) / tv0 - 1.0).max())
+    dp = int(np.abs(np.asarray(pdf, dtype=np.int64) - pdf0).max())
+    return {"parity_vs_1gpu": bool(dv <= 1e-10 and dp <= 2), "parity_true_variance_max_rel": dv, "parity_fmaxpdf_max_bin_diff": dp,
+            "parity_fixture_gpus": fx["n_gpus"]}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -187,6 +204,26 @@ def run_b200(args):
     checks = {"pdf_total_is_ncells": bool(int(pdf.sum()) == N ** 3),
               "variance_ladder_monotone": bool(np.isfinite(tvar).all() and (np.diff(tvar) > 0).all()),
               "collapsed_fraction": round(float(pdf[10:].sum()) / float(N) ** 3, 6)}
+    # the measured variance of the smoothed field against the one the host cosmology predicts for each radius
+    # (the reference logs both as "expected sigma" / "computed sigma", src/fmax.c:141-147): a size-independent
+    # check of the whole FFT path that also holds for the 2048^3 box no single GPU can cross-check
+    try:
+        from pinocchio_b200.cosmology import set_smoothing
+        theo = set_smoothing(cosmo, 1.0 / 0.7)
+        if theo.Variance.size == tvar.size:
+            big = theo.Radius >= 2.0 / 0.7      # radii of at least two cells: below, the grid's own cut-off in k dominates
+            checks["sigma_vs_theory_max_rel"] = round(float(np.abs(np.sqrt(tvar / theo.Variance) - 1.0)[big].max()), 5)
+            checks["sigma_vs_theory_radii"] = int(big.sum())
+    except Exception as ex:  # noqa: BLE001
+        checks["sigma_vs_theory_max_rel"] = str(ex)[:100]
+    # parity of the slab-decomposed runs with the single-GPU run of the same 1024^3 box (fixture written by
+    # `bench.py --write-parity-fixture` on one GPU): TrueVariance[S] and the 210-bin Fmax histogram
+    if rank == 0:
+        checks.update(parity_vs_fixture(N, world, tvar, pdf))
+        if args.write_parity_fixture and world == 1:
+            Path(args.write_parity_fixture).write_text(json.dumps({"grid": N, "n_gpus": 1, "radii": HMF_RADII, "seed": 486604,
+                                                                   "true_variance": [float(v) for v in tvar],
+                                                                   "fmax_pdf": [int(v) for v in pdf]}))
 
     # ---- per-kernel device times measured live (CUDA events inside the engine, same stream)
     K = args.steps
@@ -258,17 +295,30 @@ def run_b200(args):
                               "per_radius_frac_of_summed_roofline": round((t_hbm + t_nvl) / (rad_ms * 1e-3), 4)}
     launches = int(tm1.kernel_launches - tm0.kernel_launches)
 
-    # ---- e2e: host buffers through the reference-facing calls (H2D kdensity, D2H products[])
+    # ---- e2e: host buffers through the reference-facing calls.  One step = H2D of kdensity from pinned memory,
+    #      the sweep + 3LPT, and the hand-off to the fragmentation exactly as the drop-in does it
+    #      (shim/fmax_b200.c download_products_compact): D2H of Fmax of every cell, of the cell indices of the
+    #      collapsed cells (Fmax >= Flast = 1, selected and ordered on the device) and of their 56-byte records --
+    #      what src/distribute.c reads of products[].  The plain copy of all 56-byte records (r01's e2e) is timed
+    #      once beside it (`full_aos`).
     e2e = None
     if not args.no_e2e:
         import ctypes
         from pinocchio_b200.engine import _PD, ProductLayout
         ncell_local = lx * N * N
-        chunk = min(ncell_local, 1 << 26)
+        f = PRODUCT_DTYPE_3LPT.fields
+        lay = ProductLayout(56, 4, f["Rmax"][1], f["Fmax"][1], f["Vel"][1], f["Vel_2LPT"][1], f["Vel_3LPT_1"][1],
+                            f["Vel_3LPT_2"][1])
+        flast = 1.0
+        cnt = ctypes.c_size_t(0)
+        pin._ck(pin.lib.pinb200_collapsed_cells(pin.h, flast, None, 0, ctypes.byref(cnt)))     # same field every step
+        ncoll = int(cnt.value)
         err = ""
-        try:   # pinned staging: 8.6 GB (kdensity slab) + one 64 Mi-cell chunk of products per rank
+        try:   # pinned host buffers: kdensity slab (8.6 GB), Fmax (4.3 GB), indices + records of the collapsed cells (38 GB)
             kd_host = torch.empty((N, lx, N // 2 + 1, 2), dtype=torch.float64, pin_memory=True)
-            stage = torch.empty((chunk * PRODUCT_DTYPE_3LPT.itemsize,), dtype=torch.uint8, pin_memory=True)
+            fm_host = torch.empty((ncell_local,), dtype=torch.float32, pin_memory=True)
+            idx_host = torch.empty((max(ncoll, 1),), dtype=torch.int32, pin_memory=True)
+            rec_host = torch.empty((max(ncoll, 1) * 56,), dtype=torch.uint8, pin_memory=True)
         except Exception as ex:
             err = str(ex)[:200]
         okf = torch.tensor([0 if err else 1], device="cuda")
@@ -278,42 +328,86 @@ def run_b200(args):
             e2e = {"value": None, "unit": "Mcells/s", "error": err or "pinned host allocation failed on a peer rank"}
         else:
             pin._ck(pin.lib.pinb200_download_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
-            stage_np = stage.numpy().view(PRODUCT_DTYPE_3LPT)
-            f = PRODUCT_DTYPE_3LPT.fields
-            lay = ProductLayout(56, 4, f["Rmax"][1], f["Fmax"][1], f["Vel"][1], f["Vel_2LPT"][1], f["Vel_3LPT_1"][1],
-                                f["Vel_3LPT_2"][1])
+            rec_np = rec_host.numpy().view(PRODUCT_DTYPE_3LPT)
+            PU = ctypes.POINTER(ctypes.c_uint)
+
+            phases = {"h2d_kdensity": 0.0, "compute": 0.0, "d2h_fmax": 0.0, "select_sort_d2h_index": 0.0, "d2h_records": 0.0}
 
             def e2e_step():
+                t = [time.perf_counter()]          # every library call returns with its work done: wall-clock phases
                 pin._ck(pin.lib.pinb200_upload_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
+                t.append(time.perf_counter())
                 pin.compute_fmax(displacements=True)
-                chk = 0.0
-                for b in range(0, ncell_local, chunk):
-                    n = min(chunk, ncell_local - b)
-                    pin._ck(pin.lib.pinb200_download_products(pin.h, ctypes.c_void_p(stage.data_ptr()), ctypes.byref(lay), b, n))
-                    chk += float(stage_np["Fmax"][0])
-                return chk
+                t.append(time.perf_counter())
+                pin._ck(pin.lib.pinb200_download_field(pin.h, 0, ctypes.c_void_p(fm_host.data_ptr())))
+                t.append(time.perf_counter())
+                c = ctypes.c_size_t(0)
+                pin._ck(pin.lib.pinb200_collapsed_cells(pin.h, flast, ctypes.cast(idx_host.data_ptr(), PU), ncoll, ctypes.byref(c)))
+                assert int(c.value) == ncoll
+                t.append(time.perf_counter())
+                pin._ck(pin.lib.pinb200_download_products_sorted(pin.h, ctypes.c_void_p(rec_host.data_ptr()), ctypes.byref(lay), 0, ncoll))
+                t.append(time.perf_counter())
+                for k, name in enumerate(phases):
+                    phases[name] += t[k + 1] - t[k]
+                return float(rec_np["Fmax"][0]) + float(fm_host[0])
 
             e2e_step()
             barrier()
+            for k in phases:
+                phases[k] = 0.0
             w0 = time.perf_counter()
             ne = max(1, min(args.steps, 3))
             for _ in range(ne):
                 e2e_step()
             barrier()
             w = (time.perf_counter() - w0) / ne
+            sort_ms = pin.timers().sort_ms
             tw = torch.tensor([w], device="cuda", dtype=torch.float64)
+            tc = torch.tensor([float(ncoll)], device="cuda", dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+            ncoll_all = int(tc.item())
+            # the hand-off is what the fragmentation would get: ordered, all collapsed cells, records of the right cells
+            fs = rec_np["Fmax"][:ncoll]
+            order_ok = bool(ncoll == 0 or ((np.diff(fs[:: max(1, ncoll // (1 << 22))]) <= 0).all() and fs[-1] >= flast
+                                           and np.array_equal(fs[:4096], fm_host.numpy()[idx_host.numpy()[:4096].view(np.uint32)])))
             e2e = {"value": round(cells / float(tw.item()) / 1e6, 2), "unit": "Mcells/s",
-                   "h2d_bytes_per_step": int(N * N * (N // 2 + 1) * 16), "d2h_bytes_per_step": int(N ** 3 * 56),
-                   "steps": ne, "ms_per_step": round(float(tw.item()) * 1e3, 2)}
+                   "h2d_bytes_per_step": int(N * N * (N // 2 + 1) * 16),
+                   "d2h_bytes_per_step": int(4 * N ** 3 + 60 * ncoll_all),
+                   "steps": ne, "ms_per_step": round(float(tw.item()) * 1e3, 2),
+                   "handoff": "Fmax of every cell + index list and 56-byte records of the cells with Fmax >= 1 in order of descending "
+                              "Fmax (device-side selection + radix sort), as shim/fmax_b200.c fills products[] for src/distribute.c",
+                   "collapsed_cells": ncoll_all, "select_sort_ms_device": round(float(sort_ms), 2), "handoff_ok": order_ok,
+                   "phases_ms_rank0": {k: round(v / ne * 1e3, 1) for k, v in phases.items()}}
+            # the plain copy of every record, once, for comparison (r01's e2e definition)
+            try:
+                chunk = min(ncell_local, 1 << 26)
+                nst = min(chunk * 56, rec_host.numel())
+                chunk = nst // 56
+                barrier()
+                w0 = time.perf_counter()
+                pin._ck(pin.lib.pinb200_upload_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
+                pin.compute_fmax(displacements=True)
+                for b0 in range(0, ncell_local, chunk):
+                    nn = min(chunk, ncell_local - b0)
+                    pin._ck(pin.lib.pinb200_download_products(pin.h, ctypes.c_void_p(rec_host.data_ptr()), ctypes.byref(lay), b0, nn))
+                barrier()
+                wf = time.perf_counter() - w0
+                twf = torch.tensor([wf], device="cuda", dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(twf, op=dist.ReduceOp.MAX)
+                e2e["full_aos"] = {"ms_per_step": round(float(twf.item()) * 1e3, 2), "value": round(cells / float(twf.item()) / 1e6, 2),
+                                   "d2h_bytes_per_step": int(N ** 3 * 56), "steps": 1}
+            except Exception as ex:  # noqa: BLE001
+                e2e["full_aos"] = {"error": str(ex)[:200]}
             # the e2e step is PCIe-bound: report the bare pinned-copy rates of this box beside it, so that
             # (h2d_bytes / h2d_gbs + d2h_bytes / d2h_gbs + device step) can be compared with ms_per_step
             try:
-                nb = int(min(stage.numel(), 1 << 30))
+                nb = int(min(rec_host.numel(), 1 << 30))
                 dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
                 rates = {}
-                for name, (dst, src) in {"d2h_gbs": (stage[:nb], dbuf), "h2d_gbs": (dbuf, stage[:nb])}.items():
+                for name, (dst, src) in {"d2h_gbs": (rec_host[:nb], dbuf), "h2d_gbs": (dbuf, rec_host[:nb])}.items():
                     dst.copy_(src, non_blocking=True)
                     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     ev0.record()
@@ -328,6 +422,7 @@ def run_b200(args):
                 e2e["pcie_floor_ms_per_step"] = round(pcie_ms, 1)
             except Exception as ex:  # noqa: BLE001
                 e2e["pcie_pinned_copy"] = {"error": str(ex)[:200]}
+            del kd_host, fm_host, idx_host, rec_host
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -379,6 +474,26 @@ def run_b200(args):
             ctable = json.loads(line[-1]) if line else {"error": (r.stderr or r.stdout)[-300:]}
         except Exception as ex:  # noqa: BLE001
             ctable = {"error": str(ex)[:300]}
+
+    # ---- N > 1 on a box other than the fixture's (2048^3 on 8 GPUs): the same ranks also run the 1024^3 box of the
+    #      fixture once (sweep only, not timed), so that the slab decomposition is cross-checked against the
+    #      single-GPU result in every scaling run
+    if world > 1 and N != 1024 and PARITY_FIXTURE.exists():
+        try:
+            pin.close()
+            torch.cuda.empty_cache()
+            sub = Pinocchio(RunConfig(GridSize=1024, BoxSize_htrue=1024 / 0.7, lpt_order=3), cosmo, device=local, smoothing=lad,
+                            rank=rank, nranks=world)
+            sub.set_stream(stream.cuda_stream)
+            sub.GenIC_large()
+            sub.compute_fmax(displacements=False)
+            spdf = sub.Fmax_PDF()
+            stv = np.asarray(sub.TrueVariance, dtype=np.float64)
+            sub.close()
+            if rank == 0:
+                checks["subrun_1024"] = parity_vs_fixture(1024, world, stv, spdf)
+        except Exception as ex:  # noqa: BLE001
+            checks["subrun_1024"] = {"error": str(ex)[:200]}
 
     if rank == 0:
         out = {"metric": METRIC, "value": round(value, 2), "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
@@ -490,6 +605,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-handoff", action="store_true", help="skip the fragmentation hand-off probe (fresh process, N=1 only)")
+    ap.add_argument("--write-parity-fixture", default="", help="N=1: write TrueVariance and FmaxPDF of this run as the fixture the N>1 runs are compared with")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

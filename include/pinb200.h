@@ -54,6 +54,7 @@ typedef struct {
                                     y pass, z pass + collapse                                  */
   double disp_sources, disp_vel; /* displacement stage: sources + k-vectors; 4 x first derivatives */
   unsigned long long kernel_launches;  /* kernels launched by this context so far            */
+  double sort_ms;                      /* last pinb200_collapsed_cells: selection + sort on the device, milliseconds */
 } pinb200_timers;
 
 /* ---- life cycle ---------------------------------------------------------------------- */
@@ -183,6 +184,24 @@ int pinb200_download_products_sorted(pinb200_ctx* ctx, void* products, const pin
  * 8..10 Vel_3LPT_1 11..13 Vel_3LPT_2; dst holds N^3 (local) 4-byte values. */
 int pinb200_download_field(pinb200_ctx* ctx, int which, void* dst);
 int pinb200_get_timers(pinb200_ctx* ctx, pinb200_timers* t);
+
+/* On-disk formats whose payload is the device SoA, written to an open file descriptor
+ * straight from the device through two pinned staging buffers (copy engine and write(2) overlap), without a
+ * host products[] array:
+ *  - pinb200_write_products: the AoS records of cells [cell_begin, +ncells) as DumpProducts/Task.<rank> holds them
+ *    (src/fmax.c:418-420: fwrite(products, sizeof(product_data), total_local_size)); members of the record that
+ *    this path does not compute are written as zero bytes;
+ *  - pinb200_write_block: the payload of one block of the timeless snapshot for those cells, as initialize_FMAX /
+ *    _RMAX / _ZEL / _2LPT / _3LPT_1 / _3LPT_2 fill it (src/write_snapshot.c:695-860): float, int, or three
+ *    interleaved floats (AuxStruct) per cell.  Block headers and the INFO block stay with the caller. */
+#define PINB200_BLOCK_FMAX 0
+#define PINB200_BLOCK_RMAX 1
+#define PINB200_BLOCK_ZEL 2
+#define PINB200_BLOCK_2LPT 3
+#define PINB200_BLOCK_3LPT_1 4
+#define PINB200_BLOCK_3LPT_2 5
+int pinb200_write_products(pinb200_ctx* ctx, int fd, const pinb200_product_layout* layout, size_t cell_begin, size_t ncells);
+int pinb200_write_block(pinb200_ctx* ctx, int fd, int block, size_t cell_begin, size_t ncells);
 
 /* ---- finer-grained entry points (reference function granularity; used by the parity tests) */
 /* forward_transform / reverse_transform (src/fmax-pfft.c:191-228) on host arrays:

@@ -84,16 +84,19 @@ PINB_HD double sc_coef(int i) {
 // the three values cos(t/3), cos((t+2pi)/3), cos((t+4pi)/3) for t in [0, pi]:
 // sin and cos of a = t/3 in [0, ~1.05] by Taylor series in a^2 (truncation < 1e-18), then
 // cos(a + 2pi/3) = -c/2 - (sqrt3/2) s,  cos(a + 4pi/3) = -c/2 + (sqrt3/2) s
+// (both polynomials by Estrin's scheme: four dependent FMA levels instead of nine / ten)
 PINB_HD void cos_thirds(double t, double& c0, double& c1, double& c2) {
   const double a = t * sc_coef(19);
   const double z = a * a;
-  double ps = sc_coef(0);
-#pragma unroll
-  for (int i = 1; i < 9; i++) ps = ps * z + sc_coef(i);
+  const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+  const double q0 = fma_rn(sc_coef(7), z, sc_coef(8)), q1 = fma_rn(sc_coef(5), z, sc_coef(6));
+  const double q2 = fma_rn(sc_coef(3), z, sc_coef(4)), q3 = fma_rn(sc_coef(1), z, sc_coef(2));
+  const double ps = fma_rn(z8, sc_coef(0), fma_rn(z4, fma_rn(z2, q3, q2), fma_rn(z2, q1, q0)));
   const double s = a + a * (z * ps);
-  double pc = sc_coef(9);
-#pragma unroll
-  for (int i = 10; i < 19; i++) pc = pc * z + sc_coef(i);
+  const double u0 = fma_rn(sc_coef(17), z, sc_coef(18)), u1 = fma_rn(sc_coef(15), z, sc_coef(16));
+  const double u2 = fma_rn(sc_coef(13), z, sc_coef(14)), u3 = fma_rn(sc_coef(11), z, sc_coef(12));
+  const double u4 = fma_rn(sc_coef(9), z, sc_coef(10));
+  const double pc = fma_rn(z8, u4, fma_rn(z4, fma_rn(z2, u3, u2), fma_rn(z2, u1, u0)));
   const double c = 1.0 + z * pc;
   const double hs = sc_coef(20) * s;
   c0 = c;
@@ -186,9 +189,15 @@ PINB_HD double ell_classic_flat(double l1, double l2, double l3) {
   // cell in __cuda_sm20_div_rn_f64_full / dsqrt_rn_f64_mediumpath before this guard).
   const bool c1 = r_2_q_3 > 0;
   // case 1 (r^2 - q^3 > 0)
-  const double sqa = cbrt(fm_sqrt_pair(c1 ? r_2_q_3 : 1.0).s + fabs(r));
+  // cube root and its reciprocal from one Newton chain.  q / sq is formed with the remainder step of fm_div
+  // (seeded by sq^-1), i.e. as the quotient by the ROUNDED sq itself: s + q/s is stationary in s where s^2 = q,
+  // so an error of sq then cancels to second order, as in the reference's expression (independent roundings
+  // of sq and sq^-1 would not: 1e-7 on the cells next to r^2 = q^3)
+  const CbrtPair sqa = fm_cbrt_pair(fm_sqrt_pair(c1 ? r_2_q_3 : 1.0).s + fabs(r));
   const double sg = (r > 0.) ? -1.0 : ((r < 0.) ? 1.0 : NAN);
-  double ella = sg * (sqa + fm_div(q, sqa)) - a1_3;
+  const double qs0 = q * sqa.rc;
+  const double qs = fma_rn(fma_rn(-sqa.c, qs0, q), sqa.rc, qs0);
+  double ella = sg * (sqa.c + qs) - a1_3;
   ella = (ella < 0.) ? -.1 : ella;
   // case 2 (r^2 <= q^3, hence q >= 0; a NaN discriminant lands here as in the reference)
   // 2 r / (q * 2 sqrt q) = r * (1/sqrt q)^3: sqrt and its reciprocal come from one Newton chain
@@ -208,9 +217,14 @@ PINB_HD double ell_classic_flat(double l1, double l2, double l3) {
   ellb = (s3 < ellb ? s3 : ellb);
   ellb = (ellb == 1.e10) ? -.1 : ellb;
   double ell = c1 ? ella : ellb;
-  const double inv_del = fm_rcp(del);  // NaN for del = 0: corr is then unused
-  const double corr = mc(MC_M0364) * inv_del * fm_exp_neg((mc(MC_M65) * (l1 - l2) + mc(MC_M28) * (l2 - l3)) * inv_del);
-  if (del > 0. && ell > 0.) ell += corr;
+  // the correction is used for del > 0 only, where its exponent is <= 0 (l1 >= l2 >= l3); the other lanes get a
+  // benign 0 instead of a positive argument that would send the warp through libm's exp (r02 ncu: 3 % of the
+  // kernel's instructions, del < 0 in half of the cells)
+  const bool use_corr = del > 0.;
+  const double inv_del = fm_rcp(use_corr ? del : 1.0);
+  const double xe = (mc(MC_M65) * (l1 - l2) + mc(MC_M28) * (l2 - l3)) * inv_del;
+  const double corr = mc(MC_M0364) * inv_del * fm_exp_neg(use_corr ? xe : 0.0);
+  if (use_corr && ell > 0.) ell += corr;
   return ell;
 }
 

@@ -16,8 +16,10 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cerrno>
 #include <cstdio>
 #include <cstdlib>
+#include <unistd.h>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,7 +28,6 @@
 #include "launch.h"
 #include "product_merge.h"
 #include "seed_plane.h"
-#include "sort_cells.cuh"
 
 using namespace pinb;
 
@@ -39,6 +40,10 @@ struct pinb200_ctx {
   int lx_shift = 0, ly_shift = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;          // D2H of packed records (stream_records)
+  cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // staging buffer b: [b] packed, [2 + b] copied out
+  unsigned char* pinned = nullptr;             // two pinned host buffers of the file writers
+  size_t pinned_bytes = 0;
   std::string err;
   size_t field_elems = 0;  // double2 elements of one field (lx*N*P == N*ly*P)
   size_t ncells = 0;       // lx*N*N
@@ -266,6 +271,9 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->d.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
   }
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -975,7 +983,8 @@ extern "C" int pinb200_displacements_scaledep(pinb200_ctx* ctx, int compute_sour
 
 // Cells with Fmax >= f_last in order of descending Fmax (ties: ascending cell index): the selection
 // of src/distribute.c:58-175,547-600 and the ordering of sort_and_organize (src/fragment.c:484-520),
-// done on the device.  LSD radix sort, four 8-bit passes, filter folded into the first.
+// done on the device (k_sort.cu): stable compaction of (key, index) pairs, then an LSD radix sort over the
+// bits in which the keys differ.  One host synchronisation (the count of selected cells sizes the buffers).
 extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned int* cell_index_out, size_t capacity,
                                        size_t* count) {
   if (!ctx || !count) return 1;
@@ -984,65 +993,77 @@ extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned 
   if (ctx->ncells > 0xffffffffull) FAIL("more than 2^32 local cells");
   CK(cudaSetDevice(ctx->d.device));
   for (auto& w : ctx->D) TRY(dev_free(ctx, &w));  // y-pass scratch of the displacement stage: dead by now
-  const unsigned int ntiles_all = (unsigned int)((ctx->ncells + SORT_TILE - 1) / SORT_TILE);
-  unsigned int *counts = nullptr, *key[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr};
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  const unsigned long long nc = ctx->ncells;
+  const size_t ntsel = cell_sort_ntiles_select(nc);
+  unsigned int *tile_counts = nullptr, *bsums = nullptr, *range = nullptr, *counts = nullptr, *key[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr};
   unsigned long long* d_total = nullptr;
-  TRY(dev_alloc(ctx, &counts, (size_t)256 * ntiles_all));
+  TRY(dev_alloc(ctx, &tile_counts, ntsel));
+  TRY(dev_alloc(ctx, &bsums, cell_sort_scan_blocks(ntsel) + 1));
+  TRY(dev_alloc(ctx, &range, (size_t)2));
   TRY(dev_alloc(ctx, &d_total, (size_t)1));
-  SortPassParams p{};
-  p.fmax = ctx->fmax;
-  p.f_last = f_last;
-  p.n = ctx->ncells;
-  p.shift = 0;
-  p.counts = counts;
-  p.ntiles = ntiles_all;
-  // the first pass needs its output size before the buffers exist: count + scan first
+  const unsigned int range_init[2] = {0xffffffffu, 0u};
+  CK(cudaMemcpyAsync(range, range_init, sizeof range_init, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(launch_select_count(ctx->fmax, nc, f_last, tile_counts, range, ctx->stream));
+  LAUNCH(launch_scan_u32(tile_counts, ntsel, bsums, d_total, ctx->stream));
+  ctx->launches += 2;
   unsigned long long n = 0;
-  {
-    // a counting-only run of the first pass sizes the (key, index) buffers: worst case all cells
-    // collapse (16 bytes per cell for the two ping-pong pairs), typically 60 %
-    SortPassParams c = p;
-    c.key_out = nullptr;
-    c.idx_out = nullptr;
-    LAUNCH(launch_sort_count(c, d_total, ctx->stream));
-    CK(cudaMemcpyAsync(&n, d_total, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-  }
+  unsigned int hrange[2] = {0, 0};
+  CK(cudaMemcpyAsync(&n, d_total, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(hrange, range, sizeof hrange, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   *count = (size_t)n;
   if (n > 0 && cell_index_out && capacity > 0) {
     for (int b = 0; b < 2; b++) {
       TRY(dev_alloc(ctx, &key[b], (size_t)n));
       TRY(dev_alloc(ctx, &idx[b], (size_t)n));
     }
+    LAUNCH(launch_select_write(ctx->fmax, nc, f_last, tile_counts, range, key[0], idx[0], ctx->stream));
+    // digits: the keys are offsets from the smallest one, so only the bits of (kmax - kmin) take part
+    int sig = 0;
+    while (sig < 32 && ((unsigned long long)(hrange[1] - hrange[0]) >> sig) != 0) sig++;
+    int maxbits = 0;
+    while ((1 << maxbits) < cell_sort_max_bins()) maxbits++;
+    const int npass = (sig + maxbits - 1) / maxbits;
     int cur = 0;
-    for (int pass = 0; pass < 4; pass++) {
-      p.shift = 8 * pass;
-      p.key_out = key[cur];
-      p.idx_out = idx[cur];
-      LAUNCH(launch_sort_pass(p, d_total, ctx->stream));
-      ctx->launches += 2;  // a pass is three kernels
-      // the next pass reads what this one wrote
-      p.fmax = nullptr;
-      p.key_in = key[cur];
-      p.idx_in = idx[cur];
-      p.n = n;
-      p.ntiles = (unsigned int)((n + SORT_TILE - 1) / SORT_TILE);
-      cur ^= 1;
+    if (npass > 0) {
+      const size_t ntr = cell_sort_ntiles_radix(n);
+      TRY(dev_alloc(ctx, &counts, (size_t)cell_sort_max_bins() * ntr));
+      unsigned int* bs2 = nullptr;
+      TRY(dev_alloc(ctx, &bs2, cell_sort_scan_blocks((unsigned long long)cell_sort_max_bins() * ntr) + 1));
+      int shift = 0;
+      for (int pass = 0; pass < npass; pass++) {
+        const int bits = (sig - shift + (npass - pass) - 1) / (npass - pass);  // spread the significant bits evenly
+        LAUNCH(launch_radix_hist(key[cur], n, shift, bits, counts, ctx->stream));
+        LAUNCH(launch_scan_u32(counts, ((unsigned long long)1 << bits) * ntr, bs2, nullptr, ctx->stream));
+        LAUNCH(launch_radix_scatter(key[cur], idx[cur], key[cur ^ 1], idx[cur ^ 1], n, shift, bits, counts, ctx->stream));
+        ctx->launches += 2;
+        shift += bits;
+        cur ^= 1;
+      }
+      TRY(dev_free(ctx, &bs2));
     }
     const size_t ncopy = capacity < (size_t)n ? capacity : (size_t)n;
-    CK(cudaMemcpyAsync(cell_index_out, idx[cur ^ 1], ncopy * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    CK(cudaMemcpyAsync(cell_index_out, idx[cur], ncopy * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+    ctx->tm.sort_ms = ms;  // selection + sort on the device (without the download of the index list)
     // the ordered indices stay resident for pinb200_download_products_sorted
     TRY(dev_free(ctx, &ctx->sorted_idx));
-    ctx->sorted_idx = idx[cur ^ 1];
+    ctx->sorted_idx = idx[cur];
     ctx->sorted_n = (size_t)n;
-    idx[cur ^ 1] = nullptr;
+    idx[cur] = nullptr;
   }
   for (int b = 0; b < 2; b++) {
     TRY(dev_free(ctx, &key[b]));
     TRY(dev_free(ctx, &idx[b]));
   }
   TRY(dev_free(ctx, &counts));
+  TRY(dev_free(ctx, &tile_counts));
+  TRY(dev_free(ctx, &bsums));
+  TRY(dev_free(ctx, &range));
   TRY(dev_free(ctx, &d_total));
   return 0;
 }
@@ -1061,23 +1082,37 @@ extern "C" int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts) {
   return 0;
 }
 
-extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t cell_begin,
-                                         size_t ncells) {
-  if (!ctx || !products || !L) return 1;
-  // special mode 3 (displacements without an Fmax sweep, src/pinocchio.c:170-200) leaves Fmax/Rmax zero
-  if (!ctx->fmax && !ctx->vel[0]) FAIL("products not computed");
-  if (cell_begin + ncells > ctx->ncells) FAIL("cell range outside the local slab");
-  if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
-  CK(cudaSetDevice(ctx->d.device));
-  if (ncells == 0) return 0;
-  unsigned char* d = nullptr;
-  TRY(dev_alloc(ctx, &d, ncells * L->stride));
-  CK(cudaMemsetAsync(d, 0, ncells * L->stride, ctx->stream));
+// Records [first, first + n) of a record stream -- cells in index order (gather == nullptr) or in the order of an
+// index list -- packed on the device and copied to the host in chunks through TWO device staging buffers: the
+// pack kernel of chunk k+1 runs on the compute stream while the copy engine moves chunk k on a second stream,
+// so the PCIe link never waits for a kernel and the device needs 2 x 16 Mi records of staging, not n records
+// (r01 staged a whole call at once: 60 GB for the AoS of a 1024^3 slab).  sink != nullptr: records holding
+// members that are not ours are staged on the host and merged member by member instead (product_merge.h).
+// fd >= 0: the records go to that file descriptor instead of `host`, through two pinned host buffers: the copy
+// engine fills one while write(2) drains the other (snapshot blocks and product dumps written from the device SoA).
+static int write_all(pinb200_ctx* ctx, int fd, const unsigned char* p, size_t bytes) {
+  while (bytes > 0) {
+    const ssize_t w = write(fd, p, bytes);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      ctx->err = std::string("write failed: ") + strerror(errno);
+      return 1;
+    }
+    p += w;
+    bytes -= (size_t)w;
+  }
+  return 0;
+}
+
+static int stream_records(pinb200_ctx* ctx, void* host, const pinb200_product_layout* L, const unsigned int* gather, size_t first, size_t n,
+                          int fd = -1) {
+  if (n == 0) return 0;
+  const size_t max_chunk = fd >= 0 ? ((size_t)1 << 21) : ((size_t)1 << 24);
+  const size_t chunk = n < max_chunk ? n : max_chunk;
   PackParams p{};
   p.fmax = ctx->fmax;
   p.rmax = ctx->rmax;
   for (int i = 0; i < 12; i++) p.vel[i] = ctx->vel[i];
-  p.out = d;
   p.stride = L->stride;
   p.prodfloat_bytes = L->prodfloat_bytes;
   p.off_rmax = L->off_Rmax;
@@ -1086,34 +1121,124 @@ extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const
   p.off_vel[1] = L->off_Vel_2LPT;
   p.off_vel[2] = L->off_Vel_3LPT_1;
   p.off_vel[3] = L->off_Vel_3LPT_2;
-  p.cell_begin = cell_begin;
-  p.ncells = ncells;
-  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
-  LAUNCH(launch_pack_products(p, ctx->stream));
-  // Records whose every byte is a member we deliver (the default 56-byte product_data) are copied
-  // straight over the caller's; records with foreign members (*_prev of RECOMPUTE_DISPLACEMENTS,
-  // zacc/group_ID of SNAPSHOT) are staged and merged member by member (product_merge.h).
+  p.gather = gather;
   const bool has_vel[4] = {ctx->vel[0] != nullptr, ctx->vel[3] != nullptr, ctx->vel[6] != nullptr, ctx->vel[9] != nullptr};
   const std::vector<MemberRange> members = product_members(*L, ctx->fmax != nullptr, has_vel);
-  if (members_cover_record(members, L->stride)) {
-    CK(cudaMemcpyAsync(products, d, ncells * L->stride, cudaMemcpyDeviceToHost, ctx->stream));
-  } else {
-    const size_t chunk = (size_t)1 << 22;  // records per staging round
-    std::vector<unsigned char> stage((ncells < chunk ? ncells : chunk) * L->stride);
-    for (size_t b = 0; b < ncells; b += chunk) {
-      const size_t n = ncells - b < chunk ? ncells - b : chunk;
-      CK(cudaMemcpyAsync(stage.data(), d + b * L->stride, n * L->stride, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-      merge_product_members(static_cast<unsigned char*>(products) + b * L->stride, stage.data(), L->stride, n, members);
-    }
+  const bool direct = fd >= 0 || members_cover_record(members, L->stride);  // a file gets zero bytes for foreign members
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev_stage) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
+  unsigned char* d[2] = {nullptr, nullptr};
+  const int nbuf = n > chunk ? 2 : 1;
+  for (int b = 0; b < nbuf; b++) TRY(dev_alloc(ctx, &d[b], chunk * L->stride));
+  std::vector<unsigned char> stage;
+  if (!direct) stage.resize(chunk * L->stride);
+  unsigned char* out = static_cast<unsigned char*>(host);
+  const bool zero_fill = !members_cover_record(members, L->stride);
+  unsigned char* pinned[2] = {nullptr, nullptr};
+  size_t pending_bytes[2] = {0, 0};
+  if (fd >= 0) {
+    if (ctx->pinned_bytes < 2 * chunk * L->stride) {
+      if (ctx->pinned) CK(cudaFreeHost(ctx->pinned));
+      ctx->pinned = nullptr;
+      CK(cudaMallocHost((void**)&ctx->pinned, 2 * chunk * L->stride));
+      ctx->pinned_bytes = 2 * chunk * L->stride;
+    }
+    pinned[0] = ctx->pinned;
+    pinned[1] = ctx->pinned + chunk * L->stride;
+  }
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, k++) {
+    const int b = (int)(k & 1);
+    const size_t m = n - off < chunk ? n - off : chunk;
+    if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage[2 + b], 0));  // the copy of chunk k-2 has left this buffer
+    if (zero_fill) CK(cudaMemsetAsync(d[b], 0, m * L->stride, ctx->stream));
+    p.out = d[b];
+    p.cell_begin = first + off;
+    p.ncells = m;
+    LAUNCH(launch_pack_products(p, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_stage[b], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage[b], 0));
+    if (fd >= 0) {
+      // pinned[b] was written out before chunk k-1's copy was issued (see below), so it is free
+      CK(cudaMemcpyAsync(pinned[b], d[b], m * L->stride, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      CK(cudaEventRecord(ctx->ev_stage[2 + b], ctx->copy_stream));
+      pending_bytes[b] = m * L->stride;
+      // while chunk k crosses PCIe, chunk k-1 goes to the file
+      if (k >= 1) {
+        CK(cudaEventSynchronize(ctx->ev_stage[2 + (b ^ 1)]));
+        TRY(write_all(ctx, fd, pinned[b ^ 1], pending_bytes[b ^ 1]));
+        pending_bytes[b ^ 1] = 0;
+      }
+      continue;
+    }
+    if (direct) {
+      CK(cudaMemcpyAsync(out + off * L->stride, d[b], m * L->stride, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    } else {
+      CK(cudaMemcpyAsync(stage.data(), d[b], m * L->stride, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      CK(cudaStreamSynchronize(ctx->copy_stream));
+      merge_product_members(out + off * L->stride, stage.data(), L->stride, m, members);
+    }
+    CK(cudaEventRecord(ctx->ev_stage[2 + b], ctx->copy_stream));
+  }
+  CK(cudaStreamSynchronize(ctx->copy_stream));
+  if (fd >= 0)
+    for (int b = 0; b < 2; b++)
+      if (pending_bytes[(k + b) & 1]) TRY(write_all(ctx, fd, pinned[(k + b) & 1], pending_bytes[(k + b) & 1]));  // the last chunk
   CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
   ctx->tm.mem_transf += ms * 1e-3;
-  TRY(dev_free(ctx, &d));
+  for (int b = 0; b < nbuf; b++) TRY(dev_free(ctx, &d[b]));
   return 0;
+}
+
+extern "C" int pinb200_write_products(pinb200_ctx* ctx, int fd, const pinb200_product_layout* L, size_t cell_begin, size_t ncells) {
+  if (!ctx || !L || fd < 0) return 1;
+  if (!ctx->fmax && !ctx->vel[0]) FAIL("products not computed");
+  if (cell_begin + ncells > ctx->ncells) FAIL("cell range outside the local slab");
+  if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
+  CK(cudaSetDevice(ctx->d.device));
+  return stream_records(ctx, nullptr, L, nullptr, cell_begin, ncells, fd);
+}
+
+extern "C" int pinb200_write_block(pinb200_ctx* ctx, int fd, int block, size_t cell_begin, size_t ncells) {
+  if (!ctx || fd < 0) return 1;
+  if (cell_begin + ncells > ctx->ncells) FAIL("cell range outside the local slab");
+  // a block is a record stream with one member: 4 bytes (FMAX, RMAX) or three floats (AuxStruct of src/write_snapshot.c)
+  pinb200_product_layout L{};
+  L.prodfloat_bytes = 4;
+  L.off_Rmax = L.off_Fmax = L.off_Vel = L.off_Vel_2LPT = L.off_Vel_3LPT_1 = L.off_Vel_3LPT_2 = -1;
+  const void* need = nullptr;
+  switch (block) {
+    case PINB200_BLOCK_FMAX: L.stride = 4; L.off_Fmax = 0; need = ctx->fmax; break;
+    case PINB200_BLOCK_RMAX: L.stride = 4; L.off_Rmax = 0; need = ctx->rmax; break;
+    case PINB200_BLOCK_ZEL: L.stride = 12; L.off_Vel = 0; need = ctx->vel[0]; break;
+    case PINB200_BLOCK_2LPT: L.stride = 12; L.off_Vel_2LPT = 0; need = ctx->vel[3]; break;
+    case PINB200_BLOCK_3LPT_1: L.stride = 12; L.off_Vel_3LPT_1 = 0; need = ctx->vel[6]; break;
+    case PINB200_BLOCK_3LPT_2: L.stride = 12; L.off_Vel_3LPT_2 = 0; need = ctx->vel[9]; break;
+    default: FAIL("unknown snapshot block");
+  }
+  if (!need) FAIL("the field of this block is not resident");
+  CK(cudaSetDevice(ctx->d.device));
+  return stream_records(ctx, nullptr, &L, nullptr, cell_begin, ncells, fd);
+}
+
+extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t cell_begin,
+                                         size_t ncells) {
+  if (!ctx || !products || !L) return 1;
+  // special mode 3 (displacements without an Fmax sweep, src/pinocchio.c:170-200) leaves Fmax/Rmax zero
+  if (!ctx->fmax && !ctx->vel[0]) FAIL("products not computed");
+  if (cell_begin + ncells > ctx->ncells) FAIL("cell range outside the local slab");
+  if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
+  CK(cudaSetDevice(ctx->d.device));
+  // Records whose every byte is a member we deliver (the default 56-byte product_data) are copied
+  // straight over the caller's; records with foreign members (*_prev of RECOMPUTE_DISPLACEMENTS,
+  // zacc/group_ID of SNAPSHOT) are staged and merged member by member (product_merge.h).
+  return stream_records(ctx, products, L, nullptr, cell_begin, ncells);
 }
 
 // frag[first .. first+n) as sort_and_organize leaves it (src/fragment.c:484-520): the records of the
@@ -1126,31 +1251,7 @@ extern "C" int pinb200_download_products_sorted(pinb200_ctx* ctx, void* products
   if (first + n > ctx->sorted_n) FAIL("record range outside the ordered cell list");
   if (L->prodfloat_bytes != 4 && L->prodfloat_bytes != 8) FAIL("prodfloat_bytes must be 4 or 8");
   CK(cudaSetDevice(ctx->d.device));
-  if (n == 0) return 0;
-  unsigned char* d = nullptr;
-  TRY(dev_alloc(ctx, &d, n * L->stride));
-  CK(cudaMemsetAsync(d, 0, n * L->stride, ctx->stream));
-  PackParams p{};
-  p.fmax = ctx->fmax;
-  p.rmax = ctx->rmax;
-  for (int i = 0; i < 12; i++) p.vel[i] = ctx->vel[i];
-  p.out = d;
-  p.stride = L->stride;
-  p.prodfloat_bytes = L->prodfloat_bytes;
-  p.off_rmax = L->off_Rmax;
-  p.off_fmax = L->off_Fmax;
-  p.off_vel[0] = L->off_Vel;
-  p.off_vel[1] = L->off_Vel_2LPT;
-  p.off_vel[2] = L->off_Vel_3LPT_1;
-  p.off_vel[3] = L->off_Vel_3LPT_2;
-  p.cell_begin = first;
-  p.ncells = n;
-  p.gather = ctx->sorted_idx;
-  LAUNCH(launch_pack_products(p, ctx->stream));
-  CK(cudaMemcpyAsync(products, d, n * L->stride, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  TRY(dev_free(ctx, &d));
-  return 0;
+  return stream_records(ctx, products, L, ctx->sorted_idx, first, n);
 }
 
 extern "C" int pinb200_download_field(pinb200_ctx* ctx, int which, void* dst) {

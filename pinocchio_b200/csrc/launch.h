@@ -43,10 +43,18 @@ struct PackParams {
 };
 cudaError_t launch_pack_products(const PackParams& p, cudaStream_t s);
 
-// collapsed-cell filter + radix sort (sort_cells.cuh): one 8-bit pass = count, scan, scatter (3 launches)
-struct SortPassParams;
-cudaError_t launch_sort_pass(const SortPassParams& p, unsigned long long* total, cudaStream_t s);
-cudaError_t launch_sort_count(const SortPassParams& p, unsigned long long* total, cudaStream_t s);
+// collapsed-cell selection + radix sort (k_sort.cu)
+size_t cell_sort_ntiles_select(unsigned long long ncells);
+size_t cell_sort_ntiles_radix(unsigned long long n);
+size_t cell_sort_scan_blocks(unsigned long long len);
+int cell_sort_max_bins();
+cudaError_t launch_scan_u32(unsigned int* a, unsigned long long len, unsigned int* block_sums, unsigned long long* total, cudaStream_t s);
+cudaError_t launch_select_count(const float* fmax, unsigned long long n, float f_last, unsigned int* tile_counts, unsigned int* range, cudaStream_t s);
+cudaError_t launch_select_write(const float* fmax, unsigned long long n, float f_last, const unsigned int* tile_base, const unsigned int* range,
+                                unsigned int* key_out, unsigned int* idx_out, cudaStream_t s);
+cudaError_t launch_radix_hist(const unsigned int* key, unsigned long long n, int shift, int bits, unsigned int* counts, cudaStream_t s);
+cudaError_t launch_radix_scatter(const unsigned int* key_in, const unsigned int* idx_in, unsigned int* key_out, unsigned int* idx_out,
+                                 unsigned long long n, int shift, int bits, const unsigned int* counts, cudaStream_t s);
 
 // host <-> device layout converters (pitch P on the device, N/2+1 or N on the host)
 cudaError_t launch_repitch_c(const double2* src, double2* dst, size_t nrows, int ncols, int spitch, int dpitch, cudaStream_t s);

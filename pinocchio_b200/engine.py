@@ -57,7 +57,7 @@ class Timers(ctypes.Structure):
                 ("mem_transf", ctypes.c_double), ("per_radius", ctypes.c_double * 64),
                 ("hess_x", ctypes.c_double), ("hess_y", ctypes.c_double), ("hess_z", ctypes.c_double),
                 ("disp_sources", ctypes.c_double), ("disp_vel", ctypes.c_double),
-                ("kernel_launches", ctypes.c_ulonglong)]
+                ("kernel_launches", ctypes.c_ulonglong), ("sort_ms", ctypes.c_double)]
 
 
 # every symbol include/pinb200.h declares (checked by tests/test_abi.py)
@@ -68,6 +68,7 @@ ABI_SYMBOLS = [
     "pinb200_upload_kdensity", "pinb200_download_kdensity", "pinb200_fmax", "pinb200_displacements",
     "pinb200_displacements_scaledep", "pinb200_collapsed_cells", "pinb200_download_products_sorted",
     "pinb200_fmax_pdf", "pinb200_download_products", "pinb200_download_field", "pinb200_get_timers",
+    "pinb200_write_products", "pinb200_write_block",
     "pinb200_fft_r2c", "pinb200_fft_c2r", "pinb200_second_derivatives", "pinb200_collapse_cells",
     "pinb200_download_kvector",
     "pinb200_ct_delta_vector", "pinb200_set_collapse_tables", "pinb200_download_collapse_table",
@@ -405,6 +406,24 @@ class Pinocchio:
         self._ck(self.lib.pinb200_download_products(self.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(lay),
                                                     cell_begin, ncells))
         return out
+
+    BLOCKS = {"FMAX": 0, "RMAX": 1, "ZEL ": 2, "2LPT": 3, "31PT": 4, "32PT": 5}      # block names of src/write_snapshot.c
+
+    def write_products(self, fileno: int, cell_begin: int = 0, ncells: int | None = None, dtype=PRODUCT_DTYPE_3LPT) -> None:
+        """DumpProducts/Task.<rank> payload (src/fmax.c:418-420) written to an open descriptor from the device SoA."""
+        if ncells is None:
+            ncells = self.lx * self.N ** 2 - cell_begin
+        f = dtype.fields
+        off = lambda n: f[n][1] if n in f else -1
+        lay = ProductLayout(dtype.itemsize, dtype["Fmax"].itemsize, off("Rmax"), off("Fmax"), off("Vel"), off("Vel_2LPT"),
+                            off("Vel_3LPT_1"), off("Vel_3LPT_2"))
+        self._ck(self.lib.pinb200_write_products(self.h, int(fileno), ctypes.byref(lay), cell_begin, ncells))
+
+    def write_block(self, fileno: int, name: str, cell_begin: int = 0, ncells: int | None = None) -> None:
+        """Payload of one timeless-snapshot block (initialize_FMAX ... initialize_3LPT_2, src/write_snapshot.c:695-860)."""
+        if ncells is None:
+            ncells = self.lx * self.N ** 2 - cell_begin
+        self._ck(self.lib.pinb200_write_block(self.h, int(fileno), self.BLOCKS[name], cell_begin, ncells))
 
     def timers(self) -> Timers:
         t = Timers()

@@ -13,7 +13,9 @@
 #include "def_splines.h"
 #include "pinb200.h"
 
+#include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 
@@ -47,6 +49,80 @@ static pinb200_product_layout product_layout(void)
 #endif
 #endif
   return L;
+}
+
+/* ---- hand-off to the fragmentation ------------------------------------------------------------
+ * What the unchanged CPU stage reads of products[] (src/distribute.c:547-600, 685-698): Fmax of EVERY cell (the
+ * distribution map keeps the cells with Fmax >= outputs.Flast) and the whole record of the cells it keeps.  So
+ * only those cross PCIe: the Fmax field (4 bytes per cell) and, selected and ordered on the device
+ * (pinb200_collapsed_cells), the records of the collapsed cells -- about 60 % of the cells of a z = 0 run, 44 of
+ * the 60 GB of a 1024^3 box -- which are scattered into their places in products[] here.  Used when a record
+ * holds nothing but members of this path (no SNAPSHOT / RECOMPUTE_DISPLACEMENTS members, whose consumers read
+ * every cell); PINB200_FULL_PRODUCTS=1 forces the plain copy of every record.  (DumpProducts is written from the
+ * device, see dump_products below, so it does not need the full host array either.) */
+static int use_compact_handoff(void)
+{
+#if defined(SNAPSHOT) || defined(RECOMPUTE_DISPLACEMENTS)
+  return 0;
+#else
+  const char *env = getenv("PINB200_FULL_PRODUCTS");
+  if (env && atoi(env))
+    return 0;
+  return outputs.Flast > 0.0;
+#endif
+}
+
+static int download_products_compact(const pinb200_product_layout *L)
+{
+  const size_t n = MyGrids[0].total_local_size, chunk = (size_t)1 << 22;
+  size_t count = 0, first, k;
+  float *fm, flast;
+  unsigned int *idx;
+  unsigned char *rec;
+
+  /* (float)Fmax >= (double)Flast  <=>  Fmax >= the smallest float that is not below Flast */
+  flast = (float)outputs.Flast;
+  if ((double)flast < (double)outputs.Flast)
+    flast = nextafterf(flast, INFINITY);
+
+  fm = (float *)malloc(n * sizeof(float));
+  if (!fm)
+    return 1;
+  if (pinb200_download_field(pinb, 0, fm))
+  {
+    free(fm);
+    return pinb_fail("download Fmax");
+  }
+#pragma omp parallel for
+  for (k = 0; k < n; k++)
+    products[k].Fmax = fm[k];
+  free(fm);
+
+  if (pinb200_collapsed_cells(pinb, flast, NULL, 0, &count))
+    return pinb_fail("collapsed cells");
+  if (!count)
+    return 0;
+  idx = (unsigned int *)malloc(count * sizeof(unsigned int));
+  rec = (unsigned char *)malloc((count < chunk ? count : chunk) * L->stride);
+  if (!idx || !rec)
+    return 1;
+  if (pinb200_collapsed_cells(pinb, flast, idx, count, &count))
+    return pinb_fail("collapsed cells");
+  for (first = 0; first < count; first += chunk)
+  {
+    const size_t m = count - first < chunk ? count - first : chunk;
+    if (pinb200_download_products_sorted(pinb, rec, L, first, m))
+      return pinb_fail("download collapsed records");
+#pragma omp parallel for
+    for (k = 0; k < m; k++)
+      memcpy(&products[idx[first + k]], rec + k * L->stride, L->stride);
+  }
+  free(rec);
+  free(idx);
+  if (!ThisTask)
+    printf("[%s] products[]: Fmax of %zu cells and the records of the %zu with Fmax >= %g (compact hand-off)\n", fdate(), n, count,
+           (double)flast);
+  return 0;
 }
 
 /* ---- replaces src/fmax-pfft.c:80-134 ---------------------------------------------------- */
@@ -145,7 +221,10 @@ int finalize_fft(void)
 {
 #ifndef RECOMPUTE_DISPLACEMENTS
   /* with RECOMPUTE_DISPLACEMENTS the k-vectors must survive until the last segment
-     (src/allocations.c:578-600): the context is then released at exit */
+     (src/allocations.c:578-600): the context is then released at exit.  With DumpProducts it lives until
+     dump_products() has written Task.<rank> from the device */
+  if (params.DumpProducts && pinb)
+    return 0;
   pinb200_destroy(pinb);
   pinb = NULL;
 #endif
@@ -243,7 +322,12 @@ int compute_displacements(int compute_sources, int recompute_sd, double redshift
 
   /* products[] is carved from the reference's arena; it is only filled here, never retained */
   t0 = MPI_Wtime();
-  if (pinb200_download_products(pinb, products, &L, 0, MyGrids[0].total_local_size))
+  if (use_compact_handoff())
+  {
+    if (download_products_compact(&L))
+      return 1;
+  }
+  else if (pinb200_download_products(pinb, products, &L, 0, MyGrids[0].total_local_size))
     return pinb_fail("download products");
   cputime.mem_transf += MPI_Wtime() - t0;
   return 0;
@@ -433,6 +517,22 @@ int dump_products(void)
   MPI_Barrier(MPI_COMM_WORLD); /* the directory exists before anybody writes into it */
   if (err || !(f = dump_open("Task", ThisTask, "wb")))
     return 1;
+#if !defined(SNAPSHOT) && !defined(RECOMPUTE_DISPLACEMENTS)
+  if (pinb)
+  {
+    /* the records come straight from the device SoA through pinned staging (pinb200_write_products): the file is
+       the same, and it does not depend on what the hand-off left in the host products[] */
+    pinb200_product_layout L = product_layout();
+    fflush(f);
+    err = pinb200_write_products(pinb, fileno(f), &L, 0, MyGrids[0].total_local_size);
+    fclose(f);
+    if (err)
+      return pinb_fail("dump_products");
+    pinb200_destroy(pinb);
+    pinb = NULL;
+    return 0;
+  }
+#endif
   fwrite(products, sizeof(product_data), MyGrids[0].total_local_size, f);
   fclose(f);
   return 0;

@@ -549,6 +549,9 @@ extern "C" int emu_fastmath(int which, const double* x, long long n, double* y) 
       case 5: y[i] = fm_div(x[2 * i], x[2 * i + 1]); break;  // x holds n (a, b) pairs
       case 6: y[i] = fm_sqrt(x[i]); break;
       case 7: y[i] = fm_sqrt_pair(x[i]).rs; break;
+      case 8: y[i] = fm_cbrt_pair(x[i]).c; break;
+      case 9: y[i] = fm_cbrt_pair(x[i]).rc; break;
+      case 10: { double c0, c1, c2; cos_thirds(x[i], c0, c1, c2); y[3 * i] = c0; y[3 * i + 1] = c1; y[3 * i + 2] = c2; break; }  // y holds 3n
       default: return 1;
     }
   }

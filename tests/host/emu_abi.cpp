@@ -15,6 +15,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 #include "../../include/pinb200.h"
 #include "../../pinocchio_b200/csrc/product_merge.h"
@@ -458,6 +459,43 @@ extern "C" int pinb200_download_products(pinb200_ctx* ctx, void* products, const
   if (pinb::members_cover_record(members, L->stride)) std::memcpy(products, packed.data(), packed.size());
   else pinb::merge_product_members(static_cast<unsigned char*>(products), packed.data(), L->stride, ncells, members);
   return 0;
+}
+// the file writers of engine.cu (records / snapshot blocks straight to a descriptor), here from the host arrays
+static int emu_write_records(pinb200_ctx* ctx, int fd, const pinb200_product_layout* L, size_t cell_begin, size_t ncells) {
+  std::vector<unsigned char> packed(ncells * L->stride, 0);
+  pack_records(ctx, L, cell_begin, ncells, nullptr, packed.data());
+  size_t done = 0;
+  while (done < packed.size()) {
+    const ssize_t w = write(fd, packed.data() + done, packed.size() - done);
+    if (w <= 0) FAIL("write failed");
+    done += (size_t)w;
+  }
+  return 0;
+}
+extern "C" int pinb200_write_products(pinb200_ctx* ctx, int fd, const pinb200_product_layout* L, size_t cell_begin, size_t ncells) {
+  if (!ctx || !L || fd < 0) return 1;
+  if (ctx->fmax.empty() && ctx->vel[0].empty()) FAIL("products not computed");
+  if (cell_begin + ncells > ctx->ncells()) FAIL("cell range outside the local slab");
+  return emu_write_records(ctx, fd, L, cell_begin, ncells);
+}
+extern "C" int pinb200_write_block(pinb200_ctx* ctx, int fd, int block, size_t cell_begin, size_t ncells) {
+  if (!ctx || fd < 0) return 1;
+  if (cell_begin + ncells > ctx->ncells()) FAIL("cell range outside the local slab");
+  pinb200_product_layout L{};
+  L.prodfloat_bytes = 4;
+  L.off_Rmax = L.off_Fmax = L.off_Vel = L.off_Vel_2LPT = L.off_Vel_3LPT_1 = L.off_Vel_3LPT_2 = -1;
+  bool have = false;
+  switch (block) {
+    case PINB200_BLOCK_FMAX: L.stride = 4; L.off_Fmax = 0; have = !ctx->fmax.empty(); break;
+    case PINB200_BLOCK_RMAX: L.stride = 4; L.off_Rmax = 0; have = !ctx->rmax.empty(); break;
+    case PINB200_BLOCK_ZEL: L.stride = 12; L.off_Vel = 0; have = !ctx->vel[0].empty(); break;
+    case PINB200_BLOCK_2LPT: L.stride = 12; L.off_Vel_2LPT = 0; have = !ctx->vel[3].empty(); break;
+    case PINB200_BLOCK_3LPT_1: L.stride = 12; L.off_Vel_3LPT_1 = 0; have = !ctx->vel[6].empty(); break;
+    case PINB200_BLOCK_3LPT_2: L.stride = 12; L.off_Vel_3LPT_2 = 0; have = !ctx->vel[9].empty(); break;
+    default: FAIL("unknown snapshot block");
+  }
+  if (!have) FAIL("the field of this block is not resident");
+  return emu_write_records(ctx, fd, &L, cell_begin, ncells);
 }
 extern "C" int pinb200_download_field(pinb200_ctx* ctx, int which, void* dst) {
   if (!ctx || !dst || which < 0 || which > 13) return 1;

@@ -57,12 +57,15 @@ def runs(request, tmp_path_factory):
         pytest.skip(f"{emu.name} / {ref.name} not built")
     a = tmp_path_factory.mktemp("emu" + v)
     b = tmp_path_factory.mktemp("ref" + v)
-    return a, run32(emu, a, v), b, run32(ref, b, v)
+    return a, run32(emu, a, v), b, run32(ref, b, v), v
 
 
 def test_emulated_dropin_log(runs):
-    a, log_a, b, log_b = runs
+    a, log_a, b, log_b, v = runs
     assert "B200 path" in log_a and "Pinocchio done!" in log_a and "B200 path" not in log_b
+    # products[] filled from the device-side selection + sort (shim: download_products_compact) unless the build's
+    # records carry members of other stages (RECOMPUTE_DISPLACEMENTS: the _sd variant)
+    assert ("compact hand-off" in log_a) == (v != "_sd")
     sig = lambda log: [float(x) for x in re.findall(r"computed sigma:\s+([0-9.]+)", log)]
     assert len(sig(log_a)) == 9 and sig(log_a) == sig(log_b)
     ncoll = lambda log: int(re.search(r"Number of collapsed particles to z=0: (\d+)", log).group(1))
@@ -73,7 +76,7 @@ def test_emulated_dropin_log(runs):
 
 
 def test_emulated_dropin_fmaxpdf_identical(runs):
-    a, _, b, _ = runs
+    a, _, b, _, _ = runs
     pa = np.loadtxt(a / "pinocchio.test.FmaxPDF.out")[:, 2]
     pb = np.loadtxt(b / "pinocchio.test.FmaxPDF.out")[:, 2]
     assert pa.sum() == N ** 3
@@ -83,7 +86,7 @@ def test_emulated_dropin_fmaxpdf_identical(runs):
 def test_emulated_dropin_past_light_cone(runs):
     """the _sd variant is also built with -DPLC (BASELINE.json configs[4]: scale-dependent growth with
     past light-cone output): the light-cone catalogue and n(z) of the two programs are the same bytes"""
-    a, _, b, _ = runs
+    a, _, b, _, _ = runs
     plc = list(b.glob("*.plc.out"))
     if not plc:
         pytest.skip("variant built without -DPLC")
@@ -94,7 +97,7 @@ def test_emulated_dropin_past_light_cone(runs):
 
 @pytest.mark.parametrize("z", ["0.0000", "0.5000", "1.0000", "2.0000"])
 def test_emulated_dropin_catalogues_match(runs, z):
-    a, _, b, _ = runs
+    a, _, b, _, _ = runs
     ia, na, ca = load_catalog(a / f"pinocchio.{z}.test.catalog.out")
     ib, nb, cb = load_catalog(b / f"pinocchio.{z}.test.catalog.out")
     assert len(ib) > 20
@@ -107,7 +110,7 @@ def test_emulated_dropin_catalogues_match(runs, z):
 
 
 def test_emulated_dropin_mass_function_matches(runs):
-    a, _, b, _ = runs
+    a, _, b, _, _ = runs
     ma = np.loadtxt(a / "pinocchio.0.0000.test.mf.out")
     mb = np.loadtxt(b / "pinocchio.0.0000.test.mf.out")
     assert np.array_equal(ma[:, 4], mb[:, 4])          # halos per mass bin

@@ -267,6 +267,29 @@ def test_fastmath_div_sqrt_newton_schedules(lib):
     assert (np.abs(rs * ref - 1.0) <= 4e-16).all()
 
 
+def test_cbrt_pair_and_cos_thirds(lib):
+    """fm_cbrt_pair (cube root and its reciprocal from one Newton chain, seed cut to 20 bits on the host) and the
+    Estrin form of cos_thirds against libm."""
+    rng = np.random.default_rng(21)
+
+    def run(which, x, nout=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(x.size if nout is None else nout)
+        assert lib.emu_fastmath(which, ptr(x), ctypes.c_longlong(x.size), ptr(y)) == 0
+        return y
+
+    x = np.concatenate([10.0 ** rng.uniform(-300, 300, 300000), rng.uniform(0.5, 9.0, 100000), [1.0, 8.0, 27.0, 1e-20, 1e60, 2.0 ** -1022]])
+    ref = np.cbrt(x)
+    assert (np.abs(run(8, x) - ref) <= 5e-16 * ref).all()                     # 2 ulp
+    assert (np.abs(run(9, x) * ref - 1.0) <= 4e-16).all()
+    with np.errstate(invalid="ignore"):
+        assert np.isnan(run(8, np.array([-1.0, 0.0, np.nan, np.inf]))).all()
+    t = np.concatenate([rng.uniform(0, np.pi, 200000), [0.0, np.pi, np.pi / 2]])
+    c = run(10, t, 3 * t.size).reshape(-1, 3)
+    for j in range(3):
+        assert np.abs(c[:, j] - np.cos((t + 2 * np.pi * j) / 3)).max() < 1e-15
+
+
 @pytest.mark.parametrize("n,frac_ties", [(1, 0.0), (5000, 0.0), (16384, 0.5), (16385, 0.0), (100003, 0.3)])
 def test_collapsed_cells_filter_and_sort(lib, n, frac_ties):
     """pinb200_collapsed_cells' kernels (sort_cells.cuh) under the block emulator: cells with

@@ -228,5 +228,9 @@ int main(int argc, char** argv) {
     bench_zc<N, 1, 6, 3, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, tag);
     bench_zc<N, 1, 6, 2, 1>(g, B, tw, dspl, nspl, fmax, rmax, sums, tag);
   }
+  if (want("z2")) {  // two cells per thread and iteration
+    bench_zc<N, 1, 6, 3, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cpt2");
+    bench_zc<N, 1, 6, 2, 2>(g, B, tw, dspl, nspl, fmax, rmax, sums, "cpt2");
+  }
   return 0;
 }
