@@ -332,6 +332,7 @@ def run_b200(args):
             PU = ctypes.POINTER(ctypes.c_uint)
 
             phases = {"h2d_kdensity": 0.0, "compute": 0.0, "d2h_fmax": 0.0, "select_sort_d2h_index": 0.0, "d2h_records": 0.0}
+            tme0 = pin.timers()
 
             def e2e_step():
                 t = [time.perf_counter()]          # every library call returns with its work done: wall-clock phases
@@ -380,6 +381,9 @@ def run_b200(args):
                               "Fmax (device-side selection + radix sort), as shim/fmax_b200.c fills products[] for src/distribute.c",
                    "collapsed_cells": ncoll_all, "select_sort_ms_device": round(float(sort_ms), 2), "handoff_ok": order_ok,
                    "phases_ms_rank0": {k: round(v / ne * 1e3, 1) for k, v in phases.items()}}
+            tme1 = pin.timers()
+            # the compute phase on the device clock (CUDA events inside the engine) next to its wall-clock time above
+            e2e["phases_ms_rank0"]["compute_device_events"] = round(((tme1.fmax - tme0.fmax) + (tme1.lpt - tme0.lpt)) * 1e3 / (ne + 1), 1)
             # the plain copy of every record, once, for comparison (r01's e2e definition)
             try:
                 chunk = min(ncell_local, 1 << 26)

@@ -25,6 +25,8 @@ pytestmark = pytest.mark.skipif(not EMU_ABI.exists(), reason="oracle/_ref/libpin
     ("tests/test_zgpu_5_collapse_tables.py", "not linked", 4),
     # -DDOUBLE_PRECISION_PRODUCTS records and lpt_order 1 / 2 through the ABI (the linked programs run in test_dropin_emulated.py)
     ("tests/test_zgpu_6_build_variants.py", "widened or lower_lpt or seed_plane", 4),
+    # snapshot blocks and product dumps written from the device SoA: the 32^3 case
+    ("tests/test_zgpu_7_device_writers.py", "from_device and 32", 1),
 ])
 def test_late_gpu_tests_pass_on_the_emulated_abi(target, select, npass):
     env = dict(os.environ, PINB200_LIB=str(EMU_ABI))
