@@ -14,7 +14,8 @@
  *   - gsl_odeiv2: Runge-Kutta-Fehlberg 4(5) step, standard step-size control (S = 0.9, factors
  *     0.2 .. 5), one accepted step per evolve_apply;
  *   - gsl_root_fsolver_brent: bracketing secant/bisection steps;
- *   - gsl_spline2d (only -DREAD_PK_TABLE): traps.
+ *   - gsl_spline2d bicubic (only -DREAD_PK_TABLE): GSL's construction (derivatives from 1-D natural splines,
+ *     bicubic Hermite patch per cell), evaluated in Hermite-basis form.
  * Nothing in the product links this file. */
 #include <math.h>
 #include <stdio.h>
@@ -132,15 +133,81 @@ void gsl_spline_free(gsl_spline* s) { if (s) { gsl_interp_free(s->interp); free(
 struct gsl_interp2d_type_s { int kind; };
 static const gsl_interp2d_type t_bicubic = {0};
 const gsl_interp2d_type* gsl_interp2d_bicubic = &t_bicubic;
-static void trap2d(void) { fprintf(stderr, "oracle/ref_full: gsl_spline2d (READ_PK_TABLE) is not provided\n"); abort(); }
-gsl_spline2d* gsl_spline2d_alloc(const gsl_interp2d_type* T, size_t nx, size_t ny) { (void)T; (void)nx; (void)ny; trap2d(); return NULL; }
+/* gsl_interp2d_bicubic (GSL 2.7 interpolation/bicubic.c): the partial derivatives z_x, z_y, z_xy at the grid
+ * points come from one-dimensional natural cubic splines through the rows and columns (z_xy: through the
+ * columns of z_y), and every cell is the bicubic Hermite patch through the four corner values and derivatives.
+ * z is stored as GSL does: z[j * nx + i] = z(x_i, y_j). */
+struct gsl_spline2d_s { size_t nx, ny; double *x, *y, *z, *zx, *zy, *zxy; };
+gsl_spline2d* gsl_spline2d_alloc(const gsl_interp2d_type* T, size_t nx, size_t ny) {
+  (void)T;
+  gsl_spline2d* s = calloc(1, sizeof(gsl_spline2d));
+  s->nx = nx;
+  s->ny = ny;
+  s->x = calloc(nx, sizeof(double));
+  s->y = calloc(ny, sizeof(double));
+  s->z = calloc(nx * ny, sizeof(double));
+  s->zx = calloc(nx * ny, sizeof(double));
+  s->zy = calloc(nx * ny, sizeof(double));
+  s->zxy = calloc(nx * ny, sizeof(double));
+  return s;
+}
 int gsl_spline2d_init(gsl_spline2d* s, const double* x, const double* y, const double* z, size_t nx, size_t ny) {
-  (void)s; (void)x; (void)y; (void)z; (void)nx; (void)ny; trap2d(); return 1;
+  memcpy(s->x, x, nx * sizeof(double));
+  memcpy(s->y, y, ny * sizeof(double));
+  memcpy(s->z, z, nx * ny * sizeof(double));
+  const size_t nmax = nx > ny ? nx : ny;
+  double* col = malloc(nmax * sizeof(double));
+  gsl_spline* sx = gsl_spline_alloc(gsl_interp_cspline, nx);
+  gsl_spline* sy = gsl_spline_alloc(gsl_interp_cspline, ny);
+  for (size_t j = 0; j < ny; j++) { /* z_x: splines in x along every row j */
+    for (size_t i = 0; i < nx; i++) col[i] = z[j * nx + i];
+    gsl_spline_init(sx, x, col, nx);
+    for (size_t i = 0; i < nx; i++) s->zx[j * nx + i] = gsl_spline_eval_deriv(sx, x[i], NULL);
+  }
+  for (size_t i = 0; i < nx; i++) { /* z_y: splines in y along every column i */
+    for (size_t j = 0; j < ny; j++) col[j] = z[j * nx + i];
+    gsl_spline_init(sy, y, col, ny);
+    for (size_t j = 0; j < ny; j++) s->zy[j * nx + i] = gsl_spline_eval_deriv(sy, y[j], NULL);
+  }
+  for (size_t j = 0; j < ny; j++) { /* z_xy: splines in x through z_y */
+    for (size_t i = 0; i < nx; i++) col[i] = s->zy[j * nx + i];
+    gsl_spline_init(sx, x, col, nx);
+    for (size_t i = 0; i < nx; i++) s->zxy[j * nx + i] = gsl_spline_eval_deriv(sx, x[i], NULL);
+  }
+  gsl_spline_free(sx);
+  gsl_spline_free(sy);
+  free(col);
+  return GSL_SUCCESS;
 }
 double gsl_spline2d_eval(const gsl_spline2d* s, double x, double y, gsl_interp_accel* a, gsl_interp_accel* b) {
-  (void)s; (void)x; (void)y; (void)a; (void)b; trap2d(); return 0;
+  (void)a; (void)b;
+  const size_t nx = s->nx;
+  if (x < s->x[0] || x > s->x[nx - 1] || y < s->y[0] || y > s->y[s->ny - 1]) return NAN; /* GSL: domain error */
+  const size_t xi = bsearch_interval(s->x, nx, x), yi = bsearch_interval(s->y, s->ny, y);
+  const double dx = s->x[xi + 1] - s->x[xi], dy = s->y[yi + 1] - s->y[yi];
+  const double t = (x - s->x[xi]) / dx, u = (y - s->y[yi]) / dy;
+  const size_t i00 = yi * nx + xi, i10 = yi * nx + xi + 1, i01 = (yi + 1) * nx + xi, i11 = (yi + 1) * nx + xi + 1;
+  /* corner data in the unit square: f, f_t = z_x dx, f_u = z_y dy, f_tu = z_xy dx dy */
+  const double f[4] = {s->z[i00], s->z[i10], s->z[i01], s->z[i11]};
+  const double ft[4] = {s->zx[i00] * dx, s->zx[i10] * dx, s->zx[i01] * dx, s->zx[i11] * dx};
+  const double fu[4] = {s->zy[i00] * dy, s->zy[i10] * dy, s->zy[i01] * dy, s->zy[i11] * dy};
+  const double ftu[4] = {s->zxy[i00] * dx * dy, s->zxy[i10] * dx * dy, s->zxy[i01] * dx * dy, s->zxy[i11] * dx * dy};
+  /* cubic Hermite basis in each direction: h00 value at 0, h01 value at 1, h10 slope at 0, h11 slope at 1 */
+  const double t2 = t * t, t3 = t2 * t, u2 = u * u, u3 = u2 * u;
+  const double ht[4] = {2 * t3 - 3 * t2 + 1, -2 * t3 + 3 * t2, t3 - 2 * t2 + t, t3 - t2};
+  const double hu[4] = {2 * u3 - 3 * u2 + 1, -2 * u3 + 3 * u2, u3 - 2 * u2 + u, u3 - u2};
+  double zq = 0.0;
+  for (int jc = 0; jc < 2; jc++)   /* corner (ic, jc) is element ic + 2 jc of the arrays above */
+    for (int ic = 0; ic < 2; ic++) {
+      const int c = ic + 2 * jc;
+      zq += f[c] * ht[ic] * hu[jc] + ft[c] * ht[2 + ic] * hu[jc] + fu[c] * ht[ic] * hu[2 + jc] + ftu[c] * ht[2 + ic] * hu[2 + jc];
+    }
+  return zq;
 }
-void gsl_spline2d_free(gsl_spline2d* s) { (void)s; }
+void gsl_spline2d_free(gsl_spline2d* s) {
+  if (!s) return;
+  free(s->x); free(s->y); free(s->z); free(s->zx); free(s->zy); free(s->zxy); free(s);
+}
 
 /* ---- quadrature ------------------------------------------------------------------------------ */
 struct gsl_integration_workspace_s { size_t limit; double *a, *b, *r, *e; };

@@ -126,16 +126,18 @@ def _near_tie_mask(Fs, tol=1e-6):
     return np.abs(top2[1] - top2[0]) <= tol * np.maximum(1.0, np.abs(top2[1]))
 
 
-@pytest.mark.parametrize("N", [64, 128])
-def test_fmax_and_displacements(N, cosmo):
+@pytest.mark.parametrize("N,radii", [(64, HMF_RADII), (128, HMF_RADII), (256, [9.026099, 3.058354, 0.689079, 0.0])],
+                         ids=["64", "128", "256"])
+def test_fmax_and_displacements(N, radii, cosmo):
     """compute_fmax end to end (src/fmax.c:36-190): Fmax, Rmax, TrueVariance, FmaxPDF, the four
-    displacement fields, the LPT k-vectors and the AoS products against the oracle."""
-    p = make(N, cosmo, radii=HMF_RADII)
+    displacement fields, the LPT k-vectors and the AoS products against the oracle.  (256^3: the largest box the
+    NumPy oracle crosses in a few minutes, on four radii of the ladder; the 512-point line kernels.)"""
+    p = make(N, cosmo, radii=radii)
     p.GenIC_large()
     kd = p.read_kdensity()
     p.compute_fmax()
     growth = p.growth_rates(0.0)
-    ref = po.compute_fmax(kd, HMF_RADII, 1.0 / 0.7, cosmo.InverseGrowingMode, growth=tuple(growth), keep=True)
+    ref = po.compute_fmax(kd, radii, 1.0 / 0.7, cosmo.InverseGrowingMode, growth=tuple(growth), keep=True)
 
     assert np.abs(p.TrueVariance / ref["TrueVariance"] - 1).max() < 1e-12
     Fmax, Rmax = p.field("Fmax"), p.field("Rmax")
