@@ -428,6 +428,37 @@ def run_b200(args):
                 e2e["pcie_pinned_copy"] = {"error": str(ex)[:200]}
             del kd_host, fm_host, idx_host, rec_host
 
+    # ---- BASELINE.json configs[4]: scale-dependent growth (massive neutrinos / modified gravity) at the same grid:
+    #      the displacement fields are re-derived per redshift segment with a growth rate G(|k|) evaluated per mode in
+    #      the x-pass loader (xpass_growthk_kernel: InterpolateGrowth's ten k-bin splines, src/cosmo.c:1728-1757, a
+    #      log10 and a pow per mode).  Timed next to the scale-independent velocity stage on the resident k-vectors.
+    scaledep = None
+    if world == 1 and not args.no_scaledep:
+        try:
+            nk = 10                                                        # NkBINS, LOGKMIN = -3, DELTALOGK = 0.5 (src/def_splines.h:40-42)
+            g0 = np.log10(np.abs(pin.growth_rates(0.0)))
+            tab = np.ascontiguousarray(g0[:, None] + 0.004 * np.arange(nk)[None, :])     # a few per cent of k dependence
+            Nc = float(N) * N * (N // 2)
+            xbytes = 3 * 16 * Nc                                           # one field read, two written (kx^0 and kx^1 jobs)
+            res = {}
+            for name, fn in (("scale_independent", None), ("scale_dependent", lambda z: tab)):
+                pin.set_scale_dependent_growth(fn, -3.0, 0.5)
+                pin.compute_displacements(0, 0, 0.0)                      # warm-up
+                ta = pin.timers()
+                for _ in range(2):
+                    pin.compute_displacements(0, 0, 0.0)
+                tb = pin.timers()
+                xms = (tb.disp_x - ta.disp_x) * 1e3 / 8.0                 # four x passes per call
+                res[name] = {"velocity_stage_ms": round((tb.disp_vel - ta.disp_vel) * 1e3 / 2.0, 2),
+                             "xpass_ms_per_launch": round(xms, 3), "xpass_gbs": round(xbytes / (xms * 1e-3) / 1e9, 1)}
+            pin.set_scale_dependent_growth(None)
+            scaledep = {"workload": f"scale-dependent growth {N}^3: four first-derivative triples (Zel'dovich, 2LPT, 3LPT_1, 3LPT_2) "
+                                    "with G(|k|) per mode, NkBINS = 10 tables as the reference hands them over per redshift segment",
+                        "kernel": "xpass_growthk_kernel", "algorithmic_bytes_per_xpass": int(xbytes), **res,
+                        "xpass_frac_of_hbm_peak": round(res["scale_dependent"]["xpass_gbs"] / peak, 4)}
+        except Exception as ex:  # noqa: BLE001
+            scaledep = {"error": str(ex)[:300]}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_sample(args.cpu_grid or 256, 1)
@@ -505,7 +536,7 @@ def run_b200(args):
                "scaling": "weak" if world in (1, 8) else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": workload_config(N, world, S),
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-               "cpu_baseline": cpu_baseline, "fragment_handoff": handoff, "dropin_program": dropin, "collapse_tables": ctable, "checks": checks, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
+               "cpu_baseline": cpu_baseline, "fragment_handoff": handoff, "dropin_program": dropin, "collapse_tables": ctable, "scaledep": scaledep, "checks": checks, "genic_s": round(genic_s, 4), "setup_s": round(time.time() - t0, 1)}
         print(json.dumps(out))
     pin.close()
     if world > 1:
@@ -609,6 +640,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-handoff", action="store_true", help="skip the fragmentation hand-off probe (fresh process, N=1 only)")
+    ap.add_argument("--no-scaledep", action="store_true", help="skip the scale-dependent growth timing (configs[4], N=1 only)")
     ap.add_argument("--write-parity-fixture", default="", help="N=1: write TrueVariance and FmaxPDF of this run as the fixture the N>1 runs are compared with")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -55,6 +55,8 @@ typedef struct {
   double disp_sources, disp_vel; /* displacement stage: sources + k-vectors; 4 x first derivatives */
   unsigned long long kernel_launches;  /* kernels launched by this context so far            */
   double sort_ms;                      /* last pinb200_collapsed_cells: selection + sort on the device, milliseconds */
+  double disp_x;                       /* displacement stage: the four inverse x passes of the first derivatives, seconds
+                                          (with pinb200_displacements_scaledep: xpass_growthk_kernel, growth rate per mode) */
 } pinb200_timers;
 
 /* ---- life cycle ---------------------------------------------------------------------- */

@@ -42,6 +42,9 @@ struct pinb200_ctx {
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;          // D2H of packed records (stream_records)
   cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // staging buffer b: [b] packed, [2 + b] copied out
+  cudaStream_t xfer[3] = {nullptr, nullptr, nullptr};  // copy-engine transposes of the multi-GPU sweep (one stream per field)
+  cudaEvent_t ev_xfer[8] = {nullptr};          // [0] x pass done, [1] first barrier passed, [2..3] streams 1, 2 done, [4] all transposes landed
+  double2* stage_extra[3] = {nullptr, nullptr, nullptr};  // x-pass staging when the arena has no k-vector slots (lpt_order < 3)
   unsigned char* pinned = nullptr;             // two pinned host buffers of the file writers
   size_t pinned_bytes = 0;
   std::string err;
@@ -97,6 +100,9 @@ struct pinb200_ctx {
   pinb200_timers tm{};
   unsigned long long launches = 0;
   cudaEvent_t ev[3 * 64 + 8] = {nullptr};
+  cudaEvent_t ev_mid[64] = {nullptr};  // pipelined multi-GPU sweep: between the y pass of a radius and the x pass of the next
+  cudaEvent_t ev_dx[8] = {nullptr};   // x passes of the four first-derivative calls of the displacement stage
+  int ndx = 0;
 };
 
 #define CK(call)                                                                              \
@@ -222,6 +228,10 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
   }
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
+  for (auto& ev : ctx->ev_dx)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
+  for (auto& ev : ctx->ev_mid)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
   *out = ctx;
   return 0;
 }
@@ -271,8 +281,13 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->d.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
   }
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_dx) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_mid) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& st : ctx->xfer) if (st) cudaStreamDestroy(st);
+  for (auto& ev : ctx->ev_xfer) if (ev) cudaEventDestroy(ev);
+  for (auto& q : ctx->stage_extra) if (q) cudaFree(q);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -488,8 +503,9 @@ static const double* spline_for(pinb200_ctx* ctx, int ismooth) {
 #define NEED_PEERS() do { if (!ctx->connected) FAIL("peer arenas not connected: exchange pinb200_ipc_handle() and call pinb200_connect()"); } while (0)
 
 // cross-GPU barrier on the stream (no-op on one rank)
-static int peer_barrier(pinb200_ctx* ctx) {
+static int peer_barrier(pinb200_ctx* ctx, cudaStream_t stream = nullptr) {
   if (ctx->P == 1) return 0;
+  if (!stream) stream = ctx->stream;
   BarrierParams b{};
   for (int r = 0; r < ctx->P; r++) b.flags[r] = reinterpret_cast<unsigned long long*>(ctx->peer_arena[r] + ctx->off_flags);
   b.rank = ctx->d.rank;
@@ -497,7 +513,7 @@ static int peer_barrier(pinb200_ctx* ctx) {
   b.epoch = ++ctx->epoch;
   b.error = ctx->d_error;
   b.timeout_ns = (unsigned long long)(ctx->barrier_timeout_s * 1e9);
-  LAUNCH(launch_barrier(b, ctx->stream));
+  LAUNCH(launch_barrier(b, stream));
   return 0;
 }
 
@@ -729,6 +745,79 @@ static int ensure_products(pinb200_ctx* ctx) {
 
 // Hessian passes for one radius: fills B[0..5] (half-complex, after x and y passes).
 // slot order xx,yy,zz,xy,xz,yz (src/fmax.c:239)
+// ---- multi-GPU sweep: the transposes leave the SMs ----------------------------------------------------------
+// r01 fused the all-to-all of every inverse FFT into the x pass as peer stores: at 2048^3 on 8 GPUs that pass
+// took 55 ms per radius (32 ms of it for the line FFTs themselves, the rest waiting on NVLink: SM stores to peer
+// memory block the issuing warps), strictly before the 26 ms y pass and the 56 ms collapse pass.  Here the x pass
+// of radius r+1 writes its three fields LOCALLY, in the K layout it reads (x-major: the part destined to rank d,
+// x in [d lx, (d+1) lx), is one contiguous block), into the arena slots of the LPT k-vectors, which are idle
+// during the sweep; the copy engines then move every (field, destination) block into the owner's R-layout buffer
+// -- lx rows of ly P elements, one strided cudaMemcpy2DAsync each -- on side streams WHILE the SMs run the
+// collapse pass of radius r.  Order: y(r) -> x(r+1) [main] ; barrier, 3 x P copies, barrier [side] || z(r) [main];
+// y(r+1) waits for the side streams.  The first barrier says "every rank has finished reading A(r)", the second
+// "every block of A(r+1) has landed everywhere"; all sweep barriers are issued on one side stream, in order.
+// PINB200_PEER_STORES=1 selects the r01 schedule (peer stores, nothing overlapped).
+static int xfer_setup(pinb200_ctx* ctx) {
+  if (ctx->xfer[0]) return 0;
+  for (auto& st : ctx->xfer) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (auto& ev : ctx->ev_xfer) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  return 0;
+}
+static int xpass_staging(pinb200_ctx* ctx, double2* S[3]) {
+  for (int i = 0; i < 3; i++) {
+    if (ctx->KV[i]) { S[i] = ctx->KV[i]; continue; }
+    if (!ctx->stage_extra[i]) CK(cudaMalloc(&ctx->stage_extra[i], ctx->field_elems * sizeof(double2)));
+    S[i] = ctx->stage_extra[i];
+  }
+  return 0;
+}
+// inverse x pass of kdens for one radius into local K-layout staging (no peer traffic, no barrier)
+static int run_xpass_local(pinb200_ctx* ctx, double2* const S[3], double rsmooth) {
+  const Geom& g = ctx->g;
+  LAUNCH(launch_gauss_table(ctx->gauss, g.M, g.knorm, rsmooth, ctx->stream));
+  XPassParams p{};
+  p.src = ctx->kdens;
+  for (int i = 0; i < 3; i++) p.dst[i].r[0] = S[i];
+  p.dst_klayout = 1;
+  p.lx_shift = ctx->lx_shift;
+  p.pmask = 0x7;
+  p.ntiles_z = ntiles(ctx, xpass_tk(g.N, +1), ctx->kdens_has_nyq);
+  p.kf.gauss = ctx->gauss;
+  p.kf.scalar = 1.0 / ((double)g.N * g.N * g.N);
+  p.kf.green = 1;
+  p.kf.times_i = 0;
+  p.g = g;
+  p.tw = ctx->tw;
+  LAUNCH(launch_xpass(g.N, +1, p, g.ly, ctx->stream));
+  return 0;
+}
+// S (K layout, local) -> A (R layout) of every rank, by the copy engines; after_event: what the copies must follow
+static int transpose_dma(pinb200_ctx* ctx, double2* const S[3], cudaEvent_t after_event, cudaEvent_t done_event) {
+  const Geom& g = ctx->g;
+  const size_t row = (size_t)g.ly * g.P * sizeof(double2);          // one x plane of the local K-layout slab
+  const size_t dpitch = (size_t)g.N * g.P * sizeof(double2);        // one x plane of an R-layout slab
+  CK(cudaStreamWaitEvent(ctx->xfer[0], after_event, 0));
+  TRY(peer_barrier(ctx, ctx->xfer[0]));                             // nobody reads the old A any more
+  CK(cudaEventRecord(ctx->ev_xfer[1], ctx->xfer[0]));
+  for (int f = 0; f < 3; f++) {
+    cudaStream_t st = ctx->xfer[f];
+    if (f) CK(cudaStreamWaitEvent(st, ctx->ev_xfer[1], 0));
+    for (int k = 0; k < ctx->P; k++) {
+      const int d = (ctx->d.rank + 1 + k) % ctx->P;                 // start with the neighbour: the ranks do not all hit rank 0 first
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(S[f]) + (size_t)d * g.lx * row;
+      unsigned char* dst = ctx->peer_arena[d] + ctx->off_A[f] + (size_t)ctx->d.rank * row;
+      CK(cudaMemcpy2DAsync(dst, dpitch, src, row, row, (size_t)g.lx, cudaMemcpyDeviceToDevice, st));
+    }
+    if (f) {
+      CK(cudaEventRecord(ctx->ev_xfer[1 + f], st));
+      CK(cudaStreamWaitEvent(ctx->xfer[0], ctx->ev_xfer[1 + f], 0));
+    }
+  }
+  TRY(peer_barrier(ctx, ctx->xfer[0]));                             // every block has landed on every rank
+  CK(cudaEventRecord(done_event, ctx->xfer[0]));
+  return 0;
+}
+
 // The k = 0 constant of delta_k (the same for every radius: the window is 1 at k = 0) is read from rank 0
 // through the peer mapping.  The barrier orders the read after rank 0's GenIC / upload on ITS stream:
 // those calls end with a local synchronisation only, so without it a rank > 0 could read a stale value.
@@ -774,9 +863,35 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   CK(cudaMemsetAsync(ctx->sums, 0, sizeof(double) * 2 * 64, ctx->stream));
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   TRY(hessian_dc(ctx));
+  const char* ps_env = getenv("PINB200_PEER_STORES");
+  const bool pipelined = ctx->P > 1 && !(ps_env && atoi(ps_env));
+  double2* S[3] = {nullptr, nullptr, nullptr};
+  static const YJob hess_jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
+  if (pipelined) {
+    TRY(xfer_setup(ctx));
+    TRY(xpass_staging(ctx, S));
+    // prologue: x pass and transposes of the first radius (nothing to hide them behind)
+    TRY(run_xpass_local(ctx, S, ctx->radius[0] / cell));
+    CK(cudaEventRecord(ctx->ev_xfer[0], ctx->stream));
+    TRY(transpose_dma(ctx, S, ctx->ev_xfer[0], ctx->ev_xfer[4]));
+  }
   for (int is = 0; is < ns; is++) {
     const double rs = ctx->radius[is] / cell;  // Rsmooth in grid units, src/fmax.c:233
-    TRY(hessian_xy(ctx, rs, ctx->ev[8 + 3 * is]));
+    if (!pipelined) {
+      TRY(hessian_xy(ctx, rs, ctx->ev[8 + 3 * is]));
+    } else {
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_xfer[4], 0));      // A(is) complete on this rank
+      CK(cudaEventRecord(ctx->ev[8 + 3 * is], ctx->stream));
+      TRY(run_ypass_inv(ctx, ctx->A, ctx->B, hess_jobs, 6, ctx->kdens_has_nyq));
+      CK(cudaEventRecord(ctx->ev_mid[is], ctx->stream));
+      if (is + 1 < ns) {
+        // x pass of the next radius right behind the y pass (the staging is free: its transposes ended before
+        // this y pass began); its transposes then run under the collapse pass below
+        TRY(run_xpass_local(ctx, S, ctx->radius[is + 1] / cell));
+        CK(cudaEventRecord(ctx->ev_xfer[0], ctx->stream));
+        TRY(transpose_dma(ctx, S, ctx->ev_xfer[0], ctx->ev_xfer[4]));
+      }
+    }
     CK(cudaEventRecord(ctx->ev[8 + 3 * is + 1], ctx->stream));
     CollapseParams c{};
     for (int k = 0; k < 6; k++) {
@@ -803,6 +918,7 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     LAUNCH(launch_zpass_collapse(g.N, c, (size_t)g.lx * g.N, ctx->stream));
     CK(cudaEventRecord(ctx->ev[8 + 3 * is + 2], ctx->stream));
   }
+  if (pipelined) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_xfer[4], 0));  // (no-op: the last radius started no transposes)
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   // the Hessian kept for the LPT sources is that of the LAST radius: it is the unsmoothed one only when the
   // ladder ends with R = 0 as set_smoothing guarantees (src/initialization.c:386-435); any other ladder
@@ -824,6 +940,14 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     CK(cudaEventElapsedTime(&x, is == 0 ? ctx->ev[0] : ctx->ev[8 + 3 * is - 1], ctx->ev[8 + 3 * is]));
     CK(cudaEventElapsedTime(&y, ctx->ev[8 + 3 * is], ctx->ev[8 + 3 * is + 1]));
     CK(cudaEventElapsedTime(&z, ctx->ev[8 + 3 * is + 1], ctx->ev[8 + 3 * is + 2]));
+    if (pipelined) {
+      // x = exposed wait for the transposes (radius 0: the whole prologue) + the local x pass of the NEXT radius,
+      // which runs between this radius' y and z passes
+      float yy = 0;
+      CK(cudaEventElapsedTime(&yy, ctx->ev[8 + 3 * is], ctx->ev_mid[is]));
+      x += y - yy;
+      y = yy;
+    }
     ctx->tm.hess_x += x * 1e-3;
     ctx->tm.hess_y += y * 1e-3;
     ctx->tm.hess_z += z * 1e-3;
@@ -843,7 +967,10 @@ static int first_derivs_to_vel(pinb200_ctx* ctx, const double2* kvec, double gro
   TRY(run_dc(ctx, kvec, norm, 1));
   double2* xdst[3] = {ctx->A[1], ctx->A[0], nullptr};  // p=0 -> A1, p=1 -> A0
   // Rsmooth = 0 (src/fmax.c:200 with R = 0): window = 1
+  const int slot = ctx->ndx < 4 ? ctx->ndx++ : -1;
+  if (slot >= 0) CK(cudaEventRecord(ctx->ev_dx[2 * slot], ctx->stream));
   TRY(run_xpass_inv(ctx, kvec, xdst, 0x3, false, 1, 1, norm * growth, with_nyq, gk));
+  if (slot >= 0) CK(cudaEventRecord(ctx->ev_dx[2 * slot + 1], ctx->stream));
   const double2* ysrc[3] = {ctx->A[0], ctx->A[1], nullptr};
   double2* ydst[6] = {ctx->D[0], ctx->D[1], ctx->D[2], nullptr, nullptr, nullptr};
   static const YJob jobs[3] = {{0, 0, 0}, {1, 1, 1}, {1, 0, 2}};
@@ -935,6 +1062,7 @@ static int displacements_impl(pinb200_ctx* ctx, int compute_sources, const doubl
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   const int nvel = order == 1 ? 3 : (order == 2 ? 6 : 12);
   for (int i = 0; i < nvel; i++) TRY(dev_alloc(ctx, &ctx->vel[i], ctx->ncells));
+  ctx->ndx = 0;
   TRY(peer_barrier(ctx));  // all k-vectors complete everywhere before rank 0's k = 0 modes are read
   if (order >= 2) TRY(first_derivs_to_vel(ctx, ctx->KV[0], growth[1], ctx->vel + 3, true, gk ? gk + 1 : nullptr));   // ScaleDep.order = 2
   if (order >= 3) {
@@ -951,6 +1079,11 @@ static int displacements_impl(pinb200_ctx* ctx, int compute_sources, const doubl
   ctx->tm.lpt += (a + b) * 1e-3;
   ctx->tm.disp_sources += a * 1e-3;
   ctx->tm.disp_vel += b * 1e-3;
+  for (int i = 0; i < ctx->ndx; i++) {
+    float x = 0;
+    CK(cudaEventElapsedTime(&x, ctx->ev_dx[2 * i], ctx->ev_dx[2 * i + 1]));
+    ctx->tm.disp_x += x * 1e-3;
+  }
   return 0;
 }
 

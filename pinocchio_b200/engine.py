@@ -57,7 +57,8 @@ class Timers(ctypes.Structure):
                 ("mem_transf", ctypes.c_double), ("per_radius", ctypes.c_double * 64),
                 ("hess_x", ctypes.c_double), ("hess_y", ctypes.c_double), ("hess_z", ctypes.c_double),
                 ("disp_sources", ctypes.c_double), ("disp_vel", ctypes.c_double),
-                ("kernel_launches", ctypes.c_ulonglong), ("sort_ms", ctypes.c_double)]
+                ("kernel_launches", ctypes.c_ulonglong), ("sort_ms", ctypes.c_double),
+                ("disp_x", ctypes.c_double)]
 
 
 # every symbol include/pinb200.h declares (checked by tests/test_abi.py)

@@ -21,8 +21,9 @@ pin = Pinocchio(RunConfig(GridSize=N, BoxSize_htrue=N / 0.7, lpt_order=3), cosmo
 pin.GenIC_large()
 pin.compute_fmax()
 t0 = time.perf_counter()
-idx = pin.collapsed_cells(1.0)          # count query + filter + 4 radix passes + D2H of the index list
+idx = pin.collapsed_cells(1.0)          # count query, then selection + radix sort + D2H of the index list into pageable memory
 t_sort = time.perf_counter() - t0
+t_dev = pin.timers().sort_ms            # selection + sort on the device clock (CUDA events)
 F = pin.field("Fmax").ravel()
 Fs = F[idx]
 ok = bool(idx.size == int((F >= 1.0).sum()) and (np.diff(Fs) <= 0).all())
@@ -32,6 +33,6 @@ frag = pin.sorted_products(0, chunk)    # gathered AoS records, frag[] order
 t_dl = time.perf_counter() - t0
 ok = ok and bool(np.array_equal(frag["Fmax"], Fs[:chunk]))
 print(json.dumps({"grid": N, "collapsed_cells": int(idx.size), "collapsed_fraction": round(idx.size / float(N) ** 3, 6),
-                  "filter_sort_ms": round(t_sort * 1e3, 2), "sorted_records_downloaded": int(chunk),
+                  "filter_sort_ms": round(t_dev, 2), "filter_sort_wall_ms_incl_pageable_index_download": round(t_sort * 1e3, 2), "sorted_records_downloaded": int(chunk),
                   "sorted_download_ms": round(t_dl * 1e3, 2), "order_and_records_ok": ok}))
 pin.close()

@@ -30,7 +30,7 @@ def test_struct_sizes_match_header():
     from pinocchio_b200.engine import Desc, ProductLayout, Timers
     assert ctypes.sizeof(Desc) == 48
     assert ctypes.sizeof(ProductLayout) == 40
-    assert ctypes.sizeof(Timers) == 8 * 7 + 8 * 64 + 8 * 5 + 8 + 8      # ... kernel_launches, sort_ms
+    assert ctypes.sizeof(Timers) == 8 * 7 + 8 * 64 + 8 * 5 + 8 + 8 + 8      # ... kernel_launches, sort_ms, disp_x
 
 
 def test_no_cpu_fallback(lib):
@@ -46,3 +46,17 @@ def test_product_does_not_import_oracle():
     for f in (ROOT / "pinocchio_b200").rglob("*"):
         if f.suffix in (".py", ".cu", ".cuh", ".h"):
             assert "oracle" not in f.read_text().replace("the oracle", "").replace("an oracle", ""), f
+
+
+def test_linked_programs_find_the_library_next_to_them():
+    """oracle/_ref/pinocchio_b200*.x (and the emulated ones) must carry a RUNPATH relative to their own location
+    ($ORIGIN): the GPU box runs them from another root (an `$$ORIGIN` lost inside the Makefile's define/eval once
+    produced `RIGIN/...`, found only by the full hardware run)."""
+    import subprocess
+    exes = sorted((ROOT / "oracle" / "_ref").glob("pinocchio_b200*.x")) + sorted((ROOT / "oracle" / "_ref").glob("pinocchio_emu*.x"))
+    if not exes:
+        pytest.skip("oracle/_ref not built")
+    for exe in exes:
+        out = subprocess.run(["readelf", "-d", str(exe)], capture_output=True, text=True).stdout
+        paths = re.findall(r"(?:RUNPATH|RPATH).*\[(.*)\]", out)
+        assert paths and paths[0].startswith("$ORIGIN"), (exe.name, paths)
