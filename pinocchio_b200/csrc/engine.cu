@@ -777,8 +777,11 @@ static int run_xpass_local(pinb200_ctx* ctx, double2* const S[3], double rsmooth
   LAUNCH(launch_gauss_table(ctx->gauss, g.M, g.knorm, rsmooth, ctx->stream));
   XPassParams p{};
   p.src = ctx->kdens;
-  for (int i = 0; i < 3; i++) p.dst[i].r[0] = S[i];
-  p.dst_klayout = 1;
+  for (int i = 0; i < 3; i++) {
+    p.dst[i].r[0] = S[i];
+    p.dst[i].r[1] = ctx->A[i];   // this rank's own x planes skip the staging
+  }
+  p.dst_klayout = 2;
   p.lx_shift = ctx->lx_shift;
   p.pmask = 0x7;
   p.ntiles_z = ntiles(ctx, xpass_tk(g.N, +1), ctx->kdens_has_nyq);
@@ -802,7 +805,7 @@ static int transpose_dma(pinb200_ctx* ctx, double2* const S[3], cudaEvent_t afte
   for (int f = 0; f < 3; f++) {
     cudaStream_t st = ctx->xfer[f];
     if (f) CK(cudaStreamWaitEvent(st, ctx->ev_xfer[1], 0));
-    for (int k = 0; k < ctx->P; k++) {
+    for (int k = 0; k + 1 < ctx->P; k++) {                          // (the block of this rank itself was written in place by the x pass)
       const int d = (ctx->d.rank + 1 + k) % ctx->P;                 // start with the neighbour: the ranks do not all hit rank 0 first
       const unsigned char* src = reinterpret_cast<const unsigned char*>(S[f]) + (size_t)d * g.lx * row;
       unsigned char* dst = ctx->peer_arena[d] + ctx->off_A[f] + (size_t)ctx->d.rank * row;
@@ -863,8 +866,11 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   CK(cudaMemsetAsync(ctx->sums, 0, sizeof(double) * 2 * 64, ctx->stream));
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   TRY(hessian_dc(ctx));
+  // Worth it when the transposes fit under the collapse pass: from four ranks on.  On two ranks every GPU ships half
+  // of its x-pass output (13 GB per radius at 1024^3, 15-20 ms of NVLink) against a 24 ms collapse pass whose HBM
+  // traffic it also disturbs: measured 589 ms per step against 548 ms with peer stores (r02, 2 x B200).
   const char* ps_env = getenv("PINB200_PEER_STORES");
-  const bool pipelined = ctx->P > 1 && !(ps_env && atoi(ps_env));
+  const bool pipelined = ps_env ? (ctx->P > 1 && !atoi(ps_env)) : (ctx->P >= 4);
   double2* S[3] = {nullptr, nullptr, nullptr};
   static const YJob hess_jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
   if (pipelined) {

@@ -47,30 +47,39 @@ struct KFactor {
 
 // InterpolateGrowth (src/cosmo.c:1728-1757) at a fixed redshift, followed by the pow(10., .) of
 // GrowingMode* (src/cosmo.c:1786-1819).  kmin = 10^LOGKMIN, kmax = 10^(LOGKMIN + (n-1) DELTALOGK)
-// are recomputed with pow() exactly as src/cosmo.c:169-170 does.
+// as src/cosmo.c:169-170 computes them.
+// The reference evaluates log10(k) and pow(10., v) with libm for every mode; r02 measured the x pass with that
+// loader at 35.8 ms against 9.6 ms without it (1024^3), i.e. the pass was bound by two libm calls per mode.  Here:
+// log10 k = log10(k^2) / 2 (no square root; the clamps compare k^2 with kmin^2, kmax^2, set once per thread) and
+// the constant-bank log10 / 10^x of fastmath.cuh (1e-16 relative, as libm to the last bits; the function is
+// continuous across both clamps, so an ulp of difference at a boundary moves nothing).
 struct GrowthRange {
-  double kmin = 0.0, kmax = 0.0;
+  double kmin2 = 0.0, kmax2 = 0.0, inv_dlogk = 0.0;
   PINB_HD void set(const KFactor& kf) {
-    kmin = pow(10., kf.gk_logkmin);
-    kmax = pow(10., kf.gk_logkmin + (kf.gk_n - 1) * kf.gk_dlogk);
+    const double kmin = fm_exp10(kf.gk_logkmin);
+    const double kmax = fm_exp10(kf.gk_logkmin + (kf.gk_n - 1) * kf.gk_dlogk);
+    kmin2 = kmin * kmin;
+    kmax2 = kmax * kmax;
+    inv_dlogk = 1.0 / kf.gk_dlogk;
   }
 };
-PINB_HD double growth_of_k(const KFactor& kf, const GrowthRange& gr, double k) {
-  const double kmin = gr.kmin, kmax = gr.kmax;
+// k2 = |k|^2 (grid units, as the reference passes k_module, src/fmax-pfft.c:340)
+PINB_HD double growth_of_k2(const KFactor& kf, const GrowthRange& gr, double k2) {
   double v;
-  if (k < kmin) {
+  if (k2 < gr.kmin2) {
     v = kf.gk[0];
-  } else if (k > kmax) {
+  } else if (k2 > gr.kmax2) {
     v = kf.gk[kf.gk_n - 1];
   } else {
-    double dk = (log10(k) - kf.gk_logkmin) / kf.gk_dlogk;
-    const int kk = (int)dk;
+    double dk = (0.5 * fm_log10(k2) - kf.gk_logkmin) * gr.inv_dlogk;
+    int kk = (int)dk;
+    kk = kk < 0 ? 0 : kk;                       // rounding of log10 just below kmin
     dk -= kk;
     // k == kmax gives kk = n-1 and dk = 0: the reference reads SPLINE[pointer+kk+1] there too
     // (the next table, times zero); here the weight-zero term is dropped instead
-    v = (kk + 1 < kf.gk_n) ? dk * kf.gk[kk + 1] + (1 - dk) * kf.gk[kk] : kf.gk[kk];
+    v = (kk + 1 < kf.gk_n) ? dk * kf.gk[kk + 1] + (1 - dk) * kf.gk[kk < kf.gk_n ? kk : kf.gk_n - 1] : kf.gk[kf.gk_n - 1];
   }
-  return kf.gk_sign * pow(10., v);
+  return kf.gk_sign * fm_exp10(v);
 }
 
 // Launch shapes shared by the CUDA instantiations and the host emulator.
@@ -245,6 +254,8 @@ struct XPassParams {
   PeerPtrs dst[3];      // per power p of kx: base pointer of the destination field on every rank
   int dst_klayout;      // 0: scatter to the R layout of the owner rank (inverse transforms)
                         // 1: local K layout, dst[p].r[0] (forward transforms, in place allowed)
+                        // 2: staged transpose -- own x range straight into the local R-layout field dst[p].r[1],
+                        //    everything else into the local K-layout staging dst[p].r[0] (the copy engines move it)
   int lx_shift;         // log2(lx)
   int pmask;            // bit p set -> compute job p
   int ntiles_z;         // kz tiles per row that are processed (M/TK, +1 with the Nyquist tile)
@@ -302,7 +313,7 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
     }
     if constexpr (GK) {
       const double k2 = kx * kx + kyz2;
-      if (k2 != 0.0) f *= growth_of_k(p.kf, grange, sqrt(k2));  // k_module, src/fmax-pfft.c:340
+      if (k2 != 0.0) f *= growth_of_k2(p.kf, grange, k2);  // k_module = sqrt(k2), src/fmax-pfft.c:340
     }
     if (p.kf.gauss) f *= ld_ro(p.kf.gauss + (nx < 0 ? -nx : nx));
     f *= ipow(kx, pw);
@@ -325,7 +336,9 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   auto storef = [&](int job, int k, int tk, double2 val) {
     const int e = SPLIT ? 2 * k + (job & 1) : k;
     const PeerPtrs& dp = p.dst[jobs[SPLIT ? (job >> 1) : job]];
-    if (p.dst_klayout) {
+    if (p.dst_klayout == 2 && e >= g.x0 && e < g.x0 + g.lx) {
+      dp.r[1][(size_t)(e - g.x0) * ((size_t)g.N * g.P) + roff + tk] = val;
+    } else if (p.dst_klayout) {
       dp.r[0][(size_t)e * xstride + (size_t)yl * g.P + kz0 + tk] = val;
     } else if (!MULTI) {
       dp.r[0][(size_t)e * ((size_t)g.N * g.P) + roff + tk] = val;

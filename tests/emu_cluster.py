@@ -83,6 +83,27 @@ class EmuCluster:
                                              ptr(tab), tab.size, ctypes.c_double(gk[1]), ctypes.c_double(gk[2]),
                                              ctypes.c_double(gk[3])) == 0
 
+    def xpass_inv_staged(self, src, S, A, pmask, with_nyq, gauss, scalar, green, times_i):
+        """The pipelined multi-GPU sweep's transposes (engine.cu run_xpass_local + transpose_dma): every rank's x pass
+        writes its own x planes straight into its R-layout field A[pw][rank] and everything else into a LOCAL
+        K-layout staging field S[pw][rank] (XPassParams::dst_klayout = 2); the copy engines then move block
+        (source rank r -> destination rank d) = S[pw][r][d lx : (d+1) lx] into A[pw][d][:, r ly : (r+1) ly] --
+        done here with NumPy slices, which is exactly what the strided cudaMemcpy2DAsync calls do."""
+        lx = self.lx
+        for r in range(self.P):
+            flat = []
+            for pw in range(3):
+                flat += [S[pw][r], A[pw][r]] + [None] * (self.P - 2)
+            assert self.lib.emu_xpass(self.N, +1, r, self.P, ptr(src[r]), ptr_array(flat, 3 * self.P), 2, pmask,
+                                      with_nyq, ptr(gauss), ctypes.c_double(scalar), green, times_i, ptr(self.tw)) == 0
+        for pw in range(3):
+            if not (pmask >> pw) & 1:
+                continue
+            for r in range(self.P):
+                for d in range(self.P):
+                    if d != r:
+                        A[pw][d][:, r * lx:(r + 1) * lx, :] = S[pw][r][d * lx:(d + 1) * lx, :, :]
+
     def ypass_inv(self, srcs, dsts, jobs, with_nyq):
         ja = np.asarray(jobs, dtype=np.int32).ravel()
         for r in range(self.P):

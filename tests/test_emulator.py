@@ -145,6 +145,28 @@ def scaledep_tables(nk=10, seed=11):
     return base + 0.3 * np.cumsum(rng.uniform(-0.2, 0.2, (4, nk)), axis=1)
 
 
+@pytest.mark.parametrize("P,split", [(2, False), (4, False), (2, True)])
+def test_staged_transpose_equals_peer_stores(P, split):
+    """Multi-GPU sweep, two ways of doing the transpose behind the inverse x pass: peer stores from the kernel
+    (r01) and own planes in place + local staging + strided block copies (r02, what the copy engines do under the
+    collapse pass).  The R-layout fields must come out bit-identical, pads and Nyquist columns aside."""
+    N = 32
+    cl = EmuCluster(N, P, split=split)
+    rng = np.random.default_rng(17)
+    glob = rng.standard_normal((N, N, N // 2 + 1)) + 1j * rng.standard_normal((N, N, N // 2 + 1))
+    cl.scatter_k(glob, cl.kdens)
+    M = N // 2
+    gauss = np.exp(-0.5 * (2 * np.pi / N * np.arange(M + 1)) ** 2 * 1.7 ** 2)
+    cl.xpass_inv(cl.kdens, {0: cl.A[0], 1: cl.A[1], 2: cl.A[2]}, 7, 0, gauss, cl.norm, 1, 0)
+    want = [[a.copy() for a in cl.A[pw]] for pw in range(3)]
+    A2 = [[cl.rfield() for _ in range(P)] for _ in range(3)]
+    S = [[cl.kfield() for _ in range(P)] for _ in range(3)]
+    cl.xpass_inv_staged(cl.kdens, S, A2, 7, 0, gauss, cl.norm, 1, 0)
+    for pw in range(3):
+        for r in range(P):
+            assert np.array_equal(A2[pw][r][:, :, :M], want[pw][r][:, :, :M]), (pw, r)
+
+
 def test_interpolate_growth_clamps_and_knots():
     """Oracle restatement of InterpolateGrowth: knots are reproduced, clamped outside [kmin, kmax]."""
     tab = scaledep_tables()[0]
