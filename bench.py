@@ -238,20 +238,25 @@ def run_b200(args):
     achieved = abytes[dom] / (per_launch_ms[dom] * 1e-3) / 1e9
     rad_ms = sum(per_launch_ms.values())
     lpt_ms = (tm1.lpt - tm0.lpt) / K * 1e3
-    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same grid / GPU count only)
-    traffic, traffic_src = None, None
-    try:
-        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text()).get(dom)
-        if tj and tj["grid"] == N and tj["n_gpus"] == world:
-            traffic, traffic_src = round((tj["read_gb"] + tj["write_gb"]) * 1e9), tj["source"]
-    except (OSError, ValueError, KeyError):
-        pass
+    # DRAM bytes and instruction counts per launch from the committed ncu counter pass of this build
+    # (profiles/r02_traffic.json, written by tools/ncu_to_traffic.py; same grid / GPU count only)
+    traffic, traffic_src, prof = None, None, {}
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            prof = json.loads((ROOT / "profiles" / name).read_text())
+            tj = prof.get(dom)
+            if tj and tj["grid"] == N and tj["n_gpus"] == world:
+                traffic, traffic_src = round((tj["read_gb"] + tj["write_gb"]) * 1e9), f"profiles/{name}: {tj['source']}"
+            break
+        except (OSError, ValueError, KeyError):
+            continue
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": round(abytes[dom]), "peak_source": peak_src,
-                "note": "the dominant kernel (z pass + collapse epilogue) is FP64-issue bound, not HBM bound (r01 ncu: FP64 pipe 70 %, "
-                        "issue slots 69 % busy, DRAM 20 %); frac is against the HBM peak as the contract defines it, "
-                        "fp64_pipe.frac against the FP64 pipe",
+                "note": "the dominant kernel (z pass + collapse epilogue) is bound by instruction issue, not by HBM: an FP64 "
+                        "instruction holds a sub-partition's dispatch port for two cycles on sm_100 (tools/fp64lat.cu), and "
+                        "2 x FP64 + other instructions per cell account for its whole run time (roofline.issue); frac is "
+                        "against the HBM peak as the contract defines it",
                 "ms_per_launch": {k: round(v, 3) for k, v in per_launch_ms.items()},
                 "gbs_per_kernel": {k: round(abytes[k] / (v * 1e-3) / 1e9, 1) for k, v in per_launch_ms.items()},
                 "per_radius_ms": round(rad_ms, 3),
@@ -259,18 +264,26 @@ def run_b200(args):
                 "lpt_stage_ms": round(lpt_ms, 3),
                 "lpt_frac_of_survey_roofline": round(survey_lpt / (lpt_ms * 1e-3) / 1e9 / peak, 4),
                 "whole_step_frac_of_survey_roofline": round(survey_total / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
-    # The collapse kernel's real ceiling is the FP64 pipe: FP64-pipe instructions
-    # per cell (ncu sm__inst_executed_pipe_fp64.sum x 32 / cells = 538.6 at 1024^3,
-    # profiles/r01_ncu_zcollapse_1024_final.csv) against 148 SMs x 4 sub-partitions x one FP64 warp
-    # instruction per 2 clocks.
+    # Instruction-issue roofline of every radius kernel: a sub-partition dispatches one warp instruction per clock and an
+    # FP64 one occupies the port for two (measured: 0.5 warp-DFMA / clk / sub-partition, 8-cycle dependent latency), so
+    # a kernel needs at least (2 x FP64 + other) warp instructions / (592 sub-partitions x clock).  Instruction counts:
+    # ncu counter pass of this build (smsp__inst_executed.sum, sm__inst_executed_pipe_fp64.sum), time: live.
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    fp64_per_cell = 538.6
-    pipe_peak = 148 * 4 * sm_mhz * 1e6 / 2.0                                   # warp instructions / s
-    fp64_rate = fp64_per_cell * (cells / world / 32.0) / (per_launch_ms["zpass_collapse_kernel"] * 1e-3)
-    roofline["fp64_pipe"] = {"kernel": "zpass_collapse_kernel", "fp64_inst_per_cell": fp64_per_cell,
-                             "achieved_warp_inst_per_s": round(fp64_rate, -6), "peak_warp_inst_per_s": round(pipe_peak, -6),
-                             "frac": round(fp64_rate / pipe_peak, 4), "sm_mhz": sm_mhz,
-                             "source": "instruction count from the committed ncu capture (profiles/r01_ncu_zcollapse_1024_final.csv), time live"}
+    issue = {}
+    for k, ms_k in per_launch_ms.items():
+        e = prof.get(k)
+        if not e or not e.get("warp_inst") or e.get("grid") != N:
+            continue
+        scale = 1.0 / world if e.get("n_gpus", 1) == 1 else 1.0        # counts of the 1-GPU launch cover the whole box
+        slots = (e["warp_inst"] + e["fp64_warp_inst"]) * scale
+        floor_ms = slots / (148 * 4 * sm_mhz * 1e6) * 1e3
+        issue[k] = {"warp_inst": int(e["warp_inst"] * scale), "fp64_warp_inst": int(e["fp64_warp_inst"] * scale),
+                    "issue_floor_ms": round(floor_ms, 2), "frac_of_issue_roofline": round(floor_ms / ms_k, 4)}
+        if "fp64_inst_per_cell" in e:
+            issue[k]["fp64_inst_per_cell"] = round(e["fp64_inst_per_cell"], 1)
+            issue[k]["inst_per_cell"] = round(e["inst_per_cell"], 1)
+    roofline["issue"] = dict(issue, sm_mhz=sm_mhz, source=prof.get("_source"),
+                             model="ms >= (warp_inst + fp64_warp_inst) / (592 x sm_clock): FP64 instructions take two dispatch cycles")
     if world > 1:
         # NVLink side of the metric: the only exchange is the transpose fused into the x pass as
         # peer stores.  Per GPU and radius this design moves 3 x-transformed fields (the y pass makes the 6
@@ -284,7 +297,11 @@ def run_b200(args):
         sent_survey = 6 * 16 * Ncs * (world - 1) / world ** 2
         t_hbm = survey_rad / (peak * 1e9)
         t_nvl, t_nvl_survey = sent / (nvl_peak * 1e9), sent_survey / (nvl_peak * 1e9)
-        roofline["nvlink"] = {"kernel": "xpass_kernel (transpose fused as peer stores)", "unit": "GB/s", "peak": nvl_peak,
+        xfer_ms = (tm1.xfer - tm0.xfer) / (K * S) * 1e3                    # copy-engine transposes per radius (0: peer-store schedule)
+        roofline["nvlink"] = {"kernel": "copy-engine transposes behind a local x pass, hidden under the collapse pass" if xfer_ms > 0
+                              else "xpass_kernel (transpose fused as peer stores)", "unit": "GB/s", "peak": nvl_peak,
+                              "transposes_ms_per_radius": round(xfer_ms, 3),
+                              "transposes_gbs": round(sent / (xfer_ms * 1e-3) / 1e9, 1) if xfer_ms > 0 else None,
                               "peak_source": "nominal NVLink 5, per direction per GPU",
                               "bytes_sent_per_gpu_per_radius": round(sent),
                               "bytes_sent_per_gpu_per_radius_survey_model": round(sent_survey),

@@ -57,6 +57,9 @@ typedef struct {
   double sort_ms;                      /* last pinb200_collapsed_cells: selection + sort on the device, milliseconds */
   double disp_x;                       /* displacement stage: the four inverse x passes of the first derivatives, seconds
                                           (with pinb200_displacements_scaledep: xpass_growthk_kernel, growth rate per mode) */
+  double xfer;                         /* multi-GPU sweep: copy-engine transposes (first barrier passed -> all local copies
+                                          issued by this rank done), seconds, summed over the radii; they run under the
+                                          collapse pass of the previous radius */
 } pinb200_timers;
 
 /* ---- life cycle ---------------------------------------------------------------------- */

@@ -42,8 +42,8 @@ struct pinb200_ctx {
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;          // D2H of packed records (stream_records)
   cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // staging buffer b: [b] packed, [2 + b] copied out
-  cudaStream_t xfer[3] = {nullptr, nullptr, nullptr};  // copy-engine transposes of the multi-GPU sweep (one stream per field)
-  cudaEvent_t ev_xfer[8] = {nullptr};          // [0] x pass done, [1] first barrier passed, [2..3] streams 1, 2 done, [4] all transposes landed
+  cudaStream_t xfer[PINB_MAXR] = {nullptr};    // copy-engine transposes of the multi-GPU sweep: stream k serves destination rank + 1 + k
+  cudaEvent_t ev_xfer[8 + PINB_MAXR] = {nullptr};  // [0] x pass done, [1] first barrier passed, [4] all transposes landed, [8 + k] stream k done
   double2* stage_extra[3] = {nullptr, nullptr, nullptr};  // x-pass staging when the arena has no k-vector slots (lpt_order < 3)
   unsigned char* pinned = nullptr;             // two pinned host buffers of the file writers
   size_t pinned_bytes = 0;
@@ -100,6 +100,8 @@ struct pinb200_ctx {
   pinb200_timers tm{};
   unsigned long long launches = 0;
   cudaEvent_t ev[3 * 64 + 8] = {nullptr};
+  cudaEvent_t ev_xt[2 * 64] = {nullptr};  // timing of the transposes of radius r: [2r] first barrier passed, [2r + 1] copies done
+  int nxt = 0;
   cudaEvent_t ev_mid[64] = {nullptr};  // pipelined multi-GPU sweep: between the y pass of a radius and the x pass of the next
   cudaEvent_t ev_dx[8] = {nullptr};   // x passes of the four first-derivative calls of the displacement stage
   int ndx = 0;
@@ -232,6 +234,8 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
   for (auto& ev : ctx->ev_mid)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
+  for (auto& ev : ctx->ev_xt)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e);
   *out = ctx;
   return 0;
 }
@@ -283,6 +287,7 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_dx) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_mid) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_xt) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& st : ctx->xfer) if (st) cudaStreamDestroy(st);
@@ -759,7 +764,11 @@ static int ensure_products(pinb200_ctx* ctx) {
 // PINB200_PEER_STORES=1 selects the r01 schedule (peer stores, nothing overlapped).
 static int xfer_setup(pinb200_ctx* ctx) {
   if (ctx->xfer[0]) return 0;
-  for (auto& st : ctx->xfer) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  // highest priority: the one-block barrier kernels on these streams must get an SM slot while the collapse pass,
+  // launched right behind them with a million blocks, owns the machine
+  int lo = 0, hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  for (int k = 0; k + 1 < ctx->P; k++) CK(cudaStreamCreateWithPriority(&ctx->xfer[k], cudaStreamNonBlocking, hi));
   for (auto& ev : ctx->ev_xfer) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   return 0;
 }
@@ -802,20 +811,25 @@ static int transpose_dma(pinb200_ctx* ctx, double2* const S[3], cudaEvent_t afte
   CK(cudaStreamWaitEvent(ctx->xfer[0], after_event, 0));
   TRY(peer_barrier(ctx, ctx->xfer[0]));                             // nobody reads the old A any more
   CK(cudaEventRecord(ctx->ev_xfer[1], ctx->xfer[0]));
-  for (int f = 0; f < 3; f++) {
-    cudaStream_t st = ctx->xfer[f];
-    if (f) CK(cudaStreamWaitEvent(st, ctx->ev_xfer[1], 0));
-    for (int k = 0; k + 1 < ctx->P; k++) {                          // (the block of this rank itself was written in place by the x pass)
-      const int d = (ctx->d.rank + 1 + k) % ctx->P;                 // start with the neighbour: the ranks do not all hit rank 0 first
+  const int slot = ctx->nxt < 64 ? ctx->nxt++ : -1;
+  if (slot >= 0) CK(cudaEventRecord(ctx->ev_xt[2 * slot], ctx->xfer[0]));
+  // one stream per destination (the copies to different peers can use different copy engines and links), the three
+  // fields of a destination in a row; the block of this rank itself was written in place by the x pass
+  for (int k = 0; k + 1 < ctx->P; k++) {
+    const int d = (ctx->d.rank + 1 + k) % ctx->P;
+    cudaStream_t st = ctx->xfer[k];
+    if (k) CK(cudaStreamWaitEvent(st, ctx->ev_xfer[1], 0));
+    for (int f = 0; f < 3; f++) {
       const unsigned char* src = reinterpret_cast<const unsigned char*>(S[f]) + (size_t)d * g.lx * row;
       unsigned char* dst = ctx->peer_arena[d] + ctx->off_A[f] + (size_t)ctx->d.rank * row;
       CK(cudaMemcpy2DAsync(dst, dpitch, src, row, row, (size_t)g.lx, cudaMemcpyDeviceToDevice, st));
     }
-    if (f) {
-      CK(cudaEventRecord(ctx->ev_xfer[1 + f], st));
-      CK(cudaStreamWaitEvent(ctx->xfer[0], ctx->ev_xfer[1 + f], 0));
+    if (k) {
+      CK(cudaEventRecord(ctx->ev_xfer[8 + k], st));
+      CK(cudaStreamWaitEvent(ctx->xfer[0], ctx->ev_xfer[8 + k], 0));
     }
   }
+  if (slot >= 0) CK(cudaEventRecord(ctx->ev_xt[2 * slot + 1], ctx->xfer[0]));
   TRY(peer_barrier(ctx, ctx->xfer[0]));                             // every block has landed on every rank
   CK(cudaEventRecord(done_event, ctx->xfer[0]));
   return 0;
@@ -873,6 +887,7 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   const bool pipelined = ps_env ? (ctx->P > 1 && !atoi(ps_env)) : (ctx->P >= 4);
   double2* S[3] = {nullptr, nullptr, nullptr};
   static const YJob hess_jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
+  ctx->nxt = 0;
   if (pipelined) {
     TRY(xfer_setup(ctx));
     TRY(xpass_staging(ctx, S));
@@ -941,6 +956,14 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   ctx->tm.fmax += ms * 1e-3;
+  if (pipelined) {
+    for (auto& st : ctx->xfer) if (st) CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < ctx->nxt; i++) {
+      float t = 0;
+      CK(cudaEventElapsedTime(&t, ctx->ev_xt[2 * i], ctx->ev_xt[2 * i + 1]));
+      ctx->tm.xfer += t * 1e-3;
+    }
+  }
   for (int is = 0; is < ns; is++) {
     float x = 0, y = 0, z = 0;
     CK(cudaEventElapsedTime(&x, is == 0 ? ctx->ev[0] : ctx->ev[8 + 3 * is - 1], ctx->ev[8 + 3 * is]));

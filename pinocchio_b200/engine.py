@@ -58,7 +58,7 @@ class Timers(ctypes.Structure):
                 ("hess_x", ctypes.c_double), ("hess_y", ctypes.c_double), ("hess_z", ctypes.c_double),
                 ("disp_sources", ctypes.c_double), ("disp_vel", ctypes.c_double),
                 ("kernel_launches", ctypes.c_ulonglong), ("sort_ms", ctypes.c_double),
-                ("disp_x", ctypes.c_double)]
+                ("disp_x", ctypes.c_double), ("xfer", ctypes.c_double)]
 
 
 # every symbol include/pinb200.h declares (checked by tests/test_abi.py)

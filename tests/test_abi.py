@@ -30,7 +30,7 @@ def test_struct_sizes_match_header():
     from pinocchio_b200.engine import Desc, ProductLayout, Timers
     assert ctypes.sizeof(Desc) == 48
     assert ctypes.sizeof(ProductLayout) == 40
-    assert ctypes.sizeof(Timers) == 8 * 7 + 8 * 64 + 8 * 5 + 8 + 8 + 8      # ... kernel_launches, sort_ms, disp_x
+    assert ctypes.sizeof(Timers) == 8 * 7 + 8 * 64 + 8 * 5 + 8 + 8 + 8 + 8      # ... kernel_launches, sort_ms, disp_x, xfer
 
 
 def test_no_cpu_fallback(lib):
