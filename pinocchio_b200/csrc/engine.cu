@@ -42,8 +42,8 @@ struct pinb200_ctx {
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;          // D2H of packed records (stream_records)
   cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // staging buffer b: [b] packed, [2 + b] copied out
-  cudaStream_t xfer[PINB_MAXR] = {nullptr};    // copy-engine transposes of the multi-GPU sweep: stream k serves destination rank + 1 + k
-  cudaEvent_t ev_xfer[8 + PINB_MAXR] = {nullptr};  // [0] x pass done, [1] first barrier passed, [4] all transposes landed, [8 + k] stream k done
+  cudaStream_t xfer[PINB_MAXR] = {nullptr};    // copy-engine transposes of the multi-GPU sweep: one stream per field (three in use)
+  cudaEvent_t ev_xfer[8 + PINB_MAXR] = {nullptr};  // [0] x pass done, [1] first barrier passed, [4] all transposes landed, [8 + f] stream f done
   double2* stage_extra[3] = {nullptr, nullptr, nullptr};  // x-pass staging when the arena has no k-vector slots (lpt_order < 3)
   unsigned char* pinned = nullptr;             // two pinned host buffers of the file writers
   size_t pinned_bytes = 0;
@@ -764,11 +764,9 @@ static int ensure_products(pinb200_ctx* ctx) {
 // PINB200_PEER_STORES=1 selects the r01 schedule (peer stores, nothing overlapped).
 static int xfer_setup(pinb200_ctx* ctx) {
   if (ctx->xfer[0]) return 0;
-  // highest priority: the one-block barrier kernels on these streams must get an SM slot while the collapse pass,
-  // launched right behind them with a million blocks, owns the machine
-  int lo = 0, hi = 0;
-  CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  for (int k = 0; k + 1 < ctx->P; k++) CK(cudaStreamCreateWithPriority(&ctx->xfer[k], cudaStreamNonBlocking, hi));
+  // one stream per field.  (r02, 8 x B200, 2048^3: one high-priority stream per DESTINATION -- seven concurrent copies
+  // per GPU -- was slower, 1792 ms per step against 1685 ms; the copy engines sustain ~390-440 GB/s per GPU either way)
+  for (int k = 0; k < 3; k++) CK(cudaStreamCreateWithFlags(&ctx->xfer[k], cudaStreamNonBlocking));
   for (auto& ev : ctx->ev_xfer) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   return 0;
 }
@@ -813,20 +811,20 @@ static int transpose_dma(pinb200_ctx* ctx, double2* const S[3], cudaEvent_t afte
   CK(cudaEventRecord(ctx->ev_xfer[1], ctx->xfer[0]));
   const int slot = ctx->nxt < 64 ? ctx->nxt++ : -1;
   if (slot >= 0) CK(cudaEventRecord(ctx->ev_xt[2 * slot], ctx->xfer[0]));
-  // one stream per destination (the copies to different peers can use different copy engines and links), the three
-  // fields of a destination in a row; the block of this rank itself was written in place by the x pass
-  for (int k = 0; k + 1 < ctx->P; k++) {
-    const int d = (ctx->d.rank + 1 + k) % ctx->P;
-    cudaStream_t st = ctx->xfer[k];
-    if (k) CK(cudaStreamWaitEvent(st, ctx->ev_xfer[1], 0));
-    for (int f = 0; f < 3; f++) {
+  // one stream per field, the destinations of a field in a row starting with the neighbour (the ranks do not all hit
+  // rank 0 first); the block of this rank itself was written in place by the x pass
+  for (int f = 0; f < 3; f++) {
+    cudaStream_t st = ctx->xfer[f];
+    if (f) CK(cudaStreamWaitEvent(st, ctx->ev_xfer[1], 0));
+    for (int k = 0; k + 1 < ctx->P; k++) {
+      const int d = (ctx->d.rank + 1 + k) % ctx->P;
       const unsigned char* src = reinterpret_cast<const unsigned char*>(S[f]) + (size_t)d * g.lx * row;
       unsigned char* dst = ctx->peer_arena[d] + ctx->off_A[f] + (size_t)ctx->d.rank * row;
       CK(cudaMemcpy2DAsync(dst, dpitch, src, row, row, (size_t)g.lx, cudaMemcpyDeviceToDevice, st));
     }
-    if (k) {
-      CK(cudaEventRecord(ctx->ev_xfer[8 + k], st));
-      CK(cudaStreamWaitEvent(ctx->xfer[0], ctx->ev_xfer[8 + k], 0));
+    if (f) {
+      CK(cudaEventRecord(ctx->ev_xfer[8 + f], st));
+      CK(cudaStreamWaitEvent(ctx->xfer[0], ctx->ev_xfer[8 + f], 0));
     }
   }
   if (slot >= 0) CK(cudaEventRecord(ctx->ev_xt[2 * slot + 1], ctx->xfer[0]));
