@@ -56,7 +56,7 @@ struct pinb200_ctx {
   size_t arena_bytes = 0;
   unsigned char* peer_arena[PINB_MAXR] = {nullptr};
   bool connected = false;
-  size_t off_flags = 0, off_kdens = 0, off_A[3] = {0, 0, 0}, off_KV[3] = {0, 0, 0};
+  size_t off_flags = 0, off_kdens = 0, off_A[3] = {0, 0, 0}, off_KV[3] = {0, 0, 0}, off_A2[3] = {0, 0, 0};
   unsigned long long epoch = 0;
   double barrier_timeout_s = 600.0;
   int* d_error = nullptr;
@@ -88,7 +88,9 @@ struct pinb200_ctx {
   double2* A[3] = {nullptr, nullptr, nullptr};    // arena: x-pass destinations; LPT sources
   double2* KV[3] = {nullptr, nullptr, nullptr};   // arena: kvector_2LPT, kvector_3LPT_1, kvector_3LPT_2
   double2* B[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // y-pass outputs; Hessian of the last radius
-  double2* D[3] = {nullptr, nullptr, nullptr};    // y-pass outputs of the displacement stage
+  double2* D[3] = {nullptr, nullptr, nullptr};    // arena: y-pass outputs of the displacement stage; during the multi-GPU sweep the
+                                                  // second set of x-pass destinations (the transposes of radius r+1 land there while
+                                                  // the y and z passes of radius r still read A)
   bool kdens_valid = false, hessian_valid = false, kvec_valid = false;
   bool kdens_has_nyq = false;  // uploaded fields may carry power on the kz = N/2 plane; GenIC never fills it (src/GenIC.c:280)
   float* fmax = nullptr;
@@ -204,12 +206,13 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
   if ((e = cudaMalloc(&ctx->sums, sizeof(double) * 2 * 64)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&ctx->d_error, sizeof(int))) != cudaSuccess) return fail(e);
   if ((e = cudaMemset(ctx->d_error, 0, sizeof(int))) != cudaSuccess) return fail(e);
-  // exchange arena: [flags | kdens | A0 A1 A2 | KV0 KV1 KV2]
+  // exchange arena: [flags | kdens | A0 A1 A2 | D0 D1 D2 | KV0 KV1 KV2]
   const size_t fb = ctx->field_elems * sizeof(double2);
   size_t off = 4096;
   ctx->off_flags = 0;
   ctx->off_kdens = off; off += fb;
   for (int i = 0; i < 3; i++) { ctx->off_A[i] = off; off += fb; }
+  for (int i = 0; i < 3; i++) { ctx->off_A2[i] = off; off += fb; }
   const int nkv = desc->lpt_order >= 3 ? 3 : (desc->lpt_order == 2 ? 1 : 0);
   for (int i = 0; i < nkv; i++) { ctx->off_KV[i] = off; off += fb; }
   ctx->arena_bytes = off;
@@ -221,6 +224,7 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
   if ((e = cudaMemset(ctx->arena, 0, 4096)) != cudaSuccess) return fail(e);
   ctx->kdens = reinterpret_cast<double2*>(ctx->arena + ctx->off_kdens);
   for (int i = 0; i < 3; i++) ctx->A[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_A[i]);
+  for (int i = 0; i < 3; i++) ctx->D[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_A2[i]);
   for (int i = 0; i < nkv; i++) ctx->KV[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_KV[i]);
   ctx->peer_arena[desc->rank] = ctx->arena;
   ctx->connected = (P == 1);
@@ -276,7 +280,6 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
   fr(ctx->tw); fr(ctx->gauss); fr(ctx->dc); fr(ctx->growthk); fr(ctx->sums); fr(ctx->seeds); fr(ctx->pk); fr(ctx->spl_dev);
   fr(ctx->d_error); fr(ctx->ct_tables); fr(ctx->ct_coef); fr(ctx->ct_knots);
   for (auto p : ctx->B) fr(p);
-  for (auto p : ctx->D) fr(p);
   fr(ctx->fmax); fr(ctx->rmax); fr(ctx->sorted_idx);
   for (auto p : ctx->vel) fr(p);
   fr(ctx->arena);
@@ -779,14 +782,14 @@ static int xpass_staging(pinb200_ctx* ctx, double2* S[3]) {
   return 0;
 }
 // inverse x pass of kdens for one radius into local K-layout staging (no peer traffic, no barrier)
-static int run_xpass_local(pinb200_ctx* ctx, double2* const S[3], double rsmooth) {
+static int run_xpass_local(pinb200_ctx* ctx, double2* const S[3], double2* const own[3], double rsmooth) {
   const Geom& g = ctx->g;
   LAUNCH(launch_gauss_table(ctx->gauss, g.M, g.knorm, rsmooth, ctx->stream));
   XPassParams p{};
   p.src = ctx->kdens;
   for (int i = 0; i < 3; i++) {
     p.dst[i].r[0] = S[i];
-    p.dst[i].r[1] = ctx->A[i];   // this rank's own x planes skip the staging
+    p.dst[i].r[1] = own[i];      // this rank's own x planes skip the staging
   }
   p.dst_klayout = 2;
   p.lx_shift = ctx->lx_shift;
@@ -802,12 +805,12 @@ static int run_xpass_local(pinb200_ctx* ctx, double2* const S[3], double rsmooth
   return 0;
 }
 // S (K layout, local) -> A (R layout) of every rank, by the copy engines; after_event: what the copies must follow
-static int transpose_dma(pinb200_ctx* ctx, double2* const S[3], cudaEvent_t after_event, cudaEvent_t done_event) {
+static int transpose_dma(pinb200_ctx* ctx, double2* const S[3], const size_t dst_off[3], cudaEvent_t after_event, cudaEvent_t done_event) {
   const Geom& g = ctx->g;
   const size_t row = (size_t)g.ly * g.P * sizeof(double2);          // one x plane of the local K-layout slab
   const size_t dpitch = (size_t)g.N * g.P * sizeof(double2);        // one x plane of an R-layout slab
   CK(cudaStreamWaitEvent(ctx->xfer[0], after_event, 0));
-  TRY(peer_barrier(ctx, ctx->xfer[0]));                             // nobody reads the old A any more
+  TRY(peer_barrier(ctx, ctx->xfer[0]));                             // nobody reads the destination buffers any more
   CK(cudaEventRecord(ctx->ev_xfer[1], ctx->xfer[0]));
   const int slot = ctx->nxt < 64 ? ctx->nxt++ : -1;
   if (slot >= 0) CK(cudaEventRecord(ctx->ev_xt[2 * slot], ctx->xfer[0]));
@@ -819,7 +822,7 @@ static int transpose_dma(pinb200_ctx* ctx, double2* const S[3], cudaEvent_t afte
     for (int k = 0; k + 1 < ctx->P; k++) {
       const int d = (ctx->d.rank + 1 + k) % ctx->P;
       const unsigned char* src = reinterpret_cast<const unsigned char*>(S[f]) + (size_t)d * g.lx * row;
-      unsigned char* dst = ctx->peer_arena[d] + ctx->off_A[f] + (size_t)ctx->d.rank * row;
+      unsigned char* dst = ctx->peer_arena[d] + dst_off[f] + (size_t)ctx->d.rank * row;
       CK(cudaMemcpy2DAsync(dst, dpitch, src, row, row, (size_t)g.lx, cudaMemcpyDeviceToDevice, st));
     }
     if (f) {
@@ -866,7 +869,6 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   const Geom& g = ctx->g;
   const int ns = (int)ctx->radius.size();
   const double cell = ctx->d.box_size / g.N;  // GRID.CellSize, src/fmax-pfft.c:88
-  for (auto& w : ctx->D) TRY(dev_free(ctx, &w));
   // a new Fmax sweep re-initialises the products (src/collapse_times.c:461-492 zeroes Vel*):
   // displacement fields of an earlier call are released here and read back as zeros
   for (auto& v : ctx->vel) TRY(dev_free(ctx, &v));
@@ -886,30 +888,35 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   double2* S[3] = {nullptr, nullptr, nullptr};
   static const YJob hess_jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
   ctx->nxt = 0;
+  // x-pass destinations are double-buffered in the pipelined sweep: radius r is read from X[r & 1] while the
+  // transposes of radius r + 1 fill X[(r + 1) & 1] (the arena slots of the displacement stage's y-pass outputs)
+  double2* const* X[2] = {ctx->A, ctx->D};
+  const size_t* Xoff[2] = {ctx->off_A, ctx->off_A2};
   if (pipelined) {
     TRY(xfer_setup(ctx));
     TRY(xpass_staging(ctx, S));
     // prologue: x pass and transposes of the first radius (nothing to hide them behind)
-    TRY(run_xpass_local(ctx, S, ctx->radius[0] / cell));
+    TRY(run_xpass_local(ctx, S, X[0], ctx->radius[0] / cell));
     CK(cudaEventRecord(ctx->ev_xfer[0], ctx->stream));
-    TRY(transpose_dma(ctx, S, ctx->ev_xfer[0], ctx->ev_xfer[4]));
+    TRY(transpose_dma(ctx, S, Xoff[0], ctx->ev_xfer[0], ctx->ev_xfer[4]));
   }
   for (int is = 0; is < ns; is++) {
     const double rs = ctx->radius[is] / cell;  // Rsmooth in grid units, src/fmax.c:233
     if (!pipelined) {
       TRY(hessian_xy(ctx, rs, ctx->ev[8 + 3 * is]));
     } else {
-      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_xfer[4], 0));      // A(is) complete on this rank
+      // X[is & 1] complete on this rank, and the staging free again
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_xfer[4 + (is & 1)], 0));
       CK(cudaEventRecord(ctx->ev[8 + 3 * is], ctx->stream));
-      TRY(run_ypass_inv(ctx, ctx->A, ctx->B, hess_jobs, 6, ctx->kdens_has_nyq));
-      CK(cudaEventRecord(ctx->ev_mid[is], ctx->stream));
       if (is + 1 < ns) {
-        // x pass of the next radius right behind the y pass (the staging is free: its transposes ended before
-        // this y pass began); its transposes then run under the collapse pass below
-        TRY(run_xpass_local(ctx, S, ctx->radius[is + 1] / cell));
+        // x pass of the NEXT radius first: its transposes then have the y pass AND the collapse pass of this
+        // radius to hide behind (83 ms against ~60 ms of copies at 2048^3 on 8 GPUs)
+        TRY(run_xpass_local(ctx, S, X[(is + 1) & 1], ctx->radius[is + 1] / cell));
         CK(cudaEventRecord(ctx->ev_xfer[0], ctx->stream));
-        TRY(transpose_dma(ctx, S, ctx->ev_xfer[0], ctx->ev_xfer[4]));
+        TRY(transpose_dma(ctx, S, Xoff[(is + 1) & 1], ctx->ev_xfer[0], ctx->ev_xfer[4 + ((is + 1) & 1)]));
       }
+      CK(cudaEventRecord(ctx->ev_mid[is], ctx->stream));
+      TRY(run_ypass_inv(ctx, X[is & 1], ctx->B, hess_jobs, 6, ctx->kdens_has_nyq));
     }
     CK(cudaEventRecord(ctx->ev[8 + 3 * is + 1], ctx->stream));
     CollapseParams c{};
@@ -937,7 +944,6 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     LAUNCH(launch_zpass_collapse(g.N, c, (size_t)g.lx * g.N, ctx->stream));
     CK(cudaEventRecord(ctx->ev[8 + 3 * is + 2], ctx->stream));
   }
-  if (pipelined) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_xfer[4], 0));  // (no-op: the last radius started no transposes)
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   // the Hessian kept for the LPT sources is that of the LAST radius: it is the unsmoothed one only when the
   // ladder ends with R = 0 as set_smoothing guarantees (src/initialization.c:386-435); any other ladder
@@ -969,11 +975,11 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
     CK(cudaEventElapsedTime(&z, ctx->ev[8 + 3 * is + 1], ctx->ev[8 + 3 * is + 2]));
     if (pipelined) {
       // x = exposed wait for the transposes (radius 0: the whole prologue) + the local x pass of the NEXT radius,
-      // which runs between this radius' y and z passes
-      float yy = 0;
-      CK(cudaEventElapsedTime(&yy, ctx->ev[8 + 3 * is], ctx->ev_mid[is]));
-      x += y - yy;
-      y = yy;
+      // which runs just before this radius' y pass
+      float xl = 0;
+      CK(cudaEventElapsedTime(&xl, ctx->ev[8 + 3 * is], ctx->ev_mid[is]));
+      x += xl;
+      y -= xl;
     }
     ctx->tm.hess_x += x * 1e-3;
     ctx->tm.hess_y += y * 1e-3;
@@ -1028,7 +1034,6 @@ static int displacements_impl(pinb200_ctx* ctx, int compute_sources, const doubl
   const size_t nrows = (size_t)g.lx * g.N;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  for (int i = 0; i < 3; i++) TRY(dev_alloc(ctx, &ctx->D[i], ctx->field_elems));
   if (order >= 2 && compute_sources) {
     if (!ctx->hessian_valid)
       FAIL("second derivatives of the R=0 radius are not in place (call pinb200_fmax with a ladder ending in R = 0, or pinb200_second_derivatives(ctx, 0, NULL), first)");
@@ -1152,7 +1157,6 @@ extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned 
   if (!(f_last > 0.0f)) FAIL("f_last must be positive (F = 1 + z_collapse; the float keys are ordered by their bit patterns)");
   if (ctx->ncells > 0xffffffffull) FAIL("more than 2^32 local cells");
   CK(cudaSetDevice(ctx->d.device));
-  for (auto& w : ctx->D) TRY(dev_free(ctx, &w));  // y-pass scratch of the displacement stage: dead by now
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   const unsigned long long nc = ctx->ncells;
   const size_t ntsel = cell_sort_ntiles_select(nc);
