@@ -313,11 +313,13 @@ def run_b200(args):
     launches = int(tm1.kernel_launches - tm0.kernel_launches)
 
     # ---- e2e: host buffers through the reference-facing calls.  One step = H2D of kdensity from pinned memory,
-    #      the sweep + 3LPT, and the hand-off to the fragmentation exactly as the drop-in does it
+    #      the sweep + 3LPT, and the hand-off to the fragmentation as the drop-in does it
     #      (shim/fmax_b200.c download_products_compact): D2H of Fmax of every cell, of the cell indices of the
     #      collapsed cells (Fmax >= Flast = 1, selected and ordered on the device) and of their 56-byte records --
-    #      what src/distribute.c reads of products[].  The plain copy of all 56-byte records (r01's e2e) is timed
-    #      once beside it (`full_aos`).
+    #      what src/distribute.c reads of products[].  Fmax and the index list are final before the displacement
+    #      stage starts, so their selection, sort and downloads are started there (pinb200_handoff_begin) and hide
+    #      under it; the records follow.  The plain copy of all 56-byte records (r01's e2e) is timed once beside
+    #      it (`full_aos`).
     e2e = None
     if not args.no_e2e:
         import ctypes
@@ -348,20 +350,23 @@ def run_b200(args):
             rec_np = rec_host.numpy().view(PRODUCT_DTYPE_3LPT)
             PU = ctypes.POINTER(ctypes.c_uint)
 
-            phases = {"h2d_kdensity": 0.0, "compute": 0.0, "d2h_fmax": 0.0, "select_sort_d2h_index": 0.0, "d2h_records": 0.0}
+            phases = {"h2d_kdensity": 0.0, "compute_with_handoff_prefetch_under_lpt": 0.0, "handoff_wait": 0.0, "d2h_records": 0.0}
             tme0 = pin.timers()
 
             def e2e_step():
                 t = [time.perf_counter()]          # every library call returns with its work done: wall-clock phases
                 pin._ck(pin.lib.pinb200_upload_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
                 t.append(time.perf_counter())
-                pin.compute_fmax(displacements=True)
-                t.append(time.perf_counter())
-                pin._ck(pin.lib.pinb200_download_field(pin.h, 0, ctypes.c_void_p(fm_host.data_ptr())))
-                t.append(time.perf_counter())
+                pin.compute_fmax(displacements=False)
+                # Fmax is final: its download, the selection + sort and the download of the index list run on side
+                # streams / the copy engine UNDER the displacement stage (pinb200_handoff_begin .. _end)
                 c = ctypes.c_size_t(0)
-                pin._ck(pin.lib.pinb200_collapsed_cells(pin.h, flast, ctypes.cast(idx_host.data_ptr(), PU), ncoll, ctypes.byref(c)))
+                pin._ck(pin.lib.pinb200_handoff_begin(pin.h, flast, ctypes.cast(fm_host.data_ptr(), ctypes.POINTER(ctypes.c_float)),
+                                                      ctypes.cast(idx_host.data_ptr(), PU), ncoll, ctypes.byref(c)))
                 assert int(c.value) == ncoll
+                pin.compute_displacements(1, 0, pin.cfg.segment_redshift)
+                t.append(time.perf_counter())
+                pin._ck(pin.lib.pinb200_handoff_end(pin.h))
                 t.append(time.perf_counter())
                 pin._ck(pin.lib.pinb200_download_products_sorted(pin.h, ctypes.c_void_p(rec_host.data_ptr()), ctypes.byref(lay), 0, ncoll))
                 t.append(time.perf_counter())

@@ -180,6 +180,15 @@ int pinb200_download_products(pinb200_ctx* ctx, void* products, const pinb200_pr
  * (src/fragment.c:484-520); equal Fmax in ascending cell index.  *count = number of such cells;
  * at most `capacity` indices are written (cell_index_out may be NULL to query the count). */
 int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned int* cell_index_out, size_t capacity, size_t* count);
+/* The same selection and order, started under the displacement stage: Fmax and Rmax are final when pinb200_fmax
+ * returns, the displacement fields only after pinb200_displacements.  _begin counts the selected cells (*count, one
+ * synchronisation) and then lets the compaction, the sort and the download of the index list (at most `capacity`
+ * entries into cell_index_out) run on a side stream, and the download of the whole Fmax field into fmax_out
+ * (local cells floats; may be NULL) on the copy engine; it returns at once.  The caller then runs
+ * pinb200_displacements, and pinb200_handoff_end waits for the list.  Host arrays should be pinned (a pageable
+ * destination makes the copies synchronous).  pinb200_collapsed_cells = _begin + _end. */
+int pinb200_handoff_begin(pinb200_ctx* ctx, float f_last, float* fmax_out, unsigned int* cell_index_out, size_t capacity, size_t* count);
+int pinb200_handoff_end(pinb200_ctx* ctx);
 /* frag[first .. first+n) as sort_and_organize leaves it: the product_data records of the cells
  * listed by the last pinb200_collapsed_cells call (which must have been given an output array), in
  * that order, gathered on the device -- only collapsed cells cross PCIe and the host does not sort. */

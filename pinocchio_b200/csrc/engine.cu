@@ -33,6 +33,19 @@ using namespace pinb;
 
 static thread_local std::string g_create_error;
 
+// pinb200_handoff_begin .. _end: buffers and streams of a selection + sort in flight
+struct HandoffState {
+  bool active = false, sorted = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_ready = nullptr;
+  unsigned int *tile_counts = nullptr, *bsums = nullptr, *bs2 = nullptr, *range = nullptr, *counts = nullptr;
+  unsigned int *key[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr};
+  unsigned long long* d_total = nullptr;
+  unsigned long long n = 0;
+  int cur = 0;
+  float count_ms = 0;
+};
+
 struct pinb200_ctx {
   pinb200_desc d{};
   Geom g{};
@@ -99,6 +112,7 @@ struct pinb200_ctx {
   unsigned int* sorted_idx = nullptr;  // pinb200_collapsed_cells: cell indices in order of descending Fmax
   size_t sorted_n = 0;
 
+  HandoffState ho;
   pinb200_timers tm{};
   unsigned long long launches = 0;
   cudaEvent_t ev[3 * 64 + 8] = {nullptr};
@@ -108,6 +122,8 @@ struct pinb200_ctx {
   cudaEvent_t ev_dx[8] = {nullptr};   // x passes of the four first-derivative calls of the displacement stage
   int ndx = 0;
 };
+
+static int handoff_end_impl(pinb200_ctx* ctx);
 
 #define CK(call)                                                                              \
   do {                                                                                        \
@@ -291,6 +307,8 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
   for (auto& ev : ctx->ev_dx) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_mid) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_xt) if (ev) cudaEventDestroy(ev);
+  handoff_end_impl(ctx);
+  if (ctx->ho.stream) { cudaStreamDestroy(ctx->ho.stream); cudaEventDestroy(ctx->ho.ev0); cudaEventDestroy(ctx->ho.ev1); cudaEventDestroy(ctx->ho.ev_ready); }
   for (auto& ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& st : ctx->xfer) if (st) cudaStreamDestroy(st);
@@ -872,6 +890,7 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   // a new Fmax sweep re-initialises the products (src/collapse_times.c:461-492 zeroes Vel*):
   // displacement fields of an earlier call are released here and read back as zeros
   for (auto& v : ctx->vel) TRY(dev_free(ctx, &v));
+  TRY(handoff_end_impl(ctx));
   TRY(dev_free(ctx, &ctx->sorted_idx));
   ctx->sorted_n = 0;
   ctx->kvec_valid = false;
@@ -1150,86 +1169,137 @@ extern "C" int pinb200_displacements_scaledep(pinb200_ctx* ctx, int compute_sour
 // of src/distribute.c:58-175,547-600 and the ordering of sort_and_organize (src/fragment.c:484-520),
 // done on the device (k_sort.cu): stable compaction of (key, index) pairs, then an LSD radix sort over the
 // bits in which the keys differ.  One host synchronisation (the count of selected cells sizes the buffers).
-extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned int* cell_index_out, size_t capacity,
-                                       size_t* count) {
+//
+// pinb200_handoff_begin / _end split it so that it can run UNDER the displacement stage: Fmax and Rmax are final
+// when pinb200_fmax returns, the twelve displacement fields only 250 ms later (1024^3).  begin counts (one
+// synchronisation), then puts the compaction, the sort and the copy of the index list on a side stream and the copy
+// of the Fmax field on the copy stream, and returns; the caller runs pinb200_displacements; end waits.  With pinned
+// host arrays the two downloads (6.8 GB at 1024^3) and the 94 ms of sorting cost no wall-clock time.
+static int handoff_end_impl(pinb200_ctx* ctx) {
+  HandoffState& h = ctx->ho;
+  if (!h.active) return 0;
+  CK(cudaStreamSynchronize(h.stream));
+  if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+  if (h.sorted) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h.ev0, h.ev1));
+    ctx->tm.sort_ms = ms + h.count_ms;  // selection + sort on the device (without the downloads)
+    TRY(dev_free(ctx, &ctx->sorted_idx));
+    ctx->sorted_idx = h.idx[h.cur];      // the ordered indices stay resident for pinb200_download_products_sorted
+    ctx->sorted_n = (size_t)h.n;
+    h.idx[h.cur] = nullptr;
+  }
+  for (int b = 0; b < 2; b++) {
+    TRY(dev_free(ctx, &h.key[b]));
+    TRY(dev_free(ctx, &h.idx[b]));
+  }
+  TRY(dev_free(ctx, &h.counts));
+  TRY(dev_free(ctx, &h.tile_counts));
+  TRY(dev_free(ctx, &h.bsums));
+  TRY(dev_free(ctx, &h.bs2));
+  TRY(dev_free(ctx, &h.range));
+  TRY(dev_free(ctx, &h.d_total));
+  h.active = false;
+  h.sorted = false;
+  return 0;
+}
+
+extern "C" int pinb200_handoff_begin(pinb200_ctx* ctx, float f_last, float* fmax_out, unsigned int* cell_index_out, size_t capacity,
+                                     size_t* count) {
   if (!ctx || !count) return 1;
   if (!ctx->fmax) FAIL("Fmax not computed");
   if (!(f_last > 0.0f)) FAIL("f_last must be positive (F = 1 + z_collapse; the float keys are ordered by their bit patterns)");
   if (ctx->ncells > 0xffffffffull) FAIL("more than 2^32 local cells");
   CK(cudaSetDevice(ctx->d.device));
+  TRY(handoff_end_impl(ctx));
+  HandoffState& h = ctx->ho;
+  if (!h.stream) {
+    CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h.ev0));
+    CK(cudaEventCreate(&h.ev1));
+    CK(cudaEventCreateWithFlags(&h.ev_ready, cudaEventDisableTiming));
+  }
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev_stage) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  h.active = true;
+  // the Fmax field itself, on the copy stream (nothing below depends on it)
+  if (fmax_out) CK(cudaMemcpyAsync(fmax_out, ctx->fmax, ctx->ncells * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   const unsigned long long nc = ctx->ncells;
   const size_t ntsel = cell_sort_ntiles_select(nc);
-  unsigned int *tile_counts = nullptr, *bsums = nullptr, *range = nullptr, *counts = nullptr, *key[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr};
-  unsigned long long* d_total = nullptr;
-  TRY(dev_alloc(ctx, &tile_counts, ntsel));
-  TRY(dev_alloc(ctx, &bsums, cell_sort_scan_blocks(ntsel) + 1));
-  TRY(dev_alloc(ctx, &range, (size_t)2));
-  TRY(dev_alloc(ctx, &d_total, (size_t)1));
+  TRY(dev_alloc(ctx, &h.tile_counts, ntsel));
+  TRY(dev_alloc(ctx, &h.bsums, cell_sort_scan_blocks(ntsel) + 1));
+  TRY(dev_alloc(ctx, &h.range, (size_t)2));
+  TRY(dev_alloc(ctx, &h.d_total, (size_t)1));
   const unsigned int range_init[2] = {0xffffffffu, 0u};
-  CK(cudaMemcpyAsync(range, range_init, sizeof range_init, cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(launch_select_count(ctx->fmax, nc, f_last, tile_counts, range, ctx->stream));
-  LAUNCH(launch_scan_u32(tile_counts, ntsel, bsums, d_total, ctx->stream));
+  CK(cudaMemcpyAsync(h.range, range_init, sizeof range_init, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(launch_select_count(ctx->fmax, nc, f_last, h.tile_counts, h.range, ctx->stream));
+  LAUNCH(launch_scan_u32(h.tile_counts, ntsel, h.bsums, h.d_total, ctx->stream));
   ctx->launches += 2;
   unsigned long long n = 0;
   unsigned int hrange[2] = {0, 0};
-  CK(cudaMemcpyAsync(&n, d_total, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(hrange, range, sizeof hrange, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&n, h.d_total, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(hrange, h.range, sizeof hrange, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  float cms = 0;
+  CK(cudaEventElapsedTime(&cms, ctx->ev[5], ctx->ev[6]));
+  h.count_ms = cms;
+  h.n = n;
   *count = (size_t)n;
-  if (n > 0 && cell_index_out && capacity > 0) {
-    for (int b = 0; b < 2; b++) {
-      TRY(dev_alloc(ctx, &key[b], (size_t)n));
-      TRY(dev_alloc(ctx, &idx[b], (size_t)n));
-    }
-    LAUNCH(launch_select_write(ctx->fmax, nc, f_last, tile_counts, range, key[0], idx[0], ctx->stream));
-    // digits: the keys are offsets from the smallest one, so only the bits of (kmax - kmin) take part
-    int sig = 0;
-    while (sig < 32 && ((unsigned long long)(hrange[1] - hrange[0]) >> sig) != 0) sig++;
-    int maxbits = 0;
-    while ((1 << maxbits) < cell_sort_max_bins()) maxbits++;
-    const int npass = (sig + maxbits - 1) / maxbits;
-    int cur = 0;
-    if (npass > 0) {
-      const size_t ntr = cell_sort_ntiles_radix(n);
-      TRY(dev_alloc(ctx, &counts, (size_t)cell_sort_max_bins() * ntr));
-      unsigned int* bs2 = nullptr;
-      TRY(dev_alloc(ctx, &bs2, cell_sort_scan_blocks((unsigned long long)cell_sort_max_bins() * ntr) + 1));
-      int shift = 0;
-      for (int pass = 0; pass < npass; pass++) {
-        const int bits = (sig - shift + (npass - pass) - 1) / (npass - pass);  // spread the significant bits evenly
-        LAUNCH(launch_radix_hist(key[cur], n, shift, bits, counts, ctx->stream));
-        LAUNCH(launch_scan_u32(counts, ((unsigned long long)1 << bits) * ntr, bs2, nullptr, ctx->stream));
-        LAUNCH(launch_radix_scatter(key[cur], idx[cur], key[cur ^ 1], idx[cur ^ 1], n, shift, bits, counts, ctx->stream));
-        ctx->launches += 2;
-        shift += bits;
-        cur ^= 1;
-      }
-      TRY(dev_free(ctx, &bs2));
-    }
-    const size_t ncopy = capacity < (size_t)n ? capacity : (size_t)n;
-    CK(cudaEventRecord(ctx->ev[6], ctx->stream));
-    CK(cudaMemcpyAsync(cell_index_out, idx[cur], ncopy * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
-    ctx->tm.sort_ms = ms;  // selection + sort on the device (without the download of the index list)
-    // the ordered indices stay resident for pinb200_download_products_sorted
-    TRY(dev_free(ctx, &ctx->sorted_idx));
-    ctx->sorted_idx = idx[cur];
-    ctx->sorted_n = (size_t)n;
-    idx[cur] = nullptr;
-  }
+  if (n == 0 || !cell_index_out || capacity == 0) return 0;
   for (int b = 0; b < 2; b++) {
-    TRY(dev_free(ctx, &key[b]));
-    TRY(dev_free(ctx, &idx[b]));
+    TRY(dev_alloc(ctx, &h.key[b], (size_t)n));
+    TRY(dev_alloc(ctx, &h.idx[b], (size_t)n));
   }
-  TRY(dev_free(ctx, &counts));
-  TRY(dev_free(ctx, &tile_counts));
-  TRY(dev_free(ctx, &bsums));
-  TRY(dev_free(ctx, &range));
-  TRY(dev_free(ctx, &d_total));
+  // digits: the keys are offsets from the smallest one, so only the bits of (kmax - kmin) take part
+  int sig = 0;
+  while (sig < 32 && ((unsigned long long)(hrange[1] - hrange[0]) >> sig) != 0) sig++;
+  int maxbits = 0;
+  while ((1 << maxbits) < cell_sort_max_bins()) maxbits++;
+  const int npass = (sig + maxbits - 1) / maxbits;
+  const size_t ntr = cell_sort_ntiles_radix(n);
+  if (npass > 0) {
+    TRY(dev_alloc(ctx, &h.counts, (size_t)cell_sort_max_bins() * ntr));
+    TRY(dev_alloc(ctx, &h.bs2, cell_sort_scan_blocks((unsigned long long)cell_sort_max_bins() * ntr) + 1));
+  }
+  // the buffers were allocated in the order of the main stream: the side stream starts behind that point
+  CK(cudaEventRecord(h.ev_ready, ctx->stream));
+  CK(cudaStreamWaitEvent(h.stream, h.ev_ready, 0));
+  cudaStream_t st = h.stream;
+  CK(cudaEventRecord(h.ev0, st));
+  LAUNCH(launch_select_write(ctx->fmax, nc, f_last, h.tile_counts, h.range, h.key[0], h.idx[0], st));
+  h.cur = 0;
+  int shift = 0;
+  for (int pass = 0; pass < npass; pass++) {
+    const int bits = (sig - shift + (npass - pass) - 1) / (npass - pass);  // spread the significant bits evenly
+    LAUNCH(launch_radix_hist(h.key[h.cur], n, shift, bits, h.counts, st));
+    LAUNCH(launch_scan_u32(h.counts, ((unsigned long long)1 << bits) * ntr, h.bs2, nullptr, st));
+    LAUNCH(launch_radix_scatter(h.key[h.cur], h.idx[h.cur], h.key[h.cur ^ 1], h.idx[h.cur ^ 1], n, shift, bits, h.counts, st));
+    ctx->launches += 2;
+    shift += bits;
+    h.cur ^= 1;
+  }
+  CK(cudaEventRecord(h.ev1, st));
+  const size_t ncopy = capacity < (size_t)n ? capacity : (size_t)n;
+  CK(cudaMemcpyAsync(cell_index_out, h.idx[h.cur], ncopy * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  h.sorted = true;
   return 0;
+}
+
+extern "C" int pinb200_handoff_end(pinb200_ctx* ctx) {
+  if (!ctx) return 1;
+  CK(cudaSetDevice(ctx->d.device));
+  return handoff_end_impl(ctx);
+}
+
+extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned int* cell_index_out, size_t capacity,
+                                       size_t* count) {
+  if (!ctx || !count) return 1;
+  TRY(pinb200_handoff_begin(ctx, f_last, nullptr, cell_index_out, capacity, count));
+  return handoff_end_impl(ctx);
 }
 
 extern "C" int pinb200_fmax_pdf(pinb200_ctx* ctx, unsigned long long* counts) {

@@ -69,7 +69,7 @@ ABI_SYMBOLS = [
     "pinb200_upload_kdensity", "pinb200_download_kdensity", "pinb200_fmax", "pinb200_displacements",
     "pinb200_displacements_scaledep", "pinb200_collapsed_cells", "pinb200_download_products_sorted",
     "pinb200_fmax_pdf", "pinb200_download_products", "pinb200_download_field", "pinb200_get_timers",
-    "pinb200_write_products", "pinb200_write_block",
+    "pinb200_write_products", "pinb200_write_block", "pinb200_handoff_begin", "pinb200_handoff_end",
     "pinb200_fft_r2c", "pinb200_fft_c2r", "pinb200_second_derivatives", "pinb200_collapse_cells",
     "pinb200_download_kvector",
     "pinb200_ct_delta_vector", "pinb200_set_collapse_tables", "pinb200_download_collapse_table",
@@ -110,6 +110,11 @@ def load_library() -> ctypes.CDLL:
                                                    ctypes.c_double, _PD]
     lib.pinb200_collapsed_cells.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.POINTER(ctypes.c_uint), ctypes.c_size_t,
                                             ctypes.POINTER(ctypes.c_size_t)]
+    lib.pinb200_handoff_begin.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint),
+                                          ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    lib.pinb200_handoff_end.argtypes = [ctypes.c_void_p]
+    lib.pinb200_write_products.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ProductLayout), ctypes.c_size_t, ctypes.c_size_t]
+    lib.pinb200_write_block.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t]
     lib.pinb200_download_products_sorted.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ProductLayout),
                                                      ctypes.c_size_t, ctypes.c_size_t]
     lib.pinb200_fmax_pdf.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]

@@ -598,6 +598,14 @@ extern "C" int pinb200_collapsed_cells(pinb200_ctx* ctx, float f_last, unsigned 
   }
   return 0;
 }
+// begin / end: synchronous here (the emulated ABI has no streams)
+extern "C" int pinb200_handoff_begin(pinb200_ctx* ctx, float f_last, float* fmax_out, unsigned int* cell_index_out, size_t capacity, size_t* count) {
+  if (!ctx || !count) return 1;
+  if (pinb200_collapsed_cells(ctx, f_last, cell_index_out, capacity, count)) return 1;
+  if (fmax_out) std::memcpy(fmax_out, ctx->fmax.data(), ctx->fmax.size() * 4);
+  return 0;
+}
+extern "C" int pinb200_handoff_end(pinb200_ctx* ctx) { return ctx ? 0 : 1; }
 extern "C" int pinb200_download_products_sorted(pinb200_ctx* ctx, void* products, const pinb200_product_layout* L, size_t first, size_t n) {
   if (!ctx || !products || !L) return 1;
   if (!ctx->sorted_valid) FAIL("no ordered cell list (call pinb200_collapsed_cells with an output array first)");

@@ -60,3 +60,34 @@ def test_collapsed_cells_large_grid_properties(cosmo):
     assert (np.diff(idx.astype(np.int64))[same] > 0).all()    # ties in ascending cell index
     assert np.unique(idx).size == idx.size
     p.close()
+
+
+def test_handoff_started_under_the_displacement_stage(cosmo):
+    """pinb200_handoff_begin / _end: the selection, the sort and the two downloads run on side streams while
+    pinb200_displacements computes the velocity fields; same list and same records as the synchronous calls."""
+    import ctypes
+    N = 128
+    p = make(N, cosmo)
+    p.GenIC_large()
+    p.compute_fmax(displacements=False)
+    F = p.field("Fmax").ravel()
+    want = p.collapsed_cells(1.0).copy()
+    fm = np.zeros(N ** 3, dtype=np.float32)
+    idx = np.zeros(want.size, dtype=np.uint32)
+    n = ctypes.c_size_t(0)
+    p._ck(p.lib.pinb200_handoff_begin(p.h, 1.0, fm.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                      idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), idx.size, ctypes.byref(n)))
+    assert n.value == want.size
+    p.compute_displacements(1, 0, 0.0)                  # the stage the hand-off hides under
+    p._ck(p.lib.pinb200_handoff_end(p.h))
+    assert np.array_equal(fm, F) and np.array_equal(idx, want)
+    p._sorted_n = int(n.value)
+    prod = p.products()
+    assert np.array_equal(p.sorted_products(), prod[idx])
+    assert prod["Vel_3LPT_2"].any()
+    # a second begin without end in between, and a sweep that starts while a list is pending, are both safe
+    p._ck(p.lib.pinb200_handoff_begin(p.h, 2.0, None, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), idx.size, ctypes.byref(n)))
+    p._ck(p.lib.pinb200_handoff_begin(p.h, 1.0, None, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), idx.size, ctypes.byref(n)))
+    p.compute_fmax(displacements=False)
+    assert np.array_equal(p.collapsed_cells(1.0), want)
+    p.close()
