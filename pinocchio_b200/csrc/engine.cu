@@ -109,6 +109,7 @@ struct pinb200_ctx {
   float* fmax = nullptr;
   int* rmax = nullptr;
   float* vel[12] = {nullptr};
+  bool vel_in_B = false;  // the displacement fields live in the (dead) Hessian buffers B: two float fields per double2 field
   unsigned int* sorted_idx = nullptr;  // pinb200_collapsed_cells: cell indices in order of descending Fmax
   size_t sorted_n = 0;
 
@@ -124,6 +125,7 @@ struct pinb200_ctx {
 };
 
 static int handoff_end_impl(pinb200_ctx* ctx);
+static int release_vel(pinb200_ctx* ctx);
 
 #define CK(call)                                                                              \
   do {                                                                                        \
@@ -152,6 +154,24 @@ template <class T> static int dev_free(pinb200_ctx* ctx, T** p) {
 }
 
 static int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
+
+// The twelve float displacement fields are as large as the six double2 Hessian fields they are computed from, and the
+// Hessian is dead by the time they are written: they are placed there (vel[2k], vel[2k+1] in B[k]) instead of in
+// another 52 GB of pool memory (1024^3) -- with the hand-off buffers on top of both the stream-ordered pool had to give
+// memory back to the driver and re-map it in every step (r02: 0.7 s of host-side stalls per e2e step).
+static int release_vel(pinb200_ctx* ctx) {
+  if (ctx->vel_in_B) {
+    for (auto& v : ctx->vel) v = nullptr;
+    ctx->vel_in_B = false;
+    return 0;
+  }
+  for (auto& v : ctx->vel) {
+    if (!v) continue;
+    CK(cudaFreeAsync(v, ctx->stream));
+    v = nullptr;
+  }
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 extern "C" const char* pinb200_last_error(const pinb200_ctx* ctx) {
@@ -297,6 +317,7 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
   fr(ctx->d_error); fr(ctx->ct_tables); fr(ctx->ct_coef); fr(ctx->ct_knots);
   for (auto p : ctx->B) fr(p);
   fr(ctx->fmax); fr(ctx->rmax); fr(ctx->sorted_idx);
+  if (ctx->vel_in_B) for (auto& v : ctx->vel) v = nullptr;
   for (auto p : ctx->vel) fr(p);
   fr(ctx->arena);
   {  // hand the stream-ordered pool's cached blocks back to the driver (another context may need them)
@@ -889,7 +910,7 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   const double cell = ctx->d.box_size / g.N;  // GRID.CellSize, src/fmax-pfft.c:88
   // a new Fmax sweep re-initialises the products (src/collapse_times.c:461-492 zeroes Vel*):
   // displacement fields of an earlier call are released here and read back as zeros
-  for (auto& v : ctx->vel) TRY(dev_free(ctx, &v));
+  TRY(release_vel(ctx));
   TRY(handoff_end_impl(ctx));
   TRY(dev_free(ctx, &ctx->sorted_idx));
   ctx->sorted_n = 0;
@@ -1104,14 +1125,17 @@ static int displacements_impl(pinb200_ctx* ctx, int compute_sources, const doubl
       TRY(run_r2c(ctx, ctx->A[1], ctx->KV[1]));  // kvector_3LPT_1
       TRY(run_r2c(ctx, ctx->A[2], ctx->KV[2]));  // kvector_3LPT_2
     }
-    // the Hessian fields are dead now
-    for (auto& b : ctx->B) TRY(dev_free(ctx, &b));
+    // the Hessian fields are dead now: their memory takes the displacement fields below
     ctx->hessian_valid = false;
     ctx->kvec_valid = true;
   }
   if (order >= 2 && !ctx->kvec_valid) FAIL("LPT k-vectors are not resident (compute_sources = 0 needs an earlier call with compute_sources = 1)");
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));
   const int nvel = order == 1 ? 3 : (order == 2 ? 6 : 12);
+  if (!ctx->vel[0] && ctx->B[0] && ctx->B[5] && !ctx->hessian_valid) {
+    for (int i = 0; i < nvel; i++) ctx->vel[i] = reinterpret_cast<float*>(ctx->B[i / 2]) + (size_t)(i % 2) * ctx->ncells;
+    ctx->vel_in_B = true;
+  }
   for (int i = 0; i < nvel; i++) TRY(dev_alloc(ctx, &ctx->vel[i], ctx->ncells));
   ctx->ndx = 0;
   TRY(peer_barrier(ctx));  // all k-vectors complete everywhere before rank 0's k = 0 modes are read
@@ -1563,6 +1587,7 @@ extern "C" int pinb200_second_derivatives(pinb200_ctx* ctx, double radius, doubl
   NEED_PEERS();
   CK(cudaSetDevice(ctx->d.device));
   const Geom& g = ctx->g;
+  if (ctx->vel_in_B) TRY(release_vel(ctx));  // the displacement fields live in B: they are gone with this call
   for (int i = 0; i < 6; i++) TRY(dev_alloc(ctx, &ctx->B[i], ctx->field_elems));
   const double cell = ctx->d.box_size / g.N;
   TRY(hessian_dc(ctx));
