@@ -109,6 +109,7 @@ struct pinb200_ctx {
   float* fmax = nullptr;
   int* rmax = nullptr;
   float* vel[12] = {nullptr};
+  bool d_in_arena = false;  // D[] are arena slots (never freed) or pool allocations of the displacement stage
   bool vel_in_B = false;  // the displacement fields live in the (dead) Hessian buffers B: two float fields per double2 field
   unsigned int* sorted_idx = nullptr;  // pinb200_collapsed_cells: cell indices in order of descending Fmax
   size_t sorted_n = 0;
@@ -248,7 +249,11 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
   ctx->off_flags = 0;
   ctx->off_kdens = off; off += fb;
   for (int i = 0; i < 3; i++) { ctx->off_A[i] = off; off += fb; }
-  for (int i = 0; i < 3; i++) { ctx->off_A2[i] = off; off += fb; }
+  // second set of x-pass destinations (pipelined sweep, from four ranks on): in the arena, doubling as the y-pass
+  // outputs of the displacement stage.  With fewer ranks those three fields come from the pool when the displacement
+  // stage needs them, and the pool re-uses their memory for the hand-off buffers afterwards.
+  const bool arena_d = P >= 4;
+  if (arena_d) for (int i = 0; i < 3; i++) { ctx->off_A2[i] = off; off += fb; }
   const int nkv = desc->lpt_order >= 3 ? 3 : (desc->lpt_order == 2 ? 1 : 0);
   for (int i = 0; i < nkv; i++) { ctx->off_KV[i] = off; off += fb; }
   ctx->arena_bytes = off;
@@ -260,7 +265,8 @@ extern "C" int pinb200_create(const pinb200_desc* desc, pinb200_ctx** out) {
   if ((e = cudaMemset(ctx->arena, 0, 4096)) != cudaSuccess) return fail(e);
   ctx->kdens = reinterpret_cast<double2*>(ctx->arena + ctx->off_kdens);
   for (int i = 0; i < 3; i++) ctx->A[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_A[i]);
-  for (int i = 0; i < 3; i++) ctx->D[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_A2[i]);
+  ctx->d_in_arena = arena_d;
+  if (arena_d) for (int i = 0; i < 3; i++) ctx->D[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_A2[i]);
   for (int i = 0; i < nkv; i++) ctx->KV[i] = reinterpret_cast<double2*>(ctx->arena + ctx->off_KV[i]);
   ctx->peer_arena[desc->rank] = ctx->arena;
   ctx->connected = (P == 1);
@@ -319,6 +325,7 @@ extern "C" int pinb200_destroy(pinb200_ctx* ctx) {
   fr(ctx->fmax); fr(ctx->rmax); fr(ctx->sorted_idx);
   if (ctx->vel_in_B) for (auto& v : ctx->vel) v = nullptr;
   for (auto p : ctx->vel) fr(p);
+  if (!ctx->d_in_arena) for (auto p : ctx->D) fr(p);
   fr(ctx->arena);
   {  // hand the stream-ordered pool's cached blocks back to the driver (another context may need them)
     cudaMemPool_t pool;
@@ -615,14 +622,13 @@ extern "C" int pinb200_genic(pinb200_ctx* ctx) {
 
 // host half-complex K-layout slab [N][ly][M+1] <-> device [N][ly][P]
 static int upload_cplx(pinb200_ctx* ctx, const double* host, double2* dev) {
+  // rows of M+1 elements on the host, pitch P on the device: one strided copy, no device temporary (r01 staged the
+  // slab in another 8.6 GB and re-pitched it with a kernel)
   const Geom& g = ctx->g;
   const size_t rows = (size_t)g.N * g.ly;
-  double2* tmp = nullptr;
-  TRY(dev_alloc(ctx, &tmp, rows * (g.M + 1)));
-  CK(cudaMemcpyAsync(tmp, host, rows * (g.M + 1) * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(dev, 0, ctx->field_elems * sizeof(double2), ctx->stream));
-  LAUNCH(launch_repitch_c(tmp, dev, rows, g.M + 1, g.M + 1, g.P, ctx->stream));
-  TRY(dev_free(ctx, &tmp));
+  CK(cudaMemcpy2DAsync(dev, (size_t)g.P * sizeof(double2), host, (size_t)(g.M + 1) * sizeof(double2), (size_t)(g.M + 1) * sizeof(double2),
+                       rows, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 static int download_cplx(pinb200_ctx* ctx, const double2* dev, double* host) {
@@ -908,6 +914,7 @@ extern "C" int pinb200_fmax(pinb200_ctx* ctx, double* true_variance) {
   const Geom& g = ctx->g;
   const int ns = (int)ctx->radius.size();
   const double cell = ctx->d.box_size / g.N;  // GRID.CellSize, src/fmax-pfft.c:88
+  if (!ctx->d_in_arena) for (auto& w : ctx->D) TRY(dev_free(ctx, &w));
   // a new Fmax sweep re-initialises the products (src/collapse_times.c:461-492 zeroes Vel*):
   // displacement fields of an earlier call are released here and read back as zeros
   TRY(release_vel(ctx));
@@ -1074,6 +1081,7 @@ static int displacements_impl(pinb200_ctx* ctx, int compute_sources, const doubl
   const size_t nrows = (size_t)g.lx * g.N;
   const double norm = 1.0 / ((double)g.N * g.N * g.N);
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (!ctx->d_in_arena) for (int i = 0; i < 3; i++) TRY(dev_alloc(ctx, &ctx->D[i], ctx->field_elems));
   if (order >= 2 && compute_sources) {
     if (!ctx->hessian_valid)
       FAIL("second derivatives of the R=0 radius are not in place (call pinb200_fmax with a ladder ending in R = 0, or pinb200_second_derivatives(ctx, 0, NULL), first)");
@@ -1237,6 +1245,8 @@ extern "C" int pinb200_handoff_begin(pinb200_ctx* ctx, float f_last, float* fmax
   CK(cudaSetDevice(ctx->d.device));
   TRY(handoff_end_impl(ctx));
   HandoffState& h = ctx->ho;
+  // (the y-pass scratch of an earlier displacement stage is dead: its memory serves the buffers below)
+  if (!ctx->d_in_arena && ctx->kvec_valid && ctx->vel[0]) for (auto& w : ctx->D) TRY(dev_free(ctx, &w));
   if (!h.stream) {
     CK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h.ev0));

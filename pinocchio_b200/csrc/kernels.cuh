@@ -347,7 +347,12 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
       dp.r[owner][(size_t)xl * ((size_t)g.N * g.P) + roff + tk] = val;
     }
   };
-  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, C::CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * npw : npw, srcf, xform, storef);
+  // GK: the loader (a log10, a table interpolation and a 10^x per mode on top of the division) is ~250 instructions;
+  // unrolled over the 16 stage-0 elements of a thread it overflows the instruction cache (r02: 31 ms against 9.6 ms
+  // without G(k), although the arithmetic is worth 5 ms), so it runs as a rolled pre-pass over the tile like the
+  // split passes' combine step
+  constexpr int CHUNK = (GK && C::CHUNK == 0) ? 4 : C::CHUNK;
+  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * npw : npw, srcf, xform, storef);
 }
 
 // ---------------------------------------------------------------------------------------
