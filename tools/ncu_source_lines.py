@@ -58,7 +58,10 @@ def main():
         if base is None:
             base = addr
         off = addr - base
-        f, l, op = lines.get(off, ("?", 0, r[col["Source"]].split()[0]))
+        f, l, op = lines.get(off, ("?", 0, ""))
+        # the opcode always comes from the profile itself (the binary given for the line mapping may be a later build)
+        toks = [t for t in r[col["Source"]].split() if not t.startswith("@")]
+        op = toks[0] if toks else op
         ex = int(r[col["Instructions Executed"]] or 0)
         smp = int(r[col["# Samples"]] or 0)
         key = {"file": f, "line": f"{f}:{l}", "op": op.split(".")[0]}[by]
