@@ -236,6 +236,34 @@ int pinb200_collapse_cells(pinb200_ctx* ctx, int ismooth, const double* hessian6
  * kdensity; which = 0,1,2.  Valid after pinb200_displacements(compute_sources=1). */
 int pinb200_download_kvector(pinb200_ctx* ctx, int which, double* kvec);
 
+/* ---- start-up integrals of the scale-dependent growth (next row f4) -------------------------------------------
+ * Replaces the three gsl_integration_qags loops of set_scaledep_GM (src/initialization.c:1594-1601, :1742-1748,
+ * :1886-1892): for every smoothing radius r, every time knot i of SPLINE[SP_TIME] and the three quantities
+ * q = 0 density (Gaussian window, IntegrandForSDDensVariance :1439), 1 displacement (top-hat,
+ * IntegrandForSDDisplVariance :1449), 2 velocity (top-hat, times fomega^2, IntegrandForSDVelVariance :1489)
+ *     out[(q * nsmooth + r) * ntimes + i] = sqrt( Int dlog10k  P(k) D(t_i,k)^2 [f(t_i,k)^2] W(k R_r)^2 k^p / (2 pi^2) )
+ * i.e. the reference's vector[i] before its normalisation, all 3 x nsmooth x ntimes of them in two kernel launches.
+ * The quadrature is the caller's: nodes in log10 k over the reference's interval [-4, nyquist] and, per node,
+ * a = weight * PowerSpectrum(k) * k^p / (2 pi^2) from the host cosmology (p = 3 density, 1 displacement/velocity);
+ * shim/scaledep_gm_b200.c uses composite 8-point Gauss-Legendre.  Growth enters as the k-bin tables InterpolateGrowth
+ * (src/cosmo.c:1728-1755) interpolates: log10 GrowingMode and fomega at the NkBINS bins and the time knots.
+ * Bisection for k_GM_*, normalisation and the SPLINE_INVGROW set-up stay with the caller.  No context needed. */
+typedef struct {
+  int device;                 /* CUDA device ordinal                                                   */
+  int nnodes;                 /* quadrature nodes                                                      */
+  const double* logk;         /* [nnodes] log10 k                                                      */
+  const double* a_dens;       /* [nnodes] weight * P(k) * k^3 / (2 pi^2)                               */
+  const double* a_disp;       /* [nnodes] weight * P(k) * k / (2 pi^2)                                 */
+  int nkbins, ntimes;         /* NkBINS (1 without -DSCALE_DEPENDENT), NBINS                           */
+  double logkmin, dlogk;      /* LOGKMIN, DELTALOGK (src/def_splines.h:41-42)                          */
+  const double* log10_growth; /* [nkbins][ntimes] SPLINE[SP_GROW1 + kk] at the time knots              */
+  const double* fomega;       /* [nkbins][ntimes] SPLINE[SP_FOMEGA1 + kk] there                        */
+  int nsmooth;                /* Smoothing.Nsmooth, <= 64                                              */
+  const double* radius_dens;  /* [nsmooth] Smoothing.Radius (Gaussian)                                 */
+  const double* radius_disp;  /* [nsmooth] Smoothing.Rad_GM (top-hat)                                  */
+} pinb200_sdgm_desc;
+int pinb200_scaledep_variances(const pinb200_sdgm_desc* desc, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -777,3 +777,53 @@ def pack_products(res) -> np.ndarray:
             for a in range(3):
                 p[name][:, a] = res[name][a].ravel()
     return p
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# set_scaledep_GM (src/initialization.c:1533-2026): the variance integrals behind the per-radius inverse-growth
+# splines and the k_GM_* wavenumbers
+# ---------------------------------------------------------------------------------------------------------------
+def window_function(kind: int, kr):
+    """WindowFunction, src/cosmo.c:1611-1646: 0 Gaussian, 2 top-hat (kr < 1e-5 -> 1)."""
+    kr = np.asarray(kr, dtype=np.float64)
+    if kind == 0:
+        return np.exp(-kr * kr / 2.0)
+    out = np.ones_like(kr)
+    m = kr >= 1.0e-5
+    x = kr[m]
+    out[m] = 3.0 * (np.sin(x) / (x * x) / x - np.cos(x) / (x * x))
+    return out
+
+
+def interpolate_growth_table(tab, logk, logkmin, dlogk):
+    """InterpolateGrowth (src/cosmo.c:1728-1755) on a [nkbins][ntimes] table of spline values at the time knots:
+    returns [ntimes][len(logk)].  Below kmin the first bin, above kmax the last, linear in log10 k between."""
+    tab = np.asarray(tab, dtype=np.float64)
+    nk = tab.shape[0]
+    logk = np.asarray(logk, dtype=np.float64)
+    if nk == 1:
+        return np.repeat(tab[0][:, None], logk.size, axis=1)
+    dk = (logk - logkmin) / dlogk
+    kk = np.clip(dk.astype(np.int64), 0, nk - 2)
+    fr = dk - kk
+    val = fr[None, :] * tab[kk + 1].T + (1.0 - fr)[None, :] * tab[kk].T
+    val = np.where((logk < logkmin)[None, :], tab[0][:, None], val)
+    val = np.where((logk > logkmin + (nk - 1) * dlogk)[None, :], tab[nk - 1][:, None], val)
+    return val
+
+
+def scaledep_variances(logk, a_dens, a_disp, log10_growth, fomega, logkmin, dlogk, radius_dens, radius_disp):
+    """The three integrals of set_scaledep_GM for every radius and time knot on a FIXED quadrature (nodes logk, the
+    node weights folded into a_dens = w P k^3 / 2 pi^2 and a_disp = w P k / 2 pi^2):
+    out[0] density, IntegrandForSDDensVariance (src/initialization.c:1439-1447, Gaussian window);
+    out[1] displacement, IntegrandForSDDisplVariance (:1449-1457, top-hat);
+    out[2] velocity, IntegrandForSDVelVariance (:1489-1498, top-hat, times fomega^2); each the sqrt of the integral
+    (the reference's vector[i], :1600, :1747, :1891)."""
+    logk = np.asarray(logk, dtype=np.float64)
+    k = 10.0 ** logk
+    D2 = (10.0 ** interpolate_growth_table(log10_growth, logk, logkmin, dlogk)) ** 2          # [nt][n]
+    V2 = D2 * interpolate_growth_table(fomega, logk, logkmin, dlogk) ** 2
+    rd, rp = np.asarray(radius_dens, dtype=np.float64), np.asarray(radius_disp, dtype=np.float64)
+    Td = np.asarray(a_dens)[None, :] * window_function(0, k[None, :] * rd[:, None]) ** 2      # [ns][n]
+    Tt = np.asarray(a_disp)[None, :] * window_function(2, k[None, :] * rp[:, None]) ** 2
+    return np.sqrt(np.stack([Td @ D2.T, Tt @ D2.T, Tt @ V2.T]))

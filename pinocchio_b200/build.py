@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
-SOURCES = ["engine.cu", "k_strided.cu", "k_zpass.cu", "k_misc.cu", "k_sort.cu", "k_ctable.cu"]
+SOURCES = ["engine.cu", "k_strided.cu", "k_zpass.cu", "k_misc.cu", "k_sort.cu", "k_ctable.cu", "k_scaledep.cu"]
 # Per-file flags.  The collapse-time table kernels (ELL_SNG: one adaptive rkf45 integration per table point)
 # are compiled without FMA contraction: the reference's sng_system skips the pair (i, j) when y[i] == y[j]
 # (src/collapse_times.c:266) and relies on symmetric initial conditions (l1 == l2 or l2 == l3, 4 % of a

@@ -24,6 +24,50 @@ struct DevCtx {
     const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
   }
+  // ---- TMA tile loads (cp.async.bulk.tensor + mbarrier): one thread moves a whole strided tile, the copy
+  // engine of the SM does the address arithmetic; see strided_tile_jobs
+  static constexpr bool kTma = true;
+  __device__ __forceinline__ unsigned long long* tile_barrier() const {
+    __shared__ __align__(8) unsigned long long bar;
+    return &bar;
+  }
+  __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) const {
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) const {
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+  }
+  // waits for the phase with the given parity; a transfer that never completes (wrong byte count, bad descriptor)
+  // ends in a trap after a few seconds instead of hanging the GPU
+  __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) const {
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+    unsigned int done = 0, spins = 0;
+    while (true) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(a), "r"(parity)
+          : "memory");
+      if (done) break;
+      if (++spins > (1u << 26)) __trap();
+    }
+  }
+  // generic-proxy accesses to shared memory before it -> async-proxy (TMA) accesses after it
+  __device__ __forceinline__ void fence_async_proxy() const { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+  __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2,
+                                              unsigned long long* bar) const {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    const unsigned int b = (unsigned int)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(d), "l"(tmap), "r"(b), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  }
   __device__ __forceinline__ void mark(int) const {}  // timeline hook (tools/passbench only)
   // compiler scheduling fence: memory operations are not moved across it (bounds loads in flight)
   __device__ __forceinline__ void sched_fence() const { asm volatile("" ::: "memory"); }

@@ -32,6 +32,7 @@
 using namespace pinb;
 
 static thread_local std::string g_create_error;
+namespace pinb { void set_create_error(const std::string& s) { g_create_error = s; } }
 
 // pinb200_handoff_begin .. _end: buffers and streams of a selection + sort in flight
 struct HandoffState {
@@ -839,7 +840,7 @@ static int run_xpass_local(pinb200_ctx* ctx, double2* const S[3], double2* const
   p.dst_klayout = 2;
   p.lx_shift = ctx->lx_shift;
   p.pmask = 0x7;
-  p.ntiles_z = ntiles(ctx, xpass_tk(g.N, +1), ctx->kdens_has_nyq);
+  p.ntiles_z = ntiles(ctx, xpass_tk(g.N, +1, 2), ctx->kdens_has_nyq);
   p.kf.gauss = ctx->gauss;
   p.kf.scalar = 1.0 / ((double)g.N * g.N * g.N);
   p.kf.green = 1;

@@ -95,8 +95,12 @@ template <int L> struct StridedCfg { static constexpr int TK = (L <= 1024) ? 8 :
 #ifndef PINB_SPLIT_ABOVE
 #define PINB_SPLIT_ABOVE 1024
 #endif
-template <int L, int DIR> struct XCfg {
-  static constexpr bool SPLIT = (L > PINB_SPLIT_ABOVE) && DIR > 0;  // the forward x pass is in place (and local)
+// LOCAL: the inverse x pass of the pipelined multi-GPU sweep (XPassParams::dst_klayout == 2) stores into LOCAL memory
+// only -- the copy engines do the transpose -- so the 64-byte pieces of a TK = 4 tile never cross NVLink and the whole
+// line fits one tile again: no decimation step, no second reading of the source (r02, slab of 2048^3 on one GPU:
+// see profiles/r02_slabbench.txt).
+template <int L, int DIR, bool LOCAL = false> struct XCfg {
+  static constexpr bool SPLIT = (L > PINB_SPLIT_ABOVE) && DIR > 0 && !LOCAL;  // the forward x pass is in place (and local)
   static constexpr int LT = SPLIT ? L / 2 : L;
   static constexpr int TK = LT <= 1024 ? 8 : 4;
   static constexpr int CHUNK = SPLIT ? 4 : 0;  // see strided_tile_jobs (r01 slab benchmark: 41 -> 32 ms)
@@ -167,6 +171,19 @@ PINB_HD void strided_tile_fft(Ctx& ctx, double2* s, const double2* __restrict__ 
   ctx.sync();  // shared memory free for the next job
 }
 
+// TMA descriptor of a pitched field seen as a 3-D tensor of doubles {2 P (kz, re/im interleaved), y, x} -- the K layout
+// [N][ly][P] and the R layout [lx][N][P] alike -- with a box of one tile piece: 2 TK doubles of up to 256 consecutive
+// line elements (x pass: along dimension 2, y pass: along dimension 1).  Opaque here (CUtensorMap, 128 bytes, filled by
+// cuTensorMapEncodeTiled in k_strided.cu); the host emulator never touches it.
+struct alignas(64) TileMap { unsigned long long opaque[16]; };
+struct TileSrc {
+  const TileMap* map;
+  int c0, c1, c2;  // coordinates of the tile's first piece
+  int adv;         // the dimension (1 or 2) along which the line runs
+};
+template <class Ctx, class = void> struct CtxHasTma { static constexpr bool value = false; };
+template <class Ctx> struct CtxHasTma<Ctx, decltype((void)Ctx::kTma)> { static constexpr bool value = Ctx::kTma; };
+
 // Software-pipelined sequence of jobs on one tile.  Job j takes the raw tile at src(j, e, tk)
 // (pointer), transforms each element with xform(j, e, tk, raw) and stores with store(j, e, tk, v).
 // The raw tile travels HBM/L2 -> shared memory with cp.async (no registers in flight); each
@@ -175,16 +192,45 @@ PINB_HD void strided_tile_fft(Ctx& ctx, double2* s, const double2* __restrict__ 
 // tile is free again and the copies of job j+1 are issued: they overlap the last butterflies and
 // the global stores of job j (with one 128 KB tile per SM nothing else can hide that latency).
 // CHUNK > 0: xform is applied in a separate rolled loop, CHUNK elements per iteration.
-template <int L, int TK, int DIR, class PL, int TWS, int CHUNK = 0, class Ctx, class SrcF, class XformF, class StoreF>
+// use_tma (device contexts only): the tile is fetched by the SM's TMA unit instead -- one thread arms an mbarrier with
+// the tile's byte count and issues L/256 cp.async.bulk.tensor copies (a box = 2 TK doubles x 256 line elements, the
+// same dense [e][tk] layout in shared memory), everybody waits on the barrier's phase.  No per-thread address
+// arithmetic or LDGSTS traffic through L1; tsrc(job) names the tensor map and the tile's coordinates.
+template <int L, int TK, int DIR, class PL, int TWS, int CHUNK = 0, class Ctx, class SrcF, class XformF, class StoreF, class TsrcF>
 PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__ tw, int njobs, SrcF src, XformF xform,
-                               StoreF store) {
+                               StoreF store, bool use_tma, TsrcF tsrc) {
   constexpr int TPL = PL::TPL, RMAX = PL::RMAX;
   constexpr int T0 = L / PL::R0, NB0 = T0 / TPL;
+  constexpr int ROWS = L < 256 ? L : 256, NBOX = L / ROWS;  // TMA boxes per tile
   const int tk = ctx.tid() % TK, jl = ctx.tid() / TK;
   double2 v[RMAX];
   auto s_in = [&](int e) { return s[e * TK + tk]; };
   auto s_out = [&](int e, double2 val) { s[e * TK + tk] = val; };
+  bool tma = false;
+  unsigned long long* bar = nullptr;
+  if constexpr (CtxHasTma<Ctx>::value) {
+    tma = use_tma;
+    if (tma) {
+      bar = ctx.tile_barrier();
+      if (ctx.tid() == 0) ctx.mbar_init(bar, 1);
+      ctx.fence_async_proxy();
+      ctx.sync();
+    }
+  }
   auto issue = [&](int job) {
+    if constexpr (CtxHasTma<Ctx>::value) {
+      if (tma) {
+        if (ctx.tid() == 0) {
+          const TileSrc t = tsrc(job);
+          ctx.mbar_expect_tx(bar, (unsigned int)(L * TK * sizeof(double2)));
+#pragma unroll
+          for (int b = 0; b < NBOX; b++)
+            ctx.tma_load_3d(s + (size_t)b * ROWS * TK, t.map, t.c0, t.c1 + (t.adv == 1 ? b * ROWS : 0),
+                            t.c2 + (t.adv == 2 ? b * ROWS : 0), bar);
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int m = 0; m < NB0; m++)
 #pragma unroll
@@ -198,7 +244,14 @@ PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__
     auto raw_in = [&](int e) { return xform(job, e, tk, s[e * TK + tk]); };
     auto g_out = [&](int e, double2 val) { store(job, e, tk, val); };
     ctx.mark(4 * job + 0);
-    ctx.async_wait();  // my own elements have landed
+    bool waited = false;
+    if constexpr (CtxHasTma<Ctx>::value) {
+      if (tma) {
+        ctx.mbar_wait(bar, (unsigned int)(job & 1));  // the whole tile has landed
+        waited = true;
+      }
+    }
+    if (!waited) ctx.async_wait();  // my own elements have landed
     ctx.mark(4 * job + 1);
     if constexpr (CHUNK == 0) {
       stage_load<L, PL::R0, TPL, RMAX>(jl, v, raw_in);
@@ -222,6 +275,7 @@ PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__
       stage_store<L, PL::R1, PL::R0, DIR, TPL, RMAX>(jl, v, s_out, tw, TWS);
       ctx.sync();
       stage_load<L, PL::R2, TPL, RMAX>(jl, v, s_in);
+      if constexpr (CtxHasTma<Ctx>::value) { if (tma) ctx.fence_async_proxy(); }  // my accesses before the next TMA write
       ctx.sync();  // tile free
       ctx.mark(4 * job + 2);
       if (job + 1 < njobs) issue(job + 1);
@@ -229,6 +283,7 @@ PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__
       ctx.mark(4 * job + 3);
     } else {
       stage_load<L, PL::R1, TPL, RMAX>(jl, v, s_in);
+      if constexpr (CtxHasTma<Ctx>::value) { if (tma) ctx.fence_async_proxy(); }
       ctx.sync();  // tile free
       ctx.mark(4 * job + 2);
       if (job + 1 < njobs) issue(job + 1);
@@ -264,15 +319,17 @@ struct XPassParams {
   KFactor kf;
   Geom g;
   const double2* tw;    // N-th roots of unity
+  int use_tma;          // the source tile comes through the TMA unit (tmap; set by the launcher, never by the caller)
+  TileMap tmap;         // src as {2 P, ly, N} doubles, box {2 TK, 1, 256}
 };
 
 // MULTI = false: one rank; the owner look-up and the per-rank pointer table are compiled out
 // (they cost registers: the 1024-point kernel spilled 128 bytes with them).
 // GK = true: the scale-dependent growth rate is evaluated per mode (separate instantiation so that
 // the Hessian pass keeps its register budget).
-template <int L, int DIR, bool MULTI, class Ctx, bool GK = false>
+template <int L, int DIR, bool MULTI, class Ctx, bool GK = false, bool LOCAL = false>
 PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
-  using C = XCfg<L, DIR>;
+  using C = XCfg<L, DIR, LOCAL>;
   constexpr int TK = C::TK, LT = C::LT;
   constexpr bool SPLIT = C::SPLIT;
   const Geom& g = p.g;
@@ -352,7 +409,9 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   // without G(k), although the arithmetic is worth 5 ms), so it runs as a rolled pre-pass over the tile like the
   // split passes' combine step
   constexpr int CHUNK = (GK && C::CHUNK == 0) ? 4 : C::CHUNK;
-  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * npw : npw, srcf, xform, storef);
+  auto tsrcf = [&](int) { return TileSrc{&p.tmap, 2 * kz0, yl, 0, 2}; };
+  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * npw : npw, srcf, xform, storef,
+                                                                  p.use_tma != 0, tsrcf);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -373,6 +432,8 @@ struct YPassParams {
   int nsrc;               // distinct source fields (prefetched)
   Geom g;
   const double2* tw;
+  int use_tma;            // as in XPassParams
+  TileMap tmap[3];        // src[i] as {2 P, N, lx} doubles, box {2 TK, 256, 1}
 };
 
 template <int L, int DIR, class Ctx>
@@ -417,7 +478,9 @@ PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
       p.dst[p.job[j].dst][base + (size_t)e * g.P + tk] = val;
     }
   };
-  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, C::CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * p.njobs : p.njobs, srcf, xform, storef);
+  auto tsrcf = [&](int job) { return TileSrc{&p.tmap[p.job[SPLIT ? (job >> 1) : job].src], 2 * kz0, 0, xl, 1}; };
+  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, C::CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * p.njobs : p.njobs, srcf, xform, storef,
+                                                                     p.use_tma != 0, tsrcf);
 }
 
 // ---------------------------------------------------------------------------------------

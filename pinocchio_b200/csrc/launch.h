@@ -12,8 +12,11 @@ cudaError_t launch_ypass(int N, int dir, const YPassParams& p, int nblocks_x, cu
 cudaError_t launch_zpass_collapse(int N, const CollapseParams& p, size_t nrows, cudaStream_t s);
 cudaError_t launch_zpass_out(int N, const ZOutParams& p, size_t nrows, cudaStream_t s);
 cudaError_t launch_zpass_r2c(int N, const ZR2CParams& p, size_t nrows, cudaStream_t s);
-int xpass_tk(int N, int dir);  // kz-tile width of the x pass (dir +1 inverse, -1 forward) ...
+// kz-tile width of the x pass (dir +1 inverse, -1 forward; dst_klayout as in XPassParams: the inverse pass that only
+// stores locally, 2, never splits its lines) ...
+int xpass_tk(int N, int dir, int dst_klayout = 0);
 int ypass_tk(int N);           // ... and of the y pass for this grid
+bool strided_tma_enabled();    // the strided passes fetch their tiles through the TMA unit (PINB200_TMA=0: cp.async)
 
 cudaError_t launch_sources(const SourcesParams& p, cudaStream_t s);
 cudaError_t launch_genic(const GenicParams& p, cudaStream_t s);

@@ -51,6 +51,16 @@ H_OVER_C = 100.0 / 299792.458             # H_over_c = 100 / SPEEDOFLIGHT (src/c
 CT_NBINS_D, CT_NBINS_XY, CT_RANGE_X = 100, 50, 3.5   # src/collapse_times.c:781-787
 
 
+class SdgmDesc(ctypes.Structure):
+    """pinb200_sdgm_desc (include/pinb200.h): inputs of the batched set_scaledep_GM integrals."""
+    _fields_ = [("device", ctypes.c_int), ("nnodes", ctypes.c_int), ("logk", ctypes.POINTER(ctypes.c_double)),
+                ("a_dens", ctypes.POINTER(ctypes.c_double)), ("a_disp", ctypes.POINTER(ctypes.c_double)),
+                ("nkbins", ctypes.c_int), ("ntimes", ctypes.c_int), ("logkmin", ctypes.c_double), ("dlogk", ctypes.c_double),
+                ("log10_growth", ctypes.POINTER(ctypes.c_double)), ("fomega", ctypes.POINTER(ctypes.c_double)),
+                ("nsmooth", ctypes.c_int), ("radius_dens", ctypes.POINTER(ctypes.c_double)),
+                ("radius_disp", ctypes.POINTER(ctypes.c_double))]
+
+
 class Timers(ctypes.Structure):
     _fields_ = [("dens", ctypes.c_double), ("fmax", ctypes.c_double), ("deriv", ctypes.c_double),
                 ("fft", ctypes.c_double), ("coll", ctypes.c_double), ("lpt", ctypes.c_double),
@@ -130,6 +140,7 @@ def load_library() -> ctypes.CDLL:
     lib.pinb200_ct_delta_vector.argtypes = [_PD, ctypes.c_int]
     lib.pinb200_set_collapse_tables.argtypes = [ctypes.c_void_p, ctypes.POINTER(CTDesc), _PD, _PD, _PD]
     lib.pinb200_download_collapse_table.argtypes = [ctypes.c_void_p, ctypes.c_int, _PD]
+    lib.pinb200_scaledep_variances.argtypes = [ctypes.POINTER(SdgmDesc), _PD]
     _lib = lib
     return lib
 
@@ -137,6 +148,43 @@ def load_library() -> ctypes.CDLL:
 def _dp(a: np.ndarray):
     assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(_PD)
+
+
+def gauss_legendre_nodes(lo: float, hi: float, npanels: int = 512, order: int = 8, breaks=()):
+    """Composite Gauss-Legendre nodes and weights on [lo, hi]: the quadrature shim/scaledep_gm_b200.c hands to
+    pinb200_scaledep_variances (order 8, about 512 panels of the reference's interval [-4, nyquist] in log10 k).
+    `breaks`: points where the integrand has kinks (the k bins of InterpolateGrowth's piecewise-linear blend): panel
+    edges are put there, every segment getting its share of the panels (at least one)."""
+    x, w = np.polynomial.legendre.leggauss(order)
+    cuts = [lo] + sorted(b for b in breaks if lo < b < hi) + [hi]
+    edges = [np.array([lo])]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        m = max(1, int(np.floor(npanels * (b - a) / (hi - lo) + 0.5)))
+        edges.append(a + (b - a) * np.arange(1, m + 1) / m)
+    edges = np.concatenate(edges)
+    edges[-1] = hi
+    h = 0.5 * (edges[1:] - edges[:-1])
+    c = 0.5 * (edges[1:] + edges[:-1])
+    return (c[:, None] + h[:, None] * x[None, :]).ravel(), (h[:, None] * w[None, :]).ravel()
+
+
+def scaledep_variances(logk, a_dens, a_disp, log10_growth, fomega, logkmin, dlogk, radius_dens, radius_disp,
+                       device: int = 0) -> np.ndarray:
+    """set_scaledep_GM's integrals (src/initialization.c:1594-1601, :1742-1748, :1886-1892), all of them in one device
+    call: returns out[3][nsmooth][ntimes] = sqrt of the density / displacement / velocity integrals, the reference's
+    `vector` before its normalisation.  logk: quadrature nodes in log10 k; a_dens, a_disp: weight * P(k) * k^3 (k) /
+    (2 pi^2) per node from the host cosmology; log10_growth, fomega: [nkbins][ntimes] k-bin tables at the time knots."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (logk, a_dens, a_disp, log10_growth, fomega, radius_dens, radius_disp)]
+    lk, ad, ap, lg, fo, rd, rp = arrs
+    if lg.ndim != 2 or fo.shape != lg.shape or ad.shape != lk.shape or ap.shape != lk.shape or rd.shape != rp.shape:
+        raise ValueError("scaledep_variances: inconsistent shapes")
+    d = SdgmDesc(device, lk.size, _dp(lk), _dp(ad), _dp(ap), lg.shape[0], lg.shape[1], float(logkmin), float(dlogk),
+                 _dp(lg), _dp(fo), rd.size, _dp(rd), _dp(rp))
+    out = np.zeros((3, rd.size, lg.shape[1]))
+    lib = load_library()
+    if lib.pinb200_scaledep_variances(ctypes.byref(d), _dp(out)):
+        raise PinocchioError((lib.pinb200_last_error(None) or b"pinb200_scaledep_variances failed").decode())
+    return out
 
 
 # product_data for -DTWO_LPT -DTHREE_LPT, float products (src/pinocchio.h:233-259): 56 bytes

@@ -20,6 +20,7 @@
 
 #include "../../pinocchio_b200/csrc/kernels.cuh"
 #include "../../pinocchio_b200/csrc/sort_cells.cuh"
+#include "../../pinocchio_b200/csrc/scaledep_gm.cuh"
 
 using namespace pinb;
 
@@ -189,6 +190,16 @@ extern "C" int emu_zline_fft(int M, int dir, const double* in, double* out, cons
 
 // ---- whole kernels on pitched arrays (K layout [N][ly][P], R layout [lx][N][P]) ---------------
 template <int N, int DIR> static void xpass_run(XPassParams& p, int with_nyq) {
+  if constexpr (DIR > 0 && XCfg<N, +1>::SPLIT) {
+    if (p.dst_klayout == 2 && !p.kf.gk) {  // as xpass_launch (k_strided.cu): the all-local pass never splits its lines
+      using C = XCfg<N, +1, true>;
+      p.ntiles_z = (N / 2) / C::TK + (with_nyq ? 1 : 0);
+      std::vector<double2> smem((size_t)C::LT * C::TK);
+      run_blocks((long long)p.g.ly * p.ntiles_z, C::NT,
+                 [&](HostCtx& ctx) { xpass_body<N, +1, false, HostCtx, false, true>(ctx, smem.data(), p); });
+      return;
+    }
+  }
   using C = XCfg<N, DIR>;
   p.ntiles_z = (N / 2) / C::TK + (with_nyq ? 1 : 0);
   std::vector<double2> smem((size_t)C::LT * C::TK);
@@ -595,4 +606,21 @@ extern "C" long long emu_collapsed_cells(const float* fmax, long long n, float f
   }
   for (unsigned long long i = 0; i < m; i++) idx_out[i] = idx[cur ^ 1][i];
   return (long long)m;
+}
+
+// ---- batched set_scaledep_GM integrals (scaledep_gm.cuh): the two kernels of k_scaledep.cu, block by block ----
+extern "C" int emu_scaledep_variances(int n, const double* logk, const double* a_dens, const double* a_disp, int nk, int nt,
+                                      double logkmin, double dlogk, const double* lg, const double* fo, int ns,
+                                      const double* r_dens, const double* r_disp, double* out) {
+  constexpr int NT = 256, RC = 8;  // as k_scaledep.cu
+  std::vector<double> T((size_t)2 * ns * n);
+  SdgmParams p{};
+  p.logk = logk; p.a_dens = a_dens; p.a_disp = a_disp; p.n = n;
+  p.lg = lg; p.fo = fo; p.nk = nk; p.nt = nt; p.logkmin = logkmin; p.dlogk = dlogk;
+  p.r_dens = r_dens; p.r_disp = r_disp; p.ns = ns; p.T = T.data(); p.out = out;
+  const long long nw = 2ll * ns * n;
+  run_blocks((nw + 255) / 256, 256, [&](HostCtx& ctx) { sdgm_window_body(ctx, p); });
+  std::vector<double> scratch(NT);
+  run_blocks(nt, NT, [&](HostCtx& ctx) { sdgm_integrate_body<NT, RC>(ctx, scratch.data(), p); });
+  return 0;
 }

@@ -41,6 +41,9 @@ int emu_genic(int N, int rank, int nranks, const unsigned int* seeds, const doub
 int emu_zpass_collapse_tab(int N, int nranks, double** srcs, const int* kzpow, int has_nyq, const double* dc, const double* knots,
                            const double* coef, int nd, int nxy, double ampl, double bin_x, int ismooth, float* fmax, int* rmax,
                            double* sums, double** hdst, const double* tw);
+int emu_scaledep_variances(int n, const double* logk, const double* a_dens, const double* a_disp, int nk, int nt, double logkmin,
+                           double dlogk, const double* lg, const double* fo, int ns, const double* r_dens, const double* r_disp,
+                           double* out);
 int emu_ct_delta_vector(double* dv, int nd);
 int emu_ct_build(int model, const double* dv, int nd, int nxy, double bin_x, double ampl, const double* spline, int nspl, double D_in,
                  const double* cosmo4, int first, int npoints, double* table);
@@ -220,6 +223,18 @@ static int hessian_xy(pinb200_ctx* ctx, double rs, double& dc) {
 }
 
 // ---- TABULATED_CT: the engine's pinb200_set_collapse_tables on host arrays -------------------------
+extern "C" int pinb200_scaledep_variances(const pinb200_sdgm_desc* d, double* out) {
+  if (!d || !out || !d->logk || !d->a_dens || !d->a_disp || !d->log10_growth || !d->fomega || !d->radius_dens || !d->radius_disp) {
+    g_err = "pinb200_scaledep_variances: null argument";
+    return 1;
+  }
+  if (d->nnodes < 1 || d->nkbins < 1 || d->ntimes < 1 || d->nsmooth < 1 || d->nsmooth > 64 || !(d->dlogk > 0.0)) {
+    g_err = "pinb200_scaledep_variances: nnodes, nkbins, ntimes >= 1, 1 <= nsmooth <= 64, dlogk > 0 required";
+    return 1;
+  }
+  return emu_scaledep_variances(d->nnodes, d->logk, d->a_dens, d->a_disp, d->nkbins, d->ntimes, d->logkmin, d->dlogk, d->log10_growth,
+                                d->fomega, d->nsmooth, d->radius_dens, d->radius_disp, out);
+}
 extern "C" int pinb200_ct_delta_vector(double* dv, int nd) { return (dv && nd >= 4 && nd <= 128) ? emu_ct_delta_vector(dv, nd) : 1; }
 extern "C" int pinb200_set_collapse_tables(pinb200_ctx* ctx, const pinb200_ct_desc* desc, const double* variance, const double* d_in,
                                            const double* tables) {

@@ -149,7 +149,10 @@ def scaledep_tables(nk=10, seed=11):
 def test_staged_transpose_equals_peer_stores(P, split):
     """Multi-GPU sweep, two ways of doing the transpose behind the inverse x pass: peer stores from the kernel
     (r01) and own planes in place + local staging + strided block copies (r02, what the copy engines do under the
-    collapse pass).  The R-layout fields must come out bit-identical, pads and Nyquist columns aside."""
+    collapse pass).  The R-layout fields must come out bit-identical, pads and Nyquist columns aside -- except where
+    the scattering kernel splits its lines (the split build here, N = 2048 in the product): the all-local pass of the
+    staged transpose transforms the whole line in one tile (XCfg LOCAL), another factorisation of the same FFT, so
+    the two agree to rounding."""
     N = 32
     cl = EmuCluster(N, P, split=split)
     rng = np.random.default_rng(17)
@@ -164,7 +167,12 @@ def test_staged_transpose_equals_peer_stores(P, split):
     cl.xpass_inv_staged(cl.kdens, S, A2, 7, 0, gauss, cl.norm, 1, 0)
     for pw in range(3):
         for r in range(P):
-            assert np.array_equal(A2[pw][r][:, :, :M], want[pw][r][:, :, :M]), (pw, r)
+            got, ref = A2[pw][r][:, :, :M], want[pw][r][:, :, :M]
+            if split:
+                assert np.abs(got - ref).max() <= 1e-14 * np.abs(ref).max(), (pw, r)
+                assert not np.array_equal(got, ref) or P == 1   # the unsplit kernel really ran
+            else:
+                assert np.array_equal(got, ref), (pw, r)
 
 
 def test_interpolate_growth_clamps_and_knots():

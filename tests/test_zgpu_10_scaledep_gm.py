@@ -1,0 +1,50 @@
+"""set_scaledep_GM on the B200: pinb200_scaledep_variances through the C ABI against the oracle, and the
+reference's own function against shim/scaledep_gm_b200.c linked with libpinb200.so (oracle/sdgm_harness.c) on the
+shipped example.  CPU twin: tests/test_scaledep_gm.py."""
+import json
+
+import numpy as np
+import pytest
+
+from example_util import ROOT, run_example
+from oracle import pinocchio_oracle as po
+from test_scaledep_gm import quadrature, synthetic_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nk,ns,npanels", [(10, 5, 512), (1, 3, 64), (10, 11, 512), (10, 64, 128)])
+def test_device_integrals_against_oracle(nk, ns, npanels):
+    from pinocchio_b200.engine import scaledep_variances
+    lg, fo, rd, rp = synthetic_case(nk=nk, ns=5)
+    if ns != 5:
+        rd, rp = np.linspace(25.0, 0.0, ns), np.linspace(60.0, 0.0, ns)
+    logk, ad, ap = quadrature(npanels=npanels)
+    out = scaledep_variances(logk, ad, ap, lg, fo, -3.0, 0.5, rd, rp)
+    ref = po.scaledep_variances(logk, ad, ap, lg, fo, -3.0, 0.5, rd, rp)
+    assert out.shape == (3, ns, lg.shape[1])
+    assert np.abs(out / ref - 1).max() < 1e-12
+
+
+def test_device_rejects_bad_arguments():
+    from pinocchio_b200.engine import PinocchioError, scaledep_variances
+    lg, fo, rd, rp = synthetic_case()
+    logk, ad, ap = quadrature(npanels=4)
+    with pytest.raises(PinocchioError, match="dlogk"):
+        scaledep_variances(logk, ad, ap, lg, fo, -3.0, 0.0, rd, rp)
+    with pytest.raises(PinocchioError):
+        scaledep_variances(logk, ad, ap, lg, fo, -3.0, 0.5, np.zeros(65), np.zeros(65))
+
+
+def test_reference_set_scaledep_gm_against_linked_binding(tmp_path):
+    exe = ROOT / "oracle" / "_ref" / "sdgm_b200_ex.x"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/sdgm_b200_ex.x not built")
+    out = run_example(exe, tmp_path, grid=32, threads=8, timeout=600)
+    d = json.loads(out.strip().splitlines()[-1])
+    print({k: v for k, v in d.items() if k != "k_gm"})
+    assert d["invgrow_vector_max_rel"] < 1e-6 and d["rad_gm_max_abs"] == 0.0
+    ks = np.array([[a, b] for _, _, a, b in d["k_gm"]])
+    assert len(np.unique(ks[:, 0])) >= 4 and np.array_equal(ks[:, 0], ks[:, 1])
+    # one device call against 3 x Nsmooth x 210 adaptive integrals on one host core
+    assert d["t_b200_binding_s"] < d["t_reference_s"]

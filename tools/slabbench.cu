@@ -6,6 +6,7 @@
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I pinocchio_b200/csrc \
 //        tools/slabbench.cu -L pinocchio_b200 -lpinb200 -Xlinker -rpath=$PWD/pinocchio_b200 -o tools/slabbench
 //   tools/slabbench N P [reps]
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -104,6 +105,52 @@ int main(int argc, char** argv) {
     const int nj = pmask == 7 ? 3 : 1;
     printf("xpass inv pmask=%d tk=%d: %.2f ms  (%.0f GB/s algorithmic: 1 read + %d writes)\n", pmask, xpass_tk(N, +1), ms,
            (1 + nj) * gb / ms * 1e3, nj);
+  }
+  // ---- the same pass as the pipelined multi-GPU sweep runs it (dst_klayout = 2): own x planes into the local R-layout
+  // field, everything else into local K-layout staging; lines longer than the tile are NOT split there (XCfg LOCAL).
+  // Checked against the scattering kernel's result in the plain local K layout (dst_klayout = 1).
+  {
+    double2* S[3];
+    for (auto& b : S) CKE(cudaMalloc(&b, fe * sizeof(double2)));
+    XPassParams p{};
+    p.src = src;
+    p.lx_shift = sh; p.pmask = 7;
+    p.kf.gauss = gauss; p.kf.scalar = 1e-9; p.kf.green = 1; p.kf.times_i = 0; p.g = g; p.tw = tw;
+    // reference: every element in the K layout, by the kernel that scatters (split lines at N = 2048)
+    for (int pw = 0; pw < 3; pw++) p.dst[pw].r[0] = B[pw];
+    p.dst_klayout = 1;
+    p.ntiles_z = g.M / xpass_tk(N, +1, 1);
+    p.nblocks = g.ly * p.ntiles_z;
+    const float ms1 = timed(reps, [&] { CKE(launch_xpass(N, +1, p, g.ly, 0)); });
+    printf("xpass inv K-layout (scattering kernel, local stores) tk=%d: %.2f ms  (%.0f GB/s)\n", xpass_tk(N, +1, 1), ms1, 4 * gb / ms1 * 1e3);
+    for (int pw = 0; pw < 3; pw++) { p.dst[pw].r[0] = S[pw]; p.dst[pw].r[1] = A[pw]; }
+    p.dst_klayout = 2;
+    p.ntiles_z = g.M / xpass_tk(N, +1, 2);
+    p.nblocks = g.ly * p.ntiles_z;
+    const float ms2 = timed(reps, [&] { CKE(launch_xpass(N, +1, p, g.ly, 0)); });
+    printf("xpass inv staged (dst_klayout 2, all local) tk=%d: %.2f ms  (%.0f GB/s algorithmic: 1 read + 3 writes)\n", xpass_tk(N, +1, 2), ms2,
+           4 * gb / ms2 * 1e3);
+    // compare on the host, field by field, a few x planes at a time
+    double worst = 0, scale = 0;
+    const size_t plane = (size_t)g.ly * g.P;            // one x plane of the K-layout slab
+    std::vector<double2> h1(plane), h2(plane);
+    for (int pw = 0; pw < 3; pw++)
+      for (int e = 0; e < N; e += 37) {
+        CKE(cudaMemcpy(h1.data(), B[pw] + (size_t)e * plane, plane * sizeof(double2), cudaMemcpyDeviceToHost));
+        const bool own = e >= g.x0 && e < g.x0 + g.lx;
+        if (!own) CKE(cudaMemcpy(h2.data(), S[pw] + (size_t)e * plane, plane * sizeof(double2), cudaMemcpyDeviceToHost));
+        else  // R layout: plane (e - x0) holds N rows of P; this rank's rows are y0 .. y0 + ly
+          CKE(cudaMemcpy(h2.data(), A[pw] + (size_t)(e - g.x0) * g.N * g.P + (size_t)g.y0 * g.P, plane * sizeof(double2), cudaMemcpyDeviceToHost));
+        for (size_t yl = 0; yl < (size_t)g.ly; yl++)
+          for (int kz = 0; kz < g.M; kz++) {
+            const double2 a = h1[yl * g.P + kz], b = h2[yl * g.P + kz];
+            worst = std::max(worst, std::max(fabs(a.x - b.x), fabs(a.y - b.y)));
+            scale = std::max(scale, std::max(fabs(a.x), fabs(a.y)));
+          }
+      }
+    printf("staged vs scattering kernel: max |diff| %.3e of max |value| %.3e -> rel %.2e %s\n", worst, scale, worst / scale,
+           worst <= 1e-13 * scale ? "OK" : "MISMATCH");
+    for (auto& b : S) CKE(cudaFree(b));
   }
   // ---- inverse y pass, 6 jobs from 3 sources
   {
