@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -478,8 +479,29 @@ def run_b200(args):
                                     "with G(|k|) per mode, NkBINS = 10 tables as the reference hands them over per redshift segment",
                         "kernel": "xpass_growthk_kernel", "algorithmic_bytes_per_xpass": int(xbytes), **res,
                         "xpass_frac_of_hbm_peak": round(res["scale_dependent"]["xpass_gbs"] / peak, 4)}
+            # the start-up side of the same configuration: set_scaledep_GM's 3 x Nsmooth x 210 variance integrals in
+            # one device call (pinb200_scaledep_variances), synthetic tables of the shipped shapes
+            from pinocchio_b200.engine import gauss_legendre_nodes, scaledep_variances
+            nt, ns = 210, S
+            tt = np.linspace(-2.2, 0.05, nt)
+            lg = (1.0 - 0.05 * np.tanh(np.arange(nk) - 4.0)[:, None]) * tt[None, :]
+            fo = 0.5 + 0.45 * (1.0 - 10.0 ** tt)[None, :] + 0.03 * np.tanh(np.arange(nk) - 5.0)[:, None]
+            lk, w = gauss_legendre_nodes(-4.0, math.pi, 512, breaks=-3.0 + 0.5 * np.arange(nk))
+            kk = 10.0 ** lk
+            pk = np.array([cosmo.PowerSpectrum(float(v)) for v in kk[::8]])
+            pk = np.exp(np.interp(lk, lk[::8], np.log(pk)))
+            ad, ap = w * pk * kk ** 3 / (2 * math.pi ** 2), w * pk * kk / (2 * math.pi ** 2)
+            rd, rp = np.array(HMF_RADII[:ns]), np.linspace(30.0, 0.0, ns)
+            scaledep_variances(lk, ad, ap, lg, fo, -3.0, 0.5, rd, rp)      # warm-up (module load, allocations)
+            t_sd = time.perf_counter()
+            sv = scaledep_variances(lk, ad, ap, lg, fo, -3.0, 0.5, rd, rp)
+            t_sd = time.perf_counter() - t_sd
+            scaledep["startup_integrals"] = {"call": "pinb200_scaledep_variances", "integrals": int(3 * ns * nt), "nodes": int(lk.size),
+                                             "wall_ms_incl_copies": round(t_sd * 1e3, 3), "finite": bool(np.isfinite(sv).all()),
+                                             "replaces": "3 x Nsmooth x NBINS gsl_integration_qags calls of set_scaledep_GM "
+                                                         "(src/initialization.c:1594-1601, 1742-1748, 1886-1892)"}
         except Exception as ex:  # noqa: BLE001
-            scaledep = {"error": str(ex)[:300]}
+            scaledep = {"error": str(ex)[:300]} if scaledep is None else {**scaledep, "startup_integrals_error": str(ex)[:300]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -83,6 +83,7 @@ ABI_SYMBOLS = [
     "pinb200_fft_r2c", "pinb200_fft_c2r", "pinb200_second_derivatives", "pinb200_collapse_cells",
     "pinb200_download_kvector",
     "pinb200_ct_delta_vector", "pinb200_set_collapse_tables", "pinb200_download_collapse_table",
+    "pinb200_scaledep_variances",
 ]
 
 _lib = None

@@ -27,7 +27,8 @@ def test_header_symbols_exported(lib):
 
 
 def test_struct_sizes_match_header():
-    from pinocchio_b200.engine import Desc, ProductLayout, Timers
+    from pinocchio_b200.engine import Desc, ProductLayout, SdgmDesc, Timers
+    assert ctypes.sizeof(SdgmDesc) == 96
     assert ctypes.sizeof(Desc) == 48
     assert ctypes.sizeof(ProductLayout) == 40
     assert ctypes.sizeof(Timers) == 8 * 7 + 8 * 64 + 8 * 5 + 8 + 8 + 8 + 8      # ... kernel_launches, sort_ms, disp_x, xfer
