@@ -49,6 +49,22 @@ static bool make_tile_map(TileMap* out, const double2* field, int pitch, int ny,
 // wins (x pass, 3 outputs: 17.8 -> 15.5 ms; y pass, 6 jobs: 20.2 -> 19.2 ms); a pass with ONE job per tile has no
 // second load to overlap and does better when every thread waits for its own 16 cp.async pieces only
 // (5.95 against 6.19 ms), so those keep the LDGSTS loader.
+// Blocks of a strided pass: as many as are resident at once; each walks the tiles bid, bid + grid, ... so that the
+// load of its next tile overlaps the stores of the current one (strided_tile_jobs).  PINB200_PERSISTENT=0: one tile
+// per block.
+template <class K> static unsigned strided_grid(K kernel, int nthreads, size_t smem, unsigned ntiles, int* tile_stride) {
+  static const bool persistent = [] { const char* e = getenv("PINB200_PERSISTENT"); return !(e && !atoi(e)); }();
+  *tile_stride = 0;
+  if (!persistent) return ntiles;
+  int dev = 0, sms = 0, occ = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, nthreads, smem) != cudaSuccess || occ < 1 || sms < 1)
+    return ntiles;
+  const unsigned g = (unsigned)occ * (unsigned)sms;
+  if (g >= ntiles) return ntiles;
+  *tile_stride = (int)g;
+  return g;
+}
 template <int LT> static void xpass_tma(XPassParams& p, int tk) {
   const int npw = ((p.pmask >> 0) & 1) + ((p.pmask >> 1) & 1) + ((p.pmask >> 2) & 1);
   p.use_tma = (npw >= 2 && make_tile_map(&p.tmap, p.src, p.g.P, p.g.ly, p.g.N, tk, LT < 256 ? LT : 256, 2)) ? 1 : 0;
@@ -101,7 +117,9 @@ template <int L, int DIR, bool MULTI> static cudaError_t xpass_launch_m(const XP
   const size_t smem = (size_t)C::LT * C::TK * sizeof(double2);
   cudaError_t e = allow_smem(xpass_kernel<L, DIR, MULTI>, smem);
   if (e != cudaSuccess) return e;
-  xpass_kernel<L, DIR, MULTI><<<(unsigned)(nblocks_y * p.ntiles_z), C::NT, smem, s>>>(p);
+  p.nblocks = nblocks_y * p.ntiles_z;
+  const unsigned grid = strided_grid(xpass_kernel<L, DIR, MULTI>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride);
+  xpass_kernel<L, DIR, MULTI><<<grid, C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 template <int L, bool MULTI> static cudaError_t xpass_growthk_launch_m(const XPassParams& p_in, int nblocks_y, cudaStream_t s) {
@@ -111,7 +129,9 @@ template <int L, bool MULTI> static cudaError_t xpass_growthk_launch_m(const XPa
   const size_t smem = (size_t)C::LT * C::TK * sizeof(double2);
   cudaError_t e = allow_smem(xpass_growthk_kernel<L, MULTI>, smem);
   if (e != cudaSuccess) return e;
-  xpass_growthk_kernel<L, MULTI><<<(unsigned)(nblocks_y * p.ntiles_z), C::NT, smem, s>>>(p);
+  p.nblocks = nblocks_y * p.ntiles_z;
+  const unsigned grid = strided_grid(xpass_growthk_kernel<L, MULTI>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride);
+  xpass_growthk_kernel<L, MULTI><<<grid, C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 template <int L> static cudaError_t xpass_local_launch(const XPassParams& p_in, int nblocks_y, cudaStream_t s) {
@@ -121,7 +141,9 @@ template <int L> static cudaError_t xpass_local_launch(const XPassParams& p_in, 
   const size_t smem = (size_t)C::LT * C::TK * sizeof(double2);
   cudaError_t e = allow_smem(xpass_local_kernel<L>, smem);
   if (e != cudaSuccess) return e;
-  xpass_local_kernel<L><<<(unsigned)(nblocks_y * p.ntiles_z), C::NT, smem, s>>>(p);
+  p.nblocks = nblocks_y * p.ntiles_z;
+  const unsigned grid = strided_grid(xpass_local_kernel<L>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride);
+  xpass_local_kernel<L><<<grid, C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 template <int L, int DIR> static cudaError_t xpass_launch(const XPassParams& p, int nblocks_y, cudaStream_t s) {
@@ -146,7 +168,9 @@ template <int L, int DIR> static cudaError_t ypass_launch(const YPassParams& p_i
   const size_t smem = (size_t)C::LT * C::TK * sizeof(double2);
   cudaError_t e = allow_smem(ypass_kernel<L, DIR>, smem);
   if (e != cudaSuccess) return e;
-  ypass_kernel<L, DIR><<<(unsigned)(nblocks_x * p.ntiles_z), C::NT, smem, s>>>(p);
+  p.nblocks = nblocks_x * p.ntiles_z;
+  const unsigned grid = strided_grid(ypass_kernel<L, DIR>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride);
+  ypass_kernel<L, DIR><<<grid, C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 

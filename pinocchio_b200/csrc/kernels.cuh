@@ -196,12 +196,13 @@ template <class Ctx> struct CtxHasTma<Ctx, decltype((void)Ctx::kTma)> { static c
 // the tile's byte count and issues L/256 cp.async.bulk.tensor copies (a box = 2 TK doubles x 256 line elements, the
 // same dense [e][tk] layout in shared memory), everybody waits on the barrier's phase.  No per-thread address
 // arithmetic or LDGSTS traffic through L1; tsrc(job) names the tensor map and the tile's coordinates.
-template <int L, int TK, int DIR, class PL, int TWS, int CHUNK = 0, class Ctx, class SrcF, class XformF, class StoreF, class TsrcF>
-PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__ tw, int njobs, SrcF src, XformF xform,
-                               StoreF store, bool use_tma, TsrcF tsrc) {
+template <int L, int TK, int DIR, class PL, int TWS, int CHUNK = 0, class Ctx, class BeginF, class SrcF, class XformF, class StoreF, class TsrcF>
+PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__ tw, int njobs, int tile0, int tile_stride, int ntiles,
+                               BeginF begin_tile, SrcF src, XformF xform, StoreF store, bool use_tma, TsrcF tsrc) {
   constexpr int TPL = PL::TPL, RMAX = PL::RMAX;
   constexpr int T0 = L / PL::R0, NB0 = T0 / TPL;
   constexpr int ROWS = L < 256 ? L : 256, NBOX = L / ROWS;  // TMA boxes per tile
+  if (tile0 >= ntiles) return;  // (uniform over the block)
   const int tk = ctx.tid() % TK, jl = ctx.tid() / TK;
   double2 v[RMAX];
   auto s_in = [&](int e) { return s[e * TK + tk]; };
@@ -217,11 +218,11 @@ PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__
       ctx.sync();
     }
   }
-  auto issue = [&](int job) {
+  auto issue = [&](int tile, int job) {
     if constexpr (CtxHasTma<Ctx>::value) {
       if (tma) {
         if (ctx.tid() == 0) {
-          const TileSrc t = tsrc(job);
+          const TileSrc t = tsrc(tile, job);
           ctx.mbar_expect_tx(bar, (unsigned int)(L * TK * sizeof(double2)));
 #pragma unroll
           for (int b = 0; b < NBOX; b++)
@@ -236,18 +237,33 @@ PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__
 #pragma unroll
       for (int r = 0; r < PL::R0; r++) {
         const int e = jl + m * TPL + r * T0;
-        ctx.async_copy16(s + e * TK + tk, src(job, e, tk));
+        ctx.async_copy16(s + e * TK + tk, src(tile, job, e, tk));
       }
   };
-  issue(0);
-  for (int job = 0; job < njobs; job++) {
+  // The block walks the tiles tile0, tile0 + tile_stride, ... (< ntiles) and, on each, the jobs 0 .. njobs-1, as ONE
+  // pipelined sequence: the copies of the next tile's first job are issued where those of the next job would be, so
+  // only the very first load of a block is exposed (r02: with one tile per block that load -- 128 KB at one SM's share
+  // of the bandwidth, 3.7 k cycles -- was 9 % of an x-pass tile and 4.5 % of a y-pass tile).  begin_tile(t) sets the
+  // caller's per-tile state, which xform and store read; src / tsrc take the tile explicitly because they are called
+  // for the NEXT tile while the current one is still being stored.
+  int tile = tile0, job = 0;
+  unsigned int phase = 0;
+  issue(tile, 0);
+  begin_tile(tile);
+  while (true) {
     auto raw_in = [&](int e) { return xform(job, e, tk, s[e * TK + tk]); };
     auto g_out = [&](int e, double2 val) { store(job, e, tk, val); };
+    int ntile = tile, njob = job + 1;
+    if (njob == njobs) {
+      njob = 0;
+      ntile = tile + tile_stride;
+    }
+    const bool more = ntile < ntiles;
     ctx.mark(4 * job + 0);
     bool waited = false;
     if constexpr (CtxHasTma<Ctx>::value) {
       if (tma) {
-        ctx.mbar_wait(bar, (unsigned int)(job & 1));  // the whole tile has landed
+        ctx.mbar_wait(bar, phase);  // the whole tile has landed
         waited = true;
       }
     }
@@ -278,7 +294,7 @@ PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__
       if constexpr (CtxHasTma<Ctx>::value) { if (tma) ctx.fence_async_proxy(); }  // my accesses before the next TMA write
       ctx.sync();  // tile free
       ctx.mark(4 * job + 2);
-      if (job + 1 < njobs) issue(job + 1);
+      if (more) issue(ntile, njob);
       stage_store<L, PL::R2, PL::R0 * PL::R1, DIR, TPL, RMAX>(jl, v, g_out, tw, TWS);
       ctx.mark(4 * job + 3);
     } else {
@@ -286,10 +302,15 @@ PINB_HD void strided_tile_jobs(Ctx& ctx, double2* s, const double2* __restrict__
       if constexpr (CtxHasTma<Ctx>::value) { if (tma) ctx.fence_async_proxy(); }
       ctx.sync();  // tile free
       ctx.mark(4 * job + 2);
-      if (job + 1 < njobs) issue(job + 1);
+      if (more) issue(ntile, njob);
       stage_store<L, PL::R1, PL::R0, DIR, TPL, RMAX, decltype(g_out), (PL::R1 >= 16)>(jl, v, g_out, tw, TWS);
       ctx.mark(4 * job + 3);
     }
+    if (!more) break;
+    if (njob == 0) begin_tile(ntile);
+    tile = ntile;
+    job = njob;
+    phase ^= 1u;
   }
 }
 
@@ -314,8 +335,8 @@ struct XPassParams {
   int lx_shift;         // log2(lx)
   int pmask;            // bit p set -> compute job p
   int ntiles_z;         // kz tiles per row that are processed (M/TK, +1 with the Nyquist tile)
-  int prefetch;         // > 0: pull the source tile of block (bid + prefetch) into L2 while this one computes
-  int nblocks;
+  int nblocks;          // tiles of the pass, ly * ntiles_z (0: one tile per block, tile = block index)
+  int tile_stride;      // blocks of the launch when they walk the tiles bid, bid + stride, ... (0: one tile per block)
   KFactor kf;
   Geom g;
   const double2* tw;    // N-th roots of unity
@@ -333,31 +354,31 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   constexpr int TK = C::TK, LT = C::LT;
   constexpr bool SPLIT = C::SPLIT;
   const Geom& g = p.g;
-  const int yl = ctx.bid() / p.ntiles_z;
-  const int kz0 = (ctx.bid() % p.ntiles_z) * TK;
-  const int ny = fold(g.y0 + yl, g.N, g.M);
-  const double ky = g.knorm * ny;
   const size_t xstride = (size_t)g.ly * g.P;
-  const double2* src = p.src + (size_t)yl * g.P + kz0;
-  // With one 128 KB tile per SM the load, compute and store phases of a block do not overlap
-  // (tools/bwtest: the same access pattern without FFT runs at 4.0-6.7 TB/s).  Pulling the tile
-  // of the block that will run next on some SM into L2 now lets DRAM work during our FFT.
-  if (p.prefetch > 0 && ctx.bid() + p.prefetch < p.nblocks) {
-    const int nb = ctx.bid() + p.prefetch;
-    const double2* nsrc = p.src + (size_t)(nb / p.ntiles_z) * g.P + (size_t)(nb % p.ntiles_z) * TK;
-    for (int e = ctx.tid(); e < L; e += ctx.nthreads()) ctx.prefetch_l2(nsrc + (size_t)e * xstride);
-  }
   int jobs[3], npw = 0;
   for (int pw = 0; pw < 3; pw++)
     if ((p.pmask >> pw) & 1) jobs[npw++] = pw;
-  const size_t roff = (size_t)(g.y0 + yl) * g.P + kz0;  // offset of (y, kz0) inside an R-layout x plane
-  auto srcf = [&](int, int e, int tk) { return src + (size_t)e * xstride + tk; };
-  // per-thread invariants of the mode factor: everything that does not depend on x
+  // state of the tile being transformed and stored (begin_tile); a block walks several tiles, see strided_tile_jobs
+  int yl = 0, kz0 = 0;
+  const double2* src = p.src;
+  size_t roff = 0;      // offset of (y, kz0) inside an R-layout x plane
+  double kyz2 = 0.0, fyz = 0.0;  // per-thread invariants of the mode factor: everything that does not depend on x
   const int tk0 = ctx.tid() % TK;
-  const double kz_t = g.knorm * (kz0 + tk0);  // kz index <= M, never folded
-  const double kyz2 = ky * ky + kz_t * kz_t;
-  double fyz = p.kf.scalar;
-  if (p.kf.gauss) fyz *= ld_ro(p.kf.gauss + (ny < 0 ? -ny : ny)) * ld_ro(p.kf.gauss + kz0 + tk0);
+  auto begin_tile = [&](int t) {
+    yl = t / p.ntiles_z;
+    kz0 = (t % p.ntiles_z) * TK;
+    const int ny = fold(g.y0 + yl, g.N, g.M);
+    const double ky = g.knorm * ny;
+    src = p.src + (size_t)yl * g.P + kz0;
+    roff = (size_t)(g.y0 + yl) * g.P + kz0;
+    const double kz_t = g.knorm * (kz0 + tk0);  // kz index <= M, never folded
+    kyz2 = ky * ky + kz_t * kz_t;
+    fyz = p.kf.scalar;
+    if (p.kf.gauss) fyz *= ld_ro(p.kf.gauss + (ny < 0 ? -ny : ny)) * ld_ro(p.kf.gauss + kz0 + tk0);
+  };
+  auto srcf = [&](int t, int, int e, int tk) {
+    return p.src + (size_t)(t / p.ntiles_z) * g.P + (size_t)(t % p.ntiles_z) * TK + (size_t)e * xstride + tk;
+  };
   GrowthRange grange;
   if constexpr (GK) grange.set(p.kf);
   auto mode = [&](int pw, int e, double2 c) {
@@ -409,9 +430,11 @@ PINB_HD void xpass_body(Ctx& ctx, double2* smem, const XPassParams& p) {
   // without G(k), although the arithmetic is worth 5 ms), so it runs as a rolled pre-pass over the tile like the
   // split passes' combine step
   constexpr int CHUNK = (GK && C::CHUNK == 0) ? 4 : C::CHUNK;
-  auto tsrcf = [&](int) { return TileSrc{&p.tmap, 2 * kz0, yl, 0, 2}; };
-  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * npw : npw, srcf, xform, storef,
-                                                                  p.use_tma != 0, tsrcf);
+  auto tsrcf = [&](int t, int) { return TileSrc{&p.tmap, 2 * (t % p.ntiles_z) * TK, t / p.ntiles_z, 0, 2}; };
+  const int ntiles = p.nblocks > 0 ? p.nblocks : ctx.bid() + 1;
+  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * npw : npw, ctx.bid(),
+                                                                  p.tile_stride > 0 ? p.tile_stride : ntiles, ntiles, begin_tile, srcf,
+                                                                  xform, storef, p.use_tma != 0, tsrcf);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -427,9 +450,9 @@ struct YPassParams {
   YJob job[6];
   int njobs;
   int ntiles_z;
-  int prefetch;           // as in XPassParams
-  int nblocks;
-  int nsrc;               // distinct source fields (prefetched)
+  int nblocks;            // as in XPassParams: lx * ntiles_z, ...
+  int tile_stride;        // ... and the blocks of the launch
+  int nsrc;               // distinct source fields
   Geom g;
   const double2* tw;
   int use_tma;            // as in XPassParams
@@ -442,17 +465,21 @@ PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
   constexpr int TK = C::TK, LT = C::LT;
   constexpr bool SPLIT = C::SPLIT;
   const Geom& g = p.g;
-  const int xl = ctx.bid() / p.ntiles_z;
-  const int kz0 = (ctx.bid() % p.ntiles_z) * TK;
-  const size_t base = (size_t)xl * g.N * g.P + kz0;
-  if (p.prefetch > 0 && ctx.bid() + p.prefetch < p.nblocks) {
-    const int nb = ctx.bid() + p.prefetch;
-    const size_t nbase = (size_t)(nb / p.ntiles_z) * g.N * g.P + (size_t)(nb % p.ntiles_z) * TK;
-    for (int sidx = 0; sidx < p.nsrc; sidx++)
-      for (int e = ctx.tid(); e < L; e += ctx.nthreads()) ctx.prefetch_l2(p.src[sidx] + nbase + (size_t)e * g.P);
-  }
+  int xl = 0, kz0 = 0;
+  size_t base = 0;  // state of the tile being transformed and stored
+  auto begin_tile = [&](int t) {
+    xl = t / p.ntiles_z;
+    kz0 = (t % p.ntiles_z) * TK;
+    base = (size_t)xl * g.N * g.P + kz0;
+  };
   // SPLIT: job = 2*j + h, see XCfg
-  auto srcf = [&](int job, int e, int tk) { return p.src[p.job[SPLIT ? (job >> 1) : job].src] + base + (size_t)e * g.P + tk; };
+  auto srcf = [&](int t, int job, int e, int tk) {
+    return p.src[p.job[SPLIT ? (job >> 1) : job].src] + (size_t)(t / p.ntiles_z) * g.N * g.P + (size_t)(t % p.ntiles_z) * TK +
+           (size_t)e * g.P + tk;
+  };
+  // (r02: ky^q from an L1-resident table instead of fold + int -> double + multiply per element made the pass SLOWER,
+  // 21.0 -> 26.4 ms at 1024^3 with bit-identical output, profiles/r02_slabbench_kpow.txt: the loads sit in the
+  // dependency chain of stage 0 where the conversions do not)
   auto mode = [&](int q, int e, double2 c) {
     if (q) c = cscale(c, ipow(g.knorm * fold(e, g.N, g.M), q));
     return c;
@@ -478,9 +505,13 @@ PINB_HD void ypass_body(Ctx& ctx, double2* smem, const YPassParams& p) {
       p.dst[p.job[j].dst][base + (size_t)e * g.P + tk] = val;
     }
   };
-  auto tsrcf = [&](int job) { return TileSrc{&p.tmap[p.job[SPLIT ? (job >> 1) : job].src], 2 * kz0, 0, xl, 1}; };
-  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, C::CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * p.njobs : p.njobs, srcf, xform, storef,
-                                                                     p.use_tma != 0, tsrcf);
+  auto tsrcf = [&](int t, int job) {
+    return TileSrc{&p.tmap[p.job[SPLIT ? (job >> 1) : job].src], 2 * (t % p.ntiles_z) * TK, 0, t / p.ntiles_z, 1};
+  };
+  const int ntiles = p.nblocks > 0 ? p.nblocks : ctx.bid() + 1;
+  strided_tile_jobs<LT, TK, DIR, typename C::PL, L / LT, C::CHUNK>(ctx, smem, p.tw, SPLIT ? 2 * p.njobs : p.njobs, ctx.bid(),
+                                                                     p.tile_stride > 0 ? p.tile_stride : ntiles, ntiles, begin_tile, srcf,
+                                                                     xform, storef, p.use_tma != 0, tsrcf);
 }
 
 // ---------------------------------------------------------------------------------------

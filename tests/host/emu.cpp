@@ -189,24 +189,30 @@ extern "C" int emu_zline_fft(int M, int dir, const double* in, double* out, cons
 }
 
 // ---- whole kernels on pitched arrays (K layout [N][ly][P], R layout [lx][N][P]) ---------------
+// blocks of a strided pass: fewer than tiles, and not a divisor of their number, so that the blocks walk several tiles
+// each (as the persistent launches of k_strided.cu do) and the last round is ragged
+static int emu_grid(int ntiles) { return ntiles > 7 ? 7 : ntiles; }
 template <int N, int DIR> static void xpass_run(XPassParams& p, int with_nyq) {
   if constexpr (DIR > 0 && XCfg<N, +1>::SPLIT) {
     if (p.dst_klayout == 2 && !p.kf.gk) {  // as xpass_launch (k_strided.cu): the all-local pass never splits its lines
       using C = XCfg<N, +1, true>;
       p.ntiles_z = (N / 2) / C::TK + (with_nyq ? 1 : 0);
       std::vector<double2> smem((size_t)C::LT * C::TK);
-      run_blocks((long long)p.g.ly * p.ntiles_z, C::NT,
-                 [&](HostCtx& ctx) { xpass_body<N, +1, false, HostCtx, false, true>(ctx, smem.data(), p); });
+      p.nblocks = p.g.ly * p.ntiles_z;
+      p.tile_stride = emu_grid(p.nblocks);
+      run_blocks(p.tile_stride, C::NT, [&](HostCtx& ctx) { xpass_body<N, +1, false, HostCtx, false, true>(ctx, smem.data(), p); });
       return;
     }
   }
   using C = XCfg<N, DIR>;
   p.ntiles_z = (N / 2) / C::TK + (with_nyq ? 1 : 0);
   std::vector<double2> smem((size_t)C::LT * C::TK);
+  p.nblocks = p.g.ly * p.ntiles_z;
+  p.tile_stride = emu_grid(p.nblocks);
   if (p.kf.gk)
-    run_blocks((long long)p.g.ly * p.ntiles_z, C::NT, [&](HostCtx& ctx) { xpass_body<N, DIR, true, HostCtx, true>(ctx, smem.data(), p); });
+    run_blocks(p.tile_stride, C::NT, [&](HostCtx& ctx) { xpass_body<N, DIR, true, HostCtx, true>(ctx, smem.data(), p); });
   else
-    run_blocks((long long)p.g.ly * p.ntiles_z, C::NT, [&](HostCtx& ctx) { xpass_body<N, DIR, true>(ctx, smem.data(), p); });
+    run_blocks(p.tile_stride, C::NT, [&](HostCtx& ctx) { xpass_body<N, DIR, true>(ctx, smem.data(), p); });
 }
 
 // dsts: 3*nranks pointers, dsts[p*nranks + r] = destination field for power p on rank r
@@ -259,7 +265,9 @@ template <int N, int DIR> static void ypass_run(YPassParams& p, int with_nyq) {
   using C = YCfg<N>;
   p.ntiles_z = (N / 2) / C::TK + (with_nyq ? 1 : 0);
   std::vector<double2> smem((size_t)C::LT * C::TK);
-  run_blocks((long long)p.g.lx * p.ntiles_z, C::NT, [&](HostCtx& ctx) { ypass_body<N, DIR>(ctx, smem.data(), p); });
+  p.nblocks = p.g.lx * p.ntiles_z;
+  p.tile_stride = emu_grid(p.nblocks);
+  run_blocks(p.tile_stride, C::NT, [&](HostCtx& ctx) { ypass_body<N, DIR>(ctx, smem.data(), p); });
 }
 
 // srcs[3], dsts[6]: pointers (may be null); kdsts[nranks] (forward scatter); jobs: njobs x (src, q, dst)

@@ -249,7 +249,7 @@ def test_reference_disagrees_with_itself_only_on_flagged_cells(cosmo):
     inverse_collapse_time, compiled from the same sources under three code generations (oracle/Makefile: -O3,
     -O0 -ffp-contract=off, -O3 -mfma -ffp-contract=fast), differs from itself by more than the 1e-6 contract on
     some cells -- and every such cell is one the perturbation test flags.  Outside the mask the three builds agree
-    to 1e-7, so a comparison there is meaningful; inside it "the reference's value" depends on the compiler."""
+    to 2e-7, so a comparison there is meaningful; inside it "the reference's value" depends on the compiler."""
     libs = {}
     for tag in ("", "_O0", "_fma"):
         path = ROOT / "oracle" / "_ref" / f"libpinocchio_ref{tag}.so"
@@ -287,5 +287,6 @@ def test_reference_disagrees_with_itself_only_on_flagged_cells(cosmo):
     assert self_dis.sum() >= 1                       # the effect exists in the reference's own code ...
     assert not (self_dis & ~mask).any()              # ... and only on flagged cells
     assert mask.mean() < 2e-4
-    loose = differ(F[""], F["_O0"], 1e-7) | differ(F[""], F["_fma"], 1e-7)
-    assert not (loose & ~mask).any()                 # elsewhere the three builds agree to 1e-7, ten times inside the contract
+    loose = differ(F[""], F["_O0"], 2e-7) | differ(F[""], F["_fma"], 2e-7)
+    assert not (loose & ~mask).any()                 # elsewhere the three builds agree to 2e-7, five times inside the contract
+    # (the worst unflagged cell of this set: 1.1e-7 between -O3 and -mfma, a cell with F = 0.916 < 1)

@@ -89,7 +89,7 @@ template <int N, int TK, int MINB> void bench_x(const Geom& g, double2* src, dou
   CKE(cudaFuncSetAttribute(xk<N, TK, +1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   XPassParams p{};
   p.src = src; p.dst[0].r[0] = A[0]; p.dst[1].r[0] = A[1]; p.dst[2].r[0] = A[2]; p.dst_klayout = 0; p.lx_shift = 10; p.pmask = pmask; p.ntiles_z = g.M / TK;
-  p.kf.gauss = gauss; p.kf.scalar = 1e-9; p.kf.green = 1; p.kf.times_i = 0; p.g = g; p.tw = tw; p.prefetch = pf; p.nblocks = g.ly * p.ntiles_z;
+  p.kf.gauss = gauss; p.kf.scalar = 1e-9; p.kf.green = 1; p.kf.times_i = 0; p.g = g; p.tw = tw; p.nblocks = g.ly * p.ntiles_z;
   Timer t;
   float ms = t.run([&] { xk<N, TK, +1, MINB><<<g.ly * p.ntiles_z, NT, smem>>>(p); });
   int nout = __builtin_popcount(pmask);
@@ -108,7 +108,7 @@ template <int N, int TK, int MINB> void bench_y(const Geom& g, double2** A, doub
   for (int i = 0; i < 6; i++) p.dst[i] = B[i];
   static const YJob jobs[6] = {{2, 0, 0}, {0, 2, 1}, {0, 0, 2}, {1, 1, 3}, {1, 0, 4}, {0, 1, 5}};
   for (int i = 0; i < njobs; i++) p.job[i] = jobs[i];
-  p.njobs = njobs; p.dst_klayout = 0; p.ly_shift = 10; p.ntiles_z = g.M / TK; p.g = g; p.tw = tw; p.prefetch = pf; p.nblocks = g.lx * p.ntiles_z; p.nsrc = njobs == 6 ? 3 : 1; if (njobs == 1) p.job[0] = YJob{0, 0, 0};
+  p.njobs = njobs; p.dst_klayout = 0; p.ly_shift = 10; p.ntiles_z = g.M / TK; p.g = g; p.tw = tw; p.nblocks = g.lx * p.ntiles_z; p.nsrc = njobs == 6 ? 3 : 1; if (njobs == 1) p.job[0] = YJob{0, 0, 0};
   Timer t;
   float ms = t.run([&] { yk<N, TK, +1, MINB><<<g.lx * p.ntiles_z, NT, smem>>>(p); });
   double gb = (njobs == 6 ? 9 : 2 * njobs) * 16.0 * g.N * g.N * g.M / 1e9;
