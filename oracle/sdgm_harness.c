@@ -48,9 +48,13 @@ int main(int argc, char **argv) {
   const double t1 = wall();
   if (set_scaledep_GM()) return 1;
   const double t_ref = wall() - t1;
+  /* twice: the first call pays for the CUDA context of this process */
   const double t2 = wall();
   if (set_scaledep_GM_b200()) return 1;
-  const double t_b200 = wall() - t2;
+  const double t_b200_first = wall() - t2;
+  const double t3 = wall();
+  if (set_scaledep_GM_b200()) return 1;
+  const double t_b200 = wall() - t3;
 
   double worst_vec = 0.0, worst_rad = 0.0;
   for (int r = 0; r < S; r++) {
@@ -61,9 +65,9 @@ int main(int argc, char **argv) {
       worst_vec = fmax(worst_vec, fabs(a - b) / b);
     }
   }
-  printf("\n{\"nsmooth\": %d, \"nbins\": %d, \"nkbins\": %d, \"t_initialization_s\": %.3f, \"t_reference_s\": %.4f, \"t_b200_binding_s\": %.4f, "
+  printf("\n{\"nsmooth\": %d, \"nbins\": %d, \"nkbins\": %d, \"t_initialization_s\": %.3f, \"t_reference_s\": %.4f, \"t_b200_binding_first_call_s\": %.4f, \"t_b200_binding_s\": %.4f, "
          "\"invgrow_vector_max_rel\": %.3e, \"rad_gm_max_abs\": %.3e, \"k_gm\": [",
-         S, NBINS, NkBINS, t_init, t_ref, t_b200, worst_vec, worst_rad);
+         S, NBINS, NkBINS, t_init, t_ref, t_b200_first, t_b200, worst_vec, worst_rad);
   const double *mine[3] = {Smoothing.k_GM_dens, Smoothing.k_GM_displ, Smoothing.k_GM_vel};
   for (int q = 0; q < 3; q++)
     for (int r = 0; r < S; r++) printf("%s[%d, %d, %.17g, %.17g]", (q || r) ? ", " : "", q, r, ref_k[q * S + r], mine[q][r]);

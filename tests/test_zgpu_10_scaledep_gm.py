@@ -46,5 +46,5 @@ def test_reference_set_scaledep_gm_against_linked_binding(tmp_path):
     assert d["invgrow_vector_max_rel"] < 1e-6 and d["rad_gm_max_abs"] == 0.0
     ks = np.array([[a, b] for _, _, a, b in d["k_gm"]])
     assert len(np.unique(ks[:, 0])) >= 4 and np.array_equal(ks[:, 0], ks[:, 1])
-    # one device call against 3 x Nsmooth x 210 adaptive integrals on one host core
-    assert d["t_b200_binding_s"] < d["t_reference_s"]
+    # (timings are printed, not asserted: both include the host-side bisection, and the binding's first call the CUDA
+    # context; the device call itself is timed by bench.py, scaledep.startup_integrals)
