@@ -52,10 +52,14 @@ static bool make_tile_map(TileMap* out, const double2* field, int pitch, int ny,
 // Blocks of a strided pass: as many as are resident at once; each walks the tiles bid, bid + grid, ... so that the
 // load of its next tile overlaps the stores of the current one (strided_tile_jobs).  PINB200_PERSISTENT=0: one tile
 // per block.
-template <class K> static unsigned strided_grid(K kernel, int nthreads, size_t smem, unsigned ntiles, int* tile_stride) {
+// Passes that store into PEER memory keep one tile per block: on 8 GPUs the displacement stage, whose transposes are
+// peer stores, took 2.3 s instead of 0.5 s with walking blocks (r02, profiles/r02_multi/bench_8gpu_2048_walk_everywhere.json)
+// -- a block that walks on to its next tile while the NVLink stores of the last one drain stalls behind them, where a
+// fresh block on another SM does not.
+template <class K> static unsigned strided_grid(K kernel, int nthreads, size_t smem, unsigned ntiles, int* tile_stride, bool peer_stores) {
   static const bool persistent = [] { const char* e = getenv("PINB200_PERSISTENT"); return !(e && !atoi(e)); }();
   *tile_stride = 0;
-  if (!persistent) return ntiles;
+  if (!persistent || peer_stores) return ntiles;
   int dev = 0, sms = 0, occ = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, nthreads, smem) != cudaSuccess || occ < 1 || sms < 1)
@@ -118,7 +122,7 @@ template <int L, int DIR, bool MULTI> static cudaError_t xpass_launch_m(const XP
   cudaError_t e = allow_smem(xpass_kernel<L, DIR, MULTI>, smem);
   if (e != cudaSuccess) return e;
   p.nblocks = nblocks_y * p.ntiles_z;
-  const unsigned grid = strided_grid(xpass_kernel<L, DIR, MULTI>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride);
+  const unsigned grid = strided_grid(xpass_kernel<L, DIR, MULTI>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride, MULTI && p.dst_klayout == 0);
   xpass_kernel<L, DIR, MULTI><<<grid, C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
@@ -130,7 +134,7 @@ template <int L, bool MULTI> static cudaError_t xpass_growthk_launch_m(const XPa
   cudaError_t e = allow_smem(xpass_growthk_kernel<L, MULTI>, smem);
   if (e != cudaSuccess) return e;
   p.nblocks = nblocks_y * p.ntiles_z;
-  const unsigned grid = strided_grid(xpass_growthk_kernel<L, MULTI>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride);
+  const unsigned grid = strided_grid(xpass_growthk_kernel<L, MULTI>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride, MULTI && p.dst_klayout == 0);
   xpass_growthk_kernel<L, MULTI><<<grid, C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
@@ -142,7 +146,7 @@ template <int L> static cudaError_t xpass_local_launch(const XPassParams& p_in, 
   cudaError_t e = allow_smem(xpass_local_kernel<L>, smem);
   if (e != cudaSuccess) return e;
   p.nblocks = nblocks_y * p.ntiles_z;
-  const unsigned grid = strided_grid(xpass_local_kernel<L>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride);
+  const unsigned grid = strided_grid(xpass_local_kernel<L>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride, false);
   xpass_local_kernel<L><<<grid, C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
@@ -169,7 +173,7 @@ template <int L, int DIR> static cudaError_t ypass_launch(const YPassParams& p_i
   cudaError_t e = allow_smem(ypass_kernel<L, DIR>, smem);
   if (e != cudaSuccess) return e;
   p.nblocks = nblocks_x * p.ntiles_z;
-  const unsigned grid = strided_grid(ypass_kernel<L, DIR>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride);
+  const unsigned grid = strided_grid(ypass_kernel<L, DIR>, C::NT, smem, (unsigned)p.nblocks, &p.tile_stride, p.dst_klayout != 0 && p.g.lx != p.g.N);
   ypass_kernel<L, DIR><<<grid, C::NT, smem, s>>>(p);
   return cudaGetLastError();
 }
