@@ -263,6 +263,11 @@ def run_b200(args):
                 "per_radius_ms": round(rad_ms, 3),
                 "per_radius_frac_of_survey_roofline": round(survey_rad / (rad_ms * 1e-3) / 1e9 / peak, 4),
                 "lpt_stage_ms": round(lpt_ms, 3),
+                # the engine's own split of the displacement stage: sources + k-vectors (three r2c, the contraction),
+                # the four velocity triples, and inside those the four inverse x passes (peer stores at N > 1)
+                "lpt_breakdown_ms": {"sources_and_kvectors": round((tm1.disp_sources - tm0.disp_sources) / K * 1e3, 2),
+                                     "velocities": round((tm1.disp_vel - tm0.disp_vel) / K * 1e3, 2),
+                                     "velocity_x_passes": round((tm1.disp_x - tm0.disp_x) / K * 1e3, 2)},
                 "lpt_frac_of_survey_roofline": round(survey_lpt / (lpt_ms * 1e-3) / 1e9 / peak, 4),
                 "whole_step_frac_of_survey_roofline": round(survey_total / (ms_per_step * 1e-3) / 1e9 / peak, 4)}
     # Instruction-issue roofline of every radius kernel: a sub-partition dispatches one warp instruction per clock and an
