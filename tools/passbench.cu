@@ -1,5 +1,5 @@
 // Stand-alone tuning harness: times variants of the FFT pass kernels on synthetic 1024^3 buffers.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/passbench tools/passbench.cu
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -o tools/passbench tools/passbench.cu
 // Not part of the product library.
 #include <cstdio>
 #include <cstdlib>
