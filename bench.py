@@ -380,81 +380,95 @@ def run_b200(args):
                     phases[name] += t[k + 1] - t[k]
                 return float(rec_np["Fmax"][0]) + float(fm_host[0])
 
-            e2e_step()
-            barrier()
-            for k in phases:
-                phases[k] = 0.0
-            w0 = time.perf_counter()
+            # A failing library call (an allocation, say) fails on every rank alike -- same sizes, same order of calls --
+            # so all ranks leave the block together and the line is still printed, with the reason in e2e.error.
+            e2e_err = ""
             ne = max(1, min(args.steps, 3))
-            for _ in range(ne):
+            w = float("nan")
+            try:
                 e2e_step()
-            barrier()
-            w = (time.perf_counter() - w0) / ne
-            sort_ms = pin.timers().sort_ms
-            tw = torch.tensor([w], device="cuda", dtype=torch.float64)
-            tc = torch.tensor([float(ncoll)], device="cuda", dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-                dist.all_reduce(tc, op=dist.ReduceOp.SUM)
-            ncoll_all = int(tc.item())
-            # the hand-off is what the fragmentation would get: ordered, all collapsed cells, records of the right cells
-            fs = rec_np["Fmax"][:ncoll]
-            order_ok = bool(ncoll == 0 or ((np.diff(fs[:: max(1, ncoll // (1 << 22))]) <= 0).all() and fs[-1] >= flast
-                                           and np.array_equal(fs[:4096], fm_host.numpy()[idx_host.numpy()[:4096].view(np.uint32)])))
-            e2e = {"value": round(cells / float(tw.item()) / 1e6, 2), "unit": "Mcells/s",
-                   "h2d_bytes_per_step": int(N * N * (N // 2 + 1) * 16),
-                   "d2h_bytes_per_step": int(4 * N ** 3 + 60 * ncoll_all),
-                   "steps": ne, "ms_per_step": round(float(tw.item()) * 1e3, 2),
-                   "handoff": "Fmax of every cell + index list and 56-byte records of the cells with Fmax >= 1 in order of descending "
-                              "Fmax (device-side selection + radix sort), as shim/fmax_b200.c fills products[] for src/distribute.c",
-                   "collapsed_cells": ncoll_all, "select_sort_ms_device": round(float(sort_ms), 2), "handoff_ok": order_ok,
-                   "phases_ms_rank0": {k: round(v / ne * 1e3, 1) for k, v in phases.items()}}
-            tme1 = pin.timers()
-            # the compute phase on the device clock (CUDA events inside the engine) next to its wall-clock time above
-            e2e["phases_ms_rank0"]["compute_device_events"] = round(((tme1.fmax - tme0.fmax) + (tme1.lpt - tme0.lpt)) * 1e3 / (ne + 1), 1)
-            # the plain copy of every record, once, for comparison (r01's e2e definition)
-            try:
-                chunk = min(ncell_local, 1 << 26)
-                nst = min(chunk * 56, rec_host.numel())
-                chunk = nst // 56
                 barrier()
+                for k in phases:
+                    phases[k] = 0.0
                 w0 = time.perf_counter()
-                pin._ck(pin.lib.pinb200_upload_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
-                pin.compute_fmax(displacements=True)
-                for b0 in range(0, ncell_local, chunk):
-                    nn = min(chunk, ncell_local - b0)
-                    pin._ck(pin.lib.pinb200_download_products(pin.h, ctypes.c_void_p(rec_host.data_ptr()), ctypes.byref(lay), b0, nn))
+                for _ in range(ne):
+                    e2e_step()
                 barrier()
-                wf = time.perf_counter() - w0
-                twf = torch.tensor([wf], device="cuda", dtype=torch.float64)
+                w = (time.perf_counter() - w0) / ne
+            except Exception as ex:  # noqa: BLE001
+                e2e_err = str(ex)[:300] or type(ex).__name__
+            okf = torch.tensor([0 if e2e_err else 1], device="cuda")
+            if world > 1:
+                dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if int(okf.item()) == 0:
+                e2e = {"value": None, "unit": "Mcells/s", "error": e2e_err or "the e2e step failed on a peer rank"}
+                del kd_host, fm_host, idx_host, rec_host
+            if e2e is None:
+                sort_ms = pin.timers().sort_ms
+                tw = torch.tensor([w], device="cuda", dtype=torch.float64)
+                tc = torch.tensor([float(ncoll)], device="cuda", dtype=torch.float64)
                 if world > 1:
-                    dist.all_reduce(twf, op=dist.ReduceOp.MAX)
-                e2e["full_aos"] = {"ms_per_step": round(float(twf.item()) * 1e3, 2), "value": round(cells / float(twf.item()) / 1e6, 2),
-                                   "d2h_bytes_per_step": int(N ** 3 * 56), "steps": 1}
-            except Exception as ex:  # noqa: BLE001
-                e2e["full_aos"] = {"error": str(ex)[:200]}
-            # the e2e step is PCIe-bound: report the bare pinned-copy rates of this box beside it, so that
-            # (h2d_bytes / h2d_gbs + d2h_bytes / d2h_gbs + device step) can be compared with ms_per_step
-            try:
-                nb = int(min(rec_host.numel(), 1 << 30))
-                dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
-                rates = {}
-                for name, (dst, src) in {"d2h_gbs": (rec_host[:nb], dbuf), "h2d_gbs": (dbuf, rec_host[:nb])}.items():
-                    dst.copy_(src, non_blocking=True)
-                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    ev0.record()
-                    for _ in range(3):
+                    dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+                ncoll_all = int(tc.item())
+                # the hand-off is what the fragmentation would get: ordered, all collapsed cells, records of the right cells
+                fs = rec_np["Fmax"][:ncoll]
+                order_ok = bool(ncoll == 0 or ((np.diff(fs[:: max(1, ncoll // (1 << 22))]) <= 0).all() and fs[-1] >= flast
+                                               and np.array_equal(fs[:4096], fm_host.numpy()[idx_host.numpy()[:4096].view(np.uint32)])))
+                e2e = {"value": round(cells / float(tw.item()) / 1e6, 2), "unit": "Mcells/s",
+                       "h2d_bytes_per_step": int(N * N * (N // 2 + 1) * 16),
+                       "d2h_bytes_per_step": int(4 * N ** 3 + 60 * ncoll_all),
+                       "steps": ne, "ms_per_step": round(float(tw.item()) * 1e3, 2),
+                       "handoff": "Fmax of every cell + index list and 56-byte records of the cells with Fmax >= 1 in order of descending "
+                                  "Fmax (device-side selection + radix sort), as shim/fmax_b200.c fills products[] for src/distribute.c",
+                       "collapsed_cells": ncoll_all, "select_sort_ms_device": round(float(sort_ms), 2), "handoff_ok": order_ok,
+                       "phases_ms_rank0": {k: round(v / ne * 1e3, 1) for k, v in phases.items()}}
+                tme1 = pin.timers()
+                # the compute phase on the device clock (CUDA events inside the engine) next to its wall-clock time above
+                e2e["phases_ms_rank0"]["compute_device_events"] = round(((tme1.fmax - tme0.fmax) + (tme1.lpt - tme0.lpt)) * 1e3 / (ne + 1), 1)
+                # the plain copy of every record, once, for comparison (r01's e2e definition)
+                try:
+                    chunk = min(ncell_local, 1 << 26)
+                    nst = min(chunk * 56, rec_host.numel())
+                    chunk = nst // 56
+                    barrier()
+                    w0 = time.perf_counter()
+                    pin._ck(pin.lib.pinb200_upload_kdensity(pin.h, ctypes.cast(kd_host.data_ptr(), _PD)))
+                    pin.compute_fmax(displacements=True)
+                    for b0 in range(0, ncell_local, chunk):
+                        nn = min(chunk, ncell_local - b0)
+                        pin._ck(pin.lib.pinb200_download_products(pin.h, ctypes.c_void_p(rec_host.data_ptr()), ctypes.byref(lay), b0, nn))
+                    barrier()
+                    wf = time.perf_counter() - w0
+                    twf = torch.tensor([wf], device="cuda", dtype=torch.float64)
+                    if world > 1:
+                        dist.all_reduce(twf, op=dist.ReduceOp.MAX)
+                    e2e["full_aos"] = {"ms_per_step": round(float(twf.item()) * 1e3, 2), "value": round(cells / float(twf.item()) / 1e6, 2),
+                                       "d2h_bytes_per_step": int(N ** 3 * 56), "steps": 1}
+                except Exception as ex:  # noqa: BLE001
+                    e2e["full_aos"] = {"error": str(ex)[:200]}
+                # the e2e step is PCIe-bound: report the bare pinned-copy rates of this box beside it, so that
+                # (h2d_bytes / h2d_gbs + d2h_bytes / d2h_gbs + device step) can be compared with ms_per_step
+                try:
+                    nb = int(min(rec_host.numel(), 1 << 30))
+                    dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+                    rates = {}
+                    for name, (dst, src) in {"d2h_gbs": (rec_host[:nb], dbuf), "h2d_gbs": (dbuf, rec_host[:nb])}.items():
                         dst.copy_(src, non_blocking=True)
-                    ev1.record()
-                    ev1.synchronize()
-                    rates[name] = round(3 * nb / (ev0.elapsed_time(ev1) * 1e-3) / 1e9, 1)
-                del dbuf
-                e2e["pcie_pinned_copy"] = dict(rates, bytes=nb)
-                pcie_ms = (e2e["h2d_bytes_per_step"] / rates["h2d_gbs"] + e2e["d2h_bytes_per_step"] / rates["d2h_gbs"]) / world / 1e6
-                e2e["pcie_floor_ms_per_step"] = round(pcie_ms, 1)
-            except Exception as ex:  # noqa: BLE001
-                e2e["pcie_pinned_copy"] = {"error": str(ex)[:200]}
-            del kd_host, fm_host, idx_host, rec_host
+                        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        ev0.record()
+                        for _ in range(3):
+                            dst.copy_(src, non_blocking=True)
+                        ev1.record()
+                        ev1.synchronize()
+                        rates[name] = round(3 * nb / (ev0.elapsed_time(ev1) * 1e-3) / 1e9, 1)
+                    del dbuf
+                    e2e["pcie_pinned_copy"] = dict(rates, bytes=nb)
+                    pcie_ms = (e2e["h2d_bytes_per_step"] / rates["h2d_gbs"] + e2e["d2h_bytes_per_step"] / rates["d2h_gbs"]) / world / 1e6
+                    e2e["pcie_floor_ms_per_step"] = round(pcie_ms, 1)
+                except Exception as ex:  # noqa: BLE001
+                    e2e["pcie_pinned_copy"] = {"error": str(ex)[:200]}
+                del kd_host, fm_host, idx_host, rec_host
 
     # ---- BASELINE.json configs[4]: scale-dependent growth (massive neutrinos / modified gravity) at the same grid:
     #      the displacement fields are re-derived per redshift segment with a growth rate G(|k|) evaluated per mode in
