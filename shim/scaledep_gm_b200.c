@@ -6,7 +6,7 @@
  * reference's: Smoothing.Rad_GM, Smoothing.k_GM_dens / _displ / _vel and, with -DELL_CLASSIC, the per-radius
  * inverse-growth splines SPLINE_INVGROW[] that InverseGrowingMode (src/cosmo.c:1828) and, through
  * pinb200_set_invgrow_spline, the collapse kernel read.  A maintainer's one-line change is at the call site
- * (INTEGRATION.md section 6): `if (set_scaledep_GM_b200()) return 1;`.
+ * (INTEGRATION.md section 7a): `if (set_scaledep_GM_b200()) return 1;`.
  *
  * What runs where.  Host, unchanged reference calls: PowerSpectrum(k) at the quadrature nodes (any WhichSpectrum,
  * WDM cut included), the k-bin growth splines at the time knots (my_spline_eval on SPLINE[SP_GROW1 + kk],
